@@ -1,0 +1,281 @@
+// Element mathematics of the Newmark Kelvin-Voigt solid on P1 simplices (fp64).
+//
+// Stands in for the FFC/UFLACS-generated tabulate_tensor of the reference's UFL forms
+// (/root/reference/src/femvf/equations/form.py:516-533 inertia, :540-572 elastic,
+//  :965-990 Kelvin-Voigt, :733-756 follower pressure, :759-794 contact traction,
+//  :800-855 membrane, :1067-1113 Newmark substitution; equations/uflcontinuum.py:9-26,
+//  :73-88, :172-186).  Closed forms: SURVEY.md App. A.3.
+//
+// Everything here is __host__ __device__ so that tests/hostcheck can run the very same
+// arithmetic on the CPU against the oracle.  The product path only ever calls it from
+// CUDA kernels.
+#pragma once
+
+#if defined(__CUDACC__)
+#define VF_HD __host__ __device__ __forceinline__
+#else
+#define VF_HD inline
+#endif
+
+namespace vf {
+
+// Newmark constants of the reference (form.py:1083-1084): gamma = 1/2, beta = 1/4.
+constexpr double kGamma = 0.5;
+constexpr double kBeta = 0.25;
+
+VF_HD double newmark_cv(double dt) { return kGamma / kBeta / dt; }          // d v1 / d u1
+VF_HD double newmark_ca(double dt) { return 1.0 / kBeta / (dt * dt); }      // d a1 / d u1
+
+// newmark.py:8-29
+VF_HD double newmark_v(double u1, double u0, double v0, double a0, double dt) {
+  return kGamma / kBeta / dt * (u1 - u0) - (kGamma / kBeta - 1.0) * v0 -
+         dt * (kGamma / 2.0 / kBeta - 1.0) * a0;
+}
+// newmark.py:57-73
+VF_HD double newmark_a(double u1, double u0, double v0, double a0, double dt) {
+  return 1.0 / kBeta / (dt * dt) * (u1 - u0 - dt * v0) - (1.0 / 2.0 / kBeta - 1.0) * a0;
+}
+
+template <int D>
+struct CellGeo {
+  double G[D + 1][D];  // constant shape-function gradients
+  double vol;          // cell measure |K|
+};
+
+VF_HD void p1_geometry(const double (&x)[3][2], CellGeo<2>& g) {
+  const double e1x = x[1][0] - x[0][0], e1y = x[1][1] - x[0][1];
+  const double e2x = x[2][0] - x[0][0], e2y = x[2][1] - x[0][1];
+  const double det = e1x * e2y - e1y * e2x;
+  const double inv = 1.0 / det;
+  g.vol = 0.5 * det;
+  g.G[1][0] = e2y * inv;
+  g.G[1][1] = -e2x * inv;
+  g.G[2][0] = -e1y * inv;
+  g.G[2][1] = e1x * inv;
+  g.G[0][0] = -(g.G[1][0] + g.G[2][0]);
+  g.G[0][1] = -(g.G[1][1] + g.G[2][1]);
+}
+
+VF_HD void cross3(const double* a, const double* b, double* c) {
+  c[0] = a[1] * b[2] - a[2] * b[1];
+  c[1] = a[2] * b[0] - a[0] * b[2];
+  c[2] = a[0] * b[1] - a[1] * b[0];
+}
+
+VF_HD void p1_geometry(const double (&x)[4][3], CellGeo<3>& g) {
+  double e1[3], e2[3], e3[3], c23[3], c31[3], c12[3];
+  for (int i = 0; i < 3; ++i) {
+    e1[i] = x[1][i] - x[0][i];
+    e2[i] = x[2][i] - x[0][i];
+    e3[i] = x[3][i] - x[0][i];
+  }
+  cross3(e2, e3, c23);
+  cross3(e3, e1, c31);
+  cross3(e1, e2, c12);
+  const double det = e1[0] * c23[0] + e1[1] * c23[1] + e1[2] * c23[2];
+  const double inv = 1.0 / det;
+  g.vol = det / 6.0;
+  for (int i = 0; i < 3; ++i) {
+    g.G[1][i] = c23[i] * inv;
+    g.G[2][i] = c31[i] * inv;
+    g.G[3][i] = c12[i] * inv;
+    g.G[0][i] = -(g.G[1][i] + g.G[2][i] + g.G[3][i]);
+  }
+}
+
+// Per-cell material factors already multiplied by |K| and the Newmark coefficients.
+struct CellCoef {
+  double lamv;   // lambda |K|
+  double muv;    // mu |K|
+  double visv;   // eta/2 |K|           (viscous stress is eta*eps(v), form.py:984)
+  double massv;  // rho |K| / ((d+1)(d+2))
+};
+
+template <int D>
+VF_HD CellCoef cell_coef(double emod, double nu, double eta, double rho, double vol) {
+  CellCoef c;
+  const double lam = emod * nu / (1.0 + nu) / (1.0 - 2.0 * nu);  // uflcontinuum.py:22
+  const double mu = emod / 2.0 / (1.0 + nu);                     // uflcontinuum.py:23
+  c.lamv = lam * vol;
+  c.muv = mu * vol;
+  c.visv = 0.5 * eta * vol;
+  c.massv = rho * vol / double((D + 1) * (D + 2));
+  return c;
+}
+
+// Block (a, c) of d F_u / d u1 from the cell integrals: 4M/dt^2 + 2C/dt + K  (App. A.3).
+template <int D>
+VF_HD void cell_block(const CellGeo<D>& g, const CellCoef& cf, double cv, double ca, int a,
+                      int c, double (&blk)[D][D]) {
+  double gg = 0.0;
+  for (int i = 0; i < D; ++i) gg += g.G[a][i] * g.G[c][i];
+  const double mv = cf.muv + cv * cf.visv;
+  for (int i = 0; i < D; ++i)
+    for (int j = 0; j < D; ++j)
+      blk[i][j] = cf.lamv * g.G[a][i] * g.G[c][j] + mv * g.G[c][i] * g.G[a][j];
+  const double dg = mv * gg + ca * cf.massv * (a == c ? 2.0 : 1.0);
+  for (int i = 0; i < D; ++i) blk[i][i] += dg;
+}
+
+// Residual of the cell integrals at local node a.  U, V, A: nodal u1, v_nmk, a_nmk.
+template <int D>
+VF_HD void cell_residual(const CellGeo<D>& g, const CellCoef& cf, int a,
+                         const double (&U)[D + 1][D], const double (&V)[D + 1][D],
+                         const double (&A)[D + 1][D], double (&r)[D]) {
+  double gu[D][D], gv[D][D];
+  for (int i = 0; i < D; ++i)
+    for (int j = 0; j < D; ++j) {
+      double su = 0.0, sv = 0.0;
+      for (int b = 0; b <= D; ++b) {
+        su += U[b][i] * g.G[b][j];
+        sv += V[b][i] * g.G[b][j];
+      }
+      gu[i][j] = su;
+      gv[i][j] = sv;
+    }
+  double tr = 0.0;
+  for (int i = 0; i < D; ++i) tr += gu[i][i];
+  for (int i = 0; i < D; ++i) {
+    double s = 0.0;
+    for (int j = 0; j < D; ++j) {
+      double sig = cf.muv * (gu[i][j] + gu[j][i]) + cf.visv * (gv[i][j] + gv[j][i]);
+      if (i == j) sig += cf.lamv * tr;
+      s += sig * g.G[a][j];
+    }
+    double m = 0.0;
+    for (int b = 0; b <= D; ++b) m += (a == b ? 2.0 : 1.0) * A[b][i];
+    r[i] = s + cf.massv * m;
+  }
+}
+
+// --- exterior-facet terms ---------------------------------------------------------
+// A facet is stored as (parent cell, local vertex o opposite the facet).  Its outward
+// unit normal is -G_o / |G_o| and its measure is d |K| |G_o|.
+template <int D>
+VF_HD void facet_geometry(const CellGeo<D>& g, int o, double (&N)[D], double& meas) {
+  double n2 = 0.0;
+  for (int i = 0; i < D; ++i) n2 += g.G[o][i] * g.G[o][i];
+  const double nrm = sqrt(n2);
+  for (int i = 0; i < D; ++i) N[i] = -g.G[o][i] / nrm;
+  meas = double(D) * g.vol * nrm;
+}
+
+// grad u1 from the nodal values of the cell
+template <int D>
+VF_HD void grad_u(const CellGeo<D>& g, const double (&U)[D + 1][D], double (&gu)[D][D]) {
+  for (int i = 0; i < D; ++i)
+    for (int j = 0; j < D; ++j) {
+      double s = 0.0;
+      for (int b = 0; b <= D; ++b) s += U[b][i] * g.G[b][j];
+      gu[i][j] = s;
+    }
+}
+
+// c = cof(I + grad u) N      (uflcontinuum.py:172-186)
+VF_HD void cof_normal(const double (&gu)[2][2], const double (&N)[2], double (&c)[2]) {
+  const double F00 = 1.0 + gu[0][0], F01 = gu[0][1], F10 = gu[1][0], F11 = 1.0 + gu[1][1];
+  c[0] = F11 * N[0] - F10 * N[1];
+  c[1] = -F01 * N[0] + F00 * N[1];
+}
+
+VF_HD void cof_normal(const double (&gu)[3][3], const double (&N)[3], double (&c)[3]) {
+  double F[3][3];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) F[i][j] = gu[i][j] + (i == j ? 1.0 : 0.0);
+  for (int i = 0; i < 3; ++i) {
+    double row[3];
+    cross3(F[(i + 1) % 3], F[(i + 2) % 3], row);
+    c[i] = row[0] * N[0] + row[1] * N[1] + row[2] * N[2];
+  }
+}
+
+// d c / d U_b for c = cof(F) N  (App. A.3): 2D  t_b [[0,1],[-1,0]];  3D  -[F (N x G_b)]_x
+VF_HD void dcof_normal(const double (&gu)[2][2], const double (&N)[2], const double* Gb,
+                       double (&dc)[2][2]) {
+  (void)gu;
+  const double t = Gb[1] * N[0] - Gb[0] * N[1];
+  dc[0][0] = 0.0;
+  dc[0][1] = t;
+  dc[1][0] = -t;
+  dc[1][1] = 0.0;
+}
+
+VF_HD void dcof_normal(const double (&gu)[3][3], const double (&N)[3], const double* Gb,
+                       double (&dc)[3][3]) {
+  double nxg[3], q[3];
+  cross3(N, Gb, nxg);
+  for (int i = 0; i < 3; ++i) {
+    double s = 0.0;
+    for (int j = 0; j < 3; ++j) s += (gu[i][j] + (i == j ? 1.0 : 0.0)) * nxg[j];
+    q[i] = s;
+  }
+  dc[0][0] = 0.0;
+  dc[0][1] = q[2];
+  dc[0][2] = -q[1];
+  dc[1][0] = -q[2];
+  dc[1][1] = 0.0;
+  dc[1][2] = q[0];
+  dc[2][0] = q[1];
+  dc[2][1] = -q[0];
+  dc[2][2] = 0.0;
+}
+
+// Cubic contact penalty (form.py:1173-1202).
+VF_HD double positive_gap(double gap) {
+  double pg = (gap + fabs(gap)) / 2.0;
+  // gap == -inf gives nan above; the reference maps it to 0 (form.py:1184)
+  if (gap < 0.0 && isinf(gap)) pg = 0.0;
+  return pg;
+}
+// magnitude of tc = -k (g+)^3 n  ->  returns -k (g+)^3
+VF_HD double contact_pressure(double gap, double k) {
+  const double pg = positive_gap(gap);
+  return -k * pg * pg * pg;
+}
+// the reference's per-DOF derivative factor: d tc_j / d u_j = -3 k (g+)^2 sign(g) n_j
+VF_HD double contact_dpressure(double gap, double k) {
+  const double pg = positive_gap(gap);
+  const double sg = (gap > 0.0) ? 1.0 : ((gap < 0.0) ? -1.0 : 0.0);
+  return -3.0 * k * pg * pg * sg;
+}
+
+// Membrane (form.py:812-855): with P = I - n n^T (n embedded in 3D, zero z in 2D),
+//   S = 2 mu_m P eps P + lambda_pp tr(P eps P) P,   R_a = th |f| (P S P)[:d,:d] G_a .
+// Since P is a projector, P S P = S.  Computes the d x d upper-left part of S for a given
+// (not necessarily symmetric) displacement gradient gu.
+template <int D>
+VF_HD void membrane_stress(const double (&gu)[D][D], const double (&N)[D], double mu_m,
+                           double lam_pp, double (&S)[D][D]) {
+  double P[3][3], e[3][3], t[3][3], epp[3][3];
+  double n3[3] = {0.0, 0.0, 0.0};
+  for (int i = 0; i < D; ++i) n3[i] = N[i];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      P[i][j] = (i == j ? 1.0 : 0.0) - n3[i] * n3[j];
+      e[i][j] = (i < D && j < D) ? 0.5 * (gu[i][j] + gu[j][i]) : 0.0;
+    }
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double s = 0.0;
+      for (int k = 0; k < 3; ++k) s += P[i][k] * e[k][j];
+      t[i][j] = s;
+    }
+  double tr = 0.0;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double s = 0.0;
+      for (int k = 0; k < 3; ++k) s += t[i][k] * P[k][j];
+      epp[i][j] = s;
+      if (i == j) tr += s;
+    }
+  for (int i = 0; i < D; ++i)
+    for (int j = 0; j < D; ++j) S[i][j] = 2.0 * mu_m * epp[i][j] + lam_pp * tr * P[i][j];
+}
+
+VF_HD void membrane_coef(double emod_m, double nu_m, double& mu_m, double& lam_pp) {
+  mu_m = emod_m / 2.0 / (1.0 + nu_m);
+  const double lam = emod_m * nu_m / (1.0 + nu_m) / (1.0 - 2.0 * nu_m);
+  lam_pp = (emod_m == 0.0) ? 0.0 : 2.0 * mu_m * lam / (lam + 2.0 * mu_m);  // form.py:848-850
+}
+
+}  // namespace vf

@@ -1,0 +1,244 @@
+// Owner-computes ("sorted-segment") assembly of one node's block row of
+// J_uu = d F_u / d u1 and of its residual entries F_u.
+//
+// Stands in for DOLFIN's assemble_cells / assemble_exterior_facets + MatSetValues +
+// DirichletBC.apply as driven by the reference at
+// /root/reference/src/femvf/models/transient.py:363-406 (assem_res, assem_dres_dstate1)
+// and :516-583 (NodalContactModel).  One caller (a thread) owns node i: it visits the
+// cells and pressure facets adjacent to i in a fixed order, so no atomics are needed and
+// the result is bit-reproducible run to run.
+//
+// Layout of a block row (identical in shared memory tiles and in the global CSR array):
+// the d rows of node i are stored one after another, row a at rowblk + a*ld with
+// ld = d*deg(i); entry for neighbour slot k, component b at k*d + b.  With
+// rowblk = J + d*d*brptr[i] this is exactly the canonical scalar CSR (columns ascending,
+// full d x d blocks, explicit zeros kept).
+#pragma once
+
+#include "elem.cuh"
+
+namespace vf {
+
+// indices into the per-member scalar property block
+enum ScalarProp {
+  SC_NU = 0,
+  SC_YCONTACT = 1,
+  SC_KCONTACT = 2,
+  SC_NCONTACT = 3,  // 3 entries
+  SC_YMID = 6,
+  SC_COUNT = 8
+};
+
+struct MeshView {
+  int dim, nn, ne, nfp;
+  const double* xyz;    // SoA coordinates: xyz[c*nn + node]
+  const int* cells;     // SoA connectivity: cells[a*ne + e]
+  const int* brptr;     // node graph = block CSR pattern of J
+  const int* bcol;
+  const int* n2e_ptr;   // node -> adjacent cells, packed e*4 + local index
+  const int* n2e;
+  const int* n2f_ptr;   // node -> adjacent pressure facets, packed f*4 + local index in parent cell
+  const int* n2f;
+  const int* pf_cell;   // pressure facet -> parent cell
+  const int* pf_opp;    // pressure facet -> local vertex of the parent cell opposite to it
+  const unsigned char* bc;  // per-DOF Dirichlet flag
+};
+
+struct PropView {
+  const double* rho;   // DG0, per cell
+  const double* eta;
+  const double* emod;
+  const double* scal;  // ScalarProp block
+  const double* emod_m;  // membrane DG0 fields (may be null when membrane == 0)
+  const double* nu_m;
+  const double* th_m;
+  int contact;   // NodalContactModel semantics on/off (App. C, Q3)
+  int membrane;  // KelvinVoigtWEpithelium membrane term on/off
+};
+
+struct StateView {
+  const double* u1;
+  const double* u0;
+  const double* v0;
+  const double* a0;
+  const double* p1;  // nodal pressure control (nn)
+  double dt;
+};
+
+VF_HD int find_slot(const int* bcol_i, int deg, int node) {
+  int k = 0;
+  while (k < deg - 1 && bcol_i[k] < node) ++k;
+  return k;
+}
+
+template <int D>
+VF_HD void load_cell(const MeshView& m, int e, int (&nd)[D + 1], double (&x)[D + 1][D]) {
+  for (int a = 0; a <= D; ++a) {
+    nd[a] = m.cells[a * m.ne + e];
+    for (int c = 0; c < D; ++c) x[a][c] = m.xyz[c * m.nn + nd[a]];
+  }
+}
+
+template <int D>
+VF_HD void gather_vec(const double* v, const int (&nd)[D + 1], double (&out)[D + 1][D]) {
+  for (int a = 0; a <= D; ++a)
+    for (int c = 0; c < D; ++c) out[a][c] = v[D * nd[a] + c];
+}
+
+template <int D>
+VF_HD void add_block(double* rowblk, int ld, int k, const double (&blk)[D][D], double scale) {
+  for (int a = 0; a < D; ++a)
+    for (int b = 0; b < D; ++b) rowblk[a * ld + k * D + b] += scale * blk[a][b];
+}
+
+template <int D, bool JAC, bool RES>
+VF_HD void assemble_node(int i, const MeshView& m, const PropView& p, const StateView& s,
+                         double* rowblk, double (&res)[D]) {
+  const int b0 = m.brptr[i];
+  const int deg = m.brptr[i + 1] - b0;
+  const int ld = D * deg;
+  const int* bcol_i = m.bcol + b0;
+  if (JAC)
+    for (int t = 0; t < D * ld; ++t) rowblk[t] = 0.0;
+  if (RES)
+    for (int c = 0; c < D; ++c) res[c] = 0.0;
+
+  const double nu = p.scal[SC_NU];
+  const double cv = newmark_cv(s.dt), ca = newmark_ca(s.dt);
+
+  // ---- cell integrals --------------------------------------------------------
+  for (int t = m.n2e_ptr[i]; t < m.n2e_ptr[i + 1]; ++t) {
+    const int ref = m.n2e[t];
+    const int e = ref >> 2, a = ref & 3;
+    int nd[D + 1];
+    double x[D + 1][D];
+    load_cell<D>(m, e, nd, x);
+    CellGeo<D> g;
+    p1_geometry(x, g);
+    const CellCoef cf = cell_coef<D>(p.emod[e], nu, p.eta[e], p.rho[e], g.vol);
+    if (JAC) {
+      for (int c = 0; c <= D; ++c) {
+        double blk[D][D];
+        cell_block<D>(g, cf, cv, ca, a, c, blk);
+        add_block<D>(rowblk, ld, find_slot(bcol_i, deg, nd[c]), blk, 1.0);
+      }
+    }
+    if (RES) {
+      double U[D + 1][D], V[D + 1][D], A[D + 1][D];
+      for (int b = 0; b <= D; ++b)
+        for (int c = 0; c < D; ++c) {
+          const int dof = D * nd[b] + c;
+          const double u1 = s.u1[dof], u0 = s.u0[dof], v0 = s.v0[dof], a0 = s.a0[dof];
+          U[b][c] = u1;
+          V[b][c] = newmark_v(u1, u0, v0, a0, s.dt);
+          A[b][c] = newmark_a(u1, u0, v0, a0, s.dt);
+        }
+      double r[D];
+      cell_residual<D>(g, cf, a, U, V, A, r);
+      for (int c = 0; c < D; ++c) res[c] += r[c];
+    }
+  }
+
+  // ---- 'pressure' exterior facets: follower pressure, contact, membrane ------------
+  for (int t = m.n2f_ptr[i]; t < m.n2f_ptr[i + 1]; ++t) {
+    const int ref = m.n2f[t];
+    const int f = ref >> 2, a = ref & 3;
+    const int e = m.pf_cell[f], o = m.pf_opp[f];
+    int nd[D + 1];
+    double x[D + 1][D];
+    load_cell<D>(m, e, nd, x);
+    CellGeo<D> g;
+    p1_geometry(x, g);
+    double N[D], meas;
+    facet_geometry<D>(g, o, N, meas);
+    double U[D + 1][D], gu[D][D];
+    gather_vec<D>(s.u1, nd, U);
+    grad_u<D>(g, U, gu);
+    const double mw = meas / double(D * (D + 1));  // facet mass weight: mw (1 + delta_ab)
+
+    if (a != o) {
+      // int p phi_a ds
+      double pw = 0.0;
+      for (int b = 0; b <= D; ++b)
+        if (b != o) pw += (a == b ? 2.0 : 1.0) * s.p1[nd[b]];
+      pw *= mw;
+      if (RES) {
+        double c[D];
+        cof_normal(gu, N, c);
+        for (int k = 0; k < D; ++k) res[k] += pw * c[k];
+      }
+      if (JAC) {
+        for (int b = 0; b <= D; ++b) {
+          double dc[D][D];
+          dcof_normal(gu, N, g.G[b], dc);
+          add_block<D>(rowblk, ld, find_slot(bcol_i, deg, nd[b]), dc, pw);
+        }
+      }
+      if (p.contact) {
+        const double yc = p.scal[SC_YCONTACT], kc = p.scal[SC_KCONTACT];
+        for (int b = 0; b <= D; ++b) {
+          if (b == o) continue;
+          double gap = -yc;
+          for (int k = 0; k < D; ++k) gap += (x[b][k] + U[b][k]) * p.scal[SC_NCONTACT + k];
+          const double mab = mw * (a == b ? 2.0 : 1.0);
+          if (RES) {
+            const double pc = contact_pressure(gap, kc);  // tc_b = pc * n
+            for (int k = 0; k < D; ++k) res[k] -= mab * pc * p.scal[SC_NCONTACT + k];
+          }
+          if (JAC) {
+            const double dp = contact_dpressure(gap, kc);
+            const int slot = find_slot(bcol_i, deg, nd[b]);
+            for (int k = 0; k < D; ++k)
+              rowblk[k * ld + slot * D + k] -= mab * dp * p.scal[SC_NCONTACT + k];
+          }
+        }
+      }
+    }
+    if (p.membrane) {
+      double mu_m, lam_pp;
+      membrane_coef(p.emod_m[e], p.nu_m[e], mu_m, lam_pp);
+      const double w = p.th_m[e] * meas;
+      if (RES) {
+        double S[D][D];
+        membrane_stress<D>(gu, N, mu_m, lam_pp, S);
+        for (int k = 0; k < D; ++k) {
+          double sacc = 0.0;
+          for (int j = 0; j < D; ++j) sacc += S[k][j] * g.G[a][j];
+          res[k] += w * sacc;
+        }
+      }
+      if (JAC) {
+        for (int b = 0; b <= D; ++b) {
+          double blk[D][D];
+          for (int j = 0; j < D; ++j) {
+            double gb[D][D];
+            for (int r = 0; r < D; ++r)
+              for (int c = 0; c < D; ++c) gb[r][c] = (r == j) ? g.G[b][c] : 0.0;
+            double S[D][D];
+            membrane_stress<D>(gb, N, mu_m, lam_pp, S);
+            for (int k = 0; k < D; ++k) {
+              double sacc = 0.0;
+              for (int c = 0; c < D; ++c) sacc += S[k][c] * g.G[a][c];
+              blk[k][j] = sacc;
+            }
+          }
+          add_block<D>(rowblk, ld, find_slot(bcol_i, deg, nd[b]), blk, w);
+        }
+      }
+    }
+  }
+
+  // ---- Dirichlet rows: zero row, unit diagonal, zero residual (App. A.4) ------------
+  const int self = find_slot(bcol_i, deg, i);
+  for (int a = 0; a < D; ++a) {
+    if (m.bc[D * i + a]) {
+      if (JAC) {
+        for (int t = 0; t < ld; ++t) rowblk[a * ld + t] = 0.0;
+        rowblk[a * ld + self * D + a] = 1.0;
+      }
+      if (RES) res[a] = 0.0;
+    }
+  }
+}
+
+}  // namespace vf
