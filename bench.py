@@ -1,0 +1,441 @@
+#!/usr/bin/env python
+"""
+bench.py -- residual + Jacobian assembly throughput (DOF/s) of the B200 hot path.
+
+Contract (one JSON line on stdout, rank 0):
+  python bench.py --gpus N --steps K --warmup W [--impl reference]
+  N > 1: launched by torchrun, one rank per GPU; every rank assembles its own mesh shard of
+  the same size (owner-computes rows with duplicated ghost cells need no collective), so
+  scaling is weak and `value` is the aggregate DOF/s over all ranks.
+
+Workload (config.workload): BASELINE.json configs[2] -- residual + Jacobian assembly
+microbenchmark on the M5_CB outline red-refined 7x (4.0e6 P1 triangles, 4.0e6 DOF,
+5.6e7 non-zeros).  The reference's elements are P1 only; the P2 variant named
+in BASELINE.json has no reference behaviour and is the next row to add.  One step = one
+assembly of F_u and J_uu (Dirichlet rows applied) from state/properties resident in HBM.
+
+Also measured in the same run and attached to the line: the SpMV kernel's roofline
+(`spmv`), the single-simulation forward step rate on config 1 (`forward`), the 1024-member
+ensemble of config 4 through the device-resident time loop and through the host-buffer C ABI
+(`ensemble`), and the CPU oracle timed on a bounded sample (`cpu_baseline`).
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, 'vf-fem_b200'), os.path.join(ROOT, 'tests')):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+METRIC = 'jacobian_assembly_dof_per_s'
+UNIT = 'DOF/s'
+REFINE_LEVELS = 7
+SAMPLE_LEVELS = 4  # CPU baseline sample: the same outline refined 4x (1/64 of the elements)
+BASE_H = 0.05
+
+
+def load_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+             'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', f'--query-gpu={self.QUERY}', '--format=csv,noheader,nounits',
+                 '-lms', '100', '-i', str(self.gpu)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(',')]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None,
+                'sm_max_mhz': float(np.max(smax)) if smax else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# --- workloads ----------------------------------------------------------------------------
+
+def build_big_model(levels, seed):
+    """config 3 (P1): refined M5_CB solid with random state and per-cell properties."""
+    from femvf_b200 import meshgen
+    from femvf_b200.models import transient
+    from femvf_b200.residuals import solid as slr
+    mt = meshgen.m5_cb_refined(BASE_H, levels)
+    model = transient.FenicsModel(slr.KelvinVoigt(*mt))
+    rng = np.random.default_rng(seed)
+    N = model.state0['u'].size
+    ne = model.prop['emod'].size
+    nn = N // 2
+    prop = model.prop.copy()
+    prop['emod'][:] = rng.uniform(2.5e4, 1e5, ne)
+    prop['eta'][:] = rng.uniform(1, 5, ne)
+    prop['rho'][:] = 1.0
+    prop['nu'][:] = 0.45
+    model.set_prop(prop)
+    s1 = model.state1.copy()
+    s1['u'][:] = rng.uniform(-1e-3, 1e-3, N)
+    s0 = model.state0.copy()
+    s0['u'][:] = rng.uniform(-1e-3, 1e-3, N)
+    s0['v'][:] = rng.uniform(-1e-2, 1e-2, N)
+    s0['a'][:] = rng.uniform(-1e2, 1e2, N)
+    model.set_ini_state(s0)
+    model.set_fin_state(s1)
+    ctl = model.control.copy()
+    ctl['p'][:] = rng.uniform(0, 8e3, nn)
+    model.set_control(ctl)
+    model.dt = 1e-4
+    return model
+
+
+def assembly_bytes(d, nn, ne, nnz):
+    """Algorithmic bytes of one residual + Jacobian assembly."""
+    N = d * nn
+    nen = d + 1
+    return 8 * nnz + 8 * N + 32 * N + 8 * d * nn + (4 * nen + 24) * ne + 8 * nn
+
+
+def spmv_bytes(nnz, nrows):
+    return 12 * nnz + 20 * nrows
+
+
+def time_events(fn, steps, warmup, barrier=None):
+    import torch
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if barrier:
+        barrier()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    if barrier:
+        barrier()
+    return e0.elapsed_time(e1)  # ms
+
+
+def fsi_model(h=BASE_H):
+    from femvf_b200 import meshgen
+    from femvf_b200.load import load_fsi_model
+    from femvf_b200.residuals import solid as slr, fluid as flr
+    mt = meshgen.m5_cb_mesh(h)
+    return load_fsi_model(mt, slr.KelvinVoigt, flr.BernoulliAreaRatioSep,
+                          {'dirichlet_bcs': {'state/u1': [(np.zeros(2), 'facet', 'fixed')]}}, {})
+
+
+def config1_args(model):
+    """benchmarks/setup.py:34-49."""
+    state0 = model.state0.copy(); state0[:] = 0
+    control = model.control.copy(); control[:] = 0; control['psub'][:] = 8e3
+    prop = model.prop.copy()
+    ymax = model.solid.residual.mesh().coordinates()[:, 1].max()
+    prop['emod'][:] = 5e4; prop['rho'][:] = 1; prop['eta'][:] = 3; prop['nu'][:] = 0.45
+    prop['ycontact'][:] = ymax + 0.05; prop['kcontact'][:] = 1e8; prop['ymid'][:] = 1.0
+    return state0, control, prop
+
+
+def oracle_for(model):
+    from oracle import fem, model as om
+    res = model.solid.residual if hasattr(model, 'solid') else model.residual
+    mesh = res.mesh()
+    fids, pf_cell, _ = res.pressure_facets()
+    prob = fem.SolidProblem(mesh.coordinates(), mesh.cells(), mesh.facets[fids], pf_cell,
+                            res.fixed_dofs())
+    return prob, om.SolidOracle(prob)
+
+
+def cpu_assembly_sample(levels, steps):
+    """Oracle residual + Jacobian assembly on the sample mesh; returns (DOF/s, description)."""
+    model = build_big_model(levels, seed=0)
+    prob, so = oracle_for(model)
+    prop = {k: np.array(v) for k, v in model.prop.items()}
+    u1 = model.state1['u']; st0 = tuple(model.state0.vecs); p1 = model.control['p']
+    so.res(u1, st0, model.dt, prop, p1)  # warm caches
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        so.res(u1, st0, model.dt, prop, p1)
+        so.jac(u1, model.dt, prop, p1)
+    dt = time.perf_counter() - t0
+    desc = (f"M5_CB refined {levels}x ({prob.ne} P1 triangles, {prob.N} DOF = 1/"
+            f"{4 ** (REFINE_LEVELS - levels)} of the workload), {steps} residual+Jacobian "
+            "assemblies, numpy/scipy oracle (CPU restatement of the FEniCS path)")
+    return prob.N * steps / dt, desc, dt / steps
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the reference's FEniCS/PETSc path cannot be installed, so
+    the CPU restatement (oracle) is timed on the host cores for the same metric."""
+    if rank != 0:
+        return
+    steps = max(args.steps, 1)
+    for _ in range(min(args.warmup, 1)):
+        cpu_assembly_sample(SAMPLE_LEVELS, 1)
+    value, desc, sec = cpu_assembly_sample(SAMPLE_LEVELS, min(steps, 10))
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT,
+        'n_gpus': args.gpus, 'steps': min(steps, 10), 'warmup': min(args.warmup, 1),
+        'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': workload_config(),
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': 1, 'kind': 'port',
+                         'sample': desc},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config():
+    return {
+        'workload': ('BASELINE configs[2]: residual+Jacobian assembly on M5_CB red-refined '
+                     f'{REFINE_LEVELS}x, P1 triangles (reference elements are P1 only)'),
+        'element': 'P1 triangle, plane strain, Kelvin-Voigt + Newmark + follower pressure',
+        'l2_policy': 'inputs+outputs (>= 0.6 GB per step) exceed the 126 MB L2; no explicit flush',
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--levels', type=int, default=REFINE_LEVELS)
+    ap.add_argument('--skip-extras', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
+
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: femvf_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    barrier = None
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+        barrier = dist.barrier
+    peak, peak_src = load_peaks()
+
+    # ---- primary: assembly on the large mesh --------------------------------------------------
+    model = build_big_model(args.levels, seed=rank)
+    eng = model.engine
+    model._push_all()
+    d, nn, ne, nnz, N = eng.dim, eng.nn, eng.ne, eng.nnz, eng.N
+    launches0 = eng.launch_count
+
+    def step():
+        eng.assemble(0, res=True, jac=True, dt=model.dt)
+
+    sampler = ClockSampler(local_rank)
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    sampler.start()
+    launches0 = eng.launch_count
+    ms = time_events(step, args.steps, 0, barrier)
+    launches = eng.launch_count - launches0
+    clocks = sampler.stop()
+    t = torch.tensor([ms], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = N * world * args.steps / (ms_max * 1e-3)
+    B_asm = assembly_bytes(d, nn, ne, nnz)
+    asm_gbs = B_asm / (ms / args.steps * 1e-3) / 1e9
+
+    # ---- SpMV on the same matrix ------------------------------------------------------------
+    x = torch.randn(N, dtype=torch.float64, device='cuda')
+    y = torch.empty_like(x)
+    ms_spmv = time_events(lambda: eng.spmv(x, y), max(args.steps, 20), 3)
+    n_spmv = max(args.steps, 20)
+    B_spmv = spmv_bytes(nnz, N)
+    spmv_gbs = B_spmv / (ms_spmv / n_spmv * 1e-3) / 1e9
+
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': ms_max / args.steps, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': dict(workload_config(), nn=nn, ne=ne, dof=N, nnz=nnz,
+                       parallelism=f'{world} independent mesh shards, no collective'),
+        'roofline': {'kernel': 'asm_tile_kernel<2,true,true>', 'bound': 'hbm',
+                     'achieved': asm_gbs, 'peak': peak, 'unit': 'GB/s', 'frac': asm_gbs / peak,
+                     'traffic': None, 'algorithmic_bytes': B_asm, 'peak_source': peak_src},
+        'spmv': {'kernel': 'spmv_kernel<2,8>', 'bound': 'hbm', 'achieved': spmv_gbs,
+                 'peak': peak, 'unit': 'GB/s', 'frac': spmv_gbs / peak,
+                 'algorithmic_bytes': B_spmv, 'ms': ms_spmv / n_spmv},
+        'clocks': clocks,
+        'gpu_launches': int(launches),
+    }
+
+    # ---- e2e: the public API with host buffers (set_fin_state -> assem_res + assem_dres_dstate1)
+    if rank == 0 or world > 1:
+        e2e_steps = 2
+        s1 = model.state1.copy()
+
+        def e2e_step():
+            model.set_fin_state(s1)
+            r = model.assem_res()
+            J = model.assem_dres_dstate1().sub['u', 'state/u1']
+            return r, J
+        e2e_step()
+        torch.cuda.synchronize()
+        if barrier:
+            barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt_e2e = time.perf_counter() - t0
+        te = torch.tensor([dt_e2e], dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        push = 8 * (3 * ne + 8 + 6 * N + nn)
+        line['e2e'] = {'value': N * world * e2e_steps / float(te.item()), 'unit': UNIT,
+                       'h2d_bytes_per_step': 2 * push, 'd2h_bytes_per_step': 8 * (N + nnz),
+                       'api': 'FenicsModel.set_fin_state + assem_res + assem_dres_dstate1 '
+                              '(host BlockVector in, host scipy CSR out)'}
+
+    del model, eng, x, y
+    torch.cuda.empty_cache()
+
+    # ---- forward.integrate on config 1 and the ensemble of config 4 ------------------------------
+    if not args.skip_extras:
+        from femvf_b200 import forward
+        fm = fsi_model()
+        state0, control, prop = config1_args(fm)
+        times = 1e-4 * np.arange(100)
+        forward.integrate(fm, None, state0, [control], prop, times, write=False)  # warm-up
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            forward.integrate(fm, None, state0, [control], prop, times, write=False)
+        torch.cuda.synchronize()
+        fwd = 99 * reps / (time.perf_counter() - t0)
+        line['forward'] = {'workload': 'BASELINE configs[0]: M5_CB (245 P1 triangles, 296 DOF), '
+                                       '99 steps dt=1e-4, forward.integrate(write=False)',
+                           'steps_per_s': fwd}
+
+        # ensemble: 1024 members per GPU, randomised emod / eta fields (SURVEY.md 8d cfg 4)
+        from femvf_b200.ensemble import EnsembleRunner
+        B = 1024
+        runner = EnsembleRunner(fm, B)
+        emod = np.empty((B, runner.ne)); eta = np.empty((B, runner.ne))
+        for b in range(B):
+            g = np.random.default_rng([4, rank * B + b])
+            emod[b] = 5e4 * np.exp(0.3 * g.standard_normal(runner.ne))
+            eta[b] = 3.0 * np.exp(0.3 * g.standard_normal(runner.ne))
+        ini = np.zeros((B, runner.state_size))
+        dts = np.full(99, 1e-4)
+        ctl = np.array([[[8e3], [0.0]]])
+        runner.set_common_prop(prop)
+        runner.run_host(dts, ctl, ini, emod, eta)  # warm-up
+        if barrier:
+            barrier()
+        t0 = time.perf_counter()
+        fin, series = runner.run_host(dts, ctl, ini, emod, eta)
+        dt_h = time.perf_counter() - t0
+        # device-resident timing of the same work
+        runner.upload_members(ini, emod, eta)
+        ms_dev = time_events(lambda: runner.run_device(dts, ctl), 1, 0, barrier)
+        tt = torch.tensor([ms_dev, dt_h * 1e3], dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        line['ensemble'] = {
+            'workload': f'BASELINE configs[3]: {B} members per GPU x 99 steps, emod/eta '
+                        'log-normal per cell, seed = member id',
+            'member_steps_per_s': B * world * 99 / (float(tt[0]) * 1e-3),
+            'e2e_member_steps_per_s': B * world * 99 / (float(tt[1]) * 1e-3),
+            'h2d_bytes': int(ini.nbytes + emod.nbytes + eta.nbytes),
+            'd2h_bytes': int(fin.nbytes + series.nbytes),
+            'max_newton_iters': float(series[:, :, 0].max()),
+            'scaling': 'weak',
+        }
+
+    # ---- CPU baseline (rank 0, N = 1 only): the oracle on a bounded sample ---------------------
+    if rank == 0 and world == 1:
+        cpu_val, desc, _ = cpu_assembly_sample(SAMPLE_LEVELS, 5)
+        line['cpu_baseline'] = {'value': cpu_val, 'unit': UNIT, 'cores': 1, 'kind': 'port',
+                                'sample': desc}
+        if not args.skip_extras:
+            from oracle import model as om
+            prob, so = oracle_for(fm)
+            co = om.CoupledOracle(so, fm.fluid.residual.mesh(), fm.fsimap.dofs_solid,
+                                  fm.fsimap.dofs_fluid)
+            t0 = time.perf_counter()
+            co.integrate(tuple(state0.vecs), [{'psub': control['psub'], 'psup': control['psup']}],
+                         {k: np.array(v) for k, v in prop.items()}, times)
+            line['forward']['cpu_oracle_steps_per_s'] = 99 / (time.perf_counter() - t0)
+
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,169 @@
+/*
+ * vffem_b200 -- C ABI of the B200-native hot path of femvf.forward.integrate.
+ *
+ * The reference (jon-deng/vf-fem) is pure Python; it has no FFI seam of its own
+ * (SURVEY.md section 8b).  Each entry point below replaces the third-party native call the
+ * reference makes at the cited site; INTEGRATION.md shows the ctypes stubs a maintainer
+ * would add at those sites.
+ *
+ * Conventions: plain pointers and sizes only.  Pointers named *_host are host memory,
+ * *_dev device memory.  `stream` is a cudaStream_t passed as void* (NULL = default
+ * stream).  Every function returns 0 on success, non-zero on error; the message is
+ * available from vf_last_error().  Nothing here falls back to the CPU: if no CUDA device
+ * is usable the calls fail.
+ *
+ * Data layout (all fp64, indices int32): vector DOFs node-major interleaved (d*i + c);
+ * J_uu in scalar CSR with the canonical pattern (columns ascending, full d x d block per
+ * vertex pair sharing a cell, explicit zeros kept) stored block-row by block-row; DG0
+ * properties one value per cell; ensemble members are stored member-major (each member's
+ * arrays contiguous).
+ */
+#ifndef VFFEM_B200_H
+#define VFFEM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vf_engine vf_engine;
+
+/* Mesh, index tables (built once on the host: femvf_b200/tables.py) and model switches. */
+typedef struct vf_problem_desc {
+  int32_t dim, nn, ne, nfp;   /* dimension, #vertices, #cells, #pressure facets */
+  const double* xyz_host;     /* (dim, nn) SoA coordinates */
+  const int32_t* cells_host;  /* (dim+1, ne) SoA connectivity */
+  const int32_t* brptr_host;  /* (nn+1) node graph = block pattern of J */
+  const int32_t* bcol_host;   /* (nnzb) */
+  const int32_t* n2e_ptr_host;
+  const int32_t* n2e_host;    /* node -> cell*4 + local index */
+  const int32_t* n2f_ptr_host;
+  const int32_t* n2f_host;    /* node -> pressure facet*4 + local index in parent cell */
+  const int32_t* pf_cell_host;
+  const int32_t* pf_opp_host;
+  const uint8_t* bc_host;     /* (dim*nn) Dirichlet flag per DOF */
+  const int32_t* tile_start_host; /* (ntiles+1) node ranges of the assembly tiles */
+  int32_t ntiles;
+  int32_t tile_max_values;    /* max #doubles of J in one tile (shared-memory CSR slice) */
+  int32_t tile_threads;       /* CTA size of the tile kernel (>= max nodes per tile) */
+  /* 1D fluid + FSI map (models/fsi.py:18-88) */
+  int32_t n_fluid, ns, n_fsi;
+  const double* s_host;           /* (n_fluid, ns) arclength coordinates */
+  const int32_t* fsi_solid_host;  /* (n_fsi) scalar solid DOFs */
+  const int32_t* fsi_fluid_host;  /* (n_fsi) fluid DOFs */
+  int32_t fluid_kind;         /* 0 area-ratio sep, 1 fixed sep, 2 smooth-min sep */
+  int32_t idx_sep;
+  /* model switches */
+  int32_t contact;            /* NodalContactModel semantics */
+  int32_t membrane;           /* KelvinVoigtWEpithelium membrane term */
+  /* ensemble / solver workspace */
+  int32_t n_members;
+  int32_t gmres_restart;
+} vf_problem_desc;
+
+/* Newton options (solverconst.py:1-6) and linear-solver controls. */
+typedef struct vf_solver_opts {
+  double newton_abs_tol, newton_rel_tol;
+  int32_t newton_max_iter;
+  double gmres_rel_tol, gmres_abs_tol;
+  int32_t gmres_max_iter;
+  int32_t is_static;          /* static.py:68-168: u0 == u1, v0 = a0 = 0 */
+} vf_solver_opts;
+
+/* Named per-member arrays inside the arena. */
+enum vf_array_id {
+  VF_U0 = 0, VF_V0, VF_A0, VF_Q0, VF_P0,      /* state0: u, v, a (N), q (n_fluid), p (n_fluid*ns) */
+  VF_U1, VF_V1, VF_A1, VF_Q1, VF_PF1,         /* state1 */
+  VF_PSUB, VF_PSUP,                           /* control (n_fluid each) */
+  VF_P1,                                      /* solid control 'p1' (nn) */
+  VF_AREA,                                    /* fluid control 'area' (n_fluid*ns) */
+  VF_RHO, VF_ETA, VF_EMOD,                    /* DG0 (ne) */
+  VF_EMOD_M, VF_NU_M, VF_TH_M,                /* membrane DG0 (ne) */
+  VF_SCAL,                                    /* nu, ycontact, kcontact, ncontact[3], ymid, pad */
+  VF_FPROP,                                   /* (n_fluid, 5): rho_air r_sep area_lb zeta_min zeta_sep */
+  VF_F,                                       /* residual F_u (N) */
+  VF_J,                                       /* CSR values of J_uu (nnz) */
+  VF_DX,                                      /* last Newton update (N) */
+  VF_INFO,                                    /* num_iter abs_err rel_err gmres_iters gmres_resid ... (16) */
+  VF_ARRAY_COUNT
+};
+
+const char* vf_last_error(void);
+int vf_device_count(void);
+
+/* ---- lifecycle ------------------------------------------------------------------- */
+/* Bytes of device memory the engine needs; the caller allocates them (e.g. a torch uint8
+ * tensor) and hands the pointer to vf_create. */
+size_t vf_arena_bytes(const vf_problem_desc* desc);
+int vf_create(const vf_problem_desc* desc, void* arena_dev, size_t arena_bytes, void* stream,
+              vf_engine** out);
+void vf_destroy(vf_engine* e);
+
+/* Byte offset into the arena and element count of a named per-member array. */
+int vf_array_info(const vf_engine* e, int array_id, int member, size_t* byte_offset,
+                  size_t* count);
+/* Host <-> device copies of a named array (cudaMemcpyAsync on `stream` + synchronize). */
+int vf_upload(vf_engine* e, int array_id, int member, const double* src_host, size_t count,
+              void* stream);
+int vf_download(vf_engine* e, int array_id, int member, double* dst_host, size_t count,
+                void* stream);
+/* Scalar CSR pattern implied by the node graph (host output; sizes N+1 and nnz). */
+int vf_csr_pattern(const vf_engine* e, int32_t* rowptr_host, int32_t* colidx_host);
+int64_t vf_nnz(const vf_engine* e);
+
+/* ---- the hot path ---------------------------------------------------------------- */
+/* FenicsModel.assem_res / assem_dres_dstate1 (models/transient.py:363-406): assemble F_u
+ * (flags & 1) and/or J_uu (flags & 2) of `member` from its current state1/state0/controls/
+ * props with Dirichlet rows applied.  Replaces dfn.assemble + bc.apply
+ * (models/assemblyutils.py:49-50, transient.py:379-380, 398-399). */
+int vf_assemble(vf_engine* e, int member, int flags, double dt, int is_static, void* stream);
+
+/* y = J_uu x for `member` (PETSc MatMult; transient.py:488-489).  x, y: device, N doubles. */
+int vf_spmv(vf_engine* e, int member, const double* x_dev, double* y_dev, void* stream);
+
+/* Solve J_uu x = b with the block-Jacobi preconditioned GMRES that stands in for the PETSc
+ * LU of dfn.solve(A, x, b, 'petsc') (transient.py:487).  b, x: device, N doubles.
+ * info_host[0] = iterations, [1] = final residual norm, [2] = ||b||. */
+int vf_linear_solve(vf_engine* e, int member, const double* b_dev, double* x_dev,
+                    const vf_solver_opts* opts, double* info_host, void* stream);
+
+/* FenicsModel.solve_state1 (transient.py:441-468): Newton on F_u(u1) = 0 from the guess in
+ * VF_U1, then v1, a1 from the Newmark relations, for members [member0, member0+count). */
+int vf_solve_state1(vf_engine* e, int member0, int count, double dt, const vf_solver_opts* opts,
+                    void* stream);
+
+/* JaxModel.solve_state1 (transient.py:667-672): (q, p) from VF_AREA, VF_PSUB, VF_PSUP into
+ * VF_Q1 / VF_PF1. */
+int vf_fluid_solve(vf_engine* e, int member0, int count, void* stream);
+
+/* forward.integrate_steps with ExplicitFSIModel.solve_state1 (forward.py:139-186,
+ * transient.py:899-920), device resident for all members: nsteps steps from state0.
+ *   dts_host        (nsteps) time step sizes
+ *   controls_host   (ncontrols, 2, n_fluid) psub, psup per control; control min(n, ncontrols-1)
+ *                   is used at step n (forward.py:170)
+ *   hist_state_dev  optional (n_members, nsteps+1, 3N + n_fluid + n_fluid*ns) state history,
+ *                   row 0 = initial state (forward.py:75-86); NULL to skip
+ *   hist_info_dev   optional (n_members, nsteps+1, 4): num_iter, abs_err, rel_err, min area
+ * On return state0 holds the final state of every member. */
+int vf_integrate(vf_engine* e, int nsteps, const double* dts_host, int ncontrols,
+                 const double* controls_host, const vf_solver_opts* opts,
+                 double* hist_state_dev, double* hist_info_dev, void* stream);
+
+/* Same with host buffers end to end: uploads the initial state (n_members, state_size) and
+ * per-member DG0 properties emod/eta (n_members, ne each; NULL keeps the resident ones),
+ * integrates, downloads the final state and the (n_members, nsteps+1, 4) info series. */
+int vf_integrate_host(vf_engine* e, int nsteps, const double* dts_host, int ncontrols,
+                      const double* controls_host, const vf_solver_opts* opts,
+                      const double* ini_state_host, const double* emod_host,
+                      const double* eta_host, double* fin_state_host, double* info_series_host,
+                      void* stream);
+
+/* Number of kernel launches issued by this engine so far (bench.py's gpu_launches). */
+int64_t vf_launch_count(const vf_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VFFEM_B200_H */

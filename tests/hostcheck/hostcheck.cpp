@@ -26,7 +26,7 @@ extern "C" int hostcheck_assemble(
   vf::MeshView m{dim, nn, ne, nfp, xyz, cells, brptr, bcol, n2e_ptr, n2e,
                  n2f_ptr, n2f, pf_cell, pf_opp, bc};
   vf::PropView p{rho, eta, emod, scal, emod_m, nu_m, th_m, contact, membrane};
-  vf::StateView s{u1, u0, v0, a0, p1, dt};
+  vf::StateView s{u1, u0, v0, a0, p1, dt, 0};
   if (dim == 2) run<2>(m, p, s, J, F);
   else if (dim == 3) run<3>(m, p, s, J, F);
   else return 1;

@@ -1,0 +1,82 @@
+"""GPU parity: device assembly / SpMV / linear solve (through the C ABI) vs the oracle."""
+
+import numpy as np
+import pytest
+import scipy.sparse.linalg as spla
+
+from helpers import mesh_tuples, oracle_problem, random_solid_prop, set_model_prop, \
+    random_state, rel_row_err
+from oracle import model as om
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12  # BASELINE.json north_star: assembled entries within 1e-12 relative
+
+
+@pytest.fixture(scope='module')
+def torch_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("GPU test selected but no CUDA device is visible")
+    return torch
+
+
+@pytest.mark.parametrize('mesh_name', ['square5', 'cube332', 'm5'])
+@pytest.mark.parametrize('variant', ['kv', 'kv_contact', 'epithelium_contact'])
+def test_assembly_parity(torch_cuda, mesh_name, variant):
+    from femvf_b200.models import transient
+    from femvf_b200.residuals import solid as slr
+    rng = np.random.default_rng(42)
+    mt = mesh_tuples()[mesh_name]()
+    membrane = variant.startswith('epithelium')
+    contact = variant.endswith('contact')
+    Residual = slr.KelvinVoigtWEpithelium if membrane else slr.KelvinVoigt
+    Model = transient.NodalContactModel if contact else transient.FenicsModel
+    model = Model(Residual(*mt))
+    prob = oracle_problem(model.residual)
+    N = prob.N
+    prop = random_solid_prop(prob, rng, membrane=membrane)
+    mprop = model.prop.copy()
+    set_model_prop(mprop, prop)
+    model.set_prop(mprop)
+    u1, u0, v0, a0 = random_state(N, rng)
+    p1 = rng.uniform(0, 8e3, prob.nn)
+    dt = 1e-4
+    model.dt = dt
+    s0 = model.state0.copy(); s0['u'][:] = u0; s0['v'][:] = v0; s0['a'][:] = a0
+    s1 = model.state1.copy(); s1['u'][:] = u1
+    model.set_ini_state(s0); model.set_fin_state(s1)
+    ctl = model.control.copy(); ctl['p'][:] = p1
+    model.set_control(ctl)
+
+    so = om.SolidOracle(prob, contact=contact, membrane=membrane)
+    F_ref = so.res(u1, (u0, v0, a0), dt, prop, p1)
+    J_ref = so.jac(u1, dt, prop, p1)
+
+    res = model.assem_res()
+    assert np.max(np.abs(res['u'] - F_ref)) <= TOL * np.max(np.abs(F_ref))
+    J = model.assem_dres_dstate1().sub['u', 'state/u1']
+    # CSR sparsity pattern bit-exact
+    assert np.array_equal(J.indptr, J_ref.indptr)
+    assert np.array_equal(J.indices, J_ref.indices)
+    assert rel_row_err(J.data, J_ref) <= TOL
+
+    # run-to-run bit reproducibility (no atomics)
+    J2 = model.assem_dres_dstate1().sub['u', 'state/u1']
+    assert np.array_equal(J.data, J2.data)
+
+    # SpMV
+    torch = torch_cuda
+    x = rng.standard_normal(N)
+    xt = torch.as_tensor(x, device='cuda'); yt = torch.empty_like(xt)
+    model.engine.spmv(xt, yt)
+    y_ref = J_ref @ x
+    assert np.max(np.abs(yt.cpu().numpy() - y_ref)) <= 1e-13 * np.max(np.abs(y_ref)) * 10
+
+    # linear solve vs LU
+    b = rng.standard_normal(N)
+    bt = torch.as_tensor(b, device='cuda'); st = torch.empty_like(bt)
+    info = model.engine.linear_solve(bt, st)
+    x_ref = spla.splu(J_ref.tocsc()).solve(b)
+    err = np.linalg.norm(st.cpu().numpy() - x_ref) / np.linalg.norm(x_ref)
+    assert err < 1e-9, (err, info)

@@ -1,0 +1,439 @@
+// Device-resident Newton / GMRES / Newmark / FSI step executed by ONE thread block per
+// ensemble member (single simulations are an ensemble of one).
+//
+// Stands in for, per time step of forward.integrate_steps
+// (/root/reference/src/femvf/forward.py:169-184):
+//   ExplicitFSIModel.solve_state1             models/transient.py:899-920
+//   _set_ini_fluid_state / _set_fin_solid_state    :833-862, models/fsi.py:66-70
+//   FenicsModel.solve_state1 + nonlineq.newton_solve   :441-468, solverconst.py:1-6
+//   FenicsModel.solve_dres_dstate1 (PETSc LU)          :470-491
+//   JaxModel.solve_state1                              :667-672
+// The whole time loop runs inside one kernel launch: no host round trip per Newton
+// iteration, per Krylov iteration or per time step.  The base problem is O(10^2..10^3)
+// DOFs, i.e. latency bound; one CTA keeps the member's vectors hot in
+// L1/L2 and the 148 SMs run 148+ members concurrently.
+//
+// Linear solver: left-preconditioned restarted GMRES(m) with block-Jacobi (d x d nodal
+// blocks) and classical Gram-Schmidt with re-orthogonalisation (CGS2); all reductions are
+// fixed-order warp-shuffle trees, so results are bit-reproducible for a given CTA size.
+#pragma once
+
+#include "fluid.cuh"
+#include "node_assembly.cuh"
+
+namespace vf {
+
+constexpr int kMaxRestart = 128;
+constexpr int kInfoCount = 16;
+enum InfoSlot { INFO_NUM_ITER = 0, INFO_ABS_ERR = 1, INFO_REL_ERR = 2, INFO_GMRES_ITERS = 3,
+                INFO_GMRES_RESID = 4, INFO_MIN_AREA = 5, INFO_BNORM = 6 };
+
+struct Layout {
+  size_t off[32];   // offsets (doubles) of the public arrays inside a member block
+  size_t cnt[32];
+  size_t Dinv, V, w, z, H, cs, sn, g, y, xk;  // solver workspace
+  size_t stride;    // member block size (doubles)
+};
+
+struct SolverOpts {
+  double newton_abs_tol, newton_rel_tol;
+  int newton_max_iter;
+  double gmres_rel_tol, gmres_abs_tol;
+  int gmres_max_iter;
+  int is_static;
+};
+
+struct EngineDev {
+  MeshView mesh;
+  int d, N, n_fluid, ns, n_fsi, fluid_kind, idx_sep, contact, membrane, restart;
+  long long nnz;
+  const double* s;
+  const int* fsi_solid;
+  const int* fsi_fluid;
+  double* members;
+  Layout L;
+};
+
+// ---- block-level primitives ------------------------------------------------------
+struct BlockShared {
+  double red[40];
+  double h[kMaxRestart + 2];
+  double h2[kMaxRestart + 2];
+  double bc[8];  // broadcast scalars
+};
+
+__device__ __forceinline__ double block_sum(double v, BlockShared& sh) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if (lane == 0) sh.red[wid] = v;
+  __syncthreads();
+  if (wid == 0) {
+    double t = (lane < nw) ? sh.red[lane] : 0.0;
+    t = warp_sum(t);
+    if (lane == 0) sh.red[32] = t;
+  }
+  __syncthreads();
+  return sh.red[32];
+}
+
+template <int D>
+__device__ __forceinline__ void blk_spmv(const EngineDev& E, const double* __restrict__ J,
+                                         const double* __restrict__ x, double* __restrict__ y) {
+  for (int r = threadIdx.x; r < E.N; r += blockDim.x) {
+    const int i = r / D, a = r - i * D;
+    const int b0 = E.mesh.brptr[i], deg = E.mesh.brptr[i + 1] - b0;
+    const double* row = J + (size_t)D * D * b0 + (size_t)a * D * deg;
+    double s = 0.0;
+    for (int k = 0; k < deg; ++k) {
+      const int j = E.mesh.bcol[b0 + k];
+#pragma unroll
+      for (int c = 0; c < D; ++c) s += row[k * D + c] * x[D * j + c];
+    }
+    y[r] = s;
+  }
+}
+
+// inverse of the d x d diagonal blocks (block-Jacobi preconditioner)
+template <int D>
+__device__ __forceinline__ void blk_compute_dinv(const EngineDev& E, const double* J, double* Dinv) {
+  for (int i = threadIdx.x; i < E.mesh.nn; i += blockDim.x) {
+    const int b0 = E.mesh.brptr[i], deg = E.mesh.brptr[i + 1] - b0;
+    const int self = find_slot(E.mesh.bcol + b0, deg, i);
+    const double* blk = J + (size_t)D * D * b0;
+    double A[D][D];
+    for (int a = 0; a < D; ++a)
+      for (int c = 0; c < D; ++c) A[a][c] = blk[a * D * deg + self * D + c];
+    double* o = Dinv + (size_t)D * D * i;
+    if constexpr (D == 2) {
+      const double det = A[0][0] * A[1][1] - A[0][1] * A[1][0];
+      const double inv = 1.0 / det;
+      o[0] = A[1][1] * inv;
+      o[1] = -A[0][1] * inv;
+      o[2] = -A[1][0] * inv;
+      o[3] = A[0][0] * inv;
+    } else {
+      // A^{-1} = [r1 x r2, r2 x r0, r0 x r1] / det  (columns), r_k the rows of A
+      double c0[3], c1[3], c2[3];
+      cross3(A[1], A[2], c0);
+      cross3(A[2], A[0], c1);
+      cross3(A[0], A[1], c2);
+      const double det = A[0][0] * c0[0] + A[0][1] * c0[1] + A[0][2] * c0[2];
+      const double inv = 1.0 / det;
+      for (int k = 0; k < 3; ++k) {
+        o[k * 3 + 0] = c0[k] * inv;
+        o[k * 3 + 1] = c1[k] * inv;
+        o[k * 3 + 2] = c2[k] * inv;
+      }
+    }
+  }
+}
+
+template <int D>
+__device__ __forceinline__ void blk_apply_dinv(const EngineDev& E, const double* Dinv,
+                                               const double* v, double* z) {
+  for (int r = threadIdx.x; r < E.N; r += blockDim.x) {
+    const int i = r / D, a = r - i * D;
+    const double* o = Dinv + (size_t)D * D * i + a * D;
+    double s = 0.0;
+#pragma unroll
+    for (int c = 0; c < D; ++c) s += o[c] * v[D * i + c];
+    z[r] = s;
+  }
+}
+
+// out[j] = V_j . w for j < nvec: one warp per basis vector, fixed-order shuffle tree
+__device__ __forceinline__ void blk_dots(const double* V, int N, int nvec, const double* w,
+                                         double* out) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int j = wid; j < nvec; j += nw) {
+    const double* vj = V + (size_t)j * N;
+    double s = 0.0;
+    for (int t = lane; t < N; t += 32) s += vj[t] * w[t];
+    s = warp_sum(s);
+    if (lane == 0) out[j] = s;
+  }
+}
+
+// GMRES(m) on J x = b for one member; x starts at 0.  Left-preconditioned with the
+// block-Jacobi inverse M^{-1}: the Krylov space is built for M^{-1} J, whose rows are
+// equilibrated (Dirichlet identity rows and mass-dominated rows both have unit diagonal
+// blocks), and convergence is tested on ||M^{-1}(b - J x)|| / ||M^{-1} b||.  Returns the
+// iteration count; *resid_out is the final preconditioned residual norm, *bnorm_out
+// ||M^{-1} b||.  Every thread of the block must call it.
+template <int D>
+__device__ int blk_gmres(const EngineDev& E, double* mb, const double* b, double* x,
+                         const SolverOpts& opt, BlockShared& sh, double* resid_out,
+                         double* bnorm_out) {
+  const Layout& L = E.L;
+  const int N = E.N;
+  const int m = E.restart;
+  const double* J = mb + L.off[VF_J];
+  const double* Dinv = mb + L.Dinv;
+  double* V = mb + L.V;
+  double* w = mb + L.w;
+  double* z = mb + L.z;
+  double* H = mb + L.H;  // column-major, leading dimension m+1
+  double* cs = mb + L.cs;
+  double* sn = mb + L.sn;
+  double* g = mb + L.g;
+  double* y = mb + L.y;
+  const int ldh = m + 1;
+
+  // r0 = M^{-1} b  (x0 = 0)
+  for (int t = threadIdx.x; t < N; t += blockDim.x) x[t] = 0.0;
+  blk_apply_dinv<D>(E, Dinv, b, w);
+  __syncthreads();
+  double part = 0.0;
+  for (int t = threadIdx.x; t < N; t += blockDim.x) part += w[t] * w[t];
+  const double bnorm = sqrt(block_sum(part, sh));
+  *bnorm_out = bnorm;
+  if (bnorm == 0.0) {
+    *resid_out = 0.0;
+    return 0;
+  }
+  const double tol = fmax(opt.gmres_rel_tol * bnorm, opt.gmres_abs_tol);
+  double beta = bnorm;
+  double resid = bnorm;
+  int iters = 0;
+  bool first = true;
+  while (true) {
+    if (!first) {
+      // explicit restart residual r = M^{-1} (b - J x)
+      __syncthreads();
+      blk_spmv<D>(E, J, x, z);
+      __syncthreads();
+      for (int t = threadIdx.x; t < N; t += blockDim.x) z[t] = b[t] - z[t];
+      __syncthreads();
+      blk_apply_dinv<D>(E, Dinv, z, w);
+      __syncthreads();
+      double p2 = 0.0;
+      for (int t = threadIdx.x; t < N; t += blockDim.x) p2 += w[t] * w[t];
+      beta = sqrt(block_sum(p2, sh));
+      resid = beta;
+      if (beta <= tol) break;
+    }
+    first = false;
+    {
+      const double inv = 1.0 / beta;
+      for (int t = threadIdx.x; t < N; t += blockDim.x) V[t] = w[t] * inv;
+    }
+    if (threadIdx.x == 0) g[0] = beta;
+    __syncthreads();
+
+    int k = 0;
+    bool done = false;
+    for (; k < m && !done; ++k) {
+      const double* vk = V + (size_t)k * N;
+      blk_spmv<D>(E, J, vk, z);
+      __syncthreads();
+      blk_apply_dinv<D>(E, Dinv, z, w);
+      __syncthreads();
+      // CGS2: two classical Gram-Schmidt passes
+      blk_dots(V, N, k + 1, w, sh.h);
+      __syncthreads();
+      for (int t = threadIdx.x; t < N; t += blockDim.x) {
+        double s = w[t];
+        for (int j = 0; j <= k; ++j) s -= sh.h[j] * V[(size_t)j * N + t];
+        w[t] = s;
+      }
+      __syncthreads();
+      blk_dots(V, N, k + 1, w, sh.h2);
+      __syncthreads();
+      double p2 = 0.0;
+      for (int t = threadIdx.x; t < N; t += blockDim.x) {
+        double s = w[t];
+        for (int j = 0; j <= k; ++j) s -= sh.h2[j] * V[(size_t)j * N + t];
+        w[t] = s;
+        p2 += s * s;
+      }
+      const double hk1 = sqrt(block_sum(p2, sh));
+      if (threadIdx.x == 0) {
+        // Hessenberg column, previous Givens rotations, new rotation
+        double* hc = H + (size_t)k * ldh;
+        for (int j = 0; j <= k; ++j) hc[j] = sh.h[j] + sh.h2[j];
+        for (int j = 0; j < k; ++j) {
+          const double t0 = cs[j] * hc[j] + sn[j] * hc[j + 1];
+          hc[j + 1] = -sn[j] * hc[j] + cs[j] * hc[j + 1];
+          hc[j] = t0;
+        }
+        const double denom = sqrt(hc[k] * hc[k] + hk1 * hk1);
+        const double c = (denom == 0.0) ? 1.0 : hc[k] / denom;
+        const double s = (denom == 0.0) ? 0.0 : hk1 / denom;
+        cs[k] = c;
+        sn[k] = s;
+        hc[k] = c * hc[k] + s * hk1;
+        g[k + 1] = -s * g[k];
+        g[k] = c * g[k];
+        sh.bc[0] = fabs(g[k + 1]);
+      }
+      __syncthreads();
+      resid = sh.bc[0];
+      ++iters;
+      if (hk1 > 0.0) {
+        double* vn = V + (size_t)(k + 1) * N;
+        const double inv = 1.0 / hk1;
+        for (int t = threadIdx.x; t < N; t += blockDim.x) vn[t] = w[t] * inv;
+      }
+      if (resid <= tol || iters >= opt.gmres_max_iter || hk1 == 0.0) done = true;
+      __syncthreads();
+    }
+    // y = H^{-1} g  (k x k upper triangular), then x += V y
+    if (threadIdx.x == 0) {
+      for (int i = k - 1; i >= 0; --i) {
+        double s = g[i];
+        for (int j = i + 1; j < k; ++j) s -= H[(size_t)j * ldh + i] * y[j];
+        y[i] = s / H[(size_t)i * ldh + i];
+      }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < N; t += blockDim.x) {
+      double s = 0.0;
+      for (int j = 0; j < k; ++j) s += y[j] * V[(size_t)j * N + t];
+      x[t] += s;
+    }
+    __syncthreads();
+    if (resid <= tol || iters >= opt.gmres_max_iter) break;
+  }
+  *resid_out = resid;
+  return iters;
+}
+
+template <int D>
+__device__ __forceinline__ PropView member_props(const EngineDev& E, double* mb) {
+  const Layout& L = E.L;
+  PropView p;
+  p.rho = mb + L.off[VF_RHO];
+  p.eta = mb + L.off[VF_ETA];
+  p.emod = mb + L.off[VF_EMOD];
+  p.scal = mb + L.off[VF_SCAL];
+  p.emod_m = mb + L.off[VF_EMOD_M];
+  p.nu_m = mb + L.off[VF_NU_M];
+  p.th_m = mb + L.off[VF_TH_M];
+  p.contact = E.contact;
+  p.membrane = E.membrane;
+  return p;
+}
+
+// FenicsModel.solve_state1: Newton on F_u(u1) = 0 starting from the guess held in VF_U1,
+// then v1, a1 from the Newmark relations (App. C, Q2).
+template <int D>
+__device__ void blk_solve_solid(const EngineDev& E, double* mb, double dt, const SolverOpts& opt,
+                                BlockShared& sh) {
+  const Layout& L = E.L;
+  const int N = E.N, nn = E.mesh.nn;
+  double* u1 = mb + L.off[VF_U1];
+  double* F = mb + L.off[VF_F];
+  double* Jv = mb + L.off[VF_J];
+  double* dx = mb + L.off[VF_DX];
+  double* info = mb + L.off[VF_INFO];
+  const PropView pv = member_props<D>(E, mb);
+  StateView sv;
+  sv.u1 = u1;
+  sv.u0 = opt.is_static ? u1 : mb + L.off[VF_U0];
+  sv.v0 = mb + L.off[VF_V0];
+  sv.a0 = mb + L.off[VF_A0];
+  sv.p1 = mb + L.off[VF_P1];
+  sv.dt = dt;
+  sv.is_static = opt.is_static;
+
+  int k = 0;
+  double r0 = 0.0, abs_err = 0.0, rel_err = 0.0;
+  int gm_iters = 0;
+  double gm_resid = 0.0, gm_bnorm = 0.0;
+  while (true) {
+    // residual (and, in the first iteration, the Jacobian in the same sweep)
+    double part = 0.0;
+    for (int i = threadIdx.x; i < nn; i += blockDim.x) {
+      double res[D];
+      if (k == 0)
+        assemble_node<D, true, true>(i, E.mesh, pv, sv, Jv + (size_t)D * D * E.mesh.brptr[i], res);
+      else
+        assemble_node<D, false, true>(i, E.mesh, pv, sv, nullptr, res);
+      for (int c = 0; c < D; ++c) {
+        F[D * i + c] = res[c];
+        part += res[c] * res[c];
+      }
+    }
+    abs_err = sqrt(block_sum(part, sh));
+    if (k == 0) r0 = abs_err;
+    rel_err = (r0 > 0.0) ? abs_err / r0 : 0.0;
+    if (abs_err <= opt.newton_abs_tol || rel_err <= opt.newton_rel_tol ||
+        k >= opt.newton_max_iter)
+      break;
+    if (k > 0) {
+      for (int i = threadIdx.x; i < nn; i += blockDim.x) {
+        double res[D];
+        assemble_node<D, true, false>(i, E.mesh, pv, sv, Jv + (size_t)D * D * E.mesh.brptr[i], res);
+      }
+    }
+    __syncthreads();
+    blk_compute_dinv<D>(E, Jv, mb + L.Dinv);
+    __syncthreads();
+    gm_iters += blk_gmres<D>(E, mb, F, dx, opt, sh, &gm_resid, &gm_bnorm);
+    __syncthreads();
+    for (int t = threadIdx.x; t < N; t += blockDim.x) u1[t] -= dx[t];
+    __syncthreads();
+    ++k;
+  }
+  // Newmark velocity / acceleration
+  if (!opt.is_static) {
+    const double* u0 = mb + L.off[VF_U0];
+    const double* v0 = mb + L.off[VF_V0];
+    const double* a0 = mb + L.off[VF_A0];
+    double* v1 = mb + L.off[VF_V1];
+    double* a1 = mb + L.off[VF_A1];
+    for (int t = threadIdx.x; t < N; t += blockDim.x) {
+      v1[t] = newmark_v(u1[t], u0[t], v0[t], a0[t], dt);
+      a1[t] = newmark_a(u1[t], u0[t], v0[t], a0[t], dt);
+    }
+  }
+  if (threadIdx.x == 0) {
+    info[INFO_NUM_ITER] = double(k);
+    info[INFO_ABS_ERR] = abs_err;
+    info[INFO_REL_ERR] = rel_err;
+    info[INFO_GMRES_ITERS] = double(gm_iters);
+    info[INFO_GMRES_RESID] = gm_resid;
+    info[INFO_BNORM] = gm_bnorm;
+  }
+  __syncthreads();
+}
+
+// _set_fin_solid_state (transient.py:836-848) + fluid solve: area from u1, Bernoulli -> q1, pf1
+template <int D>
+__device__ void blk_fluid(const EngineDev& E, double* mb, BlockShared& sh) {
+  const Layout& L = E.L;
+  const double* u1 = mb + L.off[VF_U1];
+  double* area = mb + L.off[VF_AREA];
+  const double ymid = (mb + L.off[VF_SCAL])[SC_YMID];
+  for (int k = threadIdx.x; k < E.n_fsi; k += blockDim.x) {
+    const int i = E.fsi_solid[k];
+    const double y = E.mesh.xyz[(size_t)1 * E.mesh.nn + i] + u1[D * i + 1];
+    area[E.fsi_fluid[k]] = 2.0 * (ymid - y);
+  }
+  __syncthreads();
+  const int wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int f = wid; f < E.n_fluid; f += nw) {
+    bernoulli_channel(E.fluid_kind, E.idx_sep, E.ns, E.s + (size_t)f * E.ns,
+                      area + (size_t)f * E.ns, (mb + L.off[VF_PSUB])[f],
+                      (mb + L.off[VF_PSUP])[f], mb + L.off[VF_FPROP] + (size_t)f * FP_COUNT,
+                      mb + L.off[VF_Q1] + f, mb + L.off[VF_PF1] + (size_t)f * E.ns);
+  }
+  __syncthreads();
+  // glottal-width signal: min over the fluid area (postprocess/solid.py:487-501)
+  double mn = CUDART_INF;
+  for (int k = threadIdx.x; k < E.n_fluid * E.ns; k += blockDim.x) mn = fmin(mn, area[k]);
+  mn = -warp_max(-mn);
+  const int lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) sh.red[wid] = mn;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = sh.red[0];
+    for (int q = 1; q < nw; ++q) t = fmin(t, sh.red[q]);
+    (mb + L.off[VF_INFO])[INFO_MIN_AREA] = t;
+  }
+  __syncthreads();
+}
+
+}  // namespace vf

@@ -63,6 +63,7 @@ struct StateView {
   const double* a0;
   const double* p1;  // nodal pressure control (nn)
   double dt;
+  int is_static;  // static.py:105-124: u0 == u1, v0 = a0 = 0 -> no inertia / damping
 };
 
 VF_HD int find_slot(const int* bcol_i, int deg, int node) {
@@ -104,7 +105,8 @@ VF_HD void assemble_node(int i, const MeshView& m, const PropView& p, const Stat
     for (int c = 0; c < D; ++c) res[c] = 0.0;
 
   const double nu = p.scal[SC_NU];
-  const double cv = newmark_cv(s.dt), ca = newmark_ca(s.dt);
+  const double cv = s.is_static ? 0.0 : newmark_cv(s.dt);
+  const double ca = s.is_static ? 0.0 : newmark_ca(s.dt);
 
   // ---- cell integrals --------------------------------------------------------
   for (int t = m.n2e_ptr[i]; t < m.n2e_ptr[i + 1]; ++t) {
@@ -130,8 +132,8 @@ VF_HD void assemble_node(int i, const MeshView& m, const PropView& p, const Stat
           const int dof = D * nd[b] + c;
           const double u1 = s.u1[dof], u0 = s.u0[dof], v0 = s.v0[dof], a0 = s.a0[dof];
           U[b][c] = u1;
-          V[b][c] = newmark_v(u1, u0, v0, a0, s.dt);
-          A[b][c] = newmark_a(u1, u0, v0, a0, s.dt);
+          V[b][c] = s.is_static ? 0.0 : newmark_v(u1, u0, v0, a0, s.dt);
+          A[b][c] = s.is_static ? 0.0 : newmark_a(u1, u0, v0, a0, s.dt);
         }
       double r[D];
       cell_residual<D>(g, cf, a, U, V, A, r);

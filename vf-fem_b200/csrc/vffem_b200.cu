@@ -1,0 +1,807 @@
+// vffem_b200: CUDA kernels (sm_100a) and the C ABI declared in include/vffem_b200.h.
+//
+// Kernels
+//   asm_tile_kernel   K1+K2+K3: residual + Jacobian of one contiguous node tile; the tile's
+//                     slice of the CSR value array is accumulated in shared memory by the
+//                     owning threads and streamed out once with coalesced vector stores
+//   spmv_kernel       K4: block-aware CSR SpMV, L lanes per node block row
+//   fluid_kernel      K8: Bernoulli channels, one warp each
+//   member_kernel     K5-K8: persistent Newton/GMRES/Newmark/FSI time loop, one CTA per member
+// See DESIGN.md for the layout and the roofline of each.
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/vffem_b200.h"
+#include "member_solver.cuh"
+
+namespace vf {
+
+static thread_local std::string g_err;
+
+static int fail(const std::string& msg) {
+  g_err = msg;
+  return 1;
+}
+
+#define VF_CUDA(call)                                                            \
+  do {                                                                           \
+    cudaError_t _e = (call);                                                     \
+    if (_e != cudaSuccess)                                                       \
+      return fail(std::string(#call) + ": " + cudaGetErrorString(_e));           \
+  } while (0)
+
+// ---- grid-wide kernels (single large mesh) ----------------------------------------------
+
+template <int D, bool JAC, bool RES>
+__global__ void asm_tile_kernel(EngineDev E, int member, double dt, int is_static,
+                                const int* __restrict__ tile_start) {
+  extern __shared__ double tile[];
+  double* mb = E.members + (size_t)member * E.L.stride;
+  const Layout& L = E.L;
+  const int i0 = tile_start[blockIdx.x], i1 = tile_start[blockIdx.x + 1];
+  const size_t base = (size_t)D * D * E.mesh.brptr[i0];
+  const int nvals = int((size_t)D * D * E.mesh.brptr[i1] - base);
+  const int i = i0 + threadIdx.x;
+  if (i < i1) {
+    PropView pv = member_props<D>(E, mb);
+    StateView sv;
+    sv.u1 = mb + L.off[VF_U1];
+    sv.u0 = is_static ? sv.u1 : mb + L.off[VF_U0];
+    sv.v0 = mb + L.off[VF_V0];
+    sv.a0 = mb + L.off[VF_A0];
+    sv.p1 = mb + L.off[VF_P1];
+    sv.dt = dt;
+    sv.is_static = is_static;
+    double res[D];
+    double* rowblk = JAC ? tile + ((size_t)D * D * E.mesh.brptr[i] - base) : nullptr;
+    assemble_node<D, JAC, RES>(i, E.mesh, pv, sv, rowblk, res);
+    if (RES) {
+      double* F = mb + L.off[VF_F];
+#pragma unroll
+      for (int c = 0; c < D; ++c) F[D * i + c] = res[c];
+    }
+  }
+  if (JAC) {
+    __syncthreads();
+    double* Jg = mb + L.off[VF_J] + base;
+    if (D == 2) {
+      // base and nvals are multiples of 4 doubles: 16-byte vector stores, fully coalesced
+      double2* dst = reinterpret_cast<double2*>(Jg);
+      const double2* src = reinterpret_cast<const double2*>(tile);
+      for (int t = threadIdx.x; t < nvals / 2; t += blockDim.x) dst[t] = src[t];
+    } else {
+      for (int t = threadIdx.x; t < nvals; t += blockDim.x) Jg[t] = tile[t];
+    }
+  }
+}
+
+// y = J x.  L lanes cooperate on one node block row (d scalar rows share their columns).
+template <int D, int LANES>
+__global__ void spmv_kernel(MeshView m, const double* __restrict__ J,
+                            const double* __restrict__ x, double* __restrict__ y) {
+  const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+  const int node = gt / LANES;
+  const int lane = gt % LANES;
+  const bool valid = node < m.nn;
+  double acc[D];
+#pragma unroll
+  for (int a = 0; a < D; ++a) acc[a] = 0.0;
+  if (valid) {
+    const int b0 = m.brptr[node], deg = m.brptr[node + 1] - b0;
+    const double* blk = J + (size_t)D * D * b0;
+    for (int k = lane; k < deg; k += LANES) {
+      const int j = __ldg(m.bcol + b0 + k);
+      if (D == 2) {
+        const double2 xv = *reinterpret_cast<const double2*>(x + 2 * j);
+        const double2 r0 = __ldcs(reinterpret_cast<const double2*>(blk + 2 * k));
+        const double2 r1 = __ldcs(reinterpret_cast<const double2*>(blk + 2 * deg + 2 * k));
+        acc[0] += r0.x * xv.x + r0.y * xv.y;
+        acc[1] += r1.x * xv.x + r1.y * xv.y;
+      } else {
+        double xv[D];
+#pragma unroll
+        for (int c = 0; c < D; ++c) xv[c] = x[D * j + c];
+#pragma unroll
+        for (int a = 0; a < D; ++a) {
+          const double* row = blk + (size_t)a * D * deg + k * D;
+#pragma unroll
+          for (int c = 0; c < D; ++c) acc[a] += __ldcs(row + c) * xv[c];
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int off = LANES / 2; off > 0; off >>= 1)
+#pragma unroll
+    for (int a = 0; a < D; ++a) acc[a] += __shfl_down_sync(0xffffffffu, acc[a], off, LANES);
+  if (valid && lane == 0) {
+#pragma unroll
+    for (int a = 0; a < D; ++a) y[D * node + a] = acc[a];
+  }
+}
+
+__global__ void fluid_kernel(EngineDev E, int member0) {
+  double* mb = E.members + (size_t)(member0 + blockIdx.x) * E.L.stride;
+  const Layout& L = E.L;
+  const int wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int f = wid; f < E.n_fluid; f += nw) {
+    bernoulli_channel(E.fluid_kind, E.idx_sep, E.ns, E.s + (size_t)f * E.ns,
+                      mb + L.off[VF_AREA] + (size_t)f * E.ns, (mb + L.off[VF_PSUB])[f],
+                      (mb + L.off[VF_PSUP])[f], mb + L.off[VF_FPROP] + (size_t)f * FP_COUNT,
+                      mb + L.off[VF_Q1] + f, mb + L.off[VF_PF1] + (size_t)f * E.ns);
+  }
+}
+
+// Staging <-> member blocks (host-buffer entry points move one contiguous buffer over PCIe
+// and let the device do the per-member scatter/gather).
+__global__ void pack_state_kernel(EngineDev E, double* staged, int to_members) {
+  double* mb = E.members + (size_t)blockIdx.x * E.L.stride;
+  const Layout& L = E.L;
+  const int N = E.N, nq = E.n_fluid, np = E.n_fluid * E.ns;
+  const size_t SS = (size_t)3 * N + nq + np;
+  double* st = staged + (size_t)blockIdx.x * SS;
+  const int ids[5] = {VF_U0, VF_V0, VF_A0, VF_Q0, VF_P0};
+  const int cnt[5] = {N, N, N, nq, np};
+  size_t o = 0;
+  for (int k = 0; k < 5; ++k) {
+    double* arr = mb + L.off[ids[k]];
+    for (int t = threadIdx.x; t < cnt[k]; t += blockDim.x) {
+      if (to_members) arr[t] = st[o + t];
+      else st[o + t] = arr[t];
+    }
+    o += cnt[k];
+  }
+}
+
+__global__ void pack_array_kernel(EngineDev E, const double* staged, int array_id, int count) {
+  double* arr = E.members + (size_t)blockIdx.x * E.L.stride + E.L.off[array_id];
+  const double* st = staged + (size_t)blockIdx.x * count;
+  for (int t = threadIdx.x; t < count; t += blockDim.x) arr[t] = st[t];
+}
+
+// ---- persistent per-member kernel ---------------------------------------------------------
+
+enum MemberMode { MODE_SOLVE_SOLID = 0, MODE_INTEGRATE = 1, MODE_LINEAR_SOLVE = 2 };
+
+template <int D>
+__device__ void write_history(const EngineDev& E, double* mb, double* hist_state,
+                              double* hist_info, size_t row, bool zero_info) {
+  const Layout& L = E.L;
+  const int N = E.N, nq = E.n_fluid, np = E.n_fluid * E.ns;
+  if (hist_state) {
+    double* dst = hist_state + row * (size_t)(3 * N + nq + np);
+    const double* u = mb + L.off[VF_U0];
+    const double* v = mb + L.off[VF_V0];
+    const double* a = mb + L.off[VF_A0];
+    for (int t = threadIdx.x; t < N; t += blockDim.x) {
+      dst[t] = u[t];
+      dst[N + t] = v[t];
+      dst[2 * N + t] = a[t];
+    }
+    for (int t = threadIdx.x; t < nq; t += blockDim.x) dst[3 * N + t] = (mb + L.off[VF_Q0])[t];
+    for (int t = threadIdx.x; t < np; t += blockDim.x)
+      dst[3 * N + nq + t] = (mb + L.off[VF_P0])[t];
+  }
+  if (hist_info && threadIdx.x == 0) {
+    const double* info = mb + L.off[VF_INFO];
+    double* dst = hist_info + row * 4;
+    dst[0] = zero_info ? 0.0 : info[INFO_NUM_ITER];
+    dst[1] = zero_info ? 0.0 : info[INFO_ABS_ERR];
+    dst[2] = zero_info ? 0.0 : info[INFO_REL_ERR];
+    dst[3] = info[INFO_MIN_AREA];
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(512)
+member_kernel(EngineDev E, int member0, int mode, int nsteps, const double* __restrict__ dts,
+              int nctrl, const double* __restrict__ controls, SolverOpts opt, double dt_single,
+              double* hist_state, double* hist_info, const double* lin_b, double* lin_x) {
+  __shared__ BlockShared sh;
+  const int b = member0 + blockIdx.x;
+  double* mb = E.members + (size_t)b * E.L.stride;
+  const Layout& L = E.L;
+  const int N = E.N, nn = E.mesh.nn;
+
+  if (mode == MODE_SOLVE_SOLID) {
+    blk_solve_solid<D>(E, mb, dt_single, opt, sh);
+    return;
+  }
+  if (mode == MODE_LINEAR_SOLVE) {
+    double resid, bnorm;
+    blk_compute_dinv<D>(E, mb + L.off[VF_J], mb + L.Dinv);
+    __syncthreads();
+    const int it = blk_gmres<D>(E, mb, lin_b, lin_x, opt, sh, &resid, &bnorm);
+    if (threadIdx.x == 0) {
+      double* info = mb + L.off[VF_INFO];
+      info[INFO_GMRES_ITERS] = double(it);
+      info[INFO_GMRES_RESID] = resid;
+      info[INFO_BNORM] = bnorm;
+    }
+    return;
+  }
+
+  // MODE_INTEGRATE
+  double* u0 = mb + L.off[VF_U0];
+  double* v0 = mb + L.off[VF_V0];
+  double* a0 = mb + L.off[VF_A0];
+  double* u1 = mb + L.off[VF_U1];
+  double* v1 = mb + L.off[VF_V1];
+  double* a1 = mb + L.off[VF_A1];
+  double* q0 = mb + L.off[VF_Q0];
+  double* p0 = mb + L.off[VF_P0];
+  double* q1 = mb + L.off[VF_Q1];
+  double* pf1 = mb + L.off[VF_PF1];
+  double* p1 = mb + L.off[VF_P1];
+  double* psub = mb + L.off[VF_PSUB];
+  double* psup = mb + L.off[VF_PSUP];
+  const size_t hrow0 = (size_t)blockIdx.x * (size_t)(nsteps + 1);
+
+  // row 0 of the history: the initial state with zero solver info (forward.py:75-86);
+  // the min-area entry is evaluated from the initial displacement
+  {
+    const double ymid = (mb + L.off[VF_SCAL])[SC_YMID];
+    double* area = mb + L.off[VF_AREA];
+    for (int k = threadIdx.x; k < E.n_fsi; k += blockDim.x) {
+      const int i = E.fsi_solid[k];
+      area[E.fsi_fluid[k]] = 2.0 * (ymid - (E.mesh.xyz[(size_t)E.mesh.nn + i] + u0[D * i + 1]));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double mn = CUDART_INF;
+      for (int k = 0; k < E.n_fluid * E.ns; ++k) mn = fmin(mn, area[k]);
+      (mb + L.off[VF_INFO])[INFO_MIN_AREA] = mn;
+    }
+    __syncthreads();
+    write_history<D>(E, mb, hist_state, hist_info, hrow0, true);
+  }
+
+  for (int n = 0; n < nsteps; ++n) {
+    const double dt = dts[n];
+    const int ci = min(n, nctrl - 1);
+    // set_control (transient.py:797-802)
+    for (int f = threadIdx.x; f < E.n_fluid; f += blockDim.x) {
+      psub[f] = controls[((size_t)ci * 2 + 0) * E.n_fluid + f];
+      psup[f] = controls[((size_t)ci * 2 + 1) * E.n_fluid + f];
+    }
+    // _set_ini_fluid_state: p1 := 0; p1[solid_dofs] = p0[fluid_dofs]  (transient.py:850-858)
+    for (int i = threadIdx.x; i < nn; i += blockDim.x) p1[i] = 0.0;
+    // initial guess for the final state = initial state (transient.py:904)
+    for (int t = threadIdx.x; t < N; t += blockDim.x) u1[t] = u0[t];
+    __syncthreads();
+    for (int k = threadIdx.x; k < E.n_fsi; k += blockDim.x) p1[E.fsi_solid[k]] = p0[E.fsi_fluid[k]];
+    __syncthreads();
+
+    blk_solve_solid<D>(E, mb, dt, opt, sh);
+    blk_fluid<D>(E, mb, sh);
+
+    // state0 <- state1 (forward.py:184)
+    for (int t = threadIdx.x; t < N; t += blockDim.x) {
+      u0[t] = u1[t];
+      v0[t] = v1[t];
+      a0[t] = a1[t];
+    }
+    for (int t = threadIdx.x; t < E.n_fluid; t += blockDim.x) q0[t] = q1[t];
+    for (int t = threadIdx.x; t < E.n_fluid * E.ns; t += blockDim.x) p0[t] = pf1[t];
+    __syncthreads();
+    write_history<D>(E, mb, hist_state, hist_info, hrow0 + n + 1, false);
+  }
+}
+
+}  // namespace vf
+
+// ======================================= host side ===========================================
+
+using namespace vf;
+
+struct vf_engine {
+  vf_problem_desc desc;  // scalar fields only are valid after create
+  EngineDev dev;
+  char* arena;
+  size_t arena_bytes;
+  int* tile_start_dev;
+  std::vector<int32_t> brptr, bcol;
+  int member_threads;
+  int64_t launches;
+};
+
+namespace {
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct ArenaPlan {
+  // byte offsets of the shared tables
+  size_t xyz, cells, brptr, bcol, n2e_ptr, n2e, n2f_ptr, n2f, pf_cell, pf_opp, bc, tile_start, s,
+      fsi_solid, fsi_fluid, members, total;
+  Layout L;
+  long long nnz;
+  int N;
+};
+
+ArenaPlan plan_arena(const vf_problem_desc& d) {
+  ArenaPlan P{};
+  const int nen = d.dim + 1;
+  const long long nnzb = d.brptr_host ? d.brptr_host[d.nn] : 0;
+  P.nnz = nnzb * d.dim * d.dim;
+  P.N = d.dim * d.nn;
+  size_t o = 0;
+  auto take = [&](size_t bytes) {
+    size_t r = o;
+    o = align_up(o + bytes, 256);
+    return r;
+  };
+  const int n_n2e = d.n2e_ptr_host ? d.n2e_ptr_host[d.nn] : 0;
+  const int n_n2f = d.n2f_ptr_host ? d.n2f_ptr_host[d.nn] : 0;
+  P.xyz = take(sizeof(double) * d.dim * d.nn);
+  P.cells = take(sizeof(int) * nen * d.ne);
+  P.brptr = take(sizeof(int) * (d.nn + 1));
+  P.bcol = take(sizeof(int) * nnzb);
+  P.n2e_ptr = take(sizeof(int) * (d.nn + 1));
+  P.n2e = take(sizeof(int) * n_n2e);
+  P.n2f_ptr = take(sizeof(int) * (d.nn + 1));
+  P.n2f = take(sizeof(int) * std::max(n_n2f, 1));
+  P.pf_cell = take(sizeof(int) * std::max(d.nfp, 1));
+  P.pf_opp = take(sizeof(int) * std::max(d.nfp, 1));
+  P.bc = take(d.dim * d.nn);
+  P.tile_start = take(sizeof(int) * (d.ntiles + 1));
+  P.s = take(sizeof(double) * std::max(d.n_fluid * d.ns, 1));
+  P.fsi_solid = take(sizeof(int) * std::max(d.n_fsi, 1));
+  P.fsi_fluid = take(sizeof(int) * std::max(d.n_fsi, 1));
+  P.members = o;
+
+  // member block (offsets in doubles, each array aligned to 16 doubles = 128 B)
+  Layout& L = P.L;
+  size_t m = 0;
+  auto mtake = [&](size_t count) {
+    size_t r = m;
+    m = align_up(m + std::max<size_t>(count, 1), 16);
+    return r;
+  };
+  const size_t N = P.N, nq = d.n_fluid, np = (size_t)d.n_fluid * d.ns, ne = d.ne;
+  auto pub = [&](int id, size_t count) {
+    L.off[id] = mtake(count);
+    L.cnt[id] = count;
+  };
+  pub(VF_U0, N); pub(VF_V0, N); pub(VF_A0, N); pub(VF_Q0, nq); pub(VF_P0, np);
+  pub(VF_U1, N); pub(VF_V1, N); pub(VF_A1, N); pub(VF_Q1, nq); pub(VF_PF1, np);
+  pub(VF_PSUB, nq); pub(VF_PSUP, nq);
+  pub(VF_P1, d.nn);
+  pub(VF_AREA, np);
+  pub(VF_RHO, ne); pub(VF_ETA, ne); pub(VF_EMOD, ne);
+  pub(VF_EMOD_M, d.membrane ? ne : 1); pub(VF_NU_M, d.membrane ? ne : 1);
+  pub(VF_TH_M, d.membrane ? ne : 1);
+  pub(VF_SCAL, SC_COUNT);
+  pub(VF_FPROP, nq * FP_COUNT);
+  pub(VF_F, N);
+  pub(VF_J, (size_t)P.nnz);
+  pub(VF_DX, N);
+  pub(VF_INFO, kInfoCount);
+  const size_t mr = d.gmres_restart;
+  L.Dinv = mtake((size_t)d.nn * d.dim * d.dim);
+  L.V = mtake((mr + 1) * N);
+  L.w = mtake(N);
+  L.z = mtake(N);
+  L.H = mtake((mr + 1) * mr);
+  L.cs = mtake(mr);
+  L.sn = mtake(mr);
+  L.g = mtake(mr + 1);
+  L.y = mtake(mr);
+  L.xk = mtake(N);
+  L.stride = align_up(m, 32);
+  P.total = P.members + sizeof(double) * L.stride * (size_t)d.n_members;
+  return P;
+}
+
+int check_desc(const vf_problem_desc* d) {
+  if (!d) return fail("null problem descriptor");
+  if (d->dim != 2 && d->dim != 3) return fail("dim must be 2 or 3");
+  if (d->nn <= 0 || d->ne <= 0) return fail("empty mesh");
+  if (d->n_members <= 0) return fail("n_members must be positive");
+  if (d->gmres_restart <= 0 || d->gmres_restart > kMaxRestart)
+    return fail("gmres_restart must be in [1, 128]");
+  if (d->n_fluid < 0 || d->ns < 0 || d->n_fsi < 0) return fail("negative fluid sizes");
+  if (d->ntiles <= 0 || !d->tile_start_host) return fail("missing assembly tile partition");
+  if (d->tile_threads <= 0 || d->tile_threads > 1024) return fail("invalid tile_threads");
+  if ((size_t)d->tile_max_values * sizeof(double) > 227 * 1024)
+    return fail("tile exceeds the 227 KB shared memory of an SM");
+  return 0;
+}
+
+cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+double* member_array(vf_engine* e, int id, int member) {
+  return e->dev.members + (size_t)member * e->dev.L.stride + e->dev.L.off[id];
+}
+
+SolverOpts to_opts(const vf_solver_opts* o) {
+  SolverOpts s;
+  if (o) {
+    s.newton_abs_tol = o->newton_abs_tol;
+    s.newton_rel_tol = o->newton_rel_tol;
+    s.newton_max_iter = o->newton_max_iter;
+    s.gmres_rel_tol = o->gmres_rel_tol;
+    s.gmres_abs_tol = o->gmres_abs_tol;
+    s.gmres_max_iter = o->gmres_max_iter;
+    s.is_static = o->is_static;
+  } else {
+    s.newton_abs_tol = 1e-8;   // solverconst.py:1-6
+    s.newton_rel_tol = 1e-10;
+    s.newton_max_iter = 50;
+    s.gmres_rel_tol = 1e-13;
+    s.gmres_abs_tol = 0.0;
+    s.gmres_max_iter = 2000;
+    s.is_static = 0;
+  }
+  return s;
+}
+
+template <int D>
+int launch_member(vf_engine* e, int member0, int count, int mode, int nsteps, const double* dts,
+                  int nctrl, const double* controls, const SolverOpts& opt, double dt_single,
+                  double* hist_state, double* hist_info, const double* lin_b, double* lin_x,
+                  cudaStream_t st) {
+  member_kernel<D><<<count, e->member_threads, 0, st>>>(e->dev, member0, mode, nsteps, dts, nctrl,
+                                                       controls, opt, dt_single, hist_state,
+                                                       hist_info, lin_b, lin_x);
+  e->launches += 1;
+  VF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_member_any(vf_engine* e, int member0, int count, int mode, int nsteps,
+                      const double* dts, int nctrl, const double* controls,
+                      const SolverOpts& opt, double dt_single, double* hist_state,
+                      double* hist_info, const double* lin_b, double* lin_x, cudaStream_t st) {
+  if (member0 < 0 || count <= 0 || member0 + count > e->desc.n_members)
+    return fail("member range out of bounds");
+  if (e->desc.dim == 2)
+    return launch_member<2>(e, member0, count, mode, nsteps, dts, nctrl, controls, opt,
+                            dt_single, hist_state, hist_info, lin_b, lin_x, st);
+  return launch_member<3>(e, member0, count, mode, nsteps, dts, nctrl, controls, opt, dt_single,
+                          hist_state, hist_info, lin_b, lin_x, st);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* vf_last_error(void) { return g_err.c_str(); }
+
+int vf_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+size_t vf_arena_bytes(const vf_problem_desc* desc) {
+  if (check_desc(desc)) return 0;
+  return plan_arena(*desc).total;
+}
+
+int vf_create(const vf_problem_desc* desc, void* arena_dev, size_t arena_bytes, void* stream,
+              vf_engine** out) {
+  if (!out) return fail("null output handle");
+  *out = nullptr;
+  if (check_desc(desc)) return 1;
+  if (vf_device_count() <= 0)
+    return fail("no CUDA device available: vffem_b200 has no CPU fallback");
+  const vf_problem_desc& d = *desc;
+  ArenaPlan P = plan_arena(d);
+  if (!arena_dev || arena_bytes < P.total) return fail("arena too small");
+  if (reinterpret_cast<uintptr_t>(arena_dev) % 256 != 0) return fail("arena must be 256-byte aligned");
+  cudaStream_t st = as_stream(stream);
+  char* A = static_cast<char*>(arena_dev);
+  const int nen = d.dim + 1;
+  const int nnzb = d.brptr_host[d.nn];
+  const int n_n2e = d.n2e_ptr_host[d.nn];
+  const int n_n2f = d.n2f_ptr_host[d.nn];
+
+  VF_CUDA(cudaMemsetAsync(A, 0, P.total, st));
+  auto up = [&](size_t off, const void* src, size_t bytes) -> cudaError_t {
+    if (bytes == 0) return cudaSuccess;
+    return cudaMemcpyAsync(A + off, src, bytes, cudaMemcpyHostToDevice, st);
+  };
+  VF_CUDA(up(P.xyz, d.xyz_host, sizeof(double) * d.dim * d.nn));
+  VF_CUDA(up(P.cells, d.cells_host, sizeof(int) * nen * d.ne));
+  VF_CUDA(up(P.brptr, d.brptr_host, sizeof(int) * (d.nn + 1)));
+  VF_CUDA(up(P.bcol, d.bcol_host, sizeof(int) * nnzb));
+  VF_CUDA(up(P.n2e_ptr, d.n2e_ptr_host, sizeof(int) * (d.nn + 1)));
+  VF_CUDA(up(P.n2e, d.n2e_host, sizeof(int) * n_n2e));
+  VF_CUDA(up(P.n2f_ptr, d.n2f_ptr_host, sizeof(int) * (d.nn + 1)));
+  VF_CUDA(up(P.n2f, d.n2f_host, sizeof(int) * n_n2f));
+  VF_CUDA(up(P.pf_cell, d.pf_cell_host, sizeof(int) * d.nfp));
+  VF_CUDA(up(P.pf_opp, d.pf_opp_host, sizeof(int) * d.nfp));
+  VF_CUDA(up(P.bc, d.bc_host, d.dim * d.nn));
+  VF_CUDA(up(P.tile_start, d.tile_start_host, sizeof(int) * (d.ntiles + 1)));
+  VF_CUDA(up(P.s, d.s_host, sizeof(double) * d.n_fluid * d.ns));
+  VF_CUDA(up(P.fsi_solid, d.fsi_solid_host, sizeof(int) * d.n_fsi));
+  VF_CUDA(up(P.fsi_fluid, d.fsi_fluid_host, sizeof(int) * d.n_fsi));
+  VF_CUDA(cudaStreamSynchronize(st));
+
+  vf_engine* e = new vf_engine();
+  e->desc = d;
+  e->arena = A;
+  e->arena_bytes = P.total;
+  e->launches = 0;
+  e->brptr.assign(d.brptr_host, d.brptr_host + d.nn + 1);
+  e->bcol.assign(d.bcol_host, d.bcol_host + nnzb);
+  // host pointers of the descriptor are not retained
+  e->desc.xyz_host = nullptr; e->desc.cells_host = nullptr; e->desc.brptr_host = nullptr;
+  e->desc.bcol_host = nullptr; e->desc.n2e_ptr_host = nullptr; e->desc.n2e_host = nullptr;
+  e->desc.n2f_ptr_host = nullptr; e->desc.n2f_host = nullptr; e->desc.pf_cell_host = nullptr;
+  e->desc.pf_opp_host = nullptr; e->desc.bc_host = nullptr; e->desc.tile_start_host = nullptr;
+  e->desc.s_host = nullptr; e->desc.fsi_solid_host = nullptr; e->desc.fsi_fluid_host = nullptr;
+
+  EngineDev& E = e->dev;
+  E.mesh.dim = d.dim; E.mesh.nn = d.nn; E.mesh.ne = d.ne; E.mesh.nfp = d.nfp;
+  E.mesh.xyz = reinterpret_cast<const double*>(A + P.xyz);
+  E.mesh.cells = reinterpret_cast<const int*>(A + P.cells);
+  E.mesh.brptr = reinterpret_cast<const int*>(A + P.brptr);
+  E.mesh.bcol = reinterpret_cast<const int*>(A + P.bcol);
+  E.mesh.n2e_ptr = reinterpret_cast<const int*>(A + P.n2e_ptr);
+  E.mesh.n2e = reinterpret_cast<const int*>(A + P.n2e);
+  E.mesh.n2f_ptr = reinterpret_cast<const int*>(A + P.n2f_ptr);
+  E.mesh.n2f = reinterpret_cast<const int*>(A + P.n2f);
+  E.mesh.pf_cell = reinterpret_cast<const int*>(A + P.pf_cell);
+  E.mesh.pf_opp = reinterpret_cast<const int*>(A + P.pf_opp);
+  E.mesh.bc = reinterpret_cast<const unsigned char*>(A + P.bc);
+  E.d = d.dim; E.N = P.N; E.n_fluid = d.n_fluid; E.ns = d.ns; E.n_fsi = d.n_fsi;
+  E.fluid_kind = d.fluid_kind; E.idx_sep = d.idx_sep; E.contact = d.contact;
+  E.membrane = d.membrane; E.restart = d.gmres_restart; E.nnz = P.nnz;
+  E.s = reinterpret_cast<const double*>(A + P.s);
+  E.fsi_solid = reinterpret_cast<const int*>(A + P.fsi_solid);
+  E.fsi_fluid = reinterpret_cast<const int*>(A + P.fsi_fluid);
+  E.members = reinterpret_cast<double*>(A + P.members);
+  E.L = P.L;
+  e->tile_start_dev = reinterpret_cast<int*>(A + P.tile_start);
+  e->member_threads = (P.N <= 2048) ? 256 : 512;
+
+  // opt in to large dynamic shared memory for the tile kernel
+  const int smem = d.tile_max_values * (int)sizeof(double);
+  if (d.dim == 2) {
+    VF_CUDA(cudaFuncSetAttribute(asm_tile_kernel<2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    VF_CUDA(cudaFuncSetAttribute(asm_tile_kernel<2, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  } else {
+    VF_CUDA(cudaFuncSetAttribute(asm_tile_kernel<3, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    VF_CUDA(cudaFuncSetAttribute(asm_tile_kernel<3, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  }
+  *out = e;
+  return 0;
+}
+
+void vf_destroy(vf_engine* e) { delete e; }
+
+int vf_array_info(const vf_engine* e, int array_id, int member, size_t* byte_offset,
+                  size_t* count) {
+  if (!e) return fail("null engine");
+  if (array_id < 0 || array_id >= VF_ARRAY_COUNT) return fail("invalid array id");
+  if (member < 0 || member >= e->desc.n_members) return fail("member out of range");
+  const char* p = reinterpret_cast<const char*>(
+      e->dev.members + (size_t)member * e->dev.L.stride + e->dev.L.off[array_id]);
+  if (byte_offset) *byte_offset = size_t(p - e->arena);
+  if (count) *count = e->dev.L.cnt[array_id];
+  return 0;
+}
+
+int vf_upload(vf_engine* e, int array_id, int member, const double* src_host, size_t count,
+              void* stream) {
+  size_t off, cnt;
+  if (vf_array_info(e, array_id, member, &off, &cnt)) return 1;
+  if (count != cnt) return fail("vf_upload: size mismatch for array " + std::to_string(array_id));
+  VF_CUDA(cudaMemcpyAsync(e->arena + off, src_host, sizeof(double) * cnt, cudaMemcpyHostToDevice,
+                          as_stream(stream)));
+  VF_CUDA(cudaStreamSynchronize(as_stream(stream)));
+  return 0;
+}
+
+int vf_download(vf_engine* e, int array_id, int member, double* dst_host, size_t count,
+                void* stream) {
+  size_t off, cnt;
+  if (vf_array_info(e, array_id, member, &off, &cnt)) return 1;
+  if (count != cnt) return fail("vf_download: size mismatch for array " + std::to_string(array_id));
+  VF_CUDA(cudaMemcpyAsync(dst_host, e->arena + off, sizeof(double) * cnt, cudaMemcpyDeviceToHost,
+                          as_stream(stream)));
+  VF_CUDA(cudaStreamSynchronize(as_stream(stream)));
+  return 0;
+}
+
+int64_t vf_nnz(const vf_engine* e) { return e ? e->dev.nnz : 0; }
+
+int vf_csr_pattern(const vf_engine* e, int32_t* rowptr, int32_t* colidx) {
+  if (!e || !rowptr || !colidx) return fail("null argument");
+  const int d = e->desc.dim, nn = e->desc.nn;
+  int64_t pos = 0;
+  for (int i = 0; i < nn; ++i) {
+    const int b0 = e->brptr[i], deg = e->brptr[i + 1] - b0;
+    for (int a = 0; a < d; ++a) {
+      rowptr[d * i + a] = (int32_t)pos;
+      for (int k = 0; k < deg; ++k)
+        for (int b = 0; b < d; ++b) colidx[pos++] = d * e->bcol[b0 + k] + b;
+    }
+  }
+  rowptr[d * nn] = (int32_t)pos;
+  return 0;
+}
+
+int vf_assemble(vf_engine* e, int member, int flags, double dt, int is_static, void* stream) {
+  if (!e) return fail("null engine");
+  if (member < 0 || member >= e->desc.n_members) return fail("member out of range");
+  const bool res = flags & 1, jac = flags & 2;
+  if (!res && !jac) return 0;
+  cudaStream_t st = as_stream(stream);
+  const int grid = e->desc.ntiles, block = e->desc.tile_threads;
+  const size_t smem = jac ? (size_t)e->desc.tile_max_values * sizeof(double) : 0;
+#define VF_LAUNCH_ASM(D)                                                                          \
+  if (jac && res)                                                                                 \
+    asm_tile_kernel<D, true, true><<<grid, block, smem, st>>>(e->dev, member, dt, is_static,      \
+                                                              e->tile_start_dev);                 \
+  else if (jac)                                                                                   \
+    asm_tile_kernel<D, true, false><<<grid, block, smem, st>>>(e->dev, member, dt, is_static,     \
+                                                               e->tile_start_dev);                \
+  else                                                                                            \
+    asm_tile_kernel<D, false, true><<<grid, block, 0, st>>>(e->dev, member, dt, is_static,        \
+                                                            e->tile_start_dev);
+  if (e->desc.dim == 2) {
+    VF_LAUNCH_ASM(2)
+  } else {
+    VF_LAUNCH_ASM(3)
+  }
+#undef VF_LAUNCH_ASM
+  e->launches += 1;
+  VF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int vf_spmv(vf_engine* e, int member, const double* x_dev, double* y_dev, void* stream) {
+  if (!e) return fail("null engine");
+  if (member < 0 || member >= e->desc.n_members) return fail("member out of range");
+  cudaStream_t st = as_stream(stream);
+  const double* J = member_array(e, VF_J, member);
+  const int nn = e->desc.nn;
+  const int block = 256;
+  if (e->desc.dim == 2) {
+    constexpr int LN = 8;
+    const int grid = (int)(((size_t)nn * LN + block - 1) / block);
+    spmv_kernel<2, LN><<<grid, block, 0, st>>>(e->dev.mesh, J, x_dev, y_dev);
+  } else {
+    constexpr int LN = 16;
+    const int grid = (int)(((size_t)nn * LN + block - 1) / block);
+    spmv_kernel<3, LN><<<grid, block, 0, st>>>(e->dev.mesh, J, x_dev, y_dev);
+  }
+  e->launches += 1;
+  VF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int vf_linear_solve(vf_engine* e, int member, const double* b_dev, double* x_dev,
+                    const vf_solver_opts* opts, double* info_host, void* stream) {
+  if (!e) return fail("null engine");
+  cudaStream_t st = as_stream(stream);
+  SolverOpts so = to_opts(opts);
+  if (launch_member_any(e, member, 1, MODE_LINEAR_SOLVE, 0, nullptr, 0, nullptr, so, 0.0, nullptr,
+                        nullptr, b_dev, x_dev, st))
+    return 1;
+  if (info_host) {
+    double info[kInfoCount];
+    VF_CUDA(cudaMemcpyAsync(info, member_array(e, VF_INFO, member), sizeof(info),
+                            cudaMemcpyDeviceToHost, st));
+    VF_CUDA(cudaStreamSynchronize(st));
+    info_host[0] = info[INFO_GMRES_ITERS];
+    info_host[1] = info[INFO_GMRES_RESID];
+    info_host[2] = info[INFO_BNORM];
+  }
+  return 0;
+}
+
+int vf_solve_state1(vf_engine* e, int member0, int count, double dt, const vf_solver_opts* opts,
+                    void* stream) {
+  if (!e) return fail("null engine");
+  SolverOpts so = to_opts(opts);
+  return launch_member_any(e, member0, count, MODE_SOLVE_SOLID, 0, nullptr, 0, nullptr, so, dt,
+                           nullptr, nullptr, nullptr, nullptr, as_stream(stream));
+}
+
+int vf_fluid_solve(vf_engine* e, int member0, int count, void* stream) {
+  if (!e) return fail("null engine");
+  if (member0 < 0 || count <= 0 || member0 + count > e->desc.n_members)
+    return fail("member range out of bounds");
+  if (e->desc.n_fluid <= 0) return fail("model has no fluid");
+  const int warps = std::min(e->desc.n_fluid, 8);
+  fluid_kernel<<<count, 32 * warps, 0, as_stream(stream)>>>(e->dev, member0);
+  e->launches += 1;
+  VF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int vf_integrate(vf_engine* e, int nsteps, const double* dts_host, int ncontrols,
+                 const double* controls_host, const vf_solver_opts* opts, double* hist_state_dev,
+                 double* hist_info_dev, void* stream) {
+  if (!e) return fail("null engine");
+  if (nsteps <= 0) return fail("nsteps must be positive");
+  if (ncontrols <= 0 || !controls_host || !dts_host) return fail("missing dts/controls");
+  if (e->desc.n_fluid <= 0) return fail("vf_integrate needs a coupled fluid");
+  cudaStream_t st = as_stream(stream);
+  SolverOpts so = to_opts(opts);
+  so.is_static = 0;
+  const size_t nctl = (size_t)ncontrols * 2 * e->desc.n_fluid;
+  double* scratch = nullptr;
+  VF_CUDA(cudaMallocAsync(&scratch, sizeof(double) * (nsteps + nctl), st));
+  cudaError_t err = cudaMemcpyAsync(scratch, dts_host, sizeof(double) * nsteps,
+                                    cudaMemcpyHostToDevice, st);
+  if (err == cudaSuccess)
+    err = cudaMemcpyAsync(scratch + nsteps, controls_host, sizeof(double) * nctl,
+                          cudaMemcpyHostToDevice, st);
+  int rc = 0;
+  if (err != cudaSuccess) {
+    rc = fail(std::string("vf_integrate upload: ") + cudaGetErrorString(err));
+  } else {
+    rc = launch_member_any(e, 0, e->desc.n_members, MODE_INTEGRATE, nsteps, scratch, ncontrols,
+                           scratch + nsteps, so, 0.0, hist_state_dev, hist_info_dev, nullptr,
+                           nullptr, st);
+  }
+  cudaFreeAsync(scratch, st);
+  return rc;
+}
+
+int vf_integrate_host(vf_engine* e, int nsteps, const double* dts_host, int ncontrols,
+                      const double* controls_host, const vf_solver_opts* opts,
+                      const double* ini_state_host, const double* emod_host,
+                      const double* eta_host, double* fin_state_host, double* info_series_host,
+                      void* stream) {
+  if (!e) return fail("null engine");
+  if (!ini_state_host || !fin_state_host) return fail("null state buffers");
+  cudaStream_t st = as_stream(stream);
+  const int B = e->desc.n_members;
+  const size_t N = e->dev.N, nq = e->desc.n_fluid, np = (size_t)e->desc.n_fluid * e->desc.ns;
+  const size_t SS = 3 * N + nq + np, ne = e->desc.ne;
+  const size_t hcount = info_series_host ? (size_t)B * (nsteps + 1) * 4 : 0;
+  // one staging allocation: [state B*SS][emod B*ne][eta B*ne][info series]
+  double* stage = nullptr;
+  VF_CUDA(cudaMallocAsync(&stage, sizeof(double) * (B * SS + 2 * B * ne + hcount), st));
+  double* st_state = stage;
+  double* st_emod = stage + B * SS;
+  double* st_eta = st_emod + B * ne;
+  double* hist_info = hcount ? st_eta + B * ne : nullptr;
+  int rc = 0;
+  auto cp = [&](void* dst, const void* src, size_t bytes, cudaMemcpyKind kind) {
+    if (rc) return;
+    cudaError_t err = cudaMemcpyAsync(dst, src, bytes, kind, st);
+    if (err != cudaSuccess) rc = fail(std::string("vf_integrate_host copy: ") + cudaGetErrorString(err));
+  };
+  cp(st_state, ini_state_host, sizeof(double) * B * SS, cudaMemcpyHostToDevice);
+  if (emod_host) cp(st_emod, emod_host, sizeof(double) * B * ne, cudaMemcpyHostToDevice);
+  if (eta_host) cp(st_eta, eta_host, sizeof(double) * B * ne, cudaMemcpyHostToDevice);
+  if (rc == 0) {
+    pack_state_kernel<<<B, 256, 0, st>>>(e->dev, st_state, 1);
+    e->launches += 1;
+    if (emod_host) {
+      pack_array_kernel<<<B, 256, 0, st>>>(e->dev, st_emod, VF_EMOD, (int)ne);
+      e->launches += 1;
+    }
+    if (eta_host) {
+      pack_array_kernel<<<B, 256, 0, st>>>(e->dev, st_eta, VF_ETA, (int)ne);
+      e->launches += 1;
+    }
+    rc = vf_integrate(e, nsteps, dts_host, ncontrols, controls_host, opts, nullptr, hist_info, st);
+  }
+  if (rc == 0) {
+    pack_state_kernel<<<B, 256, 0, st>>>(e->dev, st_state, 0);
+    e->launches += 1;
+    cp(fin_state_host, st_state, sizeof(double) * B * SS, cudaMemcpyDeviceToHost);
+    if (hcount) cp(info_series_host, hist_info, sizeof(double) * hcount, cudaMemcpyDeviceToHost);
+  }
+  cudaFreeAsync(stage, st);
+  cudaError_t err = cudaStreamSynchronize(st);
+  if (rc == 0 && err != cudaSuccess) rc = fail(std::string("sync: ") + cudaGetErrorString(err));
+  return rc;
+}
+
+int64_t vf_launch_count(const vf_engine* e) { return e ? e->launches : 0; }
+
+}  // extern "C"

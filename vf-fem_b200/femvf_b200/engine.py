@@ -1,0 +1,256 @@
+"""
+Python owner of one device engine (``vf_engine`` of ``include/vffem_b200.h``).
+
+PyTorch supplies the device memory (one ``uint8`` arena tensor), the stream and, for
+ensembles sharded over several GPUs, ``torch.distributed``; every computation is a call
+through the C ABI.  There is no CPU fallback: constructing an ``Engine`` without a CUDA
+device raises.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _cabi
+from ._cabi import ARRAY_IDS, ProblemDesc, SolverOpts, check
+from . import tables as _tables
+from .solverconst import DEFAULT_NEWTON_SOLVER_PRM, DEFAULT_LINEAR_SOLVER_PRM
+
+SCAL = {'nu': 0, 'ycontact': 1, 'kcontact': 2, 'ncontact': 3, 'ymid': 6}
+SCAL_COUNT = 8
+FPROP = {'rho_air': 0, 'r_sep': 1, 'area_lb': 2, 'zeta_min': 3, 'zeta_sep': 4}
+FPROP_COUNT = 5
+
+
+def make_solver_opts(options: Optional[dict] = None, is_static: bool = False) -> SolverOpts:
+    """Newton options with the reference's keys (``solverconst.py:1-6``); ``linear_solver``
+    is accepted and ignored."""
+    prm = dict(DEFAULT_NEWTON_SOLVER_PRM)
+    lin = dict(DEFAULT_LINEAR_SOLVER_PRM)
+    if options:
+        for key, value in options.items():
+            if key in lin:
+                lin[key] = value
+            else:
+                prm[key] = value
+    return SolverOpts(
+        float(prm['absolute_tolerance']), float(prm['relative_tolerance']),
+        int(prm['maximum_iterations']),
+        float(lin['gmres_relative_tolerance']), float(lin['gmres_absolute_tolerance']),
+        int(lin['gmres_maximum_iterations']), int(bool(is_static)),
+    )
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Engine:
+    def __init__(
+        self,
+        tables: dict,
+        s: Optional[np.ndarray] = None,
+        fsi_solid: Optional[np.ndarray] = None,
+        fsi_fluid: Optional[np.ndarray] = None,
+        fluid_kind: int = 0,
+        idx_sep: int = 0,
+        contact: bool = False,
+        membrane: bool = False,
+        n_members: int = 1,
+        gmres_restart: int = 40,
+        device: Optional[torch.device] = None,
+    ):
+        self._lib = _cabi.load_library()
+        if not torch.cuda.is_available() or self._lib.vf_device_count() <= 0:
+            raise _cabi.VFError(
+                "femvf_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device = torch.device('cuda', torch.cuda.current_device()) if device is None \
+            else torch.device(device)
+        self.tables = tables
+        d = tables['dim']
+        self.dim, self.nn, self.ne = d, tables['nn'], tables['ne']
+        self.N = d * self.nn
+        self.n_members = int(n_members)
+
+        if d == 2:
+            nodes_per_tile, max_vals, tile_threads = 128, 6144, 128
+        else:
+            nodes_per_tile, max_vals, tile_threads = 64, 12288, 64
+        tile_start = _tables.tile_partition(tables['brptr'], d, nodes_per_tile, max_vals)
+        vals = d * d * tables['brptr'].astype(np.int64)
+        tile_max = int(np.max(vals[tile_start[1:]] - vals[tile_start[:-1]]))
+
+        if s is None:
+            s = np.zeros((0, 0))
+        s = np.ascontiguousarray(np.atleast_2d(np.asarray(s, dtype=np.float64)))
+        self.n_fluid, self.ns = (s.shape[0], s.shape[1]) if s.size else (0, 0)
+        fsi_solid = np.zeros(0, np.int32) if fsi_solid is None else \
+            np.ascontiguousarray(fsi_solid, dtype=np.int32)
+        fsi_fluid = np.zeros(0, np.int32) if fsi_fluid is None else \
+            np.ascontiguousarray(fsi_fluid, dtype=np.int32)
+        if len(fsi_solid) != len(fsi_fluid):
+            raise ValueError("solid/fluid FSI dof arrays must have the same length")
+        self.state_size = 3 * self.N + self.n_fluid + self.n_fluid * self.ns
+
+        # keep every host array referenced by the descriptor alive until vf_create returns
+        keep = dict(tables)
+        keep.update(tile_start=tile_start, s=s, fsi_solid=fsi_solid, fsi_fluid=fsi_fluid)
+        desc = ProblemDesc(
+            d, self.nn, self.ne, tables['nfp'],
+            _ptr(keep['xyz']), _ptr(keep['cells']), _ptr(keep['brptr']), _ptr(keep['bcol']),
+            _ptr(keep['n2e_ptr']), _ptr(keep['n2e']), _ptr(keep['n2f_ptr']), _ptr(keep['n2f']),
+            _ptr(keep['pf_cell']), _ptr(keep['pf_opp']), _ptr(keep['bc']),
+            _ptr(tile_start), len(tile_start) - 1, tile_max, tile_threads,
+            self.n_fluid, self.ns, len(fsi_solid), _ptr(s), _ptr(fsi_solid), _ptr(fsi_fluid),
+            int(fluid_kind), int(idx_sep), int(bool(contact)), int(bool(membrane)),
+            self.n_members, int(gmres_restart),
+        )
+        nbytes = self._lib.vf_arena_bytes(C.byref(desc))
+        if nbytes == 0:
+            raise _cabi.VFError(self._lib.vf_last_error().decode())
+        with torch.cuda.device(self.device):
+            self.arena = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            handle = C.c_void_p()
+            check(self._lib.vf_create(C.byref(desc), self.arena.data_ptr(), nbytes,
+                                      self._stream(), C.byref(handle)))
+        self._h = handle
+        self.nnz = int(self._lib.vf_nnz(self._h))
+        self._views = {}
+
+    # --- plumbing -------------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def __del__(self):
+        h = getattr(self, '_h', None)
+        if h is not None and h.value:
+            self._lib.vf_destroy(h)
+            self._h = None
+
+    def view(self, name: str, member: int = 0) -> torch.Tensor:
+        """fp64 view into the arena of a named per-member array."""
+        key = (name, member)
+        if key not in self._views:
+            off, cnt = C.c_size_t(), C.c_size_t()
+            check(self._lib.vf_array_info(self._h, ARRAY_IDS[name], member, C.byref(off),
+                                          C.byref(cnt)))
+            self._views[key] = self.arena[off.value:off.value + 8 * cnt.value].view(torch.float64)
+        return self._views[key]
+
+    def member_view(self, name: str) -> torch.Tensor:
+        """(n_members, count) strided fp64 view of a named array across all members."""
+        v0 = self.view(name, 0)
+        if self.n_members == 1:
+            return v0.unsqueeze(0)
+        off0, off1, cnt = C.c_size_t(), C.c_size_t(), C.c_size_t()
+        check(self._lib.vf_array_info(self._h, ARRAY_IDS[name], 0, C.byref(off0), C.byref(cnt)))
+        check(self._lib.vf_array_info(self._h, ARRAY_IDS[name], 1, C.byref(off1), C.byref(cnt)))
+        stride = (off1.value - off0.value) // 8
+        flat = self.arena.view(torch.float64)
+        return torch.as_strided(flat, (self.n_members, cnt.value), (stride, 1), off0.value // 8)
+
+    def upload(self, name: str, value, member: int = 0):
+        v = self.view(name, member)
+        a = np.empty(v.numel(), dtype=np.float64)
+        a[:] = np.ravel(value) if np.ndim(value) else value
+        check(self._lib.vf_upload(self._h, ARRAY_IDS[name], member, _ptr(a), a.size,
+                                  self._stream()))
+
+    def download(self, name: str, member: int = 0) -> np.ndarray:
+        v = self.view(name, member)
+        out = np.empty(v.numel(), dtype=np.float64)
+        check(self._lib.vf_download(self._h, ARRAY_IDS[name], member, _ptr(out), out.size,
+                                    self._stream()))
+        return out
+
+    def csr_pattern(self):
+        rowptr = np.empty(self.N + 1, dtype=np.int32)
+        colidx = np.empty(self.nnz, dtype=np.int32)
+        check(self._lib.vf_csr_pattern(self._h, _ptr(rowptr), _ptr(colidx)))
+        return rowptr, colidx
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.vf_launch_count(self._h))
+
+    def synchronize(self):
+        torch.cuda.current_stream(self.device).synchronize()
+
+    # --- the hot path -----------------------------------------------------------------
+    def assemble(self, member: int = 0, res: bool = True, jac: bool = True, dt: float = 1.0,
+                 is_static: bool = False):
+        flags = (1 if res else 0) | (2 if jac else 0)
+        check(self._lib.vf_assemble(self._h, member, flags, float(dt), int(is_static),
+                                    self._stream()))
+
+    def spmv(self, x: torch.Tensor, y: torch.Tensor, member: int = 0):
+        assert x.dtype == torch.float64 and y.dtype == torch.float64
+        assert x.numel() == self.N and y.numel() == self.N and x.is_cuda and y.is_cuda
+        check(self._lib.vf_spmv(self._h, member, x.data_ptr(), y.data_ptr(), self._stream()))
+
+    def linear_solve(self, b: torch.Tensor, x: torch.Tensor, member: int = 0, options=None):
+        info = np.zeros(3)
+        opts = make_solver_opts(options)
+        check(self._lib.vf_linear_solve(self._h, member, b.data_ptr(), x.data_ptr(),
+                                        C.byref(opts), _ptr(info), self._stream()))
+        return {'iterations': int(info[0]), 'residual': float(info[1]), 'bnorm': float(info[2])}
+
+    def solve_state1(self, dt: float, member0: int = 0, count: int = 1, options=None,
+                     is_static: bool = False):
+        opts = make_solver_opts(options, is_static)
+        check(self._lib.vf_solve_state1(self._h, member0, count, float(dt), C.byref(opts),
+                                        self._stream()))
+
+    def fluid_solve(self, member0: int = 0, count: int = 1):
+        check(self._lib.vf_fluid_solve(self._h, member0, count, self._stream()))
+
+    def integrate(self, dts, controls, options=None, store_states: bool = False,
+                  store_info: bool = True):
+        """
+        ``nsteps`` coupled steps for all members from ``state0``.
+
+        controls : (ncontrols, 2, n_fluid) array of (psub, psup)
+        Returns (hist_state or None, hist_info or None) as device tensors shaped
+        (n_members, nsteps+1, state_size) and (n_members, nsteps+1, 4).
+        """
+        dts = np.ascontiguousarray(dts, dtype=np.float64).reshape(-1)
+        controls = np.ascontiguousarray(controls, dtype=np.float64).reshape(-1, 2, self.n_fluid)
+        nsteps = len(dts)
+        hist_state = hist_info = None
+        if store_states:
+            hist_state = torch.empty((self.n_members, nsteps + 1, self.state_size),
+                                     dtype=torch.float64, device=self.device)
+        if store_info:
+            hist_info = torch.empty((self.n_members, nsteps + 1, 4), dtype=torch.float64,
+                                    device=self.device)
+        opts = make_solver_opts(options)
+        check(self._lib.vf_integrate(
+            self._h, nsteps, _ptr(dts), controls.shape[0], _ptr(controls), C.byref(opts),
+            None if hist_state is None else hist_state.data_ptr(),
+            None if hist_info is None else hist_info.data_ptr(), self._stream()))
+        return hist_state, hist_info
+
+    def integrate_host(self, dts, controls, ini_state: np.ndarray, emod=None, eta=None,
+                       options=None, fin_state=None, info_series=None):
+        """End-to-end variant with host buffers (host<->device copies inside the call)."""
+        dts = np.ascontiguousarray(dts, dtype=np.float64).reshape(-1)
+        controls = np.ascontiguousarray(controls, dtype=np.float64).reshape(-1, 2, self.n_fluid)
+        nsteps = len(dts)
+        B = self.n_members
+        assert ini_state.shape == (B, self.state_size) and ini_state.flags.c_contiguous
+        if fin_state is None:
+            fin_state = np.empty((B, self.state_size))
+        if info_series is None:
+            info_series = np.empty((B, nsteps + 1, 4))
+        for a in (emod, eta):
+            assert a is None or (a.shape == (B, self.ne) and a.flags.c_contiguous)
+        opts = make_solver_opts(options)
+        check(self._lib.vf_integrate_host(
+            self._h, nsteps, _ptr(dts), controls.shape[0], _ptr(controls), C.byref(opts),
+            _ptr(ini_state), _ptr(emod), _ptr(eta), _ptr(fin_state), _ptr(info_series),
+            self._stream()))
+        return fin_state, info_series

@@ -1,0 +1,610 @@
+"""
+Transient model interface: mirror of ``/root/reference/src/femvf/models/transient.py``.
+
+Class and method names, argument meaning and ``info`` keys follow the reference
+(``BaseTransientModel`` :32-154, ``FenicsModel`` :221-513, ``NodalContactModel`` :516-583,
+``JaxModel`` :590-672, ``BaseTransientFSIModel`` :678-817, ``ExplicitFSIModel`` :821-920) so
+that ``forward.integrate`` and ``StateFile`` consume these objects unchanged.  State, control
+and property vectors are host ``BlockVector``s exactly as in the reference; every assembly,
+linear solve, Newton loop and fluid evaluation is a CUDA kernel reached through the C ABI
+(``engine.Engine``).  Host vectors are pushed to the device before each such call and results
+are pulled back, which is the "host buffer" path; ``forward.integrate`` uses the
+device-resident time loop instead.
+
+Documented deviations:
+  Q1/Q2  v1, a1 are computed from the Newmark relations after the solve for u1; the
+         off-diagonal blocks returned by ``assem_dres_dstate1`` are the nodal
+         -cv*I / -ca*I consistent with the nodal v/a residual rows; ``num_iter`` counts
+         Newton updates of u1 (1 for the affine 2D problem).
+  Q3     contact is active only in ``NodalContactModel`` (as in the reference).
+"""
+
+from __future__ import annotations
+
+from typing import Any, Optional
+
+import numpy as np
+import scipy.sparse as sp
+
+from .. import blockvec as bv
+from ..blockvec import BlockVector
+from ..engine import Engine, SCAL, SCAL_COUNT, FPROP, FPROP_COUNT
+from ..equations import newmark
+from ..residuals import solid as slr, fluid as flr
+from ..solverconst import DEFAULT_NEWTON_SOLVER_PRM
+from .. import tables as _tables
+from . import fsi
+
+BlockVec = BlockVector
+
+
+class BlockMatrix:
+    """Labelled 2D collection of sparse blocks with ``.sub[row, col]`` access."""
+
+    def __init__(self, mats, shape, labels):
+        self.mats = list(mats)
+        self.shape = tuple(shape)
+        self.labels = (tuple(labels[0]), tuple(labels[1]))
+
+    class _Sub:
+        def __init__(self, bm):
+            self._bm = bm
+
+        def __getitem__(self, key):
+            r, c = key
+            i = self._bm.labels[0].index(r) if isinstance(r, str) else int(r)
+            j = self._bm.labels[1].index(c) if isinstance(c, str) else int(c)
+            return self._bm.mats[i * self._bm.shape[1] + j]
+
+    @property
+    def sub(self):
+        return BlockMatrix._Sub(self)
+
+    def __bool__(self):
+        return True
+
+
+class BaseTransientModel:
+    """One time step of a system: residual F(u1, u0, g, p, dt) (``transient.py:32-154``)."""
+
+    @property
+    def dt(self):
+        raise NotImplementedError(f"Subclass {type(self)} must implement this function")
+
+    def set_ini_state(self, state0: BlockVec):
+        raise NotImplementedError(f"Subclass {type(self)} must implement this function")
+
+    def set_fin_state(self, state1: BlockVec):
+        raise NotImplementedError(f"Subclass {type(self)} must implement this function")
+
+    def set_control(self, control: BlockVec):
+        raise NotImplementedError(f"Subclass {type(self)} must implement this function")
+
+    def set_prop(self, prop: BlockVec):
+        raise NotImplementedError(f"Subclass {type(self)} must implement this function")
+
+    def assem_res(self) -> BlockVec:
+        raise NotImplementedError(f"Subclass {type(self)} must implement this function")
+
+    def assem_dres_dstate0(self):
+        raise NotImplementedError(f"Subclass {type(self)} must implement this function")
+
+    def assem_dres_dstate1(self):
+        raise NotImplementedError(f"Subclass {type(self)} must implement this function")
+
+    def assem_dres_dcontrol(self):
+        raise NotImplementedError(f"Subclass {type(self)} must implement this function")
+
+    def assem_dres_dprops(self):
+        raise NotImplementedError(f"Subclass {type(self)} must implement this function")
+
+    def solve_state1(self, state1: BlockVec, options: Optional[dict[str, Any]]):
+        raise NotImplementedError(f"Subclass {type(self)} must implement this function")
+
+
+## Solid type models
+
+
+def properties_bvec_from_forms(form, defaults=None):
+    """Property BlockVector in coefficient insertion order (``transient.py:187-218``)."""
+    defaults = {} if defaults is None else defaults
+    labels = [key.split('/')[-1] for key in form.keys() if key.split('/', 1)[0] == 'prop']
+    vecs = []
+    for label in labels:
+        vec = np.array(form['prop/' + label].vector(), dtype=np.float64, copy=True)
+        if label in defaults:
+            vec[:] = defaults[label]
+        vecs.append(vec)
+    return BlockVector(vecs, labels=[labels])
+
+
+class FenicsModel(BaseTransientModel):
+    """Discretised governing equations of the solid (``transient.py:221-513``)."""
+
+    FORM_KEYS = ('u', 'v', 'a')
+    STATE0_KEYS = ('state/u0', 'state/v0', 'state/a0')
+    STATE1_KEYS = ('state/u1', 'state/v1', 'state/a1')
+    CONTROL_KEYS = ('control/p1',)
+    _CONTACT = False
+
+    def __init__(self, residual: slr.FenicsResidual):
+        self._residual = residual
+        form = residual.form
+        mesh = residual.mesh()
+        d = mesh.topology().dim()
+        N = d * mesh.num_vertices()
+        # modify_newmark_time_discretization (equations/form.py:1067-1113): add u0, v0, a0, dt
+        from ..residuals.base import Coefficient, FunctionSpace
+        for key in ('state/u0', 'state/v0', 'state/a0'):
+            if key not in form:
+                form.coefficients[key] = Coefficient(FunctionSpace(mesh, 'CG', 1, d))
+        if 'time/dt' not in form:
+            form.coefficients['time/dt'] = Coefficient(FunctionSpace(mesh, 'R', 0, 1),
+                                                       constant=True, default=0.0)
+
+        self.state0 = BlockVector(
+            [form['state/u0'].vector(), form['state/v0'].vector(), form['state/a0'].vector()],
+            labels=[('u', 'v', 'a')])
+        self.state1 = BlockVector(
+            [form['state/u1'].vector(), form['state/v1'].vector(), form['state/a1'].vector()],
+            labels=[('u', 'v', 'a')])
+        self.control = BlockVector([form['control/p1'].vector()], labels=[('p',)])
+        self.prop = properties_bvec_from_forms(form)
+        assert self.state0['u'].size == N
+
+        fids, pf_cell, pf_opp = residual.pressure_facets()
+        self._tables = _tables.build_tables(mesh.coordinates(), mesh.cells(), pf_cell, pf_opp,
+                                            residual.fixed_dofs())
+        self._engine: Optional[Engine] = None
+        self._engine_provider = None
+        self._member = 0
+        self.set_prop(self.prop)
+
+    # --- engine management -----------------------------------------------------------
+    @property
+    def engine(self) -> Engine:
+        if self._engine is None:
+            if self._engine_provider is not None:
+                self._engine = self._engine_provider()
+            else:
+                self._engine = Engine(
+                    self._tables, contact=self._CONTACT,
+                    membrane=self.residual.form.terms.get('membrane', False))
+        return self._engine
+
+    def _attach_engine(self, engine: Engine, member: int = 0):
+        self._engine = engine
+        self._member = member
+
+    @property
+    def assembly_tables(self) -> dict:
+        return self._tables
+
+    @property
+    def residual(self) -> slr.FenicsResidual:
+        return self._residual
+
+    @property
+    def XREF(self) -> np.ndarray:
+        """Reference nodal coordinates, interleaved (``transient.py:276-287``)."""
+        return self.residual.mesh().coordinates().reshape(-1).copy()
+
+    # --- parameter setting -------------------------------------------------------------
+    @property
+    def dt(self):
+        return self.residual.form['time/dt'].vector()[0]
+
+    @dt.setter
+    def dt(self, value):
+        self.residual.form['time/dt'].vector()[:] = value
+
+    def set_ini_state(self, state):
+        self.state0[:] = state
+
+    def set_fin_state(self, state):
+        self.state1[:] = state
+
+    def set_control(self, p1):
+        self.control[:] = p1
+
+    def set_prop(self, prop):
+        for key, value in prop.sub_items():
+            self.residual.form['prop/' + key].vector()[:] = np.ravel(value) \
+                if np.size(value) > 1 else np.ravel(value)[0]
+        if prop is not self.prop:
+            self.prop[:] = prop
+
+    # --- host -> device ----------------------------------------------------------------
+    def _scalar_block(self, ymid: float = 0.0) -> np.ndarray:
+        scal = np.zeros(SCAL_COUNT)
+        p = self.prop
+        d = self.residual.mesh().topology().dim()
+        scal[SCAL['nu']] = p['nu'][0]
+        scal[SCAL['ycontact']] = p['ycontact'][0]
+        scal[SCAL['kcontact']] = p['kcontact'][0]
+        scal[SCAL['ncontact']:SCAL['ncontact'] + d] = p['ncontact']
+        scal[SCAL['ymid']] = ymid
+        return scal
+
+    def _push_prop(self, ymid: float = 0.0):
+        e, m, p = self.engine, self._member, self.prop
+        for name in ('rho', 'eta', 'emod'):
+            e.upload(name, p[name] if name in p else 0.0, m)
+        if self.residual.form.terms.get('membrane', False):
+            for name in ('emod_membrane', 'nu_membrane', 'th_membrane'):
+                e.upload(name, p[name], m)
+        e.upload('scal', self._scalar_block(ymid), m)
+
+    def _push_state(self):
+        e, m = self.engine, self._member
+        for name, vec in zip(('u0', 'v0', 'a0'), self.state0.vecs):
+            e.upload(name, vec, m)
+        for name, vec in zip(('u1', 'v1', 'a1'), self.state1.vecs):
+            e.upload(name, vec, m)
+        e.upload('p1', self.control['p'], m)
+
+    def _push_all(self):
+        self._push_prop(getattr(self, '_ymid', 0.0))
+        self._push_state()
+
+    # --- residual and sensitivities -----------------------------------------------------
+    def assem_res(self):
+        """``transient.py:363-382``: F_u by device assembly; F_v, F_a nodal; BCs on F_u."""
+        self._push_all()
+        self.engine.assemble(self._member, res=True, jac=False, dt=self.dt)
+        res_u = self.engine.download('F', self._member)
+        u1, v1, a1 = self.state1.sub_blocks
+        res_v = v1 - newmark.newmark_v(u1, *self.state0.sub_blocks, self.dt)
+        res_a = a1 - newmark.newmark_a(u1, *self.state0.sub_blocks, self.dt)
+        return BlockVector([res_u, res_v, res_a], labels=(self.FORM_KEYS,))
+
+    def csr_pattern(self):
+        if not hasattr(self, '_pattern'):
+            self._pattern = self.engine.csr_pattern()
+        return self._pattern
+
+    def _assem_jac_uu(self, is_static: bool = False) -> sp.csr_matrix:
+        self._push_all()
+        self.engine.assemble(self._member, res=False, jac=True, dt=self.dt, is_static=is_static)
+        vals = self.engine.download('J', self._member)
+        rowptr, colidx = self.csr_pattern()
+        N = self.state0['u'].size
+        return sp.csr_matrix((vals, colidx, rowptr), shape=(N, N))
+
+    def assem_dres_dstate1(self):
+        """``transient.py:384-406``: block Jacobian labelled (FORM_KEYS, STATE1_KEYS)."""
+        N = self.state0['u'].size
+        dt = self.dt
+        eye = sp.identity(N, format='csr')
+        zero = sp.csr_matrix((N, N))
+        mats = [
+            self._assem_jac_uu(), zero, zero,
+            -newmark.newmark_v_du1(dt) * eye, eye, zero,
+            -newmark.newmark_a_du1(dt) * eye, zero, eye,
+        ]
+        return BlockMatrix(mats, (3, 3), (self.FORM_KEYS, self.STATE1_KEYS))
+
+    def assem_dres_dstate0(self):
+        raise NotImplementedError(
+            "state0 sensitivities are a listed next step (SURVEY.md section 8f-4)")
+
+    def assem_dres_dcontrol(self):
+        raise NotImplementedError(
+            "control sensitivities are a listed next step (SURVEY.md section 8f-4)")
+
+    def assem_dres_dprops(self):
+        raise NotImplementedError("Not implemented yet!")  # transient.py:437-438
+
+    # --- solvers -------------------------------------------------------------------------
+    def solve_state1(self, state1, options=None):
+        """``transient.py:441-468``: device Newton solve for u1, then Newmark v1, a1."""
+        if options is None:
+            options = DEFAULT_NEWTON_SOLVER_PRM
+        self.set_fin_state(state1)
+        self._push_all()
+        e, m = self.engine, self._member
+        e.solve_state1(self.dt, m, 1, options)
+        x = state1.copy()
+        x['u'][:] = e.download('u1', m)
+        x['v'][:] = e.download('v1', m)
+        x['a'][:] = e.download('a1', m)
+        info = e.download('info', m)
+        solve_info = {'num_iter': int(info[0]), 'abs_err': float(info[1]),
+                      'rel_err': float(info[2]), 'gmres_iters': int(info[3]),
+                      'gmres_resid': float(info[4])}
+        return x, solve_info
+
+    def solve_dres_dstate1(self, dres_dstate1, x, b):
+        """``transient.py:470-491``: one J_uu solve on the device + nodal v/a rows."""
+        import torch
+        e, m = self.engine, self._member
+        bu, bv_, ba = b.sub_blocks
+        b_t = torch.as_tensor(np.ascontiguousarray(bu), device=e.device)
+        x_t = torch.empty_like(b_t)
+        e.linear_solve(b_t, x_t, m)
+        xu = x_t.cpu().numpy()
+        x['u'][:] = xu
+        x['v'][:] = bv_ - dres_dstate1.sub['v', 'state/u1'] @ xu
+        x['a'][:] = ba - dres_dstate1.sub['a', 'state/u1'] @ xu
+        return x
+
+
+class NodalContactModel(FenicsModel):
+    """Solid with nodal cubic-penalty contact tractions (``transient.py:516-583``)."""
+
+    _CONTACT = True
+
+    def set_fin_state(self, state):
+        super().set_fin_state(state)
+        self.residual.form['control/tcontact'].vector()[:] = self._contact_traction(
+            self.state1.sub['u'])
+
+    def _contact_traction(self, u):
+        """Nodal contact traction (host mirror of ``control/tcontact``; the kernels evaluate
+        the same expression on the fly, ``csrc/elem.cuh`` ``contact_pressure``)."""
+        form = self.residual.form
+        ndim = self.residual.mesh().topology().dim()
+        ycontact = form['prop/ycontact'].values()[0]
+        ncontact = form['prop/ncontact'].values()
+        kcontact = form['prop/kcontact'].values()[0]
+        gap = np.dot((self.XREF + u).reshape(-1, ndim), ncontact) - ycontact
+        with np.errstate(invalid='ignore'):
+            pgap = np.where(gap == -np.inf, 0.0, (gap + np.abs(gap)) / 2)
+        return (-(kcontact * pgap**3)[:, None] * ncontact).reshape(-1).copy()
+
+
+## Fluid type models
+
+
+class JaxModel(BaseTransientModel):
+    """1D Bernoulli fluid (``transient.py:590-672``); evaluated by the device fluid kernel."""
+
+    def __init__(self, residual: flr.JaxResidual):
+        self._residual = residual
+        state, control, prop = residual.res_args
+        self.state0 = BlockVector(list(state.values()), labels=[list(state.keys())])
+        self.state1 = self.state0.copy()
+        self.control = BlockVector(list(control.values()), labels=[list(control.keys())])
+        self.prop = BlockVector(list(prop.values()), labels=[list(prop.keys())])
+        self._dt = 0.0
+        self._engine: Optional[Engine] = None
+        self._engine_provider = None
+        self._member = 0
+
+    @property
+    def residual(self) -> flr.JaxResidual:
+        return self._residual
+
+    @property
+    def fluid(self):
+        return self
+
+    @property
+    def engine(self) -> Engine:
+        if self._engine is None and self._engine_provider is not None:
+            self._engine = self._engine_provider()
+        if self._engine is None:
+            # a fluid on its own: the engine still needs a (dummy one-cell) solid mesh
+            coords = np.array([[0.0, 0.0], [1.0, 0.0], [0.0, 1.0]])
+            cells = np.array([[0, 1, 2]])
+            tb = _tables.build_tables(coords, cells, [], [], [])
+            r = self._residual
+            self._engine = Engine(tb, s=r.mesh(), fluid_kind=r.kind, idx_sep=r.idx_sep)
+        return self._engine
+
+    def _attach_engine(self, engine: Engine, member: int = 0):
+        self._engine = engine
+        self._member = member
+
+    @property
+    def dt(self):
+        return self._dt
+
+    @dt.setter
+    def dt(self, value):
+        self._dt = value
+
+    def set_ini_state(self, state):
+        self.state0[:] = state
+
+    def set_fin_state(self, state):
+        self.state1[:] = state
+
+    def set_control(self, control):
+        self.control[:] = control
+
+    def set_prop(self, prop):
+        self.prop[:] = prop
+
+    def _fprop_block(self) -> np.ndarray:
+        n_fluid = self.state0['q'].size
+        fp = np.zeros((n_fluid, FPROP_COUNT))
+        fp[:, FPROP['rho_air']] = 1.0
+        fp[:, FPROP['r_sep']] = 1.0
+        fp[:, FPROP['zeta_min']] = 1.0
+        fp[:, FPROP['zeta_sep']] = 1.0
+        for key, col in FPROP.items():
+            if key in self.prop:
+                fp[:, col] = self.prop[key]
+        return fp
+
+    def _push(self):
+        e, m = self.engine, self._member
+        e.upload('area', self.control['area'], m)
+        e.upload('psub', self.control['psub'], m)
+        e.upload('psup', self.control['psup'], m)
+        e.upload('fprop', self._fprop_block(), m)
+
+    def _bernoulli_qp(self) -> BlockVector:
+        self._push()
+        e, m = self.engine, self._member
+        e.fluid_solve(m, 1)
+        return BlockVector([e.download('q1', m), e.download('pf1', m)],
+                           labels=self.state1.labels)
+
+    def assem_res(self):
+        """state1 - (q, p)(control, prop)  (``fluid.py:286-294``)."""
+        return self.state1 - self._bernoulli_qp()
+
+    def solve_state1(self, state1, options=None):
+        """``transient.py:667-672``: state1 - res(state1) = Bernoulli (q, p)."""
+        info = {}
+        return self._bernoulli_qp(), info
+
+
+## Coupled models
+
+
+class BaseTransientFSIModel(BaseTransientModel):
+    """Coupled solid + 1D fluid (``transient.py:678-817``)."""
+
+    def __init__(self, solid: FenicsModel, fluid: JaxModel, solid_fsi_dofs, fluid_fsi_dofs):
+        self.solid = solid
+        self.fluid = fluid
+
+        self.state0 = bv.concatenate([solid.state0, fluid.state0])
+        self.state1 = bv.concatenate([solid.state1, fluid.state1])
+        # the control is just the subglottal and supraglottal pressures (transient.py:714-715)
+        self.control = fluid.control[1:]
+        _self_properties = BlockVector((np.array([1.0]),), labels=(('ymid',),))
+        self.prop = bv.concatenate([solid.prop, fluid.prop, _self_properties])
+
+        (self._fsimap, self._solid_area, self._dflarea_dslu, self._dslp_dflp, _) = \
+            fsi.make_coupling_stuff(solid, fluid, solid_fsi_dofs, fluid_fsi_dofs)
+
+        # one shared device engine for solid + fluid + coupling, created on first use
+        self._engine: Optional[Engine] = None
+        self._fsi_dofs = (np.asarray(solid_fsi_dofs), np.asarray(fluid_fsi_dofs))
+        solid._engine, fluid._engine = None, None
+        solid._engine_provider = lambda: self.engine
+        fluid._engine_provider = lambda: self.engine
+
+    @property
+    def engine(self) -> Engine:
+        if self._engine is None:
+            solid, r = self.solid, self.fluid.residual
+            self._engine = Engine(
+                solid.assembly_tables, s=r.mesh(), fsi_solid=self._fsi_dofs[0],
+                fsi_fluid=self._fsi_dofs[1], fluid_kind=r.kind, idx_sep=r.idx_sep,
+                contact=solid._CONTACT,
+                membrane=solid.residual.form.terms.get('membrane', False))
+        return self._engine
+
+    @property
+    def fsimap(self):
+        return self._fsimap
+
+    def _set_ini_solid_state(self, uva0):
+        raise NotImplementedError("Subclasses must implement this method")
+
+    def _set_fin_solid_state(self, uva1):
+        raise NotImplementedError("Subclasses must implement this method")
+
+    def _set_ini_fluid_state(self, qp0):
+        raise NotImplementedError("Subclasses must implement this method")
+
+    def _set_fin_fluid_state(self, qp1):
+        raise NotImplementedError("Subclasses must implement this method")
+
+    @property
+    def dt(self):
+        return self.solid.dt
+
+    @dt.setter
+    def dt(self, value):
+        self.solid.dt = value
+        self.fluid.dt = value
+
+    def set_ini_state(self, state):
+        sl_state, fl_state = bv.chunk(state, (self.solid.state0.size, self.fluid.state0.size))
+        self._set_ini_solid_state(sl_state)
+        self._set_ini_fluid_state(fl_state)
+
+    def set_fin_state(self, state):
+        sl_state, fl_state = bv.chunk(state, (self.solid.state1.size, self.fluid.state1.size))
+        self._set_fin_solid_state(sl_state)
+        self._set_fin_fluid_state(fl_state)
+
+    def set_control(self, control):
+        self.control[:] = control
+        for key, value in control.sub_items():
+            self.fluid.control[key][:] = value
+
+    def set_prop(self, prop):
+        self.prop[:] = prop
+        chunk_sizes = [model.prop.size for model in (self.solid, self.fluid)] + [1]
+        prop_chunks = bv.chunk(self.prop, chunk_sizes)[:-1]
+        for set_prop, sub in zip((self.solid.set_prop, self.fluid.set_prop), prop_chunks):
+            set_prop(sub)
+        self.solid._ymid = float(self.prop['ymid'][0])
+
+
+class ExplicitFSIModel(BaseTransientFSIModel):
+    """Explicit (staggered) coupling (``transient.py:821-920``): the solid at step n+1 is
+    loaded with the fluid pressure of step n; the fluid sees the solid geometry of step n+1."""
+
+    def _set_ini_solid_state(self, uva0):
+        self.solid.set_ini_state(uva0)
+
+    def _set_fin_solid_state(self, uva1):
+        self.solid.set_fin_state(uva1)
+        ndim = self.solid.residual.mesh().topology().dim()
+        self._solid_area[:] = 2 * (
+            self.prop['ymid'][0] - (self.solid.XREF + self.solid.state1.sub['u'])[1::ndim]
+        )
+        fl_control = self.fluid.control.copy()
+        self.fsimap.map_solid_to_fluid(self._solid_area, fl_control.sub['area'][:])
+        self.fluid.set_control(fl_control)
+
+    def _set_ini_fluid_state(self, qp0):
+        sl_control = self.solid.control.copy()
+        sl_control['p'] = 0
+        self.fluid.set_ini_state(qp0)
+        self.fsimap.map_fluid_to_solid(qp0[1], sl_control.sub['p'])
+        self.solid.set_control(sl_control)
+
+    def _set_fin_fluid_state(self, qp1):
+        self.fluid.set_fin_state(qp1)
+
+    def assem_res(self):
+        res_sl = self.solid.assem_res()
+        res_fl = self.fluid.assem_res()
+        return bv.concatenate((res_sl, res_fl))
+
+    def solve_state1(self, ini_state, options=None):
+        """``transient.py:899-920``: solid Newton solve, area update, fluid solve."""
+        self.set_fin_state(ini_state)
+        uva1, solid_info = self.solid.solve_state1(ini_state[:3], options)
+        self._set_fin_solid_state(uva1)
+        qp1s, _ = self.fluid.solve_state1(ini_state[3:], options)
+        step_info = solid_info
+        return bv.concatenate([uva1, qp1s], labels=self.state1.labels), step_info
+
+    # --- device-resident time loop used by forward.integrate -----------------------------
+    def push_to_device(self):
+        """Upload properties, state0 and fluid properties (once per ``integrate``)."""
+        self.solid._ymid = float(self.prop['ymid'][0])
+        self.solid._push_prop(self.solid._ymid)
+        e = self.engine
+        e.upload('fprop', self.fluid._fprop_block(), 0)
+        names = ('u0', 'v0', 'a0', 'q0', 'p0')
+        for name, vec in zip(names, self.state0.vecs):
+            e.upload(name, vec, 0)
+
+    def device_integrate(self, dts, controls, options=None):
+        """
+        Run ``len(dts)`` explicit-coupling steps on the device from the uploaded state0.
+
+        controls : list of control BlockVectors (psub, psup)
+        Returns (states, infos): host arrays (nsteps+1, state_size) and (nsteps+1, 4).
+        """
+        n_fluid = self.engine.n_fluid
+        ctl = np.array([[np.broadcast_to(c['psub'], (n_fluid,)),
+                         np.broadcast_to(c['psup'], (n_fluid,))] for c in controls])
+        hs, hi = self.engine.integrate(dts, ctl, options, store_states=True, store_info=True)
+        return hs[0].cpu().numpy(), hi[0].cpu().numpy()
+
+    def state_from_row(self, row: np.ndarray) -> BlockVector:
+        state = self.state0.copy()
+        state[:] = row
+        return state
