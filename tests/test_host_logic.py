@@ -1,0 +1,187 @@
+"""CPU tests of the host-side mirror of the reference interface (no device calls)."""
+
+import numpy as np
+import pytest
+
+from helpers import mesh_tuples
+from femvf_b200 import blockvec as bv, forward, load, mesh as M, meshgen, statefile as sf, tables
+from femvf_b200.models import transient
+from femvf_b200.residuals import solid as slr, fluid as flr
+from oracle import model as om
+
+
+def test_blockvector_contract():
+    a = bv.BlockVector([np.arange(3.0), np.zeros(2), np.ones(1)], labels=[('u', 'v', 'q')])
+    assert a.size == 3 and a.bshape == ((3, 2, 1),) and a.keys() == ['u', 'v', 'q']
+    a['v'][:] = 5
+    assert np.all(a.sub['v'] == 5) and np.all(a[1] == 5)
+    b = a[:2]
+    b['u'][0] = -1.0
+    assert a['u'][0] == -1.0  # slices are views
+    c = a.copy(); c[:] = 0
+    assert a['v'][0] == 5 and c.norm() == 0
+    c[:] = a
+    assert np.array_equal(c.to_mono_ndarray(), a.to_mono_ndarray())
+    c['q'] = 7
+    assert c['q'][0] == 7
+    d = bv.concatenate([a[:1], a[1:]])
+    assert d.labels == a.labels
+    sl, fl = bv.chunk(a, (2, 1))
+    assert sl.keys() == ['u', 'v'] and fl.keys() == ['q']
+    assert np.allclose((a - a * 2 + a).to_mono_ndarray(), 0)
+    assert a[['q', 'u']].keys() == ['q', 'u']
+    with pytest.raises(KeyError):
+        a['nope']
+
+
+def test_property_label_order_matches_reference():
+    mt = mesh_tuples()['square5']()
+    kv = transient.FenicsModel(slr.KelvinVoigt(*mt))
+    assert kv.prop.keys() == ['rho', 'eta', 'emod', 'nu', 'ycontact', 'ncontact', 'kcontact']
+    epi = transient.FenicsModel(slr.KelvinVoigtWEpithelium(*mesh_tuples()['square5']()))
+    assert epi.prop.keys() == ['rho', 'emod_membrane', 'nu_membrane', 'th_membrane', 'emod', 'nu',
+                               'eta', 'ycontact', 'ncontact', 'kcontact']
+    assert kv.prop['nu'][0] == 0.45 and np.isinf(kv.prop['ycontact'][0])
+    assert np.array_equal(kv.prop['ncontact'], [0.0, 1.0]) and kv.prop['kcontact'][0] == 1.0
+    assert kv.state0.keys() == ['u', 'v', 'a'] and kv.control.keys() == ['p']
+
+
+def build_fsi(name='square5', Fluid=flr.BernoulliAreaRatioSep, zs=None):
+    mt = mesh_tuples()[name]()
+    d = mt[0].topology().dim()
+    return load.load_fsi_model(
+        mt, slr.KelvinVoigt, Fluid,
+        {'dirichlet_bcs': {'state/u1': [(np.zeros(d), 'facet', 'fixed')]}}, {}, zs=zs)
+
+
+def test_load_fsi_model_layout():
+    model = build_fsi('m5')
+    assert model.state0.keys() == ['u', 'v', 'a', 'q', 'p']
+    assert model.control.keys() == ['psub', 'psup']
+    assert model.prop.keys()[-4:] == ['rho_air', 'r_sep', 'area_lb', 'ymid']
+    ns = model.fluid.state0['p'].size
+    s = model.fluid.residual.mesh()
+    assert s.shape == (ns,) and s[0] == 0 and np.all(np.diff(s) > 0)
+    # the interface follows the loaded surface from the origin towards +x
+    x = model.solid.residual.mesh().coordinates()[model.fsimap.dofs_solid]
+    assert np.allclose(x[0], [0, 0]) and np.isclose(x[-1, 0], 0.7895)
+    assert np.array_equal(model.fsimap.dofs_fluid, np.arange(ns))
+    # nearest-neighbour ordering agrees with the oracle's independent implementation
+    res = model.solid.residual
+    fids, _, _ = res.pressure_facets()
+    s_o, verts_o = om.interface_from_edges(res.mesh().coordinates(), res.mesh().facets[fids])
+    assert np.array_equal(verts_o, model.fsimap.dofs_solid) and np.allclose(s_o, s)
+
+
+def test_explicit_coupling_host_mirrors():
+    """_set_ini_fluid_state / _set_fin_solid_state semantics (transient.py:833-858)."""
+    model = build_fsi('m5')
+    prop = model.prop.copy(); prop['ymid'][:] = 0.8
+    model.set_prop(prop)
+    st = model.state0.copy(); st[:] = 0
+    st['p'][:] = np.arange(st['p'].size) + 1.0
+    model.set_ini_state(st)
+    p_solid = model.solid.control['p']
+    assert np.array_equal(p_solid[model.fsimap.dofs_solid], st['p'])
+    mask = np.ones(p_solid.size, bool); mask[model.fsimap.dofs_solid] = False
+    assert not p_solid[mask].any()
+    st['u'][1::2] = 0.01
+    model.set_fin_state(st)
+    y = model.solid.residual.mesh().coordinates()[model.fsimap.dofs_solid, 1]
+    assert np.allclose(model.fluid.control['area'], 2 * (0.8 - (y + 0.01)))
+
+
+def test_fixture_interface_includes_interior_vertices_quirk_q8():
+    model = build_fsi('square5')
+    # 'pressure' = facet value 0 = every unmarked facet, interior ones included (App. C, Q8)
+    assert model.fluid.state0['p'].size == 36
+
+
+def test_3d_interface_planes():
+    model = build_fsi('cube332', zs=np.linspace(0, 1, 3))
+    s = model.fluid.residual.mesh()
+    assert s.ndim == 2 and s.shape[0] == 3
+    assert model.fluid.state0['q'].size == 3
+    assert model.control['psub'].size == 3
+
+
+def test_integrate_argument_validation():
+    model = build_fsi('square5')
+    st = model.state0.copy(); ctl = model.control.copy(); prop = model.prop.copy()
+    with pytest.raises(ValueError):
+        forward.integrate(model, None, st, [ctl], prop, [], write=False)
+    with pytest.raises(ValueError):
+        forward.integrate(model, None, st, [ctl], prop, [0.0, 0.0], write=False)
+    with pytest.raises(NotImplementedError):
+        load.load_fsi_model(mesh_tuples()['square5'](), slr.KelvinVoigt,
+                            flr.BernoulliAreaRatioSep, {}, {}, coupling='implicit')
+    with pytest.raises(ValueError):
+        load.load_fenics_model('mesh.xml', slr.KelvinVoigt)
+
+
+def test_statefile_layout_and_roundtrip(tmp_path):
+    model = build_fsi('square5')
+    path = str(tmp_path / 'state.h5')
+    st = model.state0.copy(); st[:] = 0
+    ctl = model.control.copy(); ctl['psub'][:] = 8e3; ctl['psup'][:] = 0
+    with sf.StateFile(model, path, mode='w') as f:
+        f.init_layout()
+        for n in range(3):
+            st['u'][:] = n
+            forward.append_step_result(f, st, ctl, 0.1 * n, {'num_iter': n, 'abs_err': 0.0})
+        f.append_prop(model.prop)
+        assert f.size == 3
+        for key in ('time', 'meas_indices', 'mesh/solid/coordinates', 'mesh/solid/connectivity',
+                    'mesh/solid/dim', 'dofmap/CG1', 'state/u', 'state/q', 'control/psub',
+                    'properties/emod', 'solver_info/num_iter', 'solver_info/rel_err'):
+            assert key in f.file, key
+        assert f.file['state/u'].shape == (3, st['u'].size)
+        assert np.isnan(f.get_solver_info(2)['rel_err'])  # missing keys are written as NaN
+        assert f.file['dofmap/CG1'].shape == (model.solid.residual.mesh().num_cells(), 6)
+    with sf.StateFile(model, path, mode='r') as f:
+        assert f.size == 3
+        assert np.all(f.get_state(2)['u'] == 2) and f.get_time(1) == 0.1
+        assert f.get_control(10)['psub'][0] == 8e3
+        assert np.array_equal(f.get_prop()['emod'], model.prop['emod'])
+
+
+def test_tables_and_tiles():
+    for name in ('square5', 'cube332', 'm5'):
+        mt = mesh_tuples()[name]()
+        res = slr.KelvinVoigt(*mt)
+        mesh = res.mesh(); d = mesh.topology().dim()
+        fids, pfc, pfo = res.pressure_facets()
+        T = tables.build_tables(mesh.coordinates(), mesh.cells(), pfc, pfo, res.fixed_dofs())
+        # every cell appears once per vertex in the node->cell table, with the right local index
+        e, a = T['n2e'] >> 2, T['n2e'] & 3
+        node = np.repeat(np.arange(T['nn']), np.diff(T['n2e_ptr']))
+        assert np.array_equal(mesh.cells()[e, a], node) and len(e) == (d + 1) * T['ne']
+        # facet table: opposite vertex is not on the facet; outward normal convention
+        f, fa = T['n2f'] >> 2, T['n2f'] & 3
+        nodef = np.repeat(np.arange(T['nn']), np.diff(T['n2f_ptr']))
+        assert np.array_equal(mesh.cells()[T['pf_cell'][f], fa], nodef)
+        for k, fid in enumerate(fids):
+            opp = mesh.cells()[pfc[k], pfo[k]]
+            assert opp not in mesh.facets[fid]
+        ts = tables.tile_partition(T['brptr'], d, 16, 4096)
+        assert ts[0] == 0 and ts[-1] == T['nn'] and np.all(np.diff(ts) > 0)
+        assert np.all(np.diff(ts) <= 16)
+        vals = d * d * T['brptr'].astype(np.int64)
+        assert np.all(vals[ts[1:]] - vals[ts[:-1]] <= 4096)
+
+
+def test_mesh_generators():
+    mesh, mfs, sd = meshgen.m5_cb_mesh(0.05)
+    assert abs(mesh.signed_volumes().sum() - 0.2868) < 2e-3
+    assert np.all(mesh.signed_volumes() > 0)
+    tags = mfs[1].array(); ext = mesh.exterior_facets
+    assert set(np.unique(tags[ext])) == {sd[1]['pressure'], sd[1]['fixed']}
+    mt2 = meshgen.refine_red((mesh, mfs, sd))
+    assert mt2[0].num_cells() == 4 * mesh.num_cells()
+    assert (mt2[1][1].array() == sd[1]['pressure']).sum() == 2 * (tags == sd[1]['pressure']).sum()
+    assert abs(mt2[0].signed_volumes().sum() - mesh.signed_volumes().sum()) < 1e-12
+    mt3 = meshgen.renumber_for_locality(mt2)
+    assert (mt3[1][1].array() == sd[1]['fixed']).sum() == (mt2[1][1].array() == sd[1]['fixed']).sum()
+    m3 = meshgen.extrude_to_tets((mesh, mfs, sd), 1.5, 3)
+    assert np.isclose(m3[0].signed_volumes().sum(), 1.5 * mesh.signed_volumes().sum())
+    assert len(m3[0].exterior_facets) == 2 * mesh.num_cells() + 2 * 3 * len(ext)

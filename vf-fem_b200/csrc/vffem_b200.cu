@@ -300,6 +300,10 @@ member_kernel(EngineDev E, int member0, int mode, int nsteps, const double* __re
 
 using namespace vf;
 
+// layout pinned for the ctypes binding (femvf_b200/_cabi.py, tests/test_cabi.py)
+static_assert(sizeof(vf_solver_opts) == 48, "vf_solver_opts layout changed");
+static_assert(VF_ARRAY_COUNT == 26, "vf_array_id changed: update _cabi.ARRAY_IDS");
+
 struct vf_engine {
   vf_problem_desc desc;  // scalar fields only are valid after create
   EngineDev dev;
