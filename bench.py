@@ -320,7 +320,7 @@ def main():
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': dict(workload_config(), nn=nn, ne=ne, dof=N, nnz=nnz,
                        parallelism=f'{world} independent mesh shards, no collective'),
-        'roofline': {'kernel': 'asm_tile_kernel<2,true,true>', 'bound': 'hbm',
+        'roofline': {'kernel': 'asm_tile2_kernel<true,true> (+ facet_bc_kernel on boundary nodes)', 'bound': 'hbm',
                      'achieved': asm_gbs, 'peak': peak, 'unit': 'GB/s', 'frac': asm_gbs / peak,
                      'traffic': None, 'algorithmic_bytes': B_asm, 'peak_source': peak_src},
         'spmv': {'kernel': 'spmv_kernel<2,8>', 'bound': 'hbm', 'achieved': spmv_gbs,

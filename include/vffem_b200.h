@@ -48,6 +48,16 @@ typedef struct vf_problem_desc {
   int32_t ntiles;
   int32_t tile_max_values;    /* max #doubles of J in one tile (shared-memory CSR slice) */
   int32_t tile_threads;       /* CTA size of the tile kernel (>= max nodes per tile) */
+  /* two-phase tile kernel (triangles): cells touching each tile, packed (node, cell) pair info
+   * (femvf_b200/tables.py build_tile_elem_tables); te_ptr_host == NULL disables it */
+  const int32_t* te_ptr_host;     /* (ntiles+1) */
+  const int32_t* te_elem_host;    /* (te_ptr[ntiles]) */
+  const uint32_t* pair_info_host; /* (n2e_ptr[nn]) */
+  const int32_t* tile_desc_host;  /* (ntiles, 8): i0 i1 te0 te1 pair0 pair1 blk0 blk1 */
+  const int32_t* te_quad_host;    /* (te_ptr[ntiles], 4): the cell's 3 vertices + cell id */
+  int32_t max_tile_elems;
+  int32_t max_tile_pairs;
+  int32_t tile2_threads;
   /* 1D fluid + FSI map (models/fsi.py:18-88) */
   int32_t n_fluid, ns, n_fsi;
   const double* s_host;           /* (n_fluid, ns) arclength coordinates */

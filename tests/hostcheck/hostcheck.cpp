@@ -2,6 +2,7 @@
 // Runs vf::assemble_node (the arithmetic the CUDA kernels execute) in a plain CPU loop so
 // that the element math can be checked against the oracle without a GPU.
 #include <cmath>
+#include <cstdlib>
 using std::sqrt; using std::fabs; using std::isinf;
 #include "../../vf-fem_b200/csrc/node_assembly.cuh"
 
@@ -30,5 +31,78 @@ extern "C" int hostcheck_assemble(
   if (dim == 2) run<2>(m, p, s, J, F);
   else if (dim == 3) run<3>(m, p, s, J, F);
   else return 1;
+  return 0;
+}
+
+// CPU emulation of asm_tile2_kernel + facet_bc_kernel (two-phase tile assembly, triangles):
+// same device functions (tri_record, tri_row_block, assemble_node_facets_bc), same order.
+extern "C" int hostcheck_assemble_tile2(
+    int nn, int ne, int nfp, const double* xyz, const int* cells, const int* brptr,
+    const int* bcol, const int* n2e_ptr, const int* n2e, const int* n2f_ptr, const int* n2f,
+    const int* pf_cell, const int* pf_opp, const unsigned char* bc, const double* rho,
+    const double* eta, const double* emod, const double* scal, const double* emod_m,
+    const double* nu_m, const double* th_m, int contact, int membrane, const double* u1,
+    const double* u0, const double* v0, const double* a0, const double* p1, double dt,
+    int ntiles, const int* tile_start, const int* te_ptr, const int* te_elem,
+    const unsigned* pair_info, int max_tile_elems, double* J, double* F) {
+  vf::MeshView m{2, nn, ne, nfp, xyz, cells, brptr, bcol, n2e_ptr, n2e,
+                 n2f_ptr, n2f, pf_cell, pf_opp, bc};
+  vf::PropView p{rho, eta, emod, scal, emod_m, nu_m, th_m, contact, membrane};
+  vf::StateView s{u1, u0, v0, a0, p1, dt, 0};
+  const vf::LameFac lf = vf::lame_fac(scal[vf::SC_NU]);
+  const vf::NewmarkCoef nc = vf::newmark_coef(dt);
+  // 16-byte aligned like the shared-memory buffer of the kernel
+  double* recs = static_cast<double*>(aligned_alloc(16, sizeof(double) * (size_t)max_tile_elems * vf::kRec2D));
+  for (int t = 0; t < ntiles; ++t) {
+    const int i0 = tile_start[t], i1 = tile_start[t + 1];
+    const int q0 = te_ptr[t], q1 = te_ptr[t + 1];
+    if (q1 - q0 > max_tile_elems) return 2;
+    for (int q = q0; q < q1; ++q) {
+      const int e = te_elem[q];
+      int nd[3];
+      double x[3][2];
+      for (int a = 0; a < 3; ++a) {
+        nd[a] = cells[a * ne + e];
+        x[a][0] = xyz[nd[a]];
+        x[a][1] = xyz[nn + nd[a]];
+      }
+      vf::tri_record(x, nd, emod[e], lf, eta[e], rho[e], nc, false, true, u1, u0, v0, a0,
+                     recs + (size_t)(q - q0) * vf::kRec2D);
+    }
+    for (int i = i0; i < i1; ++i) {
+      const int b0 = brptr[i], deg = brptr[i + 1] - b0;
+      double* row0 = J + 4 * (size_t)b0;
+      double* row1 = row0 + 2 * deg;
+      for (int k = 0; k < 4 * deg; ++k) row0[k] = 0.0;
+      double r0 = 0.0, r1 = 0.0;
+      for (int q = n2e_ptr[i]; q < n2e_ptr[i + 1]; ++q) {
+        const unsigned info = pair_info[q];
+        const double* rec = recs + (size_t)(info & 0xfffu) * vf::kRec2D;
+        const int a = (info >> 12) & 3;
+        for (int c = 0; c < 3; ++c) {
+          const int slot = (info >> (14 + 6 * c)) & 63;
+          double b[2][2];
+          vf::tri_block(rec, a, c, b);
+          row0[2 * slot] += b[0][0];
+          row0[2 * slot + 1] += b[0][1];
+          row1[2 * slot] += b[1][0];
+          row1[2 * slot + 1] += b[1][1];
+        }
+        r0 += rec[9 + 2 * a];
+        r1 += rec[10 + 2 * a];
+      }
+      F[2 * i] = r0;
+      F[2 * i + 1] = r1;
+    }
+  }
+  free(recs);
+  for (int i = 0; i < nn; ++i) {
+    bool touch = n2f_ptr[i + 1] > n2f_ptr[i] || bc[2 * i] || bc[2 * i + 1];
+    if (!touch) continue;
+    double res[2] = {F[2 * i], F[2 * i + 1]};
+    vf::assemble_node_facets_bc<2, true, true>(i, m, p, s, J + 4 * (size_t)brptr[i], res);
+    F[2 * i] = res[0];
+    F[2 * i + 1] = res[1];
+  }
   return 0;
 }

@@ -36,6 +36,44 @@ VF_HD double newmark_a(double u1, double u0, double v0, double a0, double dt) {
   return 1.0 / kBeta / (dt * dt) * (u1 - u0 - dt * v0) - (1.0 / 2.0 / kBeta - 1.0) * a0;
 }
 
+// Newmark update coefficients hoisted out of the element loops.  Each member is evaluated
+// with exactly the operations of newmark.py:8-73, so v/a are bit-identical to calling
+// newmark_v / newmark_a per entry.
+struct NewmarkCoef {
+  double cv, c_v0, c_a0v;  // v1 = cv (u1-u0) - c_v0 v0 - c_a0v a0
+  double ca, c_a0a;        // a1 = ca (u1-u0-dt v0) - c_a0a a0
+  double dt;
+};
+
+VF_HD NewmarkCoef newmark_coef(double dt) {
+  NewmarkCoef c;
+  c.cv = kGamma / kBeta / dt;
+  c.c_v0 = kGamma / kBeta - 1.0;
+  c.c_a0v = dt * (kGamma / 2.0 / kBeta - 1.0);
+  c.ca = 1.0 / kBeta / (dt * dt);
+  c.c_a0a = 1.0 / 2.0 / kBeta - 1.0;
+  c.dt = dt;
+  return c;
+}
+VF_HD double newmark_v(const NewmarkCoef& c, double u1, double u0, double v0, double a0) {
+  return c.cv * (u1 - u0) - c.c_v0 * v0 - c.c_a0v * a0;
+}
+VF_HD double newmark_a(const NewmarkCoef& c, double u1, double u0, double v0, double a0) {
+  return c.ca * (u1 - u0 - c.dt * v0) - c.c_a0a * a0;
+}
+
+// Lame factors per unit modulus: lambda = emod * lam_fac, mu = emod * mu_fac
+// (uflcontinuum.py:22-23); nu is a constant, so the divisions are done once.
+struct LameFac {
+  double lam_fac, mu_fac;
+};
+VF_HD LameFac lame_fac(double nu) {
+  LameFac f;
+  f.lam_fac = nu / (1.0 + nu) / (1.0 - 2.0 * nu);
+  f.mu_fac = 1.0 / 2.0 / (1.0 + nu);
+  return f;
+}
+
 template <int D>
 struct CellGeo {
   double G[D + 1][D];  // constant shape-function gradients
@@ -92,12 +130,10 @@ struct CellCoef {
 };
 
 template <int D>
-VF_HD CellCoef cell_coef(double emod, double nu, double eta, double rho, double vol) {
+VF_HD CellCoef cell_coef(double emod, const LameFac& lf, double eta, double rho, double vol) {
   CellCoef c;
-  const double lam = emod * nu / (1.0 + nu) / (1.0 - 2.0 * nu);  // uflcontinuum.py:22
-  const double mu = emod / 2.0 / (1.0 + nu);                     // uflcontinuum.py:23
-  c.lamv = lam * vol;
-  c.muv = mu * vol;
+  c.lamv = emod * lf.lam_fac * vol;
+  c.muv = emod * lf.mu_fac * vol;
   c.visv = 0.5 * eta * vol;
   c.massv = rho * vol / double((D + 1) * (D + 2));
   return c;
@@ -276,6 +312,116 @@ VF_HD void membrane_coef(double emod_m, double nu_m, double& mu_m, double& lam_p
   mu_m = emod_m / 2.0 / (1.0 + nu_m);
   const double lam = emod_m * nu_m / (1.0 + nu_m) / (1.0 - 2.0 * nu_m);
   lam_pp = (emod_m == 0.0) ? 0.0 : 2.0 * mu_m * lam / (lam + 2.0 * mu_m);  // form.py:848-850
+}
+
+
+// ---- two-phase tile assembly (2D): per-element record + per-row accumulation -------------
+// Record of one P1 triangle in shared memory:
+//   [0..5]  G_a (a = 0,1,2; x,y)      [6] lambda|K|   [7] (mu + cv eta/2)|K|
+//   [8]     ca rho|K|/12              [9..14] cell residual at the 3 nodes   [15..17] pad
+// The stride is 18 doubles = 144 B = 36 banks: 16-byte accesses of 8 consecutive records
+// (a quarter warp) fall in 8 disjoint bank quads, where a 128-byte stride would put every
+// record on the same banks (32-way conflict).
+constexpr int kRec2D = 18;
+
+struct
+#if defined(__CUDACC__)
+    __align__(16)
+#else
+    alignas(16)
+#endif
+        D2 {
+  double x, y;
+};
+
+// u1/u0/v0/a0: interleaved nodal vectors; nd: the cell's vertices.  The nodal state is
+// consumed node by node (gradients and the lumped sums are accumulated on the fly) to keep
+// the live register set small.
+VF_HD void tri_record(const double (&x)[3][2], const int (&nd)[3], double emod,
+                      const LameFac& lf, double eta, double rho, const NewmarkCoef& nc,
+                      bool is_static, bool with_res, const double* u1, const double* u0,
+                      const double* v0, const double* a0, double* rec) {
+  CellGeo<2> g;
+  p1_geometry(x, g);
+  const CellCoef cf = cell_coef<2>(emod, lf, eta, rho, g.vol);
+  const double cv = is_static ? 0.0 : nc.cv;
+  const double ca = is_static ? 0.0 : nc.ca;
+  D2* r2 = reinterpret_cast<D2*>(rec);  // 16-byte stores
+  for (int a = 0; a < 3; ++a) r2[a] = D2{g.G[a][0], g.G[a][1]};
+  r2[3] = D2{cf.lamv, cf.muv + cv * cf.visv};
+  if (!with_res) {
+    r2[4] = D2{ca * cf.massv, 0.0};
+    return;
+  }
+  double gu[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, gv[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+  double As[2] = {0.0, 0.0}, Aa[3][2];
+  for (int a = 0; a < 3; ++a) {
+    // 16-byte gathers of the node's (x, y) pair from the interleaved vectors
+    const D2 p1 = reinterpret_cast<const D2*>(u1)[nd[a]];
+    D2 p0 = D2{0.0, 0.0}, pv = D2{0.0, 0.0}, pa = D2{0.0, 0.0};
+    if (!is_static) {
+      p0 = reinterpret_cast<const D2*>(u0)[nd[a]];
+      pv = reinterpret_cast<const D2*>(v0)[nd[a]];
+      pa = reinterpret_cast<const D2*>(a0)[nd[a]];
+    }
+    const double w1c[2] = {p1.x, p1.y}, w0c[2] = {p0.x, p0.y}, wvc[2] = {pv.x, pv.y},
+                 wac[2] = {pa.x, pa.y};
+    for (int c = 0; c < 2; ++c) {
+      const double w1 = w1c[c];
+      double v = 0.0, acc = 0.0;
+      if (!is_static) {
+        v = newmark_v(nc, w1, w0c[c], wvc[c], wac[c]);
+        acc = newmark_a(nc, w1, w0c[c], wvc[c], wac[c]);
+      }
+      gu[c][0] += w1 * g.G[a][0];
+      gu[c][1] += w1 * g.G[a][1];
+      gv[c][0] += v * g.G[a][0];
+      gv[c][1] += v * g.G[a][1];
+      As[c] += acc;
+      Aa[a][c] = acc;
+    }
+  }
+  const double tr = gu[0][0] + gu[1][1];
+  const double s00 = cf.muv * (gu[0][0] + gu[0][0]) + cf.visv * (gv[0][0] + gv[0][0]) + cf.lamv * tr;
+  const double s11 = cf.muv * (gu[1][1] + gu[1][1]) + cf.visv * (gv[1][1] + gv[1][1]) + cf.lamv * tr;
+  const double s01 = cf.muv * (gu[0][1] + gu[1][0]) + cf.visv * (gv[0][1] + gv[1][0]);
+  double r[3][2];
+  for (int a = 0; a < 3; ++a) {
+    r[a][0] = s00 * g.G[a][0] + s01 * g.G[a][1] + cf.massv * (As[0] + Aa[a][0]);
+    r[a][1] = s01 * g.G[a][0] + s11 * g.G[a][1] + cf.massv * (As[1] + Aa[a][1]);
+  }
+  r2[4] = D2{ca * cf.massv, r[0][0]};
+  r2[5] = D2{r[0][1], r[1][0]};
+  r2[6] = D2{r[1][1], r[2][0]};
+  r2[7] = D2{r[2][1], 0.0};
+}
+
+// Block (a, c) of the cell matrix from a record; identical arithmetic to cell_block<2>.
+VF_HD void tri_block(const double* rec, int a, int c, double (&b)[2][2]) {
+  const D2* r2 = reinterpret_cast<const D2*>(rec);
+  const D2 ga = r2[a], gc = r2[c], lm = r2[3];
+  const double lamv = lm.x, mv = lm.y;
+  const double dg = mv * (ga.x * gc.x + ga.y * gc.y) + rec[8] * (a == c ? 2.0 : 1.0);
+  b[0][0] = lamv * ga.x * gc.x + mv * gc.x * ga.x + dg;
+  b[0][1] = lamv * ga.x * gc.y + mv * gc.x * ga.y;
+  b[1][0] = lamv * ga.y * gc.x + mv * gc.y * ga.x;
+  b[1][1] = lamv * ga.y * gc.y + mv * gc.y * ga.y + dg;
+}
+
+// Scalar row `comp` of block (a, c) of the cell matrix, from a record; identical arithmetic
+// to cell_block<2>.
+VF_HD void tri_row_block(const double* rec, int a, int c, int comp, double& v0, double& v1) {
+  const D2* r2 = reinterpret_cast<const D2*>(rec);
+  const D2 ga = r2[a], gc = r2[c], lm = r2[3];
+  const double lamv = lm.x, mv = lm.y;
+  const double gg = ga.x * gc.x + ga.y * gc.y;
+  const double ga_i = comp == 0 ? ga.x : ga.y;
+  const double gc_i = comp == 0 ? gc.x : gc.y;
+  v0 = lamv * ga_i * gc.x + mv * gc_i * ga.x;
+  v1 = lamv * ga_i * gc.y + mv * gc_i * ga.y;
+  const double dg = mv * gg + rec[8] * (a == c ? 2.0 : 1.0);
+  if (comp == 0) v0 += dg;
+  else v1 += dg;
 }
 
 }  // namespace vf

@@ -92,55 +92,15 @@ VF_HD void add_block(double* rowblk, int ld, int k, const double (&blk)[D][D], d
     for (int b = 0; b < D; ++b) rowblk[a * ld + k * D + b] += scale * blk[a][b];
 }
 
+// Exterior-facet terms of node i (follower pressure, contact, membrane) added to its block
+// row / residual, then the Dirichlet rows (App. A.4).  Shared by all assembly kernels.
 template <int D, bool JAC, bool RES>
-VF_HD void assemble_node(int i, const MeshView& m, const PropView& p, const StateView& s,
-                         double* rowblk, double (&res)[D]) {
+VF_HD void assemble_node_facets_bc(int i, const MeshView& m, const PropView& p,
+                                   const StateView& s, double* rowblk, double (&res)[D]) {
   const int b0 = m.brptr[i];
   const int deg = m.brptr[i + 1] - b0;
   const int ld = D * deg;
   const int* bcol_i = m.bcol + b0;
-  if (JAC)
-    for (int t = 0; t < D * ld; ++t) rowblk[t] = 0.0;
-  if (RES)
-    for (int c = 0; c < D; ++c) res[c] = 0.0;
-
-  const double nu = p.scal[SC_NU];
-  const double cv = s.is_static ? 0.0 : newmark_cv(s.dt);
-  const double ca = s.is_static ? 0.0 : newmark_ca(s.dt);
-
-  // ---- cell integrals --------------------------------------------------------
-  for (int t = m.n2e_ptr[i]; t < m.n2e_ptr[i + 1]; ++t) {
-    const int ref = m.n2e[t];
-    const int e = ref >> 2, a = ref & 3;
-    int nd[D + 1];
-    double x[D + 1][D];
-    load_cell<D>(m, e, nd, x);
-    CellGeo<D> g;
-    p1_geometry(x, g);
-    const CellCoef cf = cell_coef<D>(p.emod[e], nu, p.eta[e], p.rho[e], g.vol);
-    if (JAC) {
-      for (int c = 0; c <= D; ++c) {
-        double blk[D][D];
-        cell_block<D>(g, cf, cv, ca, a, c, blk);
-        add_block<D>(rowblk, ld, find_slot(bcol_i, deg, nd[c]), blk, 1.0);
-      }
-    }
-    if (RES) {
-      double U[D + 1][D], V[D + 1][D], A[D + 1][D];
-      for (int b = 0; b <= D; ++b)
-        for (int c = 0; c < D; ++c) {
-          const int dof = D * nd[b] + c;
-          const double u1 = s.u1[dof], u0 = s.u0[dof], v0 = s.v0[dof], a0 = s.a0[dof];
-          U[b][c] = u1;
-          V[b][c] = s.is_static ? 0.0 : newmark_v(u1, u0, v0, a0, s.dt);
-          A[b][c] = s.is_static ? 0.0 : newmark_a(u1, u0, v0, a0, s.dt);
-        }
-      double r[D];
-      cell_residual<D>(g, cf, a, U, V, A, r);
-      for (int c = 0; c < D; ++c) res[c] += r[c];
-    }
-  }
-
   // ---- 'pressure' exterior facets: follower pressure, contact, membrane ------------
   for (int t = m.n2f_ptr[i]; t < m.n2f_ptr[i + 1]; ++t) {
     const int ref = m.n2f[t];
@@ -241,6 +201,59 @@ VF_HD void assemble_node(int i, const MeshView& m, const PropView& p, const Stat
       if (RES) res[a] = 0.0;
     }
   }
+}
+
+template <int D, bool JAC, bool RES>
+VF_HD void assemble_node(int i, const MeshView& m, const PropView& p, const StateView& s,
+                         double* rowblk, double (&res)[D]) {
+  const int b0 = m.brptr[i];
+  const int deg = m.brptr[i + 1] - b0;
+  const int ld = D * deg;
+  const int* bcol_i = m.bcol + b0;
+  if (JAC)
+    for (int t = 0; t < D * ld; ++t) rowblk[t] = 0.0;
+  if (RES)
+    for (int c = 0; c < D; ++c) res[c] = 0.0;
+
+  const LameFac lf = lame_fac(p.scal[SC_NU]);
+  const NewmarkCoef nc = newmark_coef(s.dt);
+  const double cv = s.is_static ? 0.0 : nc.cv;
+  const double ca = s.is_static ? 0.0 : nc.ca;
+
+  // ---- cell integrals --------------------------------------------------------
+  for (int t = m.n2e_ptr[i]; t < m.n2e_ptr[i + 1]; ++t) {
+    const int ref = m.n2e[t];
+    const int e = ref >> 2, a = ref & 3;
+    int nd[D + 1];
+    double x[D + 1][D];
+    load_cell<D>(m, e, nd, x);
+    CellGeo<D> g;
+    p1_geometry(x, g);
+    const CellCoef cf = cell_coef<D>(p.emod[e], lf, p.eta[e], p.rho[e], g.vol);
+    if (JAC) {
+      for (int c = 0; c <= D; ++c) {
+        double blk[D][D];
+        cell_block<D>(g, cf, cv, ca, a, c, blk);
+        add_block<D>(rowblk, ld, find_slot(bcol_i, deg, nd[c]), blk, 1.0);
+      }
+    }
+    if (RES) {
+      double U[D + 1][D], V[D + 1][D], A[D + 1][D];
+      for (int b = 0; b <= D; ++b)
+        for (int c = 0; c < D; ++c) {
+          const int dof = D * nd[b] + c;
+          const double u1 = s.u1[dof], u0 = s.u0[dof], v0 = s.v0[dof], a0 = s.a0[dof];
+          U[b][c] = u1;
+          V[b][c] = s.is_static ? 0.0 : newmark_v(nc, u1, u0, v0, a0);
+          A[b][c] = s.is_static ? 0.0 : newmark_a(nc, u1, u0, v0, a0);
+        }
+      double r[D];
+      cell_residual<D>(g, cf, a, U, V, A, r);
+      for (int c = 0; c < D; ++c) res[c] += r[c];
+    }
+  }
+
+  assemble_node_facets_bc<D, JAC, RES>(i, m, p, s, rowblk, res);
 }
 
 }  // namespace vf

@@ -13,6 +13,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -78,6 +79,217 @@ __global__ void asm_tile_kernel(EngineDev E, int member, double dt, int is_stati
     } else {
       for (int t = threadIdx.x; t < nvals; t += blockDim.x) Jg[t] = tile[t];
     }
+  }
+}
+
+
+constexpr int kTile2MaxThreads = 320;
+
+// Two-phase, element-centric tile assembly (triangles).  Replaces the thread-per-node gather
+// for 2D: every cell touching the tile is processed ONCE per CTA.
+//   phase 0  one 32-byte tile descriptor, then all index data of the tile (vertex quads,
+//            packed pair info, slices of brptr / n2e_ptr) is fetched with independent,
+//            coalesced loads -- a single dependent round trip instead of the chain
+//            tile_start -> te_ptr -> te_elem -> cells -> nodal data
+//   phase 1  thread per cell: 16-byte nodal gathers, geometry + material + cell residual
+//            -> one 144-byte record in shared memory
+//   phase 2  thread per scalar row (or per node) of the tile: walks the row's (node, cell)
+//            pairs in the fixed n2e order, reads the records, and accumulates its CSR row
+//            slice in shared memory (rows are private to their thread: no atomics,
+//            bit-reproducible, same summation order as assemble_node)
+//   phase 3  the tile's CSR slice and residual entries are streamed out with coalesced stores
+// The exterior-facet terms and Dirichlet rows touch O(sqrt(N)) boundary nodes only and are
+// applied afterwards by facet_bc_kernel, which keeps this kernel's register budget small.
+// Shared memory: [records: max_tile_elems x 18][CSR slice][F: 2 x nodes][pair info][brptr][n2e_ptr].
+template <bool JAC, bool RES, bool ROW, int MINB>
+__global__ void __launch_bounds__(kTile2MaxThreads, MINB) asm_tile2_kernel(
+    EngineDev E, int member, double dt, int is_static, const int4* __restrict__ tile_desc,
+    const int4* __restrict__ te_quad, const unsigned* __restrict__ pair_info, int max_tile_elems,
+    int tile_max_values, int max_tile_pairs, int max_tile_nodes) {
+  constexpr int D = 2;
+  extern __shared__ double smem[];
+  double* recs = smem;
+  double* tileJ = recs + (size_t)max_tile_elems * kRec2D;
+  double* tileF = tileJ + tile_max_values;
+  unsigned* s_pair = reinterpret_cast<unsigned*>(tileF + D * max_tile_nodes);
+  int* s_brptr = reinterpret_cast<int*>(s_pair + max_tile_pairs);
+  int* s_n2e = s_brptr + max_tile_nodes + 1;
+  double* mb = E.members + (size_t)member * E.L.stride;
+  const Layout& L = E.L;
+  const MeshView& m = E.mesh;
+
+  // ---- phase 0: descriptor, then independent index loads -------------------------------------
+  const int4 d0 = tile_desc[2 * blockIdx.x], d1 = tile_desc[2 * blockIdx.x + 1];
+  const int i0 = d0.x, i1 = d0.y, te0 = d0.z, te1 = d0.w;
+  const int pr0 = d1.x, pr1 = d1.y, bbase = d1.z, bend = d1.w;
+  const int nT = i1 - i0;
+  const size_t base = (size_t)D * D * bbase;
+  const int nvals = D * D * (bend - bbase);
+  const PropView pv = member_props<D>(E, mb);
+  const double* u1 = mb + L.off[VF_U1];
+  const double* u0 = is_static ? u1 : mb + L.off[VF_U0];
+  const double* v0 = mb + L.off[VF_V0];
+  const double* a0 = mb + L.off[VF_A0];
+
+  for (int t = threadIdx.x; t < pr1 - pr0; t += blockDim.x) s_pair[t] = pair_info[pr0 + t];
+  for (int t = threadIdx.x; t <= nT; t += blockDim.x) {
+    s_brptr[t] = m.brptr[i0 + t];
+    s_n2e[t] = m.n2e_ptr[i0 + t];
+  }
+  // Lame / Newmark coefficients: a handful of fp64 divisions, done once per CTA
+  __shared__ LameFac s_lf;
+  __shared__ NewmarkCoef s_nc;
+  if (threadIdx.x == 0) {
+    s_lf = lame_fac(pv.scal[SC_NU]);
+    s_nc = newmark_coef(dt);
+  }
+  // the vertex quads of this thread's cells (issued before the barrier: independent loads)
+  int4 quad = make_int4(0, 0, 0, 0);
+  const bool have = te0 + (int)threadIdx.x < te1;
+  if (have) quad = te_quad[te0 + threadIdx.x];
+  __syncthreads();
+
+  // ---- phase 1: one record per cell --------------------------------------------------------
+  {
+    const LameFac lf = s_lf;
+    const NewmarkCoef nc = s_nc;
+    for (int q = te0 + threadIdx.x; q < te1; q += blockDim.x) {
+      if (q != te0 + (int)threadIdx.x) quad = te_quad[q];
+      const int e = quad.w;
+      const int nd[3] = {quad.x, quad.y, quad.z};
+      double x[3][2];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        x[a][0] = m.xyz[nd[a]];
+        x[a][1] = m.xyz[m.nn + nd[a]];
+      }
+      tri_record(x, nd, pv.emod[e], lf, pv.eta[e], pv.rho[e], nc, is_static != 0, RES, u1, u0, v0,
+                 a0, recs + (size_t)(q - te0) * kRec2D);
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 2 ---------------------------------------------------------------------------------
+  if (ROW) {
+    // one thread per scalar row
+    for (int r = threadIdx.x; r < D * nT; r += blockDim.x) {
+      const int n = r >> 1, comp = r & 1;
+      const int b0 = s_brptr[n], deg = s_brptr[n + 1] - b0;
+      double* row = tileJ + D * D * (b0 - bbase) + comp * D * deg;
+      if (JAC) {
+        const D2 z = D2{0.0, 0.0};
+        for (int t = 0; t < deg; ++t) reinterpret_cast<D2*>(row)[t] = z;
+      }
+      double racc = 0.0;
+      const int qe = s_n2e[n + 1] - pr0;
+      for (int q = s_n2e[n] - pr0; q < qe; ++q) {
+        const unsigned info = s_pair[q];
+        const double* rec = recs + (size_t)(info & 0xfffu) * kRec2D;
+        const int a = (info >> 12) & 3;
+        if (JAC) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const int slot = (info >> (14 + 6 * c)) & 63;
+            double w0, w1;
+            tri_row_block(rec, a, c, comp, w0, w1);
+            D2* dst = reinterpret_cast<D2*>(row + D * slot);
+            D2 cur = *dst;
+            cur.x += w0;
+            cur.y += w1;
+            *dst = cur;
+          }
+        }
+        if (RES) racc += rec[9 + 2 * a + comp];
+      }
+      if (RES) tileF[r] = racc;
+    }
+  } else {
+    // one thread per node (both scalar rows of its block row)
+    for (int n = threadIdx.x; n < nT; n += blockDim.x) {
+      const int b0 = s_brptr[n], deg = s_brptr[n + 1] - b0;
+      double* row0 = tileJ + D * D * (b0 - bbase);
+      double* row1 = row0 + D * deg;
+      if (JAC) {
+        const D2 z = D2{0.0, 0.0};
+        for (int t = 0; t < D * deg; ++t) reinterpret_cast<D2*>(row0)[t] = z;
+      }
+      double r0 = 0.0, r1 = 0.0;
+      const int qe = s_n2e[n + 1] - pr0;
+      for (int q = s_n2e[n] - pr0; q < qe; ++q) {
+        const unsigned info = s_pair[q];
+        const double* rec = recs + (size_t)(info & 0xfffu) * kRec2D;
+        const int a = (info >> 12) & 3;
+        if (JAC) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const int slot = (info >> (14 + 6 * c)) & 63;
+            double b[2][2];
+            tri_block(rec, a, c, b);
+            D2* p0 = reinterpret_cast<D2*>(row0 + D * slot);
+            D2* p1 = reinterpret_cast<D2*>(row1 + D * slot);
+            D2 c0 = *p0, c1 = *p1;
+            c0.x += b[0][0];
+            c0.y += b[0][1];
+            c1.x += b[1][0];
+            c1.y += b[1][1];
+            *p0 = c0;
+            *p1 = c1;
+          }
+        }
+        if (RES) {
+          r0 += rec[9 + 2 * a];
+          r1 += rec[10 + 2 * a];
+        }
+      }
+      if (RES) {
+        tileF[D * n] = r0;
+        tileF[D * n + 1] = r1;
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 3: coalesced write-out ---------------------------------------------------------------
+  if (JAC) {
+    double2* dst = reinterpret_cast<double2*>(mb + L.off[VF_J] + base);
+    const double2* src = reinterpret_cast<const double2*>(tileJ);
+    for (int t = threadIdx.x; t < nvals / 2; t += blockDim.x) __stcs(dst + t, src[t]);
+  }
+  if (RES) {
+    double* F = mb + L.off[VF_F] + (size_t)D * i0;
+    for (int t = threadIdx.x; t < D * nT; t += blockDim.x) F[t] = tileF[t];
+  }
+}
+
+// Exterior-facet terms (follower pressure, contact, membrane) and Dirichlet rows of the
+// boundary nodes, applied in place to the rows the tile kernel has written.  One thread owns
+// one node: private rows, fixed order, no atomics.
+template <int D, bool JAC, bool RES>
+__global__ void facet_bc_kernel(EngineDev E, int member, double dt, int is_static,
+                                const int* __restrict__ touch_nodes, int n_touch) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_touch) return;
+  const int i = touch_nodes[t];
+  double* mb = E.members + (size_t)member * E.L.stride;
+  const Layout& L = E.L;
+  const PropView pv = member_props<D>(E, mb);
+  StateView sv;
+  sv.u1 = mb + L.off[VF_U1];
+  sv.u0 = is_static ? sv.u1 : mb + L.off[VF_U0];
+  sv.v0 = mb + L.off[VF_V0];
+  sv.a0 = mb + L.off[VF_A0];
+  sv.p1 = mb + L.off[VF_P1];
+  sv.dt = dt;
+  sv.is_static = is_static;
+  double* F = mb + L.off[VF_F];
+  double res[D];
+#pragma unroll
+  for (int c = 0; c < D; ++c) res[c] = RES ? F[D * i + c] : 0.0;
+  assemble_node_facets_bc<D, JAC, RES>(i, E.mesh, pv, sv,
+                                       mb + L.off[VF_J] + (size_t)D * D * E.mesh.brptr[i], res);
+  if (RES) {
+#pragma unroll
+    for (int c = 0; c < D; ++c) F[D * i + c] = res[c];
   }
 }
 
@@ -310,6 +522,14 @@ struct vf_engine {
   char* arena;
   size_t arena_bytes;
   int* tile_start_dev;
+  int* te_ptr_dev;
+  int* te_elem_dev;
+  unsigned* pair_info_dev;
+  int4* tile_desc_dev;
+  int4* te_quad_dev;
+  int* touch_dev;
+  int n_touch;
+  bool two_phase;
   std::vector<int32_t> brptr, bcol;
   int member_threads;
   int64_t launches;
@@ -322,7 +542,7 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 struct ArenaPlan {
   // byte offsets of the shared tables
   size_t xyz, cells, brptr, bcol, n2e_ptr, n2e, n2f_ptr, n2f, pf_cell, pf_opp, bc, tile_start, s,
-      fsi_solid, fsi_fluid, members, total;
+      fsi_solid, fsi_fluid, te_ptr, te_elem, pair_info, tile_desc, te_quad, touch, members, total;
   Layout L;
   long long nnz;
   int N;
@@ -357,6 +577,13 @@ ArenaPlan plan_arena(const vf_problem_desc& d) {
   P.s = take(sizeof(double) * std::max(d.n_fluid * d.ns, 1));
   P.fsi_solid = take(sizeof(int) * std::max(d.n_fsi, 1));
   P.fsi_fluid = take(sizeof(int) * std::max(d.n_fsi, 1));
+  const int n_te = d.te_ptr_host ? d.te_ptr_host[d.ntiles] : 0;
+  P.te_ptr = take(sizeof(int) * (d.ntiles + 1));
+  P.te_elem = take(sizeof(int) * std::max(n_te, 1));
+  P.pair_info = take(sizeof(unsigned) * std::max(d.te_ptr_host ? n_n2e : 0, 1));
+  P.tile_desc = take(sizeof(int) * 8 * (d.te_ptr_host ? d.ntiles : 1));
+  P.te_quad = take(sizeof(int) * 4 * std::max(n_te, 1));
+  P.touch = take(sizeof(int) * std::max(d.nn, 1));
   P.members = o;
 
   // member block (offsets in doubles, each array aligned to 16 doubles = 128 B)
@@ -526,6 +753,22 @@ int vf_create(const vf_problem_desc* desc, void* arena_dev, size_t arena_bytes, 
   VF_CUDA(up(P.s, d.s_host, sizeof(double) * d.n_fluid * d.ns));
   VF_CUDA(up(P.fsi_solid, d.fsi_solid_host, sizeof(int) * d.n_fsi));
   VF_CUDA(up(P.fsi_fluid, d.fsi_fluid_host, sizeof(int) * d.n_fsi));
+  const bool two_phase = d.te_ptr_host && d.te_elem_host && d.pair_info_host &&
+                         d.tile_desc_host && d.te_quad_host && d.dim == 2 && d.tile2_threads > 0;
+  std::vector<int> touch;
+  for (int i = 0; i < d.nn; ++i) {
+    bool t = d.n2f_ptr_host[i + 1] > d.n2f_ptr_host[i];
+    for (int c = 0; c < d.dim && !t; ++c) t = d.bc_host[d.dim * i + c] != 0;
+    if (t) touch.push_back(i);
+  }
+  VF_CUDA(up(P.touch, touch.data(), sizeof(int) * touch.size()));
+  if (two_phase) {
+    VF_CUDA(up(P.te_ptr, d.te_ptr_host, sizeof(int) * (d.ntiles + 1)));
+    VF_CUDA(up(P.te_elem, d.te_elem_host, sizeof(int) * d.te_ptr_host[d.ntiles]));
+    VF_CUDA(up(P.pair_info, d.pair_info_host, sizeof(unsigned) * n_n2e));
+    VF_CUDA(up(P.tile_desc, d.tile_desc_host, sizeof(int) * 8 * d.ntiles));
+    VF_CUDA(up(P.te_quad, d.te_quad_host, sizeof(int) * 4 * d.te_ptr_host[d.ntiles]));
+  }
   VF_CUDA(cudaStreamSynchronize(st));
 
   vf_engine* e = new vf_engine();
@@ -541,6 +784,16 @@ int vf_create(const vf_problem_desc* desc, void* arena_dev, size_t arena_bytes, 
   e->desc.n2f_ptr_host = nullptr; e->desc.n2f_host = nullptr; e->desc.pf_cell_host = nullptr;
   e->desc.pf_opp_host = nullptr; e->desc.bc_host = nullptr; e->desc.tile_start_host = nullptr;
   e->desc.s_host = nullptr; e->desc.fsi_solid_host = nullptr; e->desc.fsi_fluid_host = nullptr;
+  e->desc.te_ptr_host = nullptr; e->desc.te_elem_host = nullptr; e->desc.pair_info_host = nullptr;
+  e->desc.tile_desc_host = nullptr; e->desc.te_quad_host = nullptr;
+  e->two_phase = two_phase;
+  e->touch_dev = reinterpret_cast<int*>(A + P.touch);
+  e->n_touch = (int)touch.size();
+  e->te_ptr_dev = reinterpret_cast<int*>(A + P.te_ptr);
+  e->te_elem_dev = reinterpret_cast<int*>(A + P.te_elem);
+  e->pair_info_dev = reinterpret_cast<unsigned*>(A + P.pair_info);
+  e->tile_desc_dev = reinterpret_cast<int4*>(A + P.tile_desc);
+  e->te_quad_dev = reinterpret_cast<int4*>(A + P.te_quad);
 
   EngineDev& E = e->dev;
   E.mesh.dim = d.dim; E.mesh.nn = d.nn; E.mesh.ne = d.ne; E.mesh.nfp = d.nfp;
@@ -574,6 +827,25 @@ int vf_create(const vf_problem_desc* desc, void* arena_dev, size_t arena_bytes, 
   } else {
     VF_CUDA(cudaFuncSetAttribute(asm_tile_kernel<3, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     VF_CUDA(cudaFuncSetAttribute(asm_tile_kernel<3, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  }
+  if (two_phase) {
+    const int smem2 = (int)(sizeof(double) * (d.max_tile_elems * kRec2D + d.tile_max_values +
+                                              2 * d.tile_threads) +
+                            sizeof(int) * (d.max_tile_pairs + 2 * (d.tile_threads + 1)));
+    if (smem2 > 227 * 1024) {
+      delete e;
+      return fail("two-phase tile exceeds the 227 KB shared memory of an SM");
+    }
+#define VF_SMEM2(K) VF_CUDA(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2))
+    VF_SMEM2((asm_tile2_kernel<true, true, true, 2>));
+    VF_SMEM2((asm_tile2_kernel<true, true, true, 3>));
+    VF_SMEM2((asm_tile2_kernel<true, true, true, 4>));
+    VF_SMEM2((asm_tile2_kernel<true, true, false, 2>));
+    VF_SMEM2((asm_tile2_kernel<true, true, false, 3>));
+    VF_SMEM2((asm_tile2_kernel<true, true, false, 4>));
+    VF_SMEM2((asm_tile2_kernel<true, false, true, 2>));
+    VF_SMEM2((asm_tile2_kernel<false, true, true, 2>));
+#undef VF_SMEM2
   }
   *out = e;
   return 0;
@@ -640,6 +912,42 @@ int vf_assemble(vf_engine* e, int member, int flags, double dt, int is_static, v
   if (!res && !jac) return 0;
   cudaStream_t st = as_stream(stream);
   const int grid = e->desc.ntiles, block = e->desc.tile_threads;
+  if (e->two_phase) {
+    const vf_problem_desc& d = e->desc;
+    const size_t smem2 = sizeof(double) * ((size_t)d.max_tile_elems * kRec2D + d.tile_max_values +
+                                           2 * d.tile_threads) +
+                         sizeof(int) * (d.max_tile_pairs + 2 * (d.tile_threads + 1));
+#define VF_LAUNCH_ASM2(J_, R_, ROW_, MB_)                                                          \
+  asm_tile2_kernel<J_, R_, ROW_, MB_><<<grid, d.tile2_threads, smem2, st>>>(                       \
+      e->dev, member, dt, is_static, e->tile_desc_dev, e->te_quad_dev, e->pair_info_dev,          \
+      d.max_tile_elems, d.tile_max_values, d.max_tile_pairs, d.tile_threads)
+    const int v_row = getenv("VF_TILE2_ROW") ? atoi(getenv("VF_TILE2_ROW")) : 1;
+    const int v_minb = getenv("VF_TILE2_MINB") ? atoi(getenv("VF_TILE2_MINB")) : 3;
+    if (jac && res) {
+      if (v_row && v_minb == 2) VF_LAUNCH_ASM2(true, true, true, 2);
+      else if (v_row && v_minb == 3) VF_LAUNCH_ASM2(true, true, true, 3);
+      else if (v_row) VF_LAUNCH_ASM2(true, true, true, 4);
+      else if (v_minb == 2) VF_LAUNCH_ASM2(true, true, false, 2);
+      else if (v_minb == 3) VF_LAUNCH_ASM2(true, true, false, 3);
+      else VF_LAUNCH_ASM2(true, true, false, 4);
+    } else if (jac) VF_LAUNCH_ASM2(true, false, true, 2);
+    else VF_LAUNCH_ASM2(false, true, true, 2);
+#undef VF_LAUNCH_ASM2
+    e->launches += 1;
+    VF_CUDA(cudaGetLastError());
+    if (e->n_touch > 0) {
+      const int fb = 128, fg = (e->n_touch + fb - 1) / fb;
+      if (jac && res)
+        facet_bc_kernel<2, true, true><<<fg, fb, 0, st>>>(e->dev, member, dt, is_static, e->touch_dev, e->n_touch);
+      else if (jac)
+        facet_bc_kernel<2, true, false><<<fg, fb, 0, st>>>(e->dev, member, dt, is_static, e->touch_dev, e->n_touch);
+      else
+        facet_bc_kernel<2, false, true><<<fg, fb, 0, st>>>(e->dev, member, dt, is_static, e->touch_dev, e->n_touch);
+      e->launches += 1;
+      VF_CUDA(cudaGetLastError());
+    }
+    return 0;
+  }
   const size_t smem = jac ? (size_t)e->desc.tile_max_values * sizeof(double) : 0;
 #define VF_LAUNCH_ASM(D)                                                                          \
   if (jac && res)                                                                                 \

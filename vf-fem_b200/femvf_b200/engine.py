@@ -76,13 +76,30 @@ class Engine:
         self.N = d * self.nn
         self.n_members = int(n_members)
 
+        import os
         if d == 2:
-            nodes_per_tile, max_vals, tile_threads = 128, 6144, 128
+            nodes_per_tile = int(os.environ.get('VF_TILE_NODES', '96'))
+            max_vals, tile_threads = 64 * nodes_per_tile, max(nodes_per_tile, 32)
         else:
             nodes_per_tile, max_vals, tile_threads = 64, 12288, 64
         tile_start = _tables.tile_partition(tables['brptr'], d, nodes_per_tile, max_vals)
         vals = d * d * tables['brptr'].astype(np.int64)
         tile_max = int(np.max(vals[tile_start[1:]] - vals[tile_start[:-1]]))
+        # two-phase element-centric tile kernel (triangles)
+        tile2 = _tables.build_tile_elem_tables(tables, tile_start) \
+            if os.environ.get('VF_TILE2', '1') == '1' else None
+        tile2_threads = 0
+        if tile2 is not None:
+            want = max(tile2['max_tile_elems'], d * nodes_per_tile)
+            tile2_threads = int(os.environ.get('VF_TILE2_THREADS', str(-(-want // 32) * 32)))
+            smem = 8 * (18 * tile2['max_tile_elems'] + tile_max + d * nodes_per_tile) \
+                + 4 * (tile2['max_tile_pairs'] + 2 * nodes_per_tile + 8)
+            if smem > 200 * 1024 or tile2_threads > 1024:
+                tile2, tile2_threads = None, 0
+        self.tile_info = {'nodes_per_tile': nodes_per_tile, 'ntiles': len(tile_start) - 1,
+                          'tile_max_values': tile_max, 'two_phase': tile2 is not None,
+                          'max_tile_elems': tile2['max_tile_elems'] if tile2 else 0,
+                          'tile2_threads': tile2_threads}
 
         if s is None:
             s = np.zeros((0, 0))
@@ -99,12 +116,20 @@ class Engine:
         # keep every host array referenced by the descriptor alive until vf_create returns
         keep = dict(tables)
         keep.update(tile_start=tile_start, s=s, fsi_solid=fsi_solid, fsi_fluid=fsi_fluid)
+        if tile2 is not None:
+            keep.update(te_ptr=tile2['te_ptr'], te_elem=tile2['te_elem'],
+                        pair_info=tile2['pair_info'], tile_desc=tile2['tile_desc'],
+                        te_quad=tile2['te_quad'])
         desc = ProblemDesc(
             d, self.nn, self.ne, tables['nfp'],
             _ptr(keep['xyz']), _ptr(keep['cells']), _ptr(keep['brptr']), _ptr(keep['bcol']),
             _ptr(keep['n2e_ptr']), _ptr(keep['n2e']), _ptr(keep['n2f_ptr']), _ptr(keep['n2f']),
             _ptr(keep['pf_cell']), _ptr(keep['pf_opp']), _ptr(keep['bc']),
             _ptr(tile_start), len(tile_start) - 1, tile_max, tile_threads,
+            _ptr(keep.get('te_ptr')), _ptr(keep.get('te_elem')), _ptr(keep.get('pair_info')),
+            _ptr(keep.get('tile_desc')), _ptr(keep.get('te_quad')),
+            tile2['max_tile_elems'] if tile2 else 0, tile2['max_tile_pairs'] if tile2 else 0,
+            tile2_threads,
             self.n_fluid, self.ns, len(fsi_solid), _ptr(s), _ptr(fsi_solid), _ptr(fsi_fluid),
             int(fluid_kind), int(idx_sep), int(bool(contact)), int(bool(membrane)),
             self.n_members, int(gmres_restart),

@@ -250,24 +250,41 @@ def refine_red(mesh_tuple):
     return new_mesh, (new_vert_mf, new_facet_mf, new_cell_mf), subdomains
 
 
-def renumber_for_locality(mesh_tuple):
-    """
-    Renumber vertices by reverse Cuthill-McKee and sort cells by their lowest
-    vertex so that gathers of nodal data and the CSR rows written by one CTA
-    are close in memory.  Tags follow their entities.
-    """
-    from scipy.sparse import coo_matrix
-    from scipy.sparse.csgraph import reverse_cuthill_mckee
+def morton_order(x: np.ndarray, bits: int = 16) -> np.ndarray:
+    """Permutation sorting points along a Z-order (Morton) space-filling curve."""
+    d = x.shape[1]
+    lo, hi = x.min(axis=0), x.max(axis=0)
+    span = np.where(hi > lo, hi - lo, 1.0)
+    q = np.minimum(((x - lo) / span * (2**bits - 1)).astype(np.uint64), 2**bits - 1)
+    code = np.zeros(len(x), dtype=np.uint64)
+    for b in range(bits):
+        for k in range(d):
+            code |= ((q[:, k] >> np.uint64(b)) & np.uint64(1)) << np.uint64(b * d + k)
+    return np.argsort(code, kind='stable')
 
+
+def renumber_for_locality(mesh_tuple, method: str = 'morton'):
+    """
+    Renumber vertices along a space-filling curve (compact node tiles: a contiguous index
+    range is a blob, not a strip, so the cells touching it are mostly interior) or by
+    reverse Cuthill-McKee, and sort cells by their lowest vertex, so that gathers of nodal
+    data and the CSR rows written by one CTA are close in memory.  Tags follow their
+    entities.
+    """
     mesh, mfs, subdomains = mesh_tuple
     d = mesh.topology().dim()
     x = mesh.coordinates()
     c = mesh.cells()
     nn = len(x)
-    e = mesh.edges
-    g = coo_matrix((np.ones(2 * len(e)), (np.r_[e[:, 0], e[:, 1]], np.r_[e[:, 1], e[:, 0]])),
-                   shape=(nn, nn)).tocsr()
-    perm = np.asarray(reverse_cuthill_mckee(g, symmetric_mode=True), dtype=np.int64)
+    if method == 'morton':
+        perm = morton_order(x, 16 if d == 2 else 10).astype(np.int64)
+    else:
+        from scipy.sparse import coo_matrix
+        from scipy.sparse.csgraph import reverse_cuthill_mckee
+        e = mesh.edges
+        g = coo_matrix((np.ones(2 * len(e)), (np.r_[e[:, 0], e[:, 1]], np.r_[e[:, 1], e[:, 0]])),
+                       shape=(nn, nn)).tocsr()
+        perm = np.asarray(reverse_cuthill_mckee(g, symmetric_mode=True), dtype=np.int64)
     inv = np.empty(nn, dtype=np.int64)
     inv[perm] = np.arange(nn)
     newx = x[perm]

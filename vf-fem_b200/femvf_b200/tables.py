@@ -119,3 +119,81 @@ def tile_partition(brptr: np.ndarray, d: int, nodes_per_tile: int, max_tile_valu
         starts.append(j)
         i = j
     return np.asarray(starts, dtype=np.int32)
+
+
+def build_tile_elem_tables(T: dict, tile_start: np.ndarray):
+    """
+    Tables of the two-phase tile assembly kernel (``asm_tile2_kernel``, triangles only).
+
+    te_ptr/te_elem : cells touching each node tile (owned + halo), ascending
+    pair_info      : one uint32 per (node, adjacent cell) pair in ``n2e`` order:
+                     bits [0,12) index of the cell in its node's tile list, [12,14) local
+                     index a of the node in the cell, [14,20) [20,26) [26,32) CSR slots (within
+                     the node's block row) of the cell's three vertices
+    Returns None when the packing limits (4096 cells per tile, 64 blocks per row) do not hold.
+    """
+    d, nn, ne = T['dim'], T['nn'], T['ne']
+    if d != 2:
+        return None
+    cells = np.ascontiguousarray(T['cells'].T.astype(np.int64))  # (ne, 3)
+    brptr = T['brptr'].astype(np.int64)
+    bcol = T['bcol'].astype(np.int64)
+    if np.max(np.diff(brptr)) >= 64:
+        return None
+    ntiles = len(tile_start) - 1
+    tile_of_node = np.searchsorted(tile_start.astype(np.int64), np.arange(nn), side='right') - 1
+    # (tile, cell) incidences, unique and sorted by tile then cell
+    tc = tile_of_node[cells]  # (ne, 3)
+    key = (tc * ne + np.arange(ne)[:, None]).ravel()
+    key = np.unique(key)
+    te_tile = key // ne
+    te_elem = (key % ne).astype(np.int32)
+    te_ptr = np.zeros(ntiles + 1, dtype=np.int64)
+    np.add.at(te_ptr, te_tile + 1, 1)
+    te_ptr = np.cumsum(te_ptr)
+    max_tile_elems = int(np.max(np.diff(te_ptr)))
+    if max_tile_elems >= 4096:
+        return None
+
+    # per (node, cell) pair
+    n2e_ptr = T['n2e_ptr'].astype(np.int64)
+    n2e = T['n2e'].astype(np.int64)
+    pair_node = np.repeat(np.arange(nn), np.diff(n2e_ptr))
+    pe, pa = n2e >> 2, n2e & 3
+    ptile = tile_of_node[pair_node]
+    # local index of the cell in the tile list: position of (tile, cell) in the sorted keys
+    local = np.searchsorted(key, ptile * ne + pe) - te_ptr[ptile]
+    # CSR slot of each vertex of the cell in the node's block row
+    gkey = np.repeat(np.arange(nn), np.diff(brptr)) * nn + bcol  # sorted globally
+    slots = []
+    for c in range(3):
+        col = cells[pe, c]
+        pos = np.searchsorted(gkey, pair_node * nn + col)
+        slots.append(pos - brptr[pair_node])
+    info = (local.astype(np.uint64) | (pa.astype(np.uint64) << np.uint64(12))
+            | (slots[0].astype(np.uint64) << np.uint64(14))
+            | (slots[1].astype(np.uint64) << np.uint64(20))
+            | (slots[2].astype(np.uint64) << np.uint64(26)))
+    # flat per-tile descriptor and per-(tile, cell) vertex quads: everything a CTA needs is
+    # addressable after ONE dependent load (the descriptor), instead of a chain
+    # tile_start -> te_ptr -> te_elem -> cells
+    ts = tile_start.astype(np.int64)
+    desc = np.zeros((ntiles, 8), dtype=np.int32)
+    desc[:, 0] = ts[:-1]
+    desc[:, 1] = ts[1:]
+    desc[:, 2] = te_ptr[:-1]
+    desc[:, 3] = te_ptr[1:]
+    desc[:, 4] = n2e_ptr[ts[:-1]]
+    desc[:, 5] = n2e_ptr[ts[1:]]
+    desc[:, 6] = brptr[ts[:-1]]
+    desc[:, 7] = brptr[ts[1:]]
+    te_quad = np.empty((len(te_elem), 4), dtype=np.int32)
+    te_quad[:, :3] = cells[te_elem]
+    te_quad[:, 3] = te_elem
+    max_tile_pairs = int(np.max(desc[:, 5] - desc[:, 4]))
+    return {
+        'te_ptr': te_ptr.astype(np.int32), 'te_elem': te_elem,
+        'pair_info': info.astype(np.uint32), 'max_tile_elems': max_tile_elems,
+        'tile_desc': np.ascontiguousarray(desc), 'te_quad': np.ascontiguousarray(te_quad),
+        'max_tile_pairs': max_tile_pairs,
+    }
