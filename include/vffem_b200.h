@@ -61,8 +61,15 @@ typedef struct vf_problem_desc {
   /* 1D fluid + FSI map (models/fsi.py:18-88) */
   int32_t n_fluid, ns, n_fsi;
   const double* s_host;           /* (n_fluid, ns) arclength coordinates */
+  /* area gather fluid_area[fsi_fluid[k]] = solid_area[fsi_solid[k]] (fsi.py:69-70); fluid DOFs
+   * unique (the host keeps the last occurrence, numpy's assignment semantics) */
   const int32_t* fsi_solid_host;  /* (n_fsi) scalar solid DOFs */
   const int32_t* fsi_fluid_host;  /* (n_fsi) fluid DOFs */
+  /* pressure scatter solid_p[fsip_solid[k]] = fluid_p[fsip_fluid[k]] (fsi.py:66-67); solid DOFs
+   * unique (last occurrence kept) */
+  int32_t n_fsip;
+  const int32_t* fsip_solid_host;
+  const int32_t* fsip_fluid_host;
   int32_t fluid_kind;         /* 0 area-ratio sep, 1 fixed sep, 2 smooth-min sep */
   int32_t idx_sep;
   /* model switches */

@@ -71,3 +71,138 @@ def test_integrate_matches_oracle(mesh_name, tmp_path):
     q_ref = np.array([h[3][0] for h in hist])
     assert abs(fin_state['q'][0] - q_ref[-1]) <= TRAJ_TOL * abs(q_ref[-1])
     assert info['num_iter'] >= 1
+
+
+def test_per_step_api_equals_device_loop():
+    """integrate_step through the host-buffer model API (set_* + solve_state1 per step) gives
+    the same states as the device-resident loop used by forward.integrate."""
+    from femvf_b200 import forward
+    model = build_fsi('m5')
+    state0, control, prop = benchmark_setup(model)
+    times = 1e-4 * np.arange(8)
+    fin_dev, _ = forward.integrate(model, None, state0, [control], prop, times, write=False)
+    model.set_prop(prop)
+    st = state0
+    for n in range(len(times) - 1):
+        st, info = forward.integrate_step(model, st, control, prop, times[n + 1] - times[n])
+    for key in ('u', 'q', 'p'):
+        scale = max(np.max(np.abs(fin_dev[key])), 1e-300)
+        assert np.max(np.abs(st[key] - fin_dev[key])) <= 1e-12 * scale, key
+    assert set(info) >= {'num_iter', 'abs_err', 'rel_err'}
+
+
+def test_golden_forward_fixture_on_gpu():
+    import os
+    from femvf_b200 import forward
+    z = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'forward_m5.npz'))
+    model = build_fsi('m5')
+    state0, control, prop = benchmark_setup(model)
+    model.set_prop(prop)
+    model.set_ini_state(state0)
+    model.push_to_device()
+    states, infos = model.device_integrate(np.diff(z['times']), [control])
+    N = model.solid.state0['u'].size
+    q = states[:, 3 * N]
+    assert np.max(np.abs(q - z['q'])) <= TRAJ_TOL * np.max(np.abs(z['q']))
+    assert np.max(np.abs(states[-1, :N] - z['u_last'])) <= TRAJ_TOL * np.max(np.abs(z['u_last']))
+    # glottal-width series (min fluid area) written by the kernel
+    gw = infos[1:, 3]
+    assert np.max(np.abs(gw - z['min_area'][1:])) <= TRAJ_TOL * np.max(np.abs(z['min_area'][1:]))
+
+
+@pytest.mark.parametrize('variant', ['contact', 'epithelium'])
+def test_coupled_variants_match_oracle(variant):
+    """NodalContactModel solid (active contact) and the membrane residual inside the coupled loop."""
+    from femvf_b200 import forward
+    from femvf_b200.load import derive_1D_interface_from_facet_subdomain
+    from femvf_b200.models import transient
+    from femvf_b200.residuals import solid as slr, fluid as flr
+    mt = mesh_tuples()['m5']()
+    Residual = slr.KelvinVoigtWEpithelium if variant == 'epithelium' else slr.KelvinVoigt
+    residual = Residual(*mt)
+    solid = transient.NodalContactModel(residual) if variant == 'contact' \
+        else transient.FenicsModel(residual)
+    s, sdofs, fdofs = derive_1D_interface_from_facet_subdomain(
+        residual.mesh(), None, residual.mesh_function('facet'),
+        {residual.mesh_subdomain('facet')['pressure']})
+    fluid = transient.JaxModel(flr.BernoulliAreaRatioSep(s))
+    model = transient.ExplicitFSIModel(solid, fluid, sdofs, fdofs)
+    state0, control, prop = benchmark_setup(model)
+    ymax = residual.mesh().coordinates()[:, 1].max()
+    prop['ymid'][:] = ymax + 0.02
+    if variant == 'contact':
+        prop['ycontact'][:] = ymax + 0.001   # the surface bulges into the plane within a few steps
+        prop['kcontact'][:] = 1e11
+    else:
+        prop['emod_membrane'][:] = 2e5; prop['th_membrane'][:] = 0.005; prop['nu_membrane'][:] = 0.45
+    times = 1e-4 * np.arange(25)
+    fin, info = forward.integrate(model, None, state0, [control], prop, times, write=False)
+    prob = oracle_problem(residual)
+    co = om.CoupledOracle(om.SolidOracle(prob, contact=variant == 'contact',
+                                         membrane=variant == 'epithelium'), s, sdofs, fdofs)
+    oprop = {k: np.array(v) for k, v in prop.items()}
+    hist, infos = co.integrate(tuple(state0.vecs),
+                               [{'psub': control['psub'], 'psup': control['psup']}], oprop, times)
+    if variant == 'contact':
+        gap = (prob.coords[:, 1] + hist[-1][0][1::2]) - float(prop['ycontact'][0])
+        assert gap.max() > 0, "the test should exercise active contact"
+    for k, key in ((0, 'u'), (3, 'q'), (4, 'p')):
+        ref = hist[-1][k]
+        assert np.max(np.abs(fin[key] - ref)) <= TRAJ_TOL * np.max(np.abs(ref)), key
+
+
+def test_3d_coupled_steps_match_oracle():
+    """Unit-cube fixture with three fluid planes: tetrahedral kernels + nonlinear 3D pressure."""
+    from femvf_b200 import forward
+    zs = np.linspace(0, 1, 3)
+    model = build_fsi('cube332', zs=zs)
+    state0 = model.state0.copy(); state0[:] = 0
+    control = model.control.copy(); control['psub'][:] = 8e3; control['psup'][:] = 0
+    prop = model.prop.copy()
+    prop['emod'][:] = 1e5; prop['rho'][:] = 1; prop['eta'][:] = 4e-3; prop['nu'][:] = 0.45
+    prop['ymid'][:] = 1.05
+    times = 2e-5 * np.arange(10)
+    fin, info = forward.integrate(model, None, state0, [control], prop, times, write=False)
+    prob = oracle_problem(model.solid.residual)
+    co = om.CoupledOracle(om.SolidOracle(prob), model.fluid.residual.mesh(),
+                          model.fsimap.dofs_solid, model.fsimap.dofs_fluid)
+    oprop = {k: np.array(v) for k, v in prop.items()}
+    hist, infos = co.integrate(tuple(state0.vecs),
+                               [{'psub': control['psub'], 'psup': control['psup']}], oprop, times)
+    for k, key in ((0, 'u'), (3, 'q'), (4, 'p')):
+        ref = hist[-1][k]
+        assert np.max(np.abs(fin[key] - ref)) <= TRAJ_TOL * max(np.max(np.abs(ref)), 1e-300), key
+    assert info['num_iter'] >= 1
+
+
+def test_ensemble_members_and_host_entry_point():
+    """Members with identical inputs reproduce the single simulation bit for bit; the
+    host-buffer entry point equals the device-resident one; different members differ."""
+    from femvf_b200.ensemble import EnsembleRunner
+    model = build_fsi('m5')
+    state0, control, prop = benchmark_setup(model)
+    B = 5
+    runner = EnsembleRunner(model, B)
+    runner.set_common_prop(prop)
+    ne = runner.ne
+    rng = np.random.default_rng(0)
+    emod = np.tile(np.asarray(prop['emod']), (B, 1)); eta = np.tile(np.asarray(prop['eta']), (B, 1))
+    emod[3] *= np.exp(0.3 * rng.standard_normal(ne))
+    ini = np.zeros((B, runner.state_size))
+    dts = np.full(12, 1e-4)
+    ctl = np.array([[[8e3], [0.0]]])
+    fin, series = runner.run_host(dts, ctl, ini, emod, eta)
+    # the single simulation with bit-identical step sizes
+    model.set_prop(prop)
+    model.set_ini_state(state0)
+    model.push_to_device()
+    states, _ = model.device_integrate(dts, [control])
+    ref = states[-1]
+    for b in (0, 1, 2, 4):
+        assert np.array_equal(fin[b], ref), b
+    assert not np.array_equal(fin[3], ref)
+    # device-resident path gives the same numbers
+    runner.upload_members(ini, emod, eta)
+    hs, hi = runner.run_device(dts, ctl, store_states=True)
+    assert np.array_equal(hs[:, -1, :].cpu().numpy(), fin)
+    assert np.array_equal(hi.cpu().numpy(), series)

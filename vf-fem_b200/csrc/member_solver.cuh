@@ -45,11 +45,13 @@ struct SolverOpts {
 
 struct EngineDev {
   MeshView mesh;
-  int d, N, n_fluid, ns, n_fsi, fluid_kind, idx_sep, contact, membrane, restart;
+  int d, N, n_fluid, ns, n_fsi, n_fsip, fluid_kind, idx_sep, contact, membrane, restart;
   long long nnz;
   const double* s;
-  const int* fsi_solid;
+  const int* fsi_solid;   // area gather map (unique fluid DOFs)
   const int* fsi_fluid;
+  const int* fsip_solid;  // pressure scatter map (unique solid DOFs)
+  const int* fsip_fluid;
   double* members;
   Layout L;
 };

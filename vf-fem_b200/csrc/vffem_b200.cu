@@ -487,7 +487,7 @@ member_kernel(EngineDev E, int member0, int mode, int nsteps, const double* __re
     // initial guess for the final state = initial state (transient.py:904)
     for (int t = threadIdx.x; t < N; t += blockDim.x) u1[t] = u0[t];
     __syncthreads();
-    for (int k = threadIdx.x; k < E.n_fsi; k += blockDim.x) p1[E.fsi_solid[k]] = p0[E.fsi_fluid[k]];
+    for (int k = threadIdx.x; k < E.n_fsip; k += blockDim.x) p1[E.fsip_solid[k]] = p0[E.fsip_fluid[k]];
     __syncthreads();
 
     blk_solve_solid<D>(E, mb, dt, opt, sh);
@@ -542,7 +542,7 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 struct ArenaPlan {
   // byte offsets of the shared tables
   size_t xyz, cells, brptr, bcol, n2e_ptr, n2e, n2f_ptr, n2f, pf_cell, pf_opp, bc, tile_start, s,
-      fsi_solid, fsi_fluid, te_ptr, te_elem, pair_info, tile_desc, te_quad, touch, members, total;
+      fsi_solid, fsi_fluid, fsip_solid, fsip_fluid, te_ptr, te_elem, pair_info, tile_desc, te_quad, touch, members, total;
   Layout L;
   long long nnz;
   int N;
@@ -577,6 +577,8 @@ ArenaPlan plan_arena(const vf_problem_desc& d) {
   P.s = take(sizeof(double) * std::max(d.n_fluid * d.ns, 1));
   P.fsi_solid = take(sizeof(int) * std::max(d.n_fsi, 1));
   P.fsi_fluid = take(sizeof(int) * std::max(d.n_fsi, 1));
+  P.fsip_solid = take(sizeof(int) * std::max(d.n_fsip, 1));
+  P.fsip_fluid = take(sizeof(int) * std::max(d.n_fsip, 1));
   const int n_te = d.te_ptr_host ? d.te_ptr_host[d.ntiles] : 0;
   P.te_ptr = take(sizeof(int) * (d.ntiles + 1));
   P.te_elem = take(sizeof(int) * std::max(n_te, 1));
@@ -636,7 +638,8 @@ int check_desc(const vf_problem_desc* d) {
   if (d->n_members <= 0) return fail("n_members must be positive");
   if (d->gmres_restart <= 0 || d->gmres_restart > kMaxRestart)
     return fail("gmres_restart must be in [1, 128]");
-  if (d->n_fluid < 0 || d->ns < 0 || d->n_fsi < 0) return fail("negative fluid sizes");
+  if (d->n_fluid < 0 || d->ns < 0 || d->n_fsi < 0 || d->n_fsip < 0)
+    return fail("negative fluid sizes");
   if (d->ntiles <= 0 || !d->tile_start_host) return fail("missing assembly tile partition");
   if (d->tile_threads <= 0 || d->tile_threads > 1024) return fail("invalid tile_threads");
   if ((size_t)d->tile_max_values * sizeof(double) > 227 * 1024)
@@ -753,6 +756,8 @@ int vf_create(const vf_problem_desc* desc, void* arena_dev, size_t arena_bytes, 
   VF_CUDA(up(P.s, d.s_host, sizeof(double) * d.n_fluid * d.ns));
   VF_CUDA(up(P.fsi_solid, d.fsi_solid_host, sizeof(int) * d.n_fsi));
   VF_CUDA(up(P.fsi_fluid, d.fsi_fluid_host, sizeof(int) * d.n_fsi));
+  VF_CUDA(up(P.fsip_solid, d.fsip_solid_host, sizeof(int) * d.n_fsip));
+  VF_CUDA(up(P.fsip_fluid, d.fsip_fluid_host, sizeof(int) * d.n_fsip));
   const bool two_phase = d.te_ptr_host && d.te_elem_host && d.pair_info_host &&
                          d.tile_desc_host && d.te_quad_host && d.dim == 2 && d.tile2_threads > 0;
   std::vector<int> touch;
@@ -784,6 +789,7 @@ int vf_create(const vf_problem_desc* desc, void* arena_dev, size_t arena_bytes, 
   e->desc.n2f_ptr_host = nullptr; e->desc.n2f_host = nullptr; e->desc.pf_cell_host = nullptr;
   e->desc.pf_opp_host = nullptr; e->desc.bc_host = nullptr; e->desc.tile_start_host = nullptr;
   e->desc.s_host = nullptr; e->desc.fsi_solid_host = nullptr; e->desc.fsi_fluid_host = nullptr;
+  e->desc.fsip_solid_host = nullptr; e->desc.fsip_fluid_host = nullptr;
   e->desc.te_ptr_host = nullptr; e->desc.te_elem_host = nullptr; e->desc.pair_info_host = nullptr;
   e->desc.tile_desc_host = nullptr; e->desc.te_quad_host = nullptr;
   e->two_phase = two_phase;
@@ -814,6 +820,9 @@ int vf_create(const vf_problem_desc* desc, void* arena_dev, size_t arena_bytes, 
   E.s = reinterpret_cast<const double*>(A + P.s);
   E.fsi_solid = reinterpret_cast<const int*>(A + P.fsi_solid);
   E.fsi_fluid = reinterpret_cast<const int*>(A + P.fsi_fluid);
+  E.fsip_solid = reinterpret_cast<const int*>(A + P.fsip_solid);
+  E.fsip_fluid = reinterpret_cast<const int*>(A + P.fsip_fluid);
+  E.n_fsip = d.n_fsip;
   E.members = reinterpret_cast<double*>(A + P.members);
   E.L = P.L;
   e->tile_start_dev = reinterpret_cast<int*>(A + P.tile_start);

@@ -36,6 +36,7 @@ class ProblemDesc(C.Structure):
         ('tile2_threads', C.c_int32),
         ('n_fluid', C.c_int32), ('ns', C.c_int32), ('n_fsi', C.c_int32),
         ('s_host', C.c_void_p), ('fsi_solid_host', C.c_void_p), ('fsi_fluid_host', C.c_void_p),
+        ('n_fsip', C.c_int32), ('fsip_solid_host', C.c_void_p), ('fsip_fluid_host', C.c_void_p),
         ('fluid_kind', C.c_int32), ('idx_sep', C.c_int32),
         ('contact', C.c_int32), ('membrane', C.c_int32),
         ('n_members', C.c_int32), ('gmres_restart', C.c_int32),

@@ -111,11 +111,22 @@ class Engine:
             np.ascontiguousarray(fsi_fluid, dtype=np.int32)
         if len(fsi_solid) != len(fsi_fluid):
             raise ValueError("solid/fluid FSI dof arrays must have the same length")
+
+        def keep_last(key):
+            # numpy fancy assignment x[key] = v keeps the LAST value written to a repeated
+            # index; a parallel scatter needs unique targets to reproduce that
+            _, first_rev = np.unique(key[::-1], return_index=True)
+            return np.sort(len(key) - 1 - first_rev)
+        ka = keep_last(fsi_fluid) if len(fsi_fluid) else np.zeros(0, np.int64)
+        kp = keep_last(fsi_solid) if len(fsi_solid) else np.zeros(0, np.int64)
+        fsia_solid, fsia_fluid = np.ascontiguousarray(fsi_solid[ka]), np.ascontiguousarray(fsi_fluid[ka])
+        fsip_solid, fsip_fluid = np.ascontiguousarray(fsi_solid[kp]), np.ascontiguousarray(fsi_fluid[kp])
         self.state_size = 3 * self.N + self.n_fluid + self.n_fluid * self.ns
 
         # keep every host array referenced by the descriptor alive until vf_create returns
         keep = dict(tables)
-        keep.update(tile_start=tile_start, s=s, fsi_solid=fsi_solid, fsi_fluid=fsi_fluid)
+        keep.update(tile_start=tile_start, s=s, fsi_solid=fsia_solid, fsi_fluid=fsia_fluid,
+                    fsip_solid=fsip_solid, fsip_fluid=fsip_fluid)
         if tile2 is not None:
             keep.update(te_ptr=tile2['te_ptr'], te_elem=tile2['te_elem'],
                         pair_info=tile2['pair_info'], tile_desc=tile2['tile_desc'],
@@ -130,7 +141,8 @@ class Engine:
             _ptr(keep.get('tile_desc')), _ptr(keep.get('te_quad')),
             tile2['max_tile_elems'] if tile2 else 0, tile2['max_tile_pairs'] if tile2 else 0,
             tile2_threads,
-            self.n_fluid, self.ns, len(fsi_solid), _ptr(s), _ptr(fsi_solid), _ptr(fsi_fluid),
+            self.n_fluid, self.ns, len(fsia_solid), _ptr(s), _ptr(fsia_solid), _ptr(fsia_fluid),
+            len(fsip_solid), _ptr(fsip_solid), _ptr(fsip_fluid),
             int(fluid_kind), int(idx_sep), int(bool(contact)), int(bool(membrane)),
             self.n_members, int(gmres_restart),
         )

@@ -56,6 +56,8 @@ class EnsembleRunner:
         e.member_view('scal').copy_(torch.as_tensor(scal, device=dev))
         fp = m.fluid._fprop_block().reshape(-1)
         e.member_view('fprop').copy_(torch.as_tensor(fp, device=dev))
+        e.member_view('area').copy_(
+            torch.as_tensor(np.asarray(m.fluid.control['area']), device=dev))
 
     def upload_members(self, ini_state: np.ndarray, emod=None, eta=None):
         e = self.engine

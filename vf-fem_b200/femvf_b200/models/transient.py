@@ -587,6 +587,9 @@ class ExplicitFSIModel(BaseTransientFSIModel):
         self.solid._push_prop(self.solid._ymid)
         e = self.engine
         e.upload('fprop', self.fluid._fprop_block(), 0)
+        # entries of the fluid area that no solid DOF maps to keep their host value
+        # (default 1.0, residuals/fluid.py:298)
+        e.upload('area', self.fluid.control['area'], 0)
         names = ('u0', 'v0', 'a0', 'q0', 'p0')
         for name, vec in zip(names, self.state0.vecs):
             e.upload(name, vec, 0)
