@@ -87,6 +87,8 @@ typedef struct vf_solver_opts {
   double gmres_rel_tol, gmres_abs_tol;
   int32_t gmres_max_iter;
   int32_t is_static;          /* static.py:68-168: u0 == u1, v0 = a0 = 0 */
+  int32_t poly_degree;        /* Neumann-series degree of the polynomial preconditioner (0..8) */
+  int32_t reserved;
 } vf_solver_opts;
 
 /* Named per-member arrays inside the arena. */

@@ -44,7 +44,7 @@ def test_array_ids_match_header_enum(built):
 
 def test_struct_sizes_are_plain_c(built):
     # pointers and sizes only: the descriptor is a POD of int32 / pointer fields
-    assert ctypes.sizeof(built.SolverOpts) == 48  # static_assert-ed in csrc/vffem_b200.cu
+    assert ctypes.sizeof(built.SolverOpts) == 56  # static_assert-ed in csrc/vffem_b200.cu
     assert ctypes.sizeof(built.ProblemDesc) % 8 == 0
 
 

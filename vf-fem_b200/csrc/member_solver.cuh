@@ -41,6 +41,7 @@ struct SolverOpts {
   double gmres_rel_tol, gmres_abs_tol;
   int gmres_max_iter;
   int is_static;
+  int poly_degree;  // Neumann-series degree of the polynomial preconditioner (0 = block-Jacobi)
 };
 
 struct EngineDev {
@@ -61,7 +62,12 @@ struct BlockShared {
   double red[40];
   double h[kMaxRestart + 2];
   double h2[kMaxRestart + 2];
+  double cs[kMaxRestart + 2];  // Givens rotations, rhs of the least-squares problem and its
+  double sn[kMaxRestart + 2];  // solution: touched by one thread in a dependent chain, so
+  double g[kMaxRestart + 2];   // they must not live in global memory
+  double y[kMaxRestart + 2];
   double bc[8];  // broadcast scalars
+  long long cyc[8];  // cycle counters: 0 assembly 1 spmv 2 dots+update 3 givens 4 solve tail 5 fluid 6 total
 };
 
 __device__ __forceinline__ double block_sum(double v, BlockShared& sh) {
@@ -93,6 +99,84 @@ __device__ __forceinline__ void blk_spmv(const EngineDev& E, const double* __res
       for (int c = 0; c < D; ++c) s += row[k * D + c] * x[D * j + c];
     }
     y[r] = s;
+  }
+}
+
+// Solver working set of one member.  In the time loop the arrays live in shared memory when
+// they fit (flags: 1 = vectors + Dinv, 2 = Krylov basis V, 4 = CSR values J); otherwise they
+// are the member's global arrays (L2 resident).  The base problem (~300
+// DOF) fits entirely, so a Krylov iteration never leaves the SM.
+struct SolverWork {
+  double *J, *F, *dx, *Dinv, *V, *w, *z, *t, *H, *cs, *sn, *g, *y;
+};
+
+__device__ __forceinline__ SolverWork make_work(const EngineDev& E, double* mb, double* dsm,
+                                                int flags) {
+  const Layout& L = E.L;
+  SolverWork W;
+  W.J = mb + L.off[VF_J];
+  W.F = mb + L.off[VF_F];
+  W.dx = mb + L.off[VF_DX];
+  W.Dinv = mb + L.Dinv;
+  W.V = mb + L.V;
+  W.w = mb + L.w;
+  W.z = mb + L.z;
+  W.t = mb + L.xk;
+  W.H = mb + L.H;
+  W.cs = mb + L.cs;
+  W.sn = mb + L.sn;
+  W.g = mb + L.g;
+  W.y = mb + L.y;
+  size_t o = 0;
+  auto take = [&](size_t n) {
+    double* p = dsm + o;
+    o += (n + 1) & ~size_t(1);
+    return p;
+  };
+  const size_t N = E.N;
+  if (flags & 1) {
+    W.F = take(N);
+    W.dx = take(N);
+    W.w = take(N);
+    W.z = take(N);
+    W.t = take(N);
+    W.Dinv = take((size_t)E.mesh.nn * E.d * E.d);
+  }
+  if (flags & 8) W.H = take((size_t)(E.restart + 1) * E.restart);
+  if (flags & 2) W.V = take((size_t)(E.restart + 1) * N);
+  if (flags & 4) W.J = take((size_t)E.nnz);
+  return W;
+}
+
+// y = Dinv (J x): the left-preconditioned operator in one sweep, one thread per node
+template <int D>
+__device__ __forceinline__ void blk_spmv_prec(const EngineDev& E, const double* __restrict__ J,
+                                              const double* __restrict__ Dinv,
+                                              const double* __restrict__ x, double* __restrict__ y) {
+  for (int i = threadIdx.x; i < E.mesh.nn; i += blockDim.x) {
+    const int b0 = E.mesh.brptr[i], deg = E.mesh.brptr[i + 1] - b0;
+    const double* blk = J + (size_t)D * D * b0;
+    double acc[D];
+#pragma unroll
+    for (int a = 0; a < D; ++a) acc[a] = 0.0;
+    for (int k = 0; k < deg; ++k) {
+      const int j = E.mesh.bcol[b0 + k];
+      double xv[D];
+#pragma unroll
+      for (int c = 0; c < D; ++c) xv[c] = x[D * j + c];
+#pragma unroll
+      for (int a = 0; a < D; ++a)
+#pragma unroll
+        for (int c = 0; c < D; ++c) acc[a] += blk[a * D * deg + k * D + c] * xv[c];
+    }
+    const double* o = Dinv + (size_t)D * D * i;
+#pragma unroll
+    for (int a = 0; a < D; ++a) {
+      double t = 0.0;
+#pragma unroll
+      for (int c = 0; c < D; ++c) t += o[a * D + c] * acc[c];
+      y[D * i + a] = t;
+    }
   }
 }
 
@@ -144,16 +228,108 @@ __device__ __forceinline__ void blk_apply_dinv(const EngineDev& E, const double*
   }
 }
 
-// out[j] = V_j . w for j < nvec: one warp per basis vector, fixed-order shuffle tree
+// out[j] = V_j . w for j < nvec.  Each warp takes four basis vectors at a time and keeps four
+// independent accumulators / shuffle trees in flight (the cost here is dependent-chain
+// latency, not throughput); fixed order, so bit-reproducible.
 __device__ __forceinline__ void blk_dots(const double* V, int N, int nvec, const double* w,
                                          double* out) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int j = wid; j < nvec; j += nw) {
-    const double* vj = V + (size_t)j * N;
-    double s = 0.0;
-    for (int t = lane; t < N; t += 32) s += vj[t] * w[t];
-    s = warp_sum(s);
-    if (lane == 0) out[j] = s;
+  for (int j0 = wid * 4; j0 < nvec; j0 += nw * 4) {
+    const int nj = min(4, nvec - j0);
+    const double* v0 = V + (size_t)j0 * N;
+    const double* v1 = v0 + (nj > 1 ? N : 0);
+    const double* v2 = v0 + (nj > 2 ? 2 * (size_t)N : 0);
+    const double* v3 = v0 + (nj > 3 ? 3 * (size_t)N : 0);
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    for (int t = lane; t < N; t += 32) {
+      const double wt = w[t];
+      s0 += v0[t] * wt;
+      s1 += v1[t] * wt;
+      s2 += v2[t] * wt;
+      s3 += v3[t] * wt;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, off);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+      s3 += __shfl_xor_sync(0xffffffffu, s3, off);
+    }
+    if (lane == 0) {
+      out[j0] = s0;
+      if (nj > 1) out[j0 + 1] = s1;
+      if (nj > 2) out[j0 + 2] = s2;
+      if (nj > 3) out[j0 + 3] = s3;
+    }
+  }
+}
+
+// w[t] -= sum_{j<nvec} h[j] V_j[t] with four independent partial sums; returns the thread's
+// partial of ||w||^2
+__device__ __forceinline__ double blk_project_out(const double* V, int N, int nvec,
+                                                  const double* h, double* w) {
+  double p2 = 0.0;
+  for (int t = threadIdx.x; t < N; t += blockDim.x) {
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int j = 0;
+    for (; j + 3 < nvec; j += 4) {
+      a0 += h[j] * V[(size_t)j * N + t];
+      a1 += h[j + 1] * V[(size_t)(j + 1) * N + t];
+      a2 += h[j + 2] * V[(size_t)(j + 2) * N + t];
+      a3 += h[j + 3] * V[(size_t)(j + 3) * N + t];
+    }
+    for (; j < nvec; ++j) a0 += h[j] * V[(size_t)j * N + t];
+    const double s = w[t] - ((a0 + a1) + (a2 + a3));
+    w[t] = s;
+    p2 += s * s;
+  }
+  return p2;
+}
+
+// w = M^{-1} J v with M^{-1} = (I + N + ... + N^p) D^{-1}, N = I - D^{-1} J: the block-Jacobi
+// preconditioner accelerated by a truncated Neumann series (M^{-1} J = I - N^{p+1}).  For the
+// mass-dominated Newmark Jacobian the spectral radius of N is ~0.6, so p = 3 shrinks the
+// Krylov space from ~25 to ~9 vectors and with it the O(k^2) orthogonalisation work, which
+// dominates an in-CTA GMRES.  t, z: scratch vectors.
+template <int D>
+__device__ __forceinline__ void blk_apply_op(const EngineDev& E, const SolverWork& W, int p,
+                                             const double* v, double* w) {
+  if (p == 0) {
+    blk_spmv_prec<D>(E, W.J, W.Dinv, v, w);
+    __syncthreads();
+    return;
+  }
+  double* t = W.t;
+  blk_spmv_prec<D>(E, W.J, W.Dinv, v, t);  // t = D^{-1} J v
+  __syncthreads();
+  const double* cur = t;
+  for (int q = 0; q < p; ++q) {
+    // ping-pong between z and w so that the last term lands in w and dst never aliases cur
+    double* dst = ((p - q) & 1) ? w : W.z;
+    blk_spmv_prec<D>(E, W.J, W.Dinv, cur, dst);
+    __syncthreads();
+    for (int i = threadIdx.x; i < E.N; i += blockDim.x) dst[i] = t[i] + cur[i] - dst[i];
+    __syncthreads();
+    cur = dst;
+  }
+}
+
+// M^{-1} r for a residual r (used for the initial / restart residual)
+template <int D>
+__device__ __forceinline__ void blk_apply_prec(const EngineDev& E, const SolverWork& W, int p,
+                                               const double* r, double* out) {
+  blk_apply_dinv<D>(E, W.Dinv, r, out);  // z0 = D^{-1} r
+  __syncthreads();
+  if (p == 0) return;
+  double* z0 = W.t;
+  for (int i = threadIdx.x; i < E.N; i += blockDim.x) z0[i] = out[i];
+  __syncthreads();
+  for (int q = 0; q < p; ++q) {
+    // out <- z0 + out - D^{-1} J out   (needs a scratch for the product: W.z)
+    blk_spmv_prec<D>(E, W.J, W.Dinv, out, W.z);
+    __syncthreads();
+    for (int i = threadIdx.x; i < E.N; i += blockDim.x) out[i] = z0[i] + out[i] - W.z[i];
+    __syncthreads();
   }
 }
 
@@ -164,28 +340,28 @@ __device__ __forceinline__ void blk_dots(const double* V, int N, int nvec, const
 // iteration count; *resid_out is the final preconditioned residual norm, *bnorm_out
 // ||M^{-1} b||.  Every thread of the block must call it.
 template <int D>
-__device__ int blk_gmres(const EngineDev& E, double* mb, const double* b, double* x,
+__device__ int blk_gmres(const EngineDev& E, const SolverWork& W, const double* b, double* x,
                          const SolverOpts& opt, BlockShared& sh, double* resid_out,
                          double* bnorm_out) {
-  const Layout& L = E.L;
   const int N = E.N;
   const int m = E.restart;
-  const double* J = mb + L.off[VF_J];
-  const double* Dinv = mb + L.Dinv;
-  double* V = mb + L.V;
-  double* w = mb + L.w;
-  double* z = mb + L.z;
-  double* H = mb + L.H;  // column-major, leading dimension m+1
-  double* cs = mb + L.cs;
-  double* sn = mb + L.sn;
-  double* g = mb + L.g;
-  double* y = mb + L.y;
+  const double* J = W.J;
+  double* V = W.V;
+  double* w = W.w;
+  double* H = W.H;  // column-major, leading dimension m+1
+  double* cs = sh.cs;
+  double* sn = sh.sn;
+  double* g = sh.g;
+  double* y = sh.y;
   const int ldh = m + 1;
 
   // r0 = M^{-1} b  (x0 = 0)
+  // static problems have no mass term: the spectral radius of N approaches (or exceeds) 1 and
+  // the Neumann acceleration does not pay, so it is only used for the transient Jacobian
+  int pdeg = opt.is_static ? 0 : opt.poly_degree;
   for (int t = threadIdx.x; t < N; t += blockDim.x) x[t] = 0.0;
-  blk_apply_dinv<D>(E, Dinv, b, w);
   __syncthreads();
+  blk_apply_prec<D>(E, W, pdeg, b, w);
   double part = 0.0;
   for (int t = threadIdx.x; t < N; t += blockDim.x) part += w[t] * w[t];
   const double bnorm = sqrt(block_sum(part, sh));
@@ -194,21 +370,33 @@ __device__ int blk_gmres(const EngineDev& E, double* mb, const double* b, double
     *resid_out = 0.0;
     return 0;
   }
-  const double tol = fmax(opt.gmres_rel_tol * bnorm, opt.gmres_abs_tol);
+  double tol = fmax(opt.gmres_rel_tol * bnorm, opt.gmres_abs_tol);
   double beta = bnorm;
   double resid = bnorm;
   int iters = 0;
   bool first = true;
   while (true) {
     if (!first) {
+      if (pdeg > 0) {
+        // a full cycle did not converge: the Neumann series is not contracting for this
+        // matrix -- fall back to plain block-Jacobi (norms are re-based on the new M)
+        pdeg = 0;
+        __syncthreads();
+        blk_apply_prec<D>(E, W, 0, b, w);
+        double pb = 0.0;
+        for (int t = threadIdx.x; t < N; t += blockDim.x) pb += w[t] * w[t];
+        const double bn = sqrt(block_sum(pb, sh));
+        *bnorm_out = bn;
+        tol = fmax(opt.gmres_rel_tol * bn, opt.gmres_abs_tol);
+      }
       // explicit restart residual r = M^{-1} (b - J x)
       __syncthreads();
-      blk_spmv<D>(E, J, x, z);
+      // V_0 is free during a restart: use it for the unpreconditioned residual
+      blk_spmv<D>(E, J, x, V);
       __syncthreads();
-      for (int t = threadIdx.x; t < N; t += blockDim.x) z[t] = b[t] - z[t];
+      for (int t = threadIdx.x; t < N; t += blockDim.x) V[t] = b[t] - V[t];
       __syncthreads();
-      blk_apply_dinv<D>(E, Dinv, z, w);
-      __syncthreads();
+      blk_apply_prec<D>(E, W, pdeg, V, w);
       double p2 = 0.0;
       for (int t = threadIdx.x; t < N; t += blockDim.x) p2 += w[t] * w[t];
       beta = sqrt(block_sum(p2, sh));
@@ -227,29 +415,19 @@ __device__ int blk_gmres(const EngineDev& E, double* mb, const double* b, double
     bool done = false;
     for (; k < m && !done; ++k) {
       const double* vk = V + (size_t)k * N;
-      blk_spmv<D>(E, J, vk, z);
-      __syncthreads();
-      blk_apply_dinv<D>(E, Dinv, z, w);
-      __syncthreads();
+      long long t0 = clock64();
+      blk_apply_op<D>(E, W, pdeg, vk, w);
+      long long t1 = clock64();
       // CGS2: two classical Gram-Schmidt passes
       blk_dots(V, N, k + 1, w, sh.h);
       __syncthreads();
-      for (int t = threadIdx.x; t < N; t += blockDim.x) {
-        double s = w[t];
-        for (int j = 0; j <= k; ++j) s -= sh.h[j] * V[(size_t)j * N + t];
-        w[t] = s;
-      }
+      blk_project_out(V, N, k + 1, sh.h, w);
       __syncthreads();
       blk_dots(V, N, k + 1, w, sh.h2);
       __syncthreads();
-      double p2 = 0.0;
-      for (int t = threadIdx.x; t < N; t += blockDim.x) {
-        double s = w[t];
-        for (int j = 0; j <= k; ++j) s -= sh.h2[j] * V[(size_t)j * N + t];
-        w[t] = s;
-        p2 += s * s;
-      }
+      const double p2 = blk_project_out(V, N, k + 1, sh.h2, w);
       const double hk1 = sqrt(block_sum(p2, sh));
+      long long t2 = clock64();
       if (threadIdx.x == 0) {
         // Hessenberg column, previous Givens rotations, new rotation
         double* hc = H + (size_t)k * ldh;
@@ -279,13 +457,24 @@ __device__ int blk_gmres(const EngineDev& E, double* mb, const double* b, double
       }
       if (resid <= tol || iters >= opt.gmres_max_iter || hk1 == 0.0) done = true;
       __syncthreads();
+      if (threadIdx.x == 0) {
+        const long long t3 = clock64();
+        sh.cyc[1] += t1 - t0;
+        sh.cyc[2] += t2 - t1;
+        sh.cyc[3] += t3 - t2;
+      }
     }
-    // y = H^{-1} g  (k x k upper triangular), then x += V y
-    if (threadIdx.x == 0) {
+    long long t4 = clock64();
+    // y = H^{-1} g  (k x k upper triangular) by column-oriented back substitution on one
+    // warp (k dependent steps instead of k^2/2), then x += V y
+    if (threadIdx.x < 32) {
+      const int lane = threadIdx.x;
       for (int i = k - 1; i >= 0; --i) {
-        double s = g[i];
-        for (int j = i + 1; j < k; ++j) s -= H[(size_t)j * ldh + i] * y[j];
-        y[i] = s / H[(size_t)i * ldh + i];
+        const double yi = g[i] / H[(size_t)i * ldh + i];
+        __syncwarp();
+        for (int j = lane; j < i; j += 32) g[j] -= H[(size_t)i * ldh + j] * yi;
+        if (lane == 0) y[i] = yi;
+        __syncwarp();
       }
     }
     __syncthreads();
@@ -295,6 +484,7 @@ __device__ int blk_gmres(const EngineDev& E, double* mb, const double* b, double
       x[t] += s;
     }
     __syncthreads();
+    if (threadIdx.x == 0) sh.cyc[4] += clock64() - t4;
     if (resid <= tol || iters >= opt.gmres_max_iter) break;
   }
   *resid_out = resid;
@@ -320,14 +510,14 @@ __device__ __forceinline__ PropView member_props(const EngineDev& E, double* mb)
 // FenicsModel.solve_state1: Newton on F_u(u1) = 0 starting from the guess held in VF_U1,
 // then v1, a1 from the Newmark relations (App. C, Q2).
 template <int D>
-__device__ void blk_solve_solid(const EngineDev& E, double* mb, double dt, const SolverOpts& opt,
-                                BlockShared& sh) {
+__device__ void blk_solve_solid(const EngineDev& E, double* mb, const SolverWork& W, double dt,
+                                const SolverOpts& opt, BlockShared& sh) {
   const Layout& L = E.L;
   const int N = E.N, nn = E.mesh.nn;
   double* u1 = mb + L.off[VF_U1];
-  double* F = mb + L.off[VF_F];
-  double* Jv = mb + L.off[VF_J];
-  double* dx = mb + L.off[VF_DX];
+  double* F = W.F;
+  double* Jv = W.J;
+  double* dx = W.dx;
   double* info = mb + L.off[VF_INFO];
   const PropView pv = member_props<D>(E, mb);
   StateView sv;
@@ -345,6 +535,7 @@ __device__ void blk_solve_solid(const EngineDev& E, double* mb, double dt, const
   double gm_resid = 0.0, gm_bnorm = 0.0;
   while (true) {
     // residual (and, in the first iteration, the Jacobian in the same sweep)
+    const long long ta = clock64();
     double part = 0.0;
     for (int i = threadIdx.x; i < nn; i += blockDim.x) {
       double res[D];
@@ -358,6 +549,7 @@ __device__ void blk_solve_solid(const EngineDev& E, double* mb, double dt, const
       }
     }
     abs_err = sqrt(block_sum(part, sh));
+    if (threadIdx.x == 0) sh.cyc[0] += clock64() - ta;
     if (k == 0) r0 = abs_err;
     rel_err = (r0 > 0.0) ? abs_err / r0 : 0.0;
     if (abs_err <= opt.newton_abs_tol || rel_err <= opt.newton_rel_tol ||
@@ -370,9 +562,9 @@ __device__ void blk_solve_solid(const EngineDev& E, double* mb, double dt, const
       }
     }
     __syncthreads();
-    blk_compute_dinv<D>(E, Jv, mb + L.Dinv);
+    blk_compute_dinv<D>(E, Jv, W.Dinv);
     __syncthreads();
-    gm_iters += blk_gmres<D>(E, mb, F, dx, opt, sh, &gm_resid, &gm_bnorm);
+    gm_iters += blk_gmres<D>(E, W, F, dx, opt, sh, &gm_resid, &gm_bnorm);
     __syncthreads();
     for (int t = threadIdx.x; t < N; t += blockDim.x) u1[t] -= dx[t];
     __syncthreads();

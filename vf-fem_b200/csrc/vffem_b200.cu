@@ -410,26 +410,33 @@ __device__ void write_history(const EngineDev& E, double* mb, double* hist_state
   }
 }
 
-template <int D>
-__global__ void __launch_bounds__(512)
+template <int D, int NT>
+__global__ void __launch_bounds__(NT)
 member_kernel(EngineDev E, int member0, int mode, int nsteps, const double* __restrict__ dts,
               int nctrl, const double* __restrict__ controls, SolverOpts opt, double dt_single,
-              double* hist_state, double* hist_info, const double* lin_b, double* lin_x) {
+              double* hist_state, double* hist_info, const double* lin_b, double* lin_x,
+              int smem_flags) {
   __shared__ BlockShared sh;
+  extern __shared__ double dsm[];
   const int b = member0 + blockIdx.x;
   double* mb = E.members + (size_t)b * E.L.stride;
   const Layout& L = E.L;
   const int N = E.N, nn = E.mesh.nn;
+  // single solves keep the member's global J / F / dx (they are API-visible results)
+  const SolverWork W = make_work(E, mb, dsm, mode == MODE_INTEGRATE ? smem_flags : 0);
+  if (threadIdx.x < 8) sh.cyc[threadIdx.x] = 0;
+  const long long t_start = clock64();
+  __syncthreads();
 
   if (mode == MODE_SOLVE_SOLID) {
-    blk_solve_solid<D>(E, mb, dt_single, opt, sh);
+    blk_solve_solid<D>(E, mb, W, dt_single, opt, sh);
     return;
   }
   if (mode == MODE_LINEAR_SOLVE) {
     double resid, bnorm;
-    blk_compute_dinv<D>(E, mb + L.off[VF_J], mb + L.Dinv);
+    blk_compute_dinv<D>(E, W.J, W.Dinv);
     __syncthreads();
-    const int it = blk_gmres<D>(E, mb, lin_b, lin_x, opt, sh, &resid, &bnorm);
+    const int it = blk_gmres<D>(E, W, lin_b, lin_x, opt, sh, &resid, &bnorm);
     if (threadIdx.x == 0) {
       double* info = mb + L.off[VF_INFO];
       info[INFO_GMRES_ITERS] = double(it);
@@ -490,8 +497,10 @@ member_kernel(EngineDev E, int member0, int mode, int nsteps, const double* __re
     for (int k = threadIdx.x; k < E.n_fsip; k += blockDim.x) p1[E.fsip_solid[k]] = p0[E.fsip_fluid[k]];
     __syncthreads();
 
-    blk_solve_solid<D>(E, mb, dt, opt, sh);
+    blk_solve_solid<D>(E, mb, W, dt, opt, sh);
+    const long long tf = clock64();
     blk_fluid<D>(E, mb, sh);
+    if (threadIdx.x == 0) sh.cyc[5] += clock64() - tf;
 
     // state0 <- state1 (forward.py:184)
     for (int t = threadIdx.x; t < N; t += blockDim.x) {
@@ -504,6 +513,11 @@ member_kernel(EngineDev E, int member0, int mode, int nsteps, const double* __re
     __syncthreads();
     write_history<D>(E, mb, hist_state, hist_info, hrow0 + n + 1, false);
   }
+  if (threadIdx.x == 0) {
+    double* info = mb + L.off[VF_INFO];
+    for (int q = 0; q < 6; ++q) info[8 + q] = double(sh.cyc[q]);
+    info[14] = double(clock64() - t_start);
+  }
 }
 
 }  // namespace vf
@@ -513,7 +527,7 @@ member_kernel(EngineDev E, int member0, int mode, int nsteps, const double* __re
 using namespace vf;
 
 // layout pinned for the ctypes binding (femvf_b200/_cabi.py, tests/test_cabi.py)
-static_assert(sizeof(vf_solver_opts) == 48, "vf_solver_opts layout changed");
+static_assert(sizeof(vf_solver_opts) == 56, "vf_solver_opts layout changed");
 static_assert(VF_ARRAY_COUNT == 26, "vf_array_id changed: update _cabi.ARRAY_IDS");
 
 struct vf_engine {
@@ -663,6 +677,7 @@ SolverOpts to_opts(const vf_solver_opts* o) {
     s.gmres_abs_tol = o->gmres_abs_tol;
     s.gmres_max_iter = o->gmres_max_iter;
     s.is_static = o->is_static;
+    s.poly_degree = std::min(std::max(o->poly_degree, 0), 8);
   } else {
     s.newton_abs_tol = 1e-8;   // solverconst.py:1-6
     s.newton_rel_tol = 1e-10;
@@ -671,6 +686,7 @@ SolverOpts to_opts(const vf_solver_opts* o) {
     s.gmres_abs_tol = 0.0;
     s.gmres_max_iter = 2000;
     s.is_static = 0;
+    s.poly_degree = 3;
   }
   return s;
 }
@@ -680,9 +696,36 @@ int launch_member(vf_engine* e, int member0, int count, int mode, int nsteps, co
                   int nctrl, const double* controls, const SolverOpts& opt, double dt_single,
                   double* hist_state, double* hist_info, const double* lin_b, double* lin_x,
                   cudaStream_t st) {
-  member_kernel<D><<<count, e->member_threads, 0, st>>>(e->dev, member0, mode, nsteps, dts, nctrl,
-                                                       controls, opt, dt_single, hist_state,
-                                                       hist_info, lin_b, lin_x);
+  // place the solver working set in shared memory when it fits (time loop only)
+  int flags = 0;
+  size_t smem = 0;
+  if (mode == MODE_INTEGRATE) {
+    const size_t N = e->dev.N, budget = 200 * 1024;
+    auto pad = [](size_t n) { return (n + 1) & ~size_t(1); };
+    const size_t small = 8 * (5 * pad(N) + pad((size_t)e->desc.nn * D * D));
+    const size_t basis = 8 * pad((size_t)(e->dev.restart + 1) * N);
+    const size_t jac = 8 * pad((size_t)e->dev.nnz);
+    const size_t hess = 8 * pad((size_t)(e->dev.restart + 1) * e->dev.restart);
+    if (small <= budget) { flags |= 1; smem += small; }
+    if ((flags & 1) && smem + hess <= budget) { flags |= 8; smem += hess; }
+    if ((flags & 1) && smem + basis <= budget) { flags |= 2; smem += basis; }
+    if ((flags & 2) && smem + jac <= budget) { flags |= 4; smem += jac; }
+    static const char* env = getenv("VF_MEMBER_SMEM");
+    if (env && atoi(env) == 0) { flags = 0; smem = 0; }
+  }
+  if (e->member_threads == 256) {
+    VF_CUDA(cudaFuncSetAttribute(member_kernel<D, 256>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    member_kernel<D, 256><<<count, 256, smem, st>>>(e->dev, member0, mode, nsteps, dts, nctrl,
+                                                   controls, opt, dt_single, hist_state,
+                                                   hist_info, lin_b, lin_x, flags);
+  } else {
+    VF_CUDA(cudaFuncSetAttribute(member_kernel<D, 512>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    member_kernel<D, 512><<<count, 512, smem, st>>>(e->dev, member0, mode, nsteps, dts, nctrl,
+                                                   controls, opt, dt_single, hist_state,
+                                                   hist_info, lin_b, lin_x, flags);
+  }
   e->launches += 1;
   VF_CUDA(cudaGetLastError());
   return 0;

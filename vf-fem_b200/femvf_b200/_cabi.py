@@ -50,6 +50,7 @@ class SolverOpts(C.Structure):
         ('gmres_rel_tol', C.c_double), ('gmres_abs_tol', C.c_double),
         ('gmres_max_iter', C.c_int32),
         ('is_static', C.c_int32),
+        ('poly_degree', C.c_int32), ('reserved', C.c_int32),
     ]
 
 

@@ -42,6 +42,7 @@ def make_solver_opts(options: Optional[dict] = None, is_static: bool = False) ->
         int(prm['maximum_iterations']),
         float(lin['gmres_relative_tolerance']), float(lin['gmres_absolute_tolerance']),
         int(lin['gmres_maximum_iterations']), int(bool(is_static)),
+        int(lin['polynomial_degree']), 0,
     )
 
 

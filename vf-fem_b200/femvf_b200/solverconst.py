@@ -15,4 +15,6 @@ DEFAULT_LINEAR_SOLVER_PRM = {
     'gmres_relative_tolerance': 1e-13,
     'gmres_absolute_tolerance': 0.0,
     'gmres_maximum_iterations': 4000,
+    # Neumann-series degree of the polynomial acceleration of block-Jacobi (0 = plain)
+    'polynomial_degree': 3,
 }
