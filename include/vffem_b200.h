@@ -142,6 +142,25 @@ int vf_assemble(vf_engine* e, int member, int flags, double dt, int is_static, v
 /* y = J_uu x for `member` (PETSc MatMult; transient.py:488-489).  x, y: device, N doubles. */
 int vf_spmv(vf_engine* e, int member, const double* x_dev, double* y_dev, void* stream);
 
+/* Grid-wide Krylov building blocks for one large mesh or one partition of it (the PETSc KSP
+ * internals behind dfn.solve, transient.py:487): the same products on a node-row range, the
+ * block-Jacobi preconditioner, V^T w for a set of basis vectors (fixed-order reductions:
+ * bit-reproducible), w -= V h, and y = alpha x + beta y.  femvf_b200/distributed.py drives a
+ * GMRES over them, with NCCL halo exchange / all-reduce between partitions.
+ * vf_multidot needs a scratch buffer of at least 592 * nvec doubles. */
+int vf_spmv_rows(vf_engine* e, int member, const double* x_dev, double* y_dev, int node0,
+                 int node1, void* stream);
+int vf_block_jacobi_setup(vf_engine* e, int member, int node0, int node1, void* stream);
+int vf_block_jacobi_apply(vf_engine* e, int member, const double* r_dev, double* z_dev, int node0,
+                          int node1, void* stream);
+int vf_multidot(vf_engine* e, const double* V_dev, size_t ldv, int nvec, const double* w_dev,
+                size_t n, double* out_dev, double* scratch_dev, size_t scratch_count,
+                void* stream);
+int vf_multi_axpy(vf_engine* e, const double* V_dev, size_t ldv, int nvec, const double* h_dev,
+                  double* w_dev, size_t n, void* stream);
+int vf_axpby(vf_engine* e, double alpha, const double* x_dev, double beta, double* y_dev, size_t n,
+             void* stream);
+
 /* Solve J_uu x = b with the block-Jacobi preconditioned GMRES that stands in for the PETSc
  * LU of dfn.solve(A, x, b, 'petsc') (transient.py:487).  b, x: device, N doubles.
  * info_host[0] = iterations, [1] = final residual norm, [2] = ||b||. */

@@ -296,11 +296,12 @@ __global__ void facet_bc_kernel(EngineDev E, int member, double dt, int is_stati
 // y = J x.  L lanes cooperate on one node block row (d scalar rows share their columns).
 template <int D, int LANES>
 __global__ void spmv_kernel(MeshView m, const double* __restrict__ J,
-                            const double* __restrict__ x, double* __restrict__ y) {
+                            const double* __restrict__ x, double* __restrict__ y, int node0,
+                            int node1) {
   const int gt = blockIdx.x * blockDim.x + threadIdx.x;
-  const int node = gt / LANES;
+  const int node = node0 + gt / LANES;
   const int lane = gt % LANES;
-  const bool valid = node < m.nn;
+  const bool valid = node < node1;
   double acc[D];
 #pragma unroll
   for (int a = 0; a < D; ++a) acc[a] = 0.0;
@@ -336,6 +337,120 @@ __global__ void spmv_kernel(MeshView m, const double* __restrict__ J,
 #pragma unroll
     for (int a = 0; a < D; ++a) y[D * node + a] = acc[a];
   }
+}
+
+
+// ---- grid-wide Krylov building blocks (single large mesh, optionally one partition of it) ----
+
+// Block-Jacobi inverse of the d x d diagonal blocks for node rows [node0, node1)
+template <int D>
+__global__ void block_jacobi_kernel(MeshView m, const double* __restrict__ J,
+                                    double* __restrict__ Dinv, int node0, int node1) {
+  const int i = node0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= node1) return;
+  const int b0 = m.brptr[i], deg = m.brptr[i + 1] - b0;
+  const int self = find_slot(m.bcol + b0, deg, i);
+  const double* blk = J + (size_t)D * D * b0;
+  double A[D][D];
+  for (int a = 0; a < D; ++a)
+    for (int c = 0; c < D; ++c) A[a][c] = blk[a * D * deg + self * D + c];
+  double* o = Dinv + (size_t)D * D * i;
+  if constexpr (D == 2) {
+    const double inv = 1.0 / (A[0][0] * A[1][1] - A[0][1] * A[1][0]);
+    o[0] = A[1][1] * inv;
+    o[1] = -A[0][1] * inv;
+    o[2] = -A[1][0] * inv;
+    o[3] = A[0][0] * inv;
+  } else {
+    double c0[3], c1[3], c2[3];
+    cross3(A[1], A[2], c0);
+    cross3(A[2], A[0], c1);
+    cross3(A[0], A[1], c2);
+    const double inv = 1.0 / (A[0][0] * c0[0] + A[0][1] * c0[1] + A[0][2] * c0[2]);
+    for (int k = 0; k < 3; ++k) {
+      o[k * 3 + 0] = c0[k] * inv;
+      o[k * 3 + 1] = c1[k] * inv;
+      o[k * 3 + 2] = c2[k] * inv;
+    }
+  }
+}
+
+// z = Dinv r on DOFs of node rows [node0, node1)
+template <int D>
+__global__ void apply_block_jacobi_kernel(const double* __restrict__ Dinv,
+                                          const double* __restrict__ r, double* __restrict__ z,
+                                          int node0, int node1) {
+  const int i = node0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= node1) return;
+  const double* o = Dinv + (size_t)D * D * i;
+  double v[D];
+#pragma unroll
+  for (int c = 0; c < D; ++c) v[c] = r[D * i + c];
+#pragma unroll
+  for (int a = 0; a < D; ++a) {
+    double t = 0.0;
+#pragma unroll
+    for (int c = 0; c < D; ++c) t += o[a * D + c] * v[c];
+    z[D * i + a] = t;
+  }
+}
+
+// partial[b][j] = sum over the block's chunk of V_j[i] w[i]; fixed-order reductions so the
+// result is bit-reproducible; a second kernel adds the partials in block order.
+constexpr int kDotBlock = 256;
+__global__ void multidot_partial_kernel(const double* __restrict__ V, size_t ldv, int nvec,
+                                        const double* __restrict__ w, size_t n,
+                                        double* __restrict__ partial) {
+  __shared__ double red[kDotBlock / 32];
+  const size_t chunk = (n + gridDim.x - 1) / gridDim.x;
+  const size_t lo = (size_t)blockIdx.x * chunk;
+  const size_t hi = lo + chunk < n ? lo + chunk : n;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int j = 0; j < nvec; ++j) {
+    const double* vj = V + (size_t)j * ldv;
+    double s = 0.0;
+    for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) s += vj[i] * w[i];
+    s = warp_sum(s);
+    if (lane == 0) red[wid] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int q = 0; q < kDotBlock / 32; ++q) t += red[q];
+      partial[(size_t)blockIdx.x * nvec + j] = t;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void multidot_final_kernel(const double* __restrict__ partial, int nblocks, int nvec,
+                                      double* __restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nvec) return;
+  double t = 0.0;
+  for (int b = 0; b < nblocks; ++b) t += partial[(size_t)b * nvec + j];
+  out[j] = t;
+}
+
+// w -= sum_j h[j] V_j   (h on the device)
+__global__ void multi_axpy_kernel(const double* __restrict__ V, size_t ldv, int nvec,
+                                  const double* __restrict__ h, double* __restrict__ w, size_t n) {
+  extern __shared__ double hs[];
+  for (int j = threadIdx.x; j < nvec; j += blockDim.x) hs[j] = h[j];
+  __syncthreads();
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int j = 0; j < nvec; ++j) s += hs[j] * V[(size_t)j * ldv + i];
+    w[i] -= s;
+  }
+}
+
+// y = alpha x + beta y
+__global__ void axpby_kernel(double alpha, const double* __restrict__ x, double beta,
+                             double* __restrict__ y, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x)
+    y[i] = alpha * x[i] + (beta == 0.0 ? 0.0 : beta * y[i]);
 }
 
 __global__ void fluid_kernel(EngineDev E, int member0) {
@@ -410,8 +525,8 @@ __device__ void write_history(const EngineDev& E, double* mb, double* hist_state
   }
 }
 
-template <int D, int NT>
-__global__ void __launch_bounds__(NT)
+template <int D, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
 member_kernel(EngineDev E, int member0, int mode, int nsteps, const double* __restrict__ dts,
               int nctrl, const double* __restrict__ controls, SolverOpts opt, double dt_single,
               double* hist_state, double* hist_info, const double* lin_b, double* lin_x,
@@ -713,19 +828,25 @@ int launch_member(vf_engine* e, int member0, int count, int mode, int nsteps, co
     static const char* env = getenv("VF_MEMBER_SMEM");
     if (env && atoi(env) == 0) { flags = 0; smem = 0; }
   }
+#define VF_LAUNCH_MEMBER(NT_, MB_)                                                                \
+  do {                                                                                            \
+    VF_CUDA(cudaFuncSetAttribute(member_kernel<D, NT_, MB_>,                                      \
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
+    member_kernel<D, NT_, MB_><<<count, NT_, smem, st>>>(e->dev, member0, mode, nsteps, dts,      \
+                                                        nctrl, controls, opt, dt_single,          \
+                                                        hist_state, hist_info, lin_b, lin_x,      \
+                                                        flags);                                   \
+  } while (0)
+  // two resident CTAs per SM when the working set leaves room for it and there are enough
+  // members to use them (ensembles); one fat CTA otherwise
+  const bool two_per_sm = count > 148 && smem <= 100 * 1024;
   if (e->member_threads == 256) {
-    VF_CUDA(cudaFuncSetAttribute(member_kernel<D, 256>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    member_kernel<D, 256><<<count, 256, smem, st>>>(e->dev, member0, mode, nsteps, dts, nctrl,
-                                                   controls, opt, dt_single, hist_state,
-                                                   hist_info, lin_b, lin_x, flags);
+    if (two_per_sm) VF_LAUNCH_MEMBER(256, 2);
+    else VF_LAUNCH_MEMBER(256, 1);
   } else {
-    VF_CUDA(cudaFuncSetAttribute(member_kernel<D, 512>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    member_kernel<D, 512><<<count, 512, smem, st>>>(e->dev, member0, mode, nsteps, dts, nctrl,
-                                                   controls, opt, dt_single, hist_state,
-                                                   hist_info, lin_b, lin_x, flags);
+    VF_LAUNCH_MEMBER(512, 1);
   }
+#undef VF_LAUNCH_MEMBER
   e->launches += 1;
   VF_CUDA(cudaGetLastError());
   return 0;
@@ -1022,22 +1143,106 @@ int vf_assemble(vf_engine* e, int member, int flags, double dt, int is_static, v
   return 0;
 }
 
-int vf_spmv(vf_engine* e, int member, const double* x_dev, double* y_dev, void* stream) {
+int vf_spmv_rows(vf_engine* e, int member, const double* x_dev, double* y_dev, int node0,
+                 int node1, void* stream) {
   if (!e) return fail("null engine");
   if (member < 0 || member >= e->desc.n_members) return fail("member out of range");
+  if (node0 < 0 || node1 > e->desc.nn || node0 > node1) return fail("node range out of bounds");
+  if (node0 == node1) return 0;
   cudaStream_t st = as_stream(stream);
   const double* J = member_array(e, VF_J, member);
-  const int nn = e->desc.nn;
+  const int nrows = node1 - node0;
   const int block = 256;
   if (e->desc.dim == 2) {
     constexpr int LN = 8;
-    const int grid = (int)(((size_t)nn * LN + block - 1) / block);
-    spmv_kernel<2, LN><<<grid, block, 0, st>>>(e->dev.mesh, J, x_dev, y_dev);
+    const int grid = (int)(((size_t)nrows * LN + block - 1) / block);
+    spmv_kernel<2, LN><<<grid, block, 0, st>>>(e->dev.mesh, J, x_dev, y_dev, node0, node1);
   } else {
     constexpr int LN = 16;
-    const int grid = (int)(((size_t)nn * LN + block - 1) / block);
-    spmv_kernel<3, LN><<<grid, block, 0, st>>>(e->dev.mesh, J, x_dev, y_dev);
+    const int grid = (int)(((size_t)nrows * LN + block - 1) / block);
+    spmv_kernel<3, LN><<<grid, block, 0, st>>>(e->dev.mesh, J, x_dev, y_dev, node0, node1);
   }
+  e->launches += 1;
+  VF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int vf_spmv(vf_engine* e, int member, const double* x_dev, double* y_dev, void* stream) {
+  if (!e) return fail("null engine");
+  return vf_spmv_rows(e, member, x_dev, y_dev, 0, e->desc.nn, stream);
+}
+
+int vf_block_jacobi_setup(vf_engine* e, int member, int node0, int node1, void* stream) {
+  if (!e) return fail("null engine");
+  if (member < 0 || member >= e->desc.n_members) return fail("member out of range");
+  if (node0 < 0 || node1 > e->desc.nn || node0 >= node1) return fail("node range out of bounds");
+  cudaStream_t st = as_stream(stream);
+  const double* J = member_array(e, VF_J, member);
+  double* Dinv = e->dev.members + (size_t)member * e->dev.L.stride + e->dev.L.Dinv;
+  const int block = 128, grid = (node1 - node0 + block - 1) / block;
+  if (e->desc.dim == 2)
+    block_jacobi_kernel<2><<<grid, block, 0, st>>>(e->dev.mesh, J, Dinv, node0, node1);
+  else
+    block_jacobi_kernel<3><<<grid, block, 0, st>>>(e->dev.mesh, J, Dinv, node0, node1);
+  e->launches += 1;
+  VF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int vf_block_jacobi_apply(vf_engine* e, int member, const double* r_dev, double* z_dev, int node0,
+                          int node1, void* stream) {
+  if (!e) return fail("null engine");
+  if (member < 0 || member >= e->desc.n_members) return fail("member out of range");
+  if (node0 < 0 || node1 > e->desc.nn || node0 >= node1) return fail("node range out of bounds");
+  cudaStream_t st = as_stream(stream);
+  const double* Dinv = e->dev.members + (size_t)member * e->dev.L.stride + e->dev.L.Dinv;
+  const int block = 256, grid = (node1 - node0 + block - 1) / block;
+  if (e->desc.dim == 2)
+    apply_block_jacobi_kernel<2><<<grid, block, 0, st>>>(Dinv, r_dev, z_dev, node0, node1);
+  else
+    apply_block_jacobi_kernel<3><<<grid, block, 0, st>>>(Dinv, r_dev, z_dev, node0, node1);
+  e->launches += 1;
+  VF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int vf_multidot(vf_engine* e, const double* V_dev, size_t ldv, int nvec, const double* w_dev,
+                size_t n, double* out_dev, double* scratch_dev, size_t scratch_count,
+                void* stream) {
+  if (!e) return fail("null engine");
+  if (nvec <= 0 || n == 0) return fail("vf_multidot: empty problem");
+  cudaStream_t st = as_stream(stream);
+  int nblocks = (int)std::min<size_t>(148 * 4, (n + 2047) / 2048);
+  nblocks = std::max(nblocks, 1);
+  if (scratch_count < (size_t)nblocks * nvec) return fail("vf_multidot: scratch too small");
+  multidot_partial_kernel<<<nblocks, kDotBlock, 0, st>>>(V_dev, ldv, nvec, w_dev, n, scratch_dev);
+  multidot_final_kernel<<<(nvec + 63) / 64, 64, 0, st>>>(scratch_dev, nblocks, nvec, out_dev);
+  e->launches += 2;
+  VF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int vf_multi_axpy(vf_engine* e, const double* V_dev, size_t ldv, int nvec, const double* h_dev,
+                  double* w_dev, size_t n, void* stream) {
+  if (!e) return fail("null engine");
+  if (nvec <= 0 || n == 0) return 0;
+  cudaStream_t st = as_stream(stream);
+  const int block = 256;
+  const int grid = (int)std::min<size_t>(148 * 8, (n + block - 1) / block);
+  multi_axpy_kernel<<<grid, block, sizeof(double) * nvec, st>>>(V_dev, ldv, nvec, h_dev, w_dev, n);
+  e->launches += 1;
+  VF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int vf_axpby(vf_engine* e, double alpha, const double* x_dev, double beta, double* y_dev, size_t n,
+             void* stream) {
+  if (!e) return fail("null engine");
+  if (n == 0) return 0;
+  cudaStream_t st = as_stream(stream);
+  const int block = 256;
+  const int grid = (int)std::min<size_t>(148 * 8, (n + block - 1) / block);
+  axpby_kernel<<<grid, block, 0, st>>>(alpha, x_dev, beta, y_dev, n);
   e->launches += 1;
   VF_CUDA(cudaGetLastError());
   return 0;

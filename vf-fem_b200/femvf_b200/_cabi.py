@@ -65,7 +65,8 @@ EXPORTED_SYMBOLS = [
     'vf_last_error', 'vf_device_count', 'vf_arena_bytes', 'vf_create', 'vf_destroy',
     'vf_array_info', 'vf_upload', 'vf_download', 'vf_csr_pattern', 'vf_nnz', 'vf_assemble',
     'vf_spmv', 'vf_linear_solve', 'vf_solve_state1', 'vf_fluid_solve', 'vf_integrate',
-    'vf_integrate_host', 'vf_launch_count',
+    'vf_integrate_host', 'vf_launch_count', 'vf_spmv_rows', 'vf_block_jacobi_setup',
+    'vf_block_jacobi_apply', 'vf_multidot', 'vf_multi_axpy', 'vf_axpby',
 ]
 
 _lib = None
@@ -98,6 +99,17 @@ def load_library() -> C.CDLL:
     lib.vf_nnz.restype = C.c_int64
     lib.vf_assemble.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_void_p]
     lib.vf_spmv.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.vf_spmv_rows.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                 C.c_void_p]
+    lib.vf_block_jacobi_setup.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.vf_block_jacobi_apply.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                          C.c_int, C.c_void_p]
+    lib.vf_multidot.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p,
+                                C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.vf_multi_axpy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p,
+                                  C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.vf_axpby.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_double, C.c_void_p,
+                             C.c_size_t, C.c_void_p]
     lib.vf_linear_solve.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                     C.POINTER(SolverOpts), C.c_void_p, C.c_void_p]
     lib.vf_solve_state1.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double,

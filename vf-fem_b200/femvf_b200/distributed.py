@@ -1,0 +1,306 @@
+"""
+Mesh-partitioned assembly and Krylov solve over several GPUs (SURVEY.md section 8e,
+BASELINE.json configs[4]).
+
+The reference is strictly serial (``/root/reference/src/femvf/models/fsi.py:38-39``); this
+module is how its PETSc solve (``models/transient.py:487``) scales past one GPU.
+
+Partitioning: the vertices (ordered along a space-filling curve, ``meshgen.morton_order``)
+are split into ``world`` contiguous ranges; rank r owns the rows of its vertices.  It holds the
+cells touching an owned vertex and the ghost vertices they bring along, so
+
+* **assembly needs no communication** (owner-computes rows; ghost cells are duplicated);
+* an **SpMV needs one halo exchange** of the ghost entries of x (``d`` doubles per interface
+  vertex, one NCCL send/recv per neighbouring rank), issued before the local product;
+* the **Krylov reductions** (Gram-Schmidt coefficients, norms) are one small all-reduce each.
+
+One process per GPU; ``torch.distributed`` (NCCL over NVLink on the GPU box, gloo in the CPU
+tests of the index logic) is the plumbing, the numerics are the ``vf_*`` kernels.
+With ``world == 1`` the same code is the single-GPU grid-wide GMRES for large meshes.
+"""
+
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def partition_starts(nn: int, world: int) -> np.ndarray:
+    base, rem = divmod(nn, world)
+    sizes = np.full(world, base, dtype=np.int64)
+    sizes[:rem] += 1
+    return np.concatenate([[0], np.cumsum(sizes)])
+
+
+class LocalPartition:
+    """Rank-local sub-mesh: owned vertices first (global order), then ghosts (ascending)."""
+
+    def __init__(self, coords, cells, pf_cell, pf_opp, fixed_dofs, rank: int, world: int):
+        coords = np.asarray(coords)
+        cells = np.asarray(cells, dtype=np.int64)
+        nn, d = coords.shape
+        self.dim, self.rank, self.world = d, rank, world
+        self.starts = partition_starts(nn, world)
+        n0, n1 = int(self.starts[rank]), int(self.starts[rank + 1])
+        self.n0, self.n1, self.n_own = n0, n1, n1 - n0
+        owned_cell = ((cells >= n0) & (cells < n1)).any(axis=1)
+        self.cell_ids = np.nonzero(owned_cell)[0]
+        lcells_g = cells[self.cell_ids]
+        nodes = np.unique(lcells_g)
+        ghosts = nodes[(nodes < n0) | (nodes >= n1)]
+        self.ghost_global = ghosts  # ascending global ids
+        self.local_nodes = np.concatenate([np.arange(n0, n1), ghosts])
+        g2l = -np.ones(nn, dtype=np.int64)
+        g2l[self.local_nodes] = np.arange(len(self.local_nodes))
+        self.g2l = g2l
+        self.coords = coords[self.local_nodes]
+        self.cells = g2l[lcells_g]
+        # pressure facets whose parent cell is local
+        pf_cell = np.asarray(pf_cell, dtype=np.int64)
+        cell_g2l = -np.ones(len(cells), dtype=np.int64)
+        cell_g2l[self.cell_ids] = np.arange(len(self.cell_ids))
+        keep = cell_g2l[pf_cell] >= 0
+        self.pf_cell = cell_g2l[pf_cell[keep]]
+        self.pf_opp = np.asarray(pf_opp, dtype=np.int64)[keep]
+        fixed_dofs = np.asarray(fixed_dofs, dtype=np.int64)
+        fnode, fcomp = fixed_dofs // d, fixed_dofs % d
+        fk = g2l[fnode] >= 0
+        self.fixed_dofs = d * g2l[fnode[fk]] + fcomp[fk]
+
+    @property
+    def n_local(self) -> int:
+        return len(self.local_nodes)
+
+    def local_vector(self, x_global: np.ndarray) -> np.ndarray:
+        d = self.dim
+        return np.ascontiguousarray(x_global.reshape(-1, d)[self.local_nodes].reshape(-1))
+
+    def local_cell_field(self, f_global: np.ndarray) -> np.ndarray:
+        return np.ascontiguousarray(f_global[self.cell_ids])
+
+
+class HaloPlan:
+    """Who sends which owned entries to whom so that every rank's ghost entries get filled."""
+
+    def __init__(self, part: LocalPartition, group=None):
+        self.part = part
+        self.group = group
+        world, rank = part.world, part.rank
+        owner = np.searchsorted(part.starts, part.ghost_global, side='right') - 1
+        # ghosts are stored after the owned vertices in ascending global order, hence grouped by
+        # owner already
+        self.recv_from = {}
+        for r in np.unique(owner):
+            sel = np.nonzero(owner == r)[0]
+            self.recv_from[int(r)] = (part.n_own + sel, part.ghost_global[sel])
+        if world > 1 and dist.is_available() and dist.is_initialized():
+            wanted = {r: g.tolist() for r, (_, g) in self.recv_from.items()}
+            gathered = [None] * world
+            dist.all_gather_object(gathered, wanted, group=group)
+            self.send_to = {}
+            for r, req in enumerate(gathered):
+                if r != rank and rank in req and len(req[rank]):
+                    self.send_to[r] = np.asarray(req[rank], dtype=np.int64) - part.n0
+        else:
+            # no process group (single rank, or ranks emulated one after another in a test):
+            # assembly works, halo exchange is unavailable
+            self.send_to = {}
+
+    def to_device(self, device):
+        d = self.part.dim
+        comp = np.arange(d)
+        self._send_idx = {r: torch.as_tensor((d * idx[:, None] + comp).reshape(-1), device=device)
+                          for r, idx in self.send_to.items()}
+        self._recv_idx = {r: torch.as_tensor((d * loc[:, None] + comp).reshape(-1), device=device)
+                          for r, (loc, _) in self.recv_from.items()}
+        return self
+
+    def exchange(self, x_local: torch.Tensor):
+        """Fill the ghost entries of ``x_local`` (owned entries must be current)."""
+        if self.part.world == 1:
+            return
+        ops, bufs = [], []
+        for r, idx in self._send_idx.items():
+            buf = x_local[idx].contiguous()
+            ops.append(dist.P2POp(dist.isend, buf, r, group=self.group))
+            bufs.append(buf)
+        recvs = []
+        for r, idx in self._recv_idx.items():
+            buf = torch.empty(idx.numel(), dtype=x_local.dtype, device=x_local.device)
+            ops.append(dist.P2POp(dist.irecv, buf, r, group=self.group))
+            recvs.append((idx, buf))
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        for idx, buf in recvs:
+            x_local[idx] = buf
+
+    @property
+    def halo_bytes(self) -> int:
+        d = self.part.dim
+        return 8 * d * sum(len(v) for v in self.send_to.values())
+
+
+class GridGMRES:
+    """
+    Left block-Jacobi preconditioned restarted GMRES(m) with CGS2 over the rows owned by this
+    rank.  Host-side control flow (as PETSc's KSP), device kernels for every O(N) operation,
+    one halo exchange per operator application and one small all-reduce per reduction.
+    """
+
+    def __init__(self, engine, n_own_nodes: int, halo: Optional[HaloPlan] = None,
+                 restart: int = 30, group=None):
+        self.e = engine
+        self.d = engine.dim
+        self.n_own = n_own_nodes
+        self.nown = self.d * n_own_nodes          # owned DOFs
+        self.nloc = engine.N                      # owned + ghost DOFs
+        self.halo = halo
+        self.group = group
+        self.m = restart
+        dev = engine.device
+        f64 = torch.float64
+        self.V = torch.zeros((restart + 1, self.nown), dtype=f64, device=dev)
+        self.xl = torch.zeros(self.nloc, dtype=f64, device=dev)   # operand with ghosts
+        self.w = torch.zeros(self.nown, dtype=f64, device=dev)
+        self.t = torch.zeros(self.nown, dtype=f64, device=dev)
+        self.h = torch.zeros(restart + 2, dtype=f64, device=dev)
+        self.scratch = torch.zeros(592 * (restart + 2), dtype=f64, device=dev)
+        self.distributed = halo is not None and halo.part.world > 1
+        self.spmv_count = 0
+
+    def _allreduce(self, t: torch.Tensor):
+        if self.distributed:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+
+    def apply(self, v_own: torch.Tensor, out_own: torch.Tensor):
+        """out = Dinv (J v) on the owned rows; v's ghost entries are fetched first."""
+        self.xl[:self.nown].copy_(v_own)
+        if self.distributed:
+            self.halo.exchange(self.xl)
+        self.e.spmv_rows(self.xl, self.t, 0, self.n_own)
+        self.e.block_jacobi_apply(self.t, out_own, 0, self.n_own)
+        self.spmv_count += 1
+
+    def dots(self, nvec: int, w: torch.Tensor) -> torch.Tensor:
+        out = self.h[:nvec]
+        self.e.multidot(self.V, nvec, w, self.nown, out, self.scratch)
+        self._allreduce(out)
+        return out
+
+    def norm(self, w: torch.Tensor) -> float:
+        out = self.h[self.m + 1:self.m + 2]
+        self.e.multidot(w.view(1, -1), 1, w, self.nown, out, self.scratch)
+        self._allreduce(out)
+        return float(torch.sqrt(out)[0].item())
+
+    def solve(self, b_own: torch.Tensor, x_own: torch.Tensor, rtol: float = 1e-12,
+              atol: float = 0.0, maxiter: int = 2000):
+        """Solve J x = b on the owned rows; ``x_own`` is overwritten (initial guess 0)."""
+        e, m, n = self.e, self.m, self.nown
+        e.block_jacobi_setup(0, self.n_own)
+        x_own.zero_()
+        w, V = self.w, self.V
+        e.block_jacobi_apply(b_own, w, 0, self.n_own)
+        bnorm = self.norm(w)
+        info = {'iterations': 0, 'bnorm': bnorm, 'residual': bnorm, 'restarts': 0}
+        if bnorm == 0.0:
+            return info
+        tol = max(rtol * bnorm, atol)
+        beta = bnorm
+        iters = 0
+        first = True
+        H = np.zeros((m + 1, m))
+        while True:
+            if not first:
+                self.apply(x_own, w)                    # w = Dinv J x
+                e.block_jacobi_apply(b_own, self.t, 0, self.n_own)
+                e.axpby(1.0, self.t, -1.0, w, n)        # w = Dinv b - Dinv J x
+                beta = self.norm(w)
+                info['restarts'] += 1
+                if beta <= tol:
+                    info['residual'] = beta
+                    break
+            first = False
+            e.axpby(1.0 / beta, w, 0.0, V[0], n)
+            g = np.zeros(m + 1)
+            g[0] = beta
+            cs, sn = np.zeros(m), np.zeros(m)
+            k, resid = 0, beta
+            done = False
+            while k < m and not done:
+                self.apply(V[k], w)
+                h1 = self.dots(k + 1, w).clone()
+                e.multi_axpy(V, k + 1, h1, w, n)
+                h2 = self.dots(k + 1, w).clone()
+                e.multi_axpy(V, k + 1, h2, w, n)
+                hk1 = self.norm(w)
+                hc = (h1 + h2).cpu().numpy()
+                col = np.zeros(m + 1)
+                col[:k + 1] = hc
+                for j in range(k):
+                    t0 = cs[j] * col[j] + sn[j] * col[j + 1]
+                    col[j + 1] = -sn[j] * col[j] + cs[j] * col[j + 1]
+                    col[j] = t0
+                denom = np.hypot(col[k], hk1)
+                c, s_ = (1.0, 0.0) if denom == 0 else (col[k] / denom, hk1 / denom)
+                cs[k], sn[k] = c, s_
+                col[k] = c * col[k] + s_ * hk1
+                g[k + 1] = -s_ * g[k]
+                g[k] = c * g[k]
+                H[:, k] = col
+                resid = abs(g[k + 1])
+                iters += 1
+                if hk1 > 0:
+                    e.axpby(1.0 / hk1, w, 0.0, V[k + 1], n)
+                k += 1
+                if resid <= tol or iters >= maxiter or hk1 == 0:
+                    done = True
+            y = np.linalg.solve(np.triu(H[:k, :k]), g[:k]) if k else np.zeros(0)
+            yd = torch.as_tensor(-y, device=x_own.device)
+            e.multi_axpy(V, k, yd, x_own, n)            # x += V y
+            info['iterations'] = iters
+            info['residual'] = resid
+            if resid <= tol or iters >= maxiter:
+                break
+        return info
+
+
+class DistributedSolid:
+    """One rank's share of a solid model: local assembly + distributed linear solve."""
+
+    def __init__(self, residual, rank: int = 0, world: int = 1, group=None, restart: int = 30,
+                 device=None):
+        from . import tables as _tables
+        from .engine import Engine
+        mesh = residual.mesh()
+        fids, pf_cell, pf_opp = residual.pressure_facets()
+        self.part = LocalPartition(mesh.coordinates(), mesh.cells(), pf_cell, pf_opp,
+                                   residual.fixed_dofs(), rank, world)
+        p = self.part
+        self.tables = _tables.build_tables(p.coords, p.cells, p.pf_cell, p.pf_opp, p.fixed_dofs)
+        self.engine = Engine(self.tables, device=device)
+        self.halo = HaloPlan(p, group).to_device(self.engine.device)
+        self.gmres = GridGMRES(self.engine, p.n_own, self.halo, restart, group)
+        self.dim = p.dim
+
+    def upload_global(self, prop: dict, state: dict, p1: np.ndarray, scal: np.ndarray):
+        """Scatter globally defined fields to this rank (setup / test convenience)."""
+        e, p = self.engine, self.part
+        for name in ('rho', 'eta', 'emod'):
+            e.upload(name, p.local_cell_field(np.asarray(prop[name])), 0)
+        e.upload('scal', scal, 0)
+        for name in ('u1', 'u0', 'v0', 'a0'):
+            e.upload(name, p.local_vector(np.asarray(state[name])), 0)
+        e.upload('p1', np.ascontiguousarray(np.asarray(p1)[p.local_nodes]), 0)
+
+    def assemble(self, dt: float, res: bool = True, jac: bool = True):
+        self.engine.assemble(0, res=res, jac=jac, dt=dt)
+
+    def owned(self, name: str) -> torch.Tensor:
+        return self.engine.view(name)[:self.dim * self.part.n_own]
+
+    def solve(self, b_own: torch.Tensor, x_own: torch.Tensor, **kw):
+        return self.gmres.solve(b_own, x_own, **kw)

@@ -230,6 +230,34 @@ class Engine:
         assert x.numel() == self.N and y.numel() == self.N and x.is_cuda and y.is_cuda
         check(self._lib.vf_spmv(self._h, member, x.data_ptr(), y.data_ptr(), self._stream()))
 
+    # --- grid-wide Krylov building blocks (large meshes / mesh partitions) --------------
+    def spmv_rows(self, x: torch.Tensor, y: torch.Tensor, node0: int, node1: int, member: int = 0):
+        check(self._lib.vf_spmv_rows(self._h, member, x.data_ptr(), y.data_ptr(), int(node0),
+                                     int(node1), self._stream()))
+
+    def block_jacobi_setup(self, node0: int, node1: int, member: int = 0):
+        check(self._lib.vf_block_jacobi_setup(self._h, member, int(node0), int(node1),
+                                              self._stream()))
+
+    def block_jacobi_apply(self, r: torch.Tensor, z: torch.Tensor, node0: int, node1: int,
+                           member: int = 0):
+        check(self._lib.vf_block_jacobi_apply(self._h, member, r.data_ptr(), z.data_ptr(),
+                                              int(node0), int(node1), self._stream()))
+
+    def multidot(self, V: torch.Tensor, nvec: int, w: torch.Tensor, n: int, out: torch.Tensor,
+                 scratch: torch.Tensor):
+        check(self._lib.vf_multidot(self._h, V.data_ptr(), V.stride(0), int(nvec), w.data_ptr(),
+                                    int(n), out.data_ptr(), scratch.data_ptr(), scratch.numel(),
+                                    self._stream()))
+
+    def multi_axpy(self, V: torch.Tensor, nvec: int, h: torch.Tensor, w: torch.Tensor, n: int):
+        check(self._lib.vf_multi_axpy(self._h, V.data_ptr(), V.stride(0), int(nvec), h.data_ptr(),
+                                      w.data_ptr(), int(n), self._stream()))
+
+    def axpby(self, alpha: float, x: torch.Tensor, beta: float, y: torch.Tensor, n: int):
+        check(self._lib.vf_axpby(self._h, float(alpha), x.data_ptr(), float(beta), y.data_ptr(),
+                                 int(n), self._stream()))
+
     def linear_solve(self, b: torch.Tensor, x: torch.Tensor, member: int = 0, options=None):
         info = np.zeros(3)
         opts = make_solver_opts(options)

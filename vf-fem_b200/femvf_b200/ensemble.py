@@ -29,7 +29,7 @@ def shard_members(n_total: int, rank: int, world: int):
 class EnsembleRunner:
     """``n_members`` copies of a coupled model differing in their property fields."""
 
-    def __init__(self, model: ExplicitFSIModel, n_members: int, gmres_restart: int = 40):
+    def __init__(self, model: ExplicitFSIModel, n_members: int, gmres_restart: int = 16):
         self.model = model
         solid, r = model.solid, model.fluid.residual
         self.engine = Engine(
