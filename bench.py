@@ -251,7 +251,7 @@ def workload_config():
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=100)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--levels', type=int, default=REFINE_LEVELS)
@@ -328,6 +328,7 @@ def main():
                  'algorithmic_bytes': B_spmv, 'ms': ms_spmv / n_spmv},
         'clocks': clocks,
         'gpu_launches': int(launches),
+        'kernel_config': dict(model.engine.tile_info),
     }
 
     # ---- e2e: the public API with host buffers (set_fin_state -> assem_res + assem_dres_dstate1)

@@ -75,6 +75,7 @@ typedef struct vf_problem_desc {
   /* model switches */
   int32_t contact;            /* NodalContactModel semantics */
   int32_t membrane;           /* KelvinVoigtWEpithelium membrane term */
+  int32_t damping;            /* 0 Kelvin-Voigt (form.py:965-990), 1 Rayleigh (form.py:918-956) */
   /* ensemble / solver workspace */
   int32_t n_members;
   int32_t gmres_restart;
@@ -100,7 +101,7 @@ enum vf_array_id {
   VF_AREA,                                    /* fluid control 'area' (n_fluid*ns) */
   VF_RHO, VF_ETA, VF_EMOD,                    /* DG0 (ne) */
   VF_EMOD_M, VF_NU_M, VF_TH_M,                /* membrane DG0 (ne) */
-  VF_SCAL,                                    /* nu, ycontact, kcontact, ncontact[3], ymid, pad */
+  VF_SCAL,                                    /* nu, ycontact, kcontact, ncontact[3], ymid, rayleigh_m, rayleigh_k, pad (10) */
   VF_FPROP,                                   /* (n_fluid, 5): rho_air r_sep area_lb zeta_min zeta_sep */
   VF_F,                                       /* residual F_u (N) */
   VF_J,                                       /* CSR values of J_uu (nnz) */

@@ -17,6 +17,7 @@ Follows (all paths under /root/reference/src/femvf/):
   equations/form.py:516-533   InertialForm            rho * a1 . w dx
   equations/form.py:540-572   IsotropicElasticForm    sigma(eps(u1)) : eps(w) dx
   equations/form.py:965-990   KelvinVoigtForm         eta * eps(v1) : eps(w) dx
+  equations/form.py:918-956   RayleighDampingForm     (rayleigh_m rho v1 . w + rayleigh_k sigma(eps(v1)) : eps(w)) dx
   equations/form.py:733-756   SurfacePressureForm     -p cof(F) N . w ds   (subtracted)
   equations/form.py:759-794   ManualSurfaceContactTractionForm   tc . w ds (subtracted)
   equations/form.py:800-855   IsotropicMembraneForm
@@ -235,7 +236,7 @@ def assemble_res_u(prob: SolidProblem, u1, u0, v0, a0, dt, prop, p1, tcontact=No
     V = v1.reshape(nn, d)[cells]
     A = a1.reshape(nn, d)[cells]
     lam, mu = lame(np.broadcast_to(prop['emod'], (ne,)), prop['nu'])
-    eta = np.broadcast_to(prop['eta'], (ne,))
+    eta = np.broadcast_to(prop.get('eta', 0.0), (ne,))
     rho = np.broadcast_to(prop['rho'], (ne,))
 
     gu = grad_field(G, U)
@@ -245,11 +246,19 @@ def assemble_res_u(prob: SolidProblem, u1, u0, v0, a0, dt, prop, p1, tcontact=No
     tr = np.trace(eps_u, axis1=1, axis2=2)
     eye = np.eye(d)
     sigma = 2 * mu[:, None, None] * eps_u + (lam * tr)[:, None, None] * eye
-    sigma = sigma + eta[:, None, None] * eps_v  # form.py:984: eta * eps(v), no factor 2
-    Re = vol[:, None, None] * np.einsum('eij,eaj->eai', sigma, G)
     nen = d + 1
     Mw = (np.ones((nen, nen)) + np.eye(nen)) / ((d + 1) * (d + 2))
-    Re = Re + (rho * vol)[:, None, None] * np.einsum('ab,ebi->eai', Mw, A)
+    if 'rayleigh_k' in prop:
+        # Rayleigh damping (form.py:932-956): rayleigh_k * sigma_iso(eps(v)) + rayleigh_m rho v
+        rk, rm = float(np.ravel(prop['rayleigh_k'])[0]), float(np.ravel(prop['rayleigh_m'])[0])
+        trv = np.trace(eps_v, axis1=1, axis2=2)
+        sigma = sigma + rk * (2 * mu[:, None, None] * eps_v + (lam * trv)[:, None, None] * eye)
+        body = A + rm * V
+    else:
+        sigma = sigma + eta[:, None, None] * eps_v  # form.py:984: eta * eps(v), no factor 2
+        body = A
+    Re = vol[:, None, None] * np.einsum('eij,eaj->eai', sigma, G)
+    Re = Re + (rho * vol)[:, None, None] * np.einsum('ab,ebi->eai', Mw, body)
 
     F = np.zeros((nn, d))
     np.add.at(F, cells.ravel(), Re.reshape(-1, d))
@@ -342,7 +351,7 @@ def cell_matrices(prob: SolidProblem, dt, prop):
     d, ne = prob.d, prob.ne
     G, vol = prob.G, prob.vol
     lam, mu = lame(np.broadcast_to(prop['emod'], (ne,)), prop['nu'])
-    eta = np.broadcast_to(prop['eta'], (ne,))
+    eta = np.broadcast_to(prop.get('eta', 0.0), (ne,))
     rho = np.broadcast_to(prop['rho'], (ne,))
     cv = newmark_v_du1(dt)
     ca = newmark_a_du1(dt)
@@ -355,8 +364,12 @@ def cell_matrices(prob: SolidProblem, dt, prop):
     K = (lam[:, None, None, None, None] * GaGb
          + mu[:, None, None, None, None] * GbGa
          + (mu[:, None, None] * GG)[..., None, None] * eye)
-    C = 0.5 * eta[:, None, None, None, None] * (GG[..., None, None] * eye + GbGa)
     M = (rho[:, None, None] * Mw[None])[..., None, None] * eye
+    if 'rayleigh_k' in prop:
+        rk, rm = float(np.ravel(prop['rayleigh_k'])[0]), float(np.ravel(prop['rayleigh_m'])[0])
+        C = rk * K + rm * M
+    else:
+        C = 0.5 * eta[:, None, None, None, None] * (GG[..., None, None] * eye + GbGa)
     Ke = vol[:, None, None, None, None] * (K + cv * C + ca * M)
     return Ke  # (ne, nen, nen, d, d)  block [a, b] = d R_a / d U_b
 

@@ -216,6 +216,8 @@ def static_solid_configuration(solid: SolidOracle, prop, p1, options=None, u_gue
     static_prop = dict(prop)
     static_prop['rho'] = np.zeros(prob.ne)
     static_prop['eta'] = np.zeros(prob.ne)
+    static_prop.pop('rayleigh_m', None)
+    static_prop.pop('rayleigh_k', None)
     k = 0
     r0 = None
     while True:

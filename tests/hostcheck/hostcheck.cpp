@@ -21,12 +21,13 @@ extern "C" int hostcheck_assemble(
     const int* bcol, const int* n2e_ptr, const int* n2e, const int* n2f_ptr, const int* n2f,
     const int* pf_cell, const int* pf_opp, const unsigned char* bc, const double* rho,
     const double* eta, const double* emod, const double* scal, const double* emod_m,
-    const double* nu_m, const double* th_m, int contact, int membrane, const double* u1,
+    const double* nu_m, const double* th_m, int contact, int membrane, int damping,
+    const double* u1,
     const double* u0, const double* v0, const double* a0, const double* p1, double dt,
     double* J, double* F) {
   vf::MeshView m{dim, nn, ne, nfp, xyz, cells, brptr, bcol, n2e_ptr, n2e,
                  n2f_ptr, n2f, pf_cell, pf_opp, bc};
-  vf::PropView p{rho, eta, emod, scal, emod_m, nu_m, th_m, contact, membrane};
+  vf::PropView p{rho, eta, emod, scal, emod_m, nu_m, th_m, contact, membrane, damping};
   vf::StateView s{u1, u0, v0, a0, p1, dt, 0};
   if (dim == 2) run<2>(m, p, s, J, F);
   else if (dim == 3) run<3>(m, p, s, J, F);
@@ -41,13 +42,14 @@ extern "C" int hostcheck_assemble_tile2(
     const int* bcol, const int* n2e_ptr, const int* n2e, const int* n2f_ptr, const int* n2f,
     const int* pf_cell, const int* pf_opp, const unsigned char* bc, const double* rho,
     const double* eta, const double* emod, const double* scal, const double* emod_m,
-    const double* nu_m, const double* th_m, int contact, int membrane, const double* u1,
+    const double* nu_m, const double* th_m, int contact, int membrane, int damping,
+    const double* u1,
     const double* u0, const double* v0, const double* a0, const double* p1, double dt,
     int ntiles, const int* tile_start, const int* te_ptr, const int* te_elem,
     const unsigned* pair_info, int max_tile_elems, double* J, double* F) {
   vf::MeshView m{2, nn, ne, nfp, xyz, cells, brptr, bcol, n2e_ptr, n2e,
                  n2f_ptr, n2f, pf_cell, pf_opp, bc};
-  vf::PropView p{rho, eta, emod, scal, emod_m, nu_m, th_m, contact, membrane};
+  vf::PropView p{rho, eta, emod, scal, emod_m, nu_m, th_m, contact, membrane, damping};
   vf::StateView s{u1, u0, v0, a0, p1, dt, 0};
   const vf::LameFac lf = vf::lame_fac(scal[vf::SC_NU]);
   const vf::NewmarkCoef nc = vf::newmark_coef(dt);
@@ -66,7 +68,8 @@ extern "C" int hostcheck_assemble_tile2(
         x[a][0] = xyz[nd[a]];
         x[a][1] = xyz[nn + nd[a]];
       }
-      vf::tri_record(x, nd, emod[e], lf, eta[e], rho[e], nc, false, true, u1, u0, v0, a0,
+      vf::tri_record(x, nd, emod[e], lf, eta[e], rho[e], vf::prop_damping(p), nc, false, true, u1,
+                     u0, v0, a0,
                      recs + (size_t)(q - q0) * vf::kRec2D);
     }
     for (int i = i0; i < i1; ++i) {

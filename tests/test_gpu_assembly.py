@@ -22,7 +22,7 @@ def torch_cuda():
 
 
 @pytest.mark.parametrize('mesh_name', ['square5', 'cube332', 'm5'])
-@pytest.mark.parametrize('variant', ['kv', 'kv_contact', 'epithelium_contact'])
+@pytest.mark.parametrize('variant', ['kv', 'kv_contact', 'epithelium_contact', 'rayleigh'])
 def test_assembly_parity(torch_cuda, mesh_name, variant):
     from femvf_b200.models import transient
     from femvf_b200.residuals import solid as slr
@@ -31,11 +31,16 @@ def test_assembly_parity(torch_cuda, mesh_name, variant):
     membrane = variant.startswith('epithelium')
     contact = variant.endswith('contact')
     Residual = slr.KelvinVoigtWEpithelium if membrane else slr.KelvinVoigt
+    if variant == 'rayleigh':
+        Residual = slr.Rayleigh
     Model = transient.NodalContactModel if contact else transient.FenicsModel
     model = Model(Residual(*mt))
     prob = oracle_problem(model.residual)
     N = prob.N
     prop = random_solid_prop(prob, rng, membrane=membrane)
+    if variant == 'rayleigh':
+        del prop['eta']
+        prop.update(rayleigh_m=12.5, rayleigh_k=4e-5)
     mprop = model.prop.copy()
     set_model_prop(mprop, prop)
     model.set_prop(mprop)

@@ -206,3 +206,52 @@ def test_ensemble_members_and_host_entry_point():
     hs, hi = runner.run_device(dts, ctl, store_states=True)
     assert np.array_equal(hs[:, -1, :].cpu().numpy(), fin)
     assert np.array_equal(hi.cpu().numpy(), series)
+
+
+def test_rayleigh_coupled_matches_oracle():
+    """slr.Rayleigh is one of the solid residuals of the reference's test_forward.py:36-41."""
+    from femvf_b200 import forward
+    from femvf_b200.load import load_fsi_model
+    from femvf_b200.residuals import solid as slr, fluid as flr
+    mt = mesh_tuples()['m5']()
+    model = load_fsi_model(mt, slr.Rayleigh, flr.BernoulliAreaRatioSep,
+                           {'dirichlet_bcs': {'state/u1': [(np.zeros(2), 'facet', 'fixed')]}}, {})
+    assert model.solid.prop.keys() == ['rho', 'emod', 'nu', 'rayleigh_m', 'rayleigh_k',
+                                       'ycontact', 'ncontact', 'kcontact']
+    state0 = model.state0.copy(); state0[:] = 0
+    control = model.control.copy(); control[:] = 0; control['psub'][:] = 8e3
+    prop = model.prop.copy()
+    prop['emod'][:] = 5e4; prop['rho'][:] = 1; prop['nu'][:] = 0.45
+    prop['rayleigh_m'][:] = 10.0; prop['rayleigh_k'][:] = 3e-5; prop['ymid'][:] = 1.0
+    times = 1e-4 * np.arange(20)
+    fin, info = forward.integrate(model, None, state0, [control], prop, times, write=False)
+    prob = oracle_problem(model.solid.residual)
+    co = om.CoupledOracle(om.SolidOracle(prob), model.fluid.residual.mesh(),
+                          model.fsimap.dofs_solid, model.fsimap.dofs_fluid)
+    oprop = {k: np.array(v) for k, v in prop.items()}
+    hist, _ = co.integrate(tuple(state0.vecs),
+                           [{'psub': control['psub'], 'psup': control['psup']}], oprop, times)
+    for k, key in ((0, 'u'), (3, 'q'), (4, 'p')):
+        ref = hist[-1][k]
+        assert np.max(np.abs(fin[key] - ref)) <= TRAJ_TOL * np.max(np.abs(ref)), key
+
+
+def test_integrate_extend_continues_a_statefile(tmp_path):
+    """forward.integrate_extend (forward.py:105-136): restarting from the last stored state
+    gives the same trajectory as one uninterrupted run."""
+    from femvf_b200 import forward, statefile as sf
+    model = build_fsi('m5')
+    state0, control, prop = benchmark_setup(model)
+    times = 1e-4 * np.arange(13)
+    full, _ = forward.integrate(model, None, state0, [control], prop, times, write=False)
+    path = str(tmp_path / 'restart.h5')
+    with sf.StateFile(model, path, mode='w') as f:
+        forward.integrate(model, f, state0, [control], prop, times[:7])
+    with sf.StateFile(model, path, mode='a') as f:
+        assert f.size == 7
+        fin, _ = forward.integrate_extend(model, f, [control], times[6:] - times[6])
+        assert f.size == 13
+        assert np.allclose(f.get_times(), times, rtol=0, atol=1e-18)
+    for key in ('u', 'q', 'p'):
+        scale = np.max(np.abs(full[key]))
+        assert np.max(np.abs(fin[key] - full[key])) <= 1e-9 * scale, key

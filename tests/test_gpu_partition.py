@@ -30,7 +30,7 @@ def problem(levels=3, dim=2):
     state = dict(u1=rng.uniform(-1e-3, 1e-3, N), u0=rng.uniform(-1e-3, 1e-3, N),
                  v0=rng.uniform(-1e-2, 1e-2, N), a0=rng.uniform(-1e2, 1e2, N))
     p1 = rng.uniform(0, 8e3, prob.nn)
-    scal = np.zeros(8); scal[0] = 0.45; scal[1] = np.inf; scal[2] = 1.0; scal[4] = 1.0
+    scal = np.zeros(10); scal[0] = 0.45; scal[1] = np.inf; scal[2] = 1.0; scal[4] = 1.0
     return res, prob, prop, state, p1, scal
 
 

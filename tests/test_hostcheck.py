@@ -34,8 +34,8 @@ def P(a):
 
 
 @pytest.mark.parametrize('mesh_name', ['square5', 'cube332', 'm5'])
-@pytest.mark.parametrize('contact,membrane', [(0, 0), (1, 0), (1, 1)])
-def test_device_element_math_on_cpu(lib, mesh_name, contact, membrane):
+@pytest.mark.parametrize('contact,membrane,damping', [(0, 0, 0), (1, 0, 0), (1, 1, 0), (1, 0, 1)])
+def test_device_element_math_on_cpu(lib, mesh_name, contact, membrane, damping):
     rng = np.random.default_rng(7)
     Residual = slr.KelvinVoigtWEpithelium if membrane else slr.KelvinVoigt
     res = Residual(*mesh_tuples()[mesh_name]())
@@ -47,13 +47,16 @@ def test_device_element_math_on_cpu(lib, mesh_name, contact, membrane):
     assert np.array_equal(prob.rowptr, T['rowptr']) and np.array_equal(prob.colidx, T['colidx'])
     N, ne, nn = prob.N, prob.ne, prob.nn
     prop = random_solid_prop(prob, rng, membrane=True)
+    if damping:
+        prop.update(rayleigh_m=rng.uniform(5, 20), rayleigh_k=rng.uniform(1e-5, 1e-4))
     so = om.SolidOracle(prob, contact=bool(contact), membrane=bool(membrane))
     u1, u0, v0, a0 = random_state(N, rng)
     p1 = rng.uniform(0, 8e3, nn)
     dt = 1e-4
     Jo = so.jac(u1, dt, prop, p1)
     Fo = so.res(u1, (u0, v0, a0), dt, prop, p1)
-    scal = np.zeros(8)
+    scal = np.zeros(10)
+    scal[7], scal[8] = prop.get('rayleigh_m', 0.0), prop.get('rayleigh_k', 0.0)
     scal[0], scal[1], scal[2] = 0.45, prop['ycontact'], prop['kcontact']
     scal[3:3 + d] = prop['ncontact']
     J = np.zeros(len(T['colidx']))
@@ -63,15 +66,17 @@ def test_device_element_math_on_cpu(lib, mesh_name, contact, membrane):
         P(T['n2e_ptr']), P(T['n2e']), P(T['n2f_ptr']), P(T['n2f']), P(T['pf_cell']),
         P(T['pf_opp']), P(T['bc']), P(prop['rho']), P(prop['eta']), P(prop['emod']), P(scal),
         P(prop['emod_membrane']), P(prop['nu_membrane']), P(prop['th_membrane']),
-        contact, membrane, P(u1), P(u0), P(v0), P(a0), P(p1), ctypes.c_double(dt), P(J), P(F))
+        contact, membrane, damping, P(u1), P(u0), P(v0), P(a0), P(p1), ctypes.c_double(dt), P(J),
+        P(F))
     assert rc == 0
     assert rel_row_err(J, Jo) <= 1e-12
     assert np.max(np.abs(F - Fo)) <= 1e-12 * np.max(np.abs(Fo))
 
 
 @pytest.mark.parametrize('mesh_name,nodes_per_tile', [('square5', 7), ('m5', 16), ('m5', 96)])
-@pytest.mark.parametrize('contact,membrane', [(0, 0), (1, 1)])
-def test_two_phase_tile_algorithm_on_cpu(lib, mesh_name, nodes_per_tile, contact, membrane):
+@pytest.mark.parametrize('contact,membrane,damping', [(0, 0, 0), (1, 1, 0), (0, 0, 1)])
+def test_two_phase_tile_algorithm_on_cpu(lib, mesh_name, nodes_per_tile, contact, membrane,
+                                         damping):
     """CPU emulation of asm_tile2_kernel + facet_bc_kernel with the product's tile tables."""
     rng = np.random.default_rng(11)
     Residual = slr.KelvinVoigtWEpithelium if membrane else slr.KelvinVoigt
@@ -87,13 +92,16 @@ def test_two_phase_tile_algorithm_on_cpu(lib, mesh_name, nodes_per_tile, contact
     prob = oracle_problem(res)
     N, ne, nn = prob.N, prob.ne, prob.nn
     prop = random_solid_prop(prob, rng, membrane=True)
+    if damping:
+        prop.update(rayleigh_m=rng.uniform(5, 20), rayleigh_k=rng.uniform(1e-5, 1e-4))
     so = om.SolidOracle(prob, contact=bool(contact), membrane=bool(membrane))
     u1, u0, v0, a0 = random_state(N, rng)
     p1 = rng.uniform(0, 8e3, nn)
     dt = 1e-4
     Jo = so.jac(u1, dt, prop, p1)
     Fo = so.res(u1, (u0, v0, a0), dt, prop, p1)
-    scal = np.zeros(8)
+    scal = np.zeros(10)
+    scal[7], scal[8] = prop.get('rayleigh_m', 0.0), prop.get('rayleigh_k', 0.0)
     scal[0], scal[1], scal[2] = 0.45, prop['ycontact'], prop['kcontact']
     scal[3:5] = prop['ncontact']
     J = np.full(len(T['colidx']), np.nan)
@@ -103,7 +111,7 @@ def test_two_phase_tile_algorithm_on_cpu(lib, mesh_name, nodes_per_tile, contact
         P(T['n2e_ptr']), P(T['n2e']), P(T['n2f_ptr']), P(T['n2f']), P(T['pf_cell']),
         P(T['pf_opp']), P(T['bc']), P(prop['rho']), P(prop['eta']), P(prop['emod']), P(scal),
         P(prop['emod_membrane']), P(prop['nu_membrane']), P(prop['th_membrane']),
-        contact, membrane, P(u1), P(u0), P(v0), P(a0), P(p1), ctypes.c_double(dt),
+        contact, membrane, damping, P(u1), P(u0), P(v0), P(a0), P(p1), ctypes.c_double(dt),
         len(ts) - 1, P(ts), P(TT['te_ptr']), P(TT['te_elem']), P(TT['pair_info']),
         TT['max_tile_elems'], P(J), P(F))
     assert rc == 0

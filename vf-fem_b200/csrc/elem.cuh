@@ -121,21 +121,42 @@ VF_HD void p1_geometry(const double (&x)[4][3], CellGeo<3>& g) {
   }
 }
 
-// Per-cell material factors already multiplied by |K| and the Newmark coefficients.
+// Damping model of the residual: Kelvin-Voigt (form.py:965-990: stress eta*eps(v)) or Rayleigh
+// (form.py:918-956: rayleigh_m*rho*v body force + rayleigh_k*sigma_iso(eps(v))).
+enum DampingKind { DAMP_KELVIN_VOIGT = 0, DAMP_RAYLEIGH = 1 };
+struct Damping {
+  int kind;
+  double rm, rk;  // Rayleigh mass / stiffness factors
+};
+
+// Per-cell material factors already multiplied by |K|.  The viscous stress is written as
+// 2 vmu eps(v) + vlam tr(eps(v)) I and the viscous body force as vmass-weighted nodal v, which
+// covers both damping models.
 struct CellCoef {
   double lamv;   // lambda |K|
   double muv;    // mu |K|
-  double visv;   // eta/2 |K|           (viscous stress is eta*eps(v), form.py:984)
+  double vlam;   // viscous lambda |K|   (Kelvin-Voigt: 0;          Rayleigh: rk lambda |K|)
+  double vmu;    // viscous mu |K|       (Kelvin-Voigt: eta/2 |K|;  Rayleigh: rk mu |K|)
   double massv;  // rho |K| / ((d+1)(d+2))
+  double vmass;  // damping mass         (Kelvin-Voigt: 0;          Rayleigh: rm massv)
 };
 
 template <int D>
-VF_HD CellCoef cell_coef(double emod, const LameFac& lf, double eta, double rho, double vol) {
+VF_HD CellCoef cell_coef(double emod, const LameFac& lf, double eta, double rho, double vol,
+                         const Damping& dp) {
   CellCoef c;
   c.lamv = emod * lf.lam_fac * vol;
   c.muv = emod * lf.mu_fac * vol;
-  c.visv = 0.5 * eta * vol;
   c.massv = rho * vol / double((D + 1) * (D + 2));
+  if (dp.kind == DAMP_RAYLEIGH) {
+    c.vlam = dp.rk * c.lamv;
+    c.vmu = dp.rk * c.muv;
+    c.vmass = dp.rm * c.massv;
+  } else {
+    c.vlam = 0.0;
+    c.vmu = 0.5 * eta * vol;  // viscous stress is eta*eps(v), not 2 eta (form.py:984)
+    c.vmass = 0.0;
+  }
   return c;
 }
 
@@ -145,11 +166,12 @@ VF_HD void cell_block(const CellGeo<D>& g, const CellCoef& cf, double cv, double
                       int c, double (&blk)[D][D]) {
   double gg = 0.0;
   for (int i = 0; i < D; ++i) gg += g.G[a][i] * g.G[c][i];
-  const double mv = cf.muv + cv * cf.visv;
+  const double lv = cf.lamv + cv * cf.vlam;
+  const double mv = cf.muv + cv * cf.vmu;
   for (int i = 0; i < D; ++i)
     for (int j = 0; j < D; ++j)
-      blk[i][j] = cf.lamv * g.G[a][i] * g.G[c][j] + mv * g.G[c][i] * g.G[a][j];
-  const double dg = mv * gg + ca * cf.massv * (a == c ? 2.0 : 1.0);
+      blk[i][j] = lv * g.G[a][i] * g.G[c][j] + mv * g.G[c][i] * g.G[a][j];
+  const double dg = mv * gg + (ca * cf.massv + cv * cf.vmass) * (a == c ? 2.0 : 1.0);
   for (int i = 0; i < D; ++i) blk[i][i] += dg;
 }
 
@@ -169,18 +191,24 @@ VF_HD void cell_residual(const CellGeo<D>& g, const CellCoef& cf, int a,
       gu[i][j] = su;
       gv[i][j] = sv;
     }
-  double tr = 0.0;
-  for (int i = 0; i < D; ++i) tr += gu[i][i];
+  double tr = 0.0, trv = 0.0;
+  for (int i = 0; i < D; ++i) {
+    tr += gu[i][i];
+    trv += gv[i][i];
+  }
   for (int i = 0; i < D; ++i) {
     double s = 0.0;
     for (int j = 0; j < D; ++j) {
-      double sig = cf.muv * (gu[i][j] + gu[j][i]) + cf.visv * (gv[i][j] + gv[j][i]);
-      if (i == j) sig += cf.lamv * tr;
+      double sig = cf.muv * (gu[i][j] + gu[j][i]) + cf.vmu * (gv[i][j] + gv[j][i]);
+      if (i == j) sig += cf.lamv * tr + cf.vlam * trv;
       s += sig * g.G[a][j];
     }
-    double m = 0.0;
-    for (int b = 0; b <= D; ++b) m += (a == b ? 2.0 : 1.0) * A[b][i];
-    r[i] = s + cf.massv * m;
+    double m = 0.0, mvel = 0.0;
+    for (int b = 0; b <= D; ++b) {
+      m += (a == b ? 2.0 : 1.0) * A[b][i];
+      mvel += (a == b ? 2.0 : 1.0) * V[b][i];
+    }
+    r[i] = s + cf.massv * m + cf.vmass * mvel;
   }
 }
 
@@ -317,8 +345,8 @@ VF_HD void membrane_coef(double emod_m, double nu_m, double& mu_m, double& lam_p
 
 // ---- two-phase tile assembly (2D): per-element record + per-row accumulation -------------
 // Record of one P1 triangle in shared memory:
-//   [0..5]  G_a (a = 0,1,2; x,y)      [6] lambda|K|   [7] (mu + cv eta/2)|K|
-//   [8]     ca rho|K|/12              [9..14] cell residual at the 3 nodes   [15..17] pad
+//   [0..5]  G_a (a = 0,1,2; x,y)   [6] (lambda + cv lambda_v)|K|   [7] (mu + cv mu_v)|K|
+//   [8]  (ca rho + cv rm rho)|K|/12   [9..14] cell residual at the 3 nodes   [15..17] pad
 // The stride is 18 doubles = 144 B = 36 banks: 16-byte accesses of 8 consecutive records
 // (a quarter warp) fall in 8 disjoint bank quads, where a 128-byte stride would put every
 // record on the same banks (32-way conflict).
@@ -338,23 +366,24 @@ struct
 // consumed node by node (gradients and the lumped sums are accumulated on the fly) to keep
 // the live register set small.
 VF_HD void tri_record(const double (&x)[3][2], const int (&nd)[3], double emod,
-                      const LameFac& lf, double eta, double rho, const NewmarkCoef& nc,
-                      bool is_static, bool with_res, const double* u1, const double* u0,
-                      const double* v0, const double* a0, double* rec) {
+                      const LameFac& lf, double eta, double rho, const Damping& dp,
+                      const NewmarkCoef& nc, bool is_static, bool with_res, const double* u1,
+                      const double* u0, const double* v0, const double* a0, double* rec) {
   CellGeo<2> g;
   p1_geometry(x, g);
-  const CellCoef cf = cell_coef<2>(emod, lf, eta, rho, g.vol);
+  const CellCoef cf = cell_coef<2>(emod, lf, eta, rho, g.vol, dp);
   const double cv = is_static ? 0.0 : nc.cv;
   const double ca = is_static ? 0.0 : nc.ca;
   D2* r2 = reinterpret_cast<D2*>(rec);  // 16-byte stores
   for (int a = 0; a < 3; ++a) r2[a] = D2{g.G[a][0], g.G[a][1]};
-  r2[3] = D2{cf.lamv, cf.muv + cv * cf.visv};
+  r2[3] = D2{cf.lamv + cv * cf.vlam, cf.muv + cv * cf.vmu};
+  const double mass_blk = ca * cf.massv + cv * cf.vmass;
   if (!with_res) {
-    r2[4] = D2{ca * cf.massv, 0.0};
+    r2[4] = D2{mass_blk, 0.0};
     return;
   }
   double gu[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, gv[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-  double As[2] = {0.0, 0.0}, Aa[3][2];
+  double As[2] = {0.0, 0.0}, Aa[3][2];  // lumped sums: massv a + vmass v
   for (int a = 0; a < 3; ++a) {
     // 16-byte gathers of the node's (x, y) pair from the interleaved vectors
     const D2 p1 = reinterpret_cast<const D2*>(u1)[nd[a]];
@@ -377,20 +406,22 @@ VF_HD void tri_record(const double (&x)[3][2], const int (&nd)[3], double emod,
       gu[c][1] += w1 * g.G[a][1];
       gv[c][0] += v * g.G[a][0];
       gv[c][1] += v * g.G[a][1];
-      As[c] += acc;
-      Aa[a][c] = acc;
+      const double lump = cf.massv * acc + cf.vmass * v;
+      As[c] += lump;
+      Aa[a][c] = lump;
     }
   }
-  const double tr = gu[0][0] + gu[1][1];
-  const double s00 = cf.muv * (gu[0][0] + gu[0][0]) + cf.visv * (gv[0][0] + gv[0][0]) + cf.lamv * tr;
-  const double s11 = cf.muv * (gu[1][1] + gu[1][1]) + cf.visv * (gv[1][1] + gv[1][1]) + cf.lamv * tr;
-  const double s01 = cf.muv * (gu[0][1] + gu[1][0]) + cf.visv * (gv[0][1] + gv[1][0]);
+  const double tr = gu[0][0] + gu[1][1], trv = gv[0][0] + gv[1][1];
+  const double iso = cf.lamv * tr + cf.vlam * trv;
+  const double s00 = cf.muv * (gu[0][0] + gu[0][0]) + cf.vmu * (gv[0][0] + gv[0][0]) + iso;
+  const double s11 = cf.muv * (gu[1][1] + gu[1][1]) + cf.vmu * (gv[1][1] + gv[1][1]) + iso;
+  const double s01 = cf.muv * (gu[0][1] + gu[1][0]) + cf.vmu * (gv[0][1] + gv[1][0]);
   double r[3][2];
   for (int a = 0; a < 3; ++a) {
-    r[a][0] = s00 * g.G[a][0] + s01 * g.G[a][1] + cf.massv * (As[0] + Aa[a][0]);
-    r[a][1] = s01 * g.G[a][0] + s11 * g.G[a][1] + cf.massv * (As[1] + Aa[a][1]);
+    r[a][0] = s00 * g.G[a][0] + s01 * g.G[a][1] + (As[0] + Aa[a][0]);
+    r[a][1] = s01 * g.G[a][0] + s11 * g.G[a][1] + (As[1] + Aa[a][1]);
   }
-  r2[4] = D2{ca * cf.massv, r[0][0]};
+  r2[4] = D2{mass_blk, r[0][0]};
   r2[5] = D2{r[0][1], r[1][0]};
   r2[6] = D2{r[1][1], r[2][0]};
   r2[7] = D2{r[2][1], 0.0};

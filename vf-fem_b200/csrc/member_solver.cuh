@@ -46,7 +46,8 @@ struct SolverOpts {
 
 struct EngineDev {
   MeshView mesh;
-  int d, N, n_fluid, ns, n_fsi, n_fsip, fluid_kind, idx_sep, contact, membrane, restart;
+  int d, N, n_fluid, ns, n_fsi, n_fsip, fluid_kind, idx_sep, contact, membrane, damping,
+      restart;
   long long nnz;
   const double* s;
   const int* fsi_solid;   // area gather map (unique fluid DOFs)
@@ -504,6 +505,7 @@ __device__ __forceinline__ PropView member_props(const EngineDev& E, double* mb)
   p.th_m = mb + L.off[VF_TH_M];
   p.contact = E.contact;
   p.membrane = E.membrane;
+  p.damping = E.damping;
   return p;
 }
 

@@ -26,7 +26,9 @@ enum ScalarProp {
   SC_KCONTACT = 2,
   SC_NCONTACT = 3,  // 3 entries
   SC_YMID = 6,
-  SC_COUNT = 8
+  SC_RAYLEIGH_M = 7,
+  SC_RAYLEIGH_K = 8,
+  SC_COUNT = 10
 };
 
 struct MeshView {
@@ -54,7 +56,16 @@ struct PropView {
   const double* th_m;
   int contact;   // NodalContactModel semantics on/off (App. C, Q3)
   int membrane;  // KelvinVoigtWEpithelium membrane term on/off
+  int damping;   // DampingKind: Kelvin-Voigt or Rayleigh
 };
+
+VF_HD Damping prop_damping(const PropView& p) {
+  Damping d;
+  d.kind = p.damping;
+  d.rm = p.scal[SC_RAYLEIGH_M];
+  d.rk = p.scal[SC_RAYLEIGH_K];
+  return d;
+}
 
 struct StateView {
   const double* u1;
@@ -216,6 +227,7 @@ VF_HD void assemble_node(int i, const MeshView& m, const PropView& p, const Stat
     for (int c = 0; c < D; ++c) res[c] = 0.0;
 
   const LameFac lf = lame_fac(p.scal[SC_NU]);
+  const Damping dp = prop_damping(p);
   const NewmarkCoef nc = newmark_coef(s.dt);
   const double cv = s.is_static ? 0.0 : nc.cv;
   const double ca = s.is_static ? 0.0 : nc.ca;
@@ -229,7 +241,7 @@ VF_HD void assemble_node(int i, const MeshView& m, const PropView& p, const Stat
     load_cell<D>(m, e, nd, x);
     CellGeo<D> g;
     p1_geometry(x, g);
-    const CellCoef cf = cell_coef<D>(p.emod[e], lf, p.eta[e], p.rho[e], g.vol);
+    const CellCoef cf = cell_coef<D>(p.emod[e], lf, p.eta[e], p.rho[e], g.vol, dp);
     if (JAC) {
       for (int c = 0; c <= D; ++c) {
         double blk[D][D];

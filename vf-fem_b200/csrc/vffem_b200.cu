@@ -153,6 +153,7 @@ __global__ void __launch_bounds__(kTile2MaxThreads, MINB) asm_tile2_kernel(
   {
     const LameFac lf = s_lf;
     const NewmarkCoef nc = s_nc;
+    const Damping dp = prop_damping(pv);
     for (int q = te0 + threadIdx.x; q < te1; q += blockDim.x) {
       if (q != te0 + (int)threadIdx.x) quad = te_quad[q];
       const int e = quad.w;
@@ -163,8 +164,8 @@ __global__ void __launch_bounds__(kTile2MaxThreads, MINB) asm_tile2_kernel(
         x[a][0] = m.xyz[nd[a]];
         x[a][1] = m.xyz[m.nn + nd[a]];
       }
-      tri_record(x, nd, pv.emod[e], lf, pv.eta[e], pv.rho[e], nc, is_static != 0, RES, u1, u0, v0,
-                 a0, recs + (size_t)(q - te0) * kRec2D);
+      tri_record(x, nd, pv.emod[e], lf, pv.eta[e], pv.rho[e], dp, nc, is_static != 0, RES, u1, u0,
+                 v0, a0, recs + (size_t)(q - te0) * kRec2D);
     }
   }
   __syncthreads();
@@ -980,7 +981,7 @@ int vf_create(const vf_problem_desc* desc, void* arena_dev, size_t arena_bytes, 
   E.mesh.bc = reinterpret_cast<const unsigned char*>(A + P.bc);
   E.d = d.dim; E.N = P.N; E.n_fluid = d.n_fluid; E.ns = d.ns; E.n_fsi = d.n_fsi;
   E.fluid_kind = d.fluid_kind; E.idx_sep = d.idx_sep; E.contact = d.contact;
-  E.membrane = d.membrane; E.restart = d.gmres_restart; E.nnz = P.nnz;
+  E.membrane = d.membrane; E.damping = d.damping; E.restart = d.gmres_restart; E.nnz = P.nnz;
   E.s = reinterpret_cast<const double*>(A + P.s);
   E.fsi_solid = reinterpret_cast<const int*>(A + P.fsi_solid);
   E.fsi_fluid = reinterpret_cast<const int*>(A + P.fsi_fluid);

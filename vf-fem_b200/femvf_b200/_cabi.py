@@ -38,7 +38,7 @@ class ProblemDesc(C.Structure):
         ('s_host', C.c_void_p), ('fsi_solid_host', C.c_void_p), ('fsi_fluid_host', C.c_void_p),
         ('n_fsip', C.c_int32), ('fsip_solid_host', C.c_void_p), ('fsip_fluid_host', C.c_void_p),
         ('fluid_kind', C.c_int32), ('idx_sep', C.c_int32),
-        ('contact', C.c_int32), ('membrane', C.c_int32),
+        ('contact', C.c_int32), ('membrane', C.c_int32), ('damping', C.c_int32),
         ('n_members', C.c_int32), ('gmres_restart', C.c_int32),
     ]
 

@@ -20,8 +20,10 @@ from ._cabi import ARRAY_IDS, ProblemDesc, SolverOpts, check
 from . import tables as _tables
 from .solverconst import DEFAULT_NEWTON_SOLVER_PRM, DEFAULT_LINEAR_SOLVER_PRM
 
-SCAL = {'nu': 0, 'ycontact': 1, 'kcontact': 2, 'ncontact': 3, 'ymid': 6}
-SCAL_COUNT = 8
+SCAL = {'nu': 0, 'ycontact': 1, 'kcontact': 2, 'ncontact': 3, 'ymid': 6, 'rayleigh_m': 7,
+        'rayleigh_k': 8}
+SCAL_COUNT = 10
+DAMPING = {'kelvin_voigt': 0, 'rayleigh': 1}
 FPROP = {'rho_air': 0, 'r_sep': 1, 'area_lb': 2, 'zeta_min': 3, 'zeta_sep': 4}
 FPROP_COUNT = 5
 
@@ -61,6 +63,7 @@ class Engine:
         idx_sep: int = 0,
         contact: bool = False,
         membrane: bool = False,
+        damping: str = 'kelvin_voigt',
         n_members: int = 1,
         gmres_restart: int = 40,
         device: Optional[torch.device] = None,
@@ -145,6 +148,7 @@ class Engine:
             self.n_fluid, self.ns, len(fsia_solid), _ptr(s), _ptr(fsia_solid), _ptr(fsia_fluid),
             len(fsip_solid), _ptr(fsip_solid), _ptr(fsip_fluid),
             int(fluid_kind), int(idx_sep), int(bool(contact)), int(bool(membrane)),
+            DAMPING[damping],
             self.n_members, int(gmres_restart),
         )
         nbytes = self._lib.vf_arena_bytes(C.byref(desc))

@@ -36,6 +36,7 @@ class EnsembleRunner:
             solid.assembly_tables, s=r.mesh(), fsi_solid=model.fsimap.dofs_solid,
             fsi_fluid=model.fsimap.dofs_fluid, fluid_kind=r.kind, idx_sep=r.idx_sep,
             contact=solid._CONTACT, membrane=solid.residual.form.terms.get('membrane', False),
+            damping=solid.residual.form.terms.get('damping', 'kelvin_voigt'),
             n_members=n_members, gmres_restart=gmres_restart)
         self.n_members = n_members
         self.ne = self.engine.ne

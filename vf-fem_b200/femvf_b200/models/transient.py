@@ -169,7 +169,8 @@ class FenicsModel(BaseTransientModel):
             else:
                 self._engine = Engine(
                     self._tables, contact=self._CONTACT,
-                    membrane=self.residual.form.terms.get('membrane', False))
+                    membrane=self.residual.form.terms.get('membrane', False),
+                    damping=self.residual.form.terms.get('damping', 'kelvin_voigt'))
         return self._engine
 
     def _attach_engine(self, engine: Engine, member: int = 0):
@@ -224,6 +225,9 @@ class FenicsModel(BaseTransientModel):
         scal[SCAL['kcontact']] = p['kcontact'][0]
         scal[SCAL['ncontact']:SCAL['ncontact'] + d] = p['ncontact']
         scal[SCAL['ymid']] = ymid
+        if 'rayleigh_m' in p:
+            scal[SCAL['rayleigh_m']] = p['rayleigh_m'][0]
+            scal[SCAL['rayleigh_k']] = p['rayleigh_k'][0]
         return scal
 
     def _push_prop(self, ymid: float = 0.0):
@@ -487,7 +491,8 @@ class BaseTransientFSIModel(BaseTransientModel):
                 solid.assembly_tables, s=r.mesh(), fsi_solid=self._fsi_dofs[0],
                 fsi_fluid=self._fsi_dofs[1], fluid_kind=r.kind, idx_sep=r.idx_sep,
                 contact=solid._CONTACT,
-                membrane=solid.residual.form.terms.get('membrane', False))
+                membrane=solid.residual.form.terms.get('membrane', False),
+                damping=solid.residual.form.terms.get('damping', 'kelvin_voigt'))
         return self._engine
 
     @property

@@ -31,6 +31,10 @@ FORM_SPECS = {
         ('state/u1', _CG1V, 0.0), ('control/tcontact', _CG1V, 0.0),
         ('prop/ycontact', _CONST_S, np.inf), ('prop/ncontact', _CONST_V, 'e_y'),
         ('prop/kcontact', _CONST_S, 1.0)],
+    'RayleighDampingForm': [
+        ('state/v1', _CG1V, 0.0), ('prop/rho', _DG0, 0.0), ('prop/emod', _DG0, 0.0),
+        ('prop/nu', _CONST_S, 0.45), ('prop/rayleigh_m', _CONST_S, 1.0),
+        ('prop/rayleigh_k', _CONST_S, 1.0)],
     'IsotropicMembraneForm': [
         ('state/u1', _CG1V, 0.0), ('prop/emod_membrane', _DG0, 0.0),
         ('prop/nu_membrane', _DG0, 0.45), ('prop/th_membrane', _DG0, 0.0)],
@@ -85,6 +89,15 @@ class PredefinedSolidResidual(FenicsResidual):
         if not self.FORM_NAMES:
             raise NotImplementedError()
         return build_form(mesh, self.FORM_NAMES, dict(self.TERMS))
+
+
+class Rayleigh(PredefinedSolidResidual):
+    """Inertia + isotropic elasticity + Rayleigh damping - follower pressure - contact
+    traction (``solid.py:144-165``)."""
+
+    FORM_NAMES = ['InertialForm', 'IsotropicElasticForm', 'RayleighDampingForm',
+                  'SurfacePressureForm', 'ManualSurfaceContactTractionForm']
+    TERMS = {'membrane': False, 'damping': 'rayleigh'}
 
 
 class KelvinVoigt(PredefinedSolidResidual):
