@@ -289,11 +289,16 @@ def main():
     def step():
         eng.assemble(0, res=True, jac=True, dt=model.dt)
 
+    # clocks are sampled from before the warm-up (same kernel, same load) to the end of the timed
+    # region: nvidia-smi cannot sample faster than ~100 ms and the timed region may be shorter
     sampler = ClockSampler(local_rank)
-    for _ in range(args.warmup):
-        step()
-    torch.cuda.synchronize()
     sampler.start()
+    t_w = time.perf_counter()
+    n_w = 0
+    while n_w < args.warmup or time.perf_counter() - t_w < 0.6:
+        step()
+        n_w += 1
+    torch.cuda.synchronize()
     launches0 = eng.launch_count
     ms = time_events(step, args.steps, 0, barrier)
     launches = eng.launch_count - launches0
@@ -322,7 +327,11 @@ def main():
                        parallelism=f'{world} independent mesh shards, no collective'),
         'roofline': {'kernel': 'asm_tile2_kernel<true,true> (+ facet_bc_kernel on boundary nodes)', 'bound': 'hbm',
                      'achieved': asm_gbs, 'peak': peak, 'unit': 'GB/s', 'frac': asm_gbs / peak,
-                     'traffic': None, 'algorithmic_bytes': B_asm, 'peak_source': peak_src},
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel on
+                     # this workload, from the ncu --set full capture summarised in
+                     # profiles/r1_ncu_full_asm2_final.csv (not re-measured in this run)
+                     'traffic': 901188096 if args.levels == REFINE_LEVELS else None,
+                     'algorithmic_bytes': B_asm, 'peak_source': peak_src},
         'spmv': {'kernel': 'spmv_kernel<2,8>', 'bound': 'hbm', 'achieved': spmv_gbs,
                  'peak': peak, 'unit': 'GB/s', 'frac': spmv_gbs / peak,
                  'algorithmic_bytes': B_spmv, 'ms': ms_spmv / n_spmv},

@@ -233,3 +233,35 @@ def static_solid_configuration(solid: SolidOracle, prop, p1, options=None, u_gue
         u = u - spla.splu(J.tocsc()).solve(r)
         k += 1
     return u, {'num_iter': k, 'abs_err': abs_err, 'rel_err': rel_err}
+
+
+class ImplicitCoupledOracle(CoupledOracle):
+    """
+    ImplicitFSIModel (models/transient.py:964-1033): fixed-point iteration between the solid
+    (loaded with the CURRENT iterate of the fluid pressure) and the fluid.  ``nonlineq
+    .iterative_solve`` is un-vendored; the stopping rule chosen here: iterate x <- G(x); stop
+    when ||x_{k+1} - x_k||_2 <= abs_tol, or <= rel_tol * ||x_1 - x_0||_2, or after max_iter
+    (solverconst.py:14: abs 1e-8, rel 1e-11).
+    """
+
+    def step(self, state0, control, prop, dt, options=None, abs_tol=1e-8, rel_tol=1e-11,
+             max_iter=50):
+        u0, v0, a0, q0, p0 = state0
+        x = [np.array(v, dtype=float) for v in state0]
+        k, err0 = 0, None
+        while True:
+            p1 = self.solid_pressure(x[4])
+            (u1, v1, a1), info = self.solid.solve_state1((u0, v0, a0), dt, prop, p1, options,
+                                                         u_guess=x[0])
+            area = self.fluid_area(u1, float(np.ravel(prop['ymid'])[0]))
+            q1, pf1 = self.fluid_qp(area, control, prop)
+            x_new = [u1, v1, a1, q1, pf1]
+            abs_err = float(np.sqrt(sum(np.sum((a - b) ** 2) for a, b in zip(x_new, x))))
+            if err0 is None:
+                err0 = abs_err
+            rel_err = abs_err / err0 if err0 > 0 else 0.0
+            x = x_new
+            k += 1
+            if abs_err <= abs_tol or rel_err <= rel_tol or k >= max_iter:
+                break
+        return tuple(x), {'num_iter': k, 'abs_err': abs_err, 'rel_err': rel_err, 'area': area}

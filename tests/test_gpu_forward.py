@@ -255,3 +255,27 @@ def test_integrate_extend_continues_a_statefile(tmp_path):
     for key in ('u', 'q', 'p'):
         scale = np.max(np.abs(full[key]))
         assert np.max(np.abs(fin[key] - full[key])) <= 1e-9 * scale, key
+
+
+def test_implicit_coupling_matches_oracle():
+    """ImplicitFSIModel: fixed-point coupling, per-step host loop over device solves."""
+    from femvf_b200 import forward
+    from femvf_b200.load import load_fsi_model
+    from femvf_b200.residuals import solid as slr, fluid as flr
+    mt = mesh_tuples()['m5']()
+    model = load_fsi_model(mt, slr.KelvinVoigt, flr.BernoulliAreaRatioSep,
+                           {'dirichlet_bcs': {'state/u1': [(np.zeros(2), 'facet', 'fixed')]}}, {},
+                           coupling='implicit')
+    state0, control, prop = benchmark_setup(model)
+    times = 1e-4 * np.arange(6)
+    fin, info = forward.integrate(model, None, state0, [control], prop, times, write=False)
+    prob = oracle_problem(model.solid.residual)
+    co = om.ImplicitCoupledOracle(om.SolidOracle(prob), model.fluid.residual.mesh(),
+                                  model.fsimap.dofs_solid, model.fsimap.dofs_fluid)
+    oprop = {k: np.array(v) for k, v in prop.items()}
+    hist, infos = co.integrate(tuple(state0.vecs),
+                               [{'psub': control['psub'], 'psup': control['psup']}], oprop, times)
+    for k, key in ((0, 'u'), (3, 'q'), (4, 'p')):
+        ref = hist[-1][k]
+        assert np.max(np.abs(fin[key] - ref)) <= 1e-7 * np.max(np.abs(ref)), key
+    assert info['num_iter'] == infos[-1]['num_iter'] and info['num_iter'] > 1

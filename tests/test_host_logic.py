@@ -112,9 +112,9 @@ def test_integrate_argument_validation():
         forward.integrate(model, None, st, [ctl], prop, [], write=False)
     with pytest.raises(ValueError):
         forward.integrate(model, None, st, [ctl], prop, [0.0, 0.0], write=False)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError):
         load.load_fsi_model(mesh_tuples()['square5'](), slr.KelvinVoigt,
-                            flr.BernoulliAreaRatioSep, {}, {}, coupling='implicit')
+                            flr.BernoulliAreaRatioSep, {}, {}, coupling='monolithic')
     with pytest.raises(ValueError):
         load.load_fenics_model('mesh.xml', slr.KelvinVoigt)
 

@@ -86,8 +86,7 @@ def load_fsi_model(
     if model_type == 'transient' and coupling == 'explicit':
         FSIModel = transient.ExplicitFSIModel
     elif model_type == 'transient' and coupling == 'implicit':
-        raise NotImplementedError(
-            "implicit coupling is listed as a next step (SURVEY.md section 8f)")
+        FSIModel = transient.ImplicitFSIModel
     else:
         raise ValueError(f"Invalid `model_type` and `coupling` ({model_type}, {coupling})")
 

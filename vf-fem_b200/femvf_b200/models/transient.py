@@ -31,7 +31,7 @@ from ..blockvec import BlockVector
 from ..engine import Engine, SCAL, SCAL_COUNT, FPROP, FPROP_COUNT
 from ..equations import newmark
 from ..residuals import solid as slr, fluid as flr
-from ..solverconst import DEFAULT_NEWTON_SOLVER_PRM
+from ..solverconst import DEFAULT_NEWTON_SOLVER_PRM, FIXEDPOINT_SOLVER_PRM
 from .. import tables as _tables
 from . import fsi
 
@@ -616,3 +616,68 @@ class ExplicitFSIModel(BaseTransientFSIModel):
         state = self.state0.copy()
         state[:] = row
         return state
+
+
+class ImplicitFSIModel(BaseTransientFSIModel):
+    """
+    Implicit (fixed-point) coupling (``transient.py:964-1033``): the solid at step n+1 is
+    loaded with the fluid pressure of step n+1; solid and fluid are solved in turn until the
+    coupled state stops changing.
+
+    The reference's ``iterative_solve`` comes from the un-vendored ``nonlineq`` package and its
+    ``assem_res`` call is stale (``transient.py:1001``), so the stopping rule is restated
+    (documented in ``oracle/model.py`` ``ImplicitCoupledOracle``): iterate x <- G(x) with
+    G = (solid solve with p(x), area update, fluid solve); stop when ||x_{k+1} - x_k||_2 <=
+    absolute_tolerance, or <= relative_tolerance * ||x_1 - x_0||_2, or after
+    ``maximum_iterations``.  Each solid/fluid solve runs on the device.
+    """
+
+    def _set_ini_fluid_state(self, qp0):
+        self.fluid.set_ini_state(qp0)
+
+    def _set_fin_fluid_state(self, qp1):
+        sl_control = self.solid.control.copy()
+        sl_control['p'] = 0
+        self.fluid.set_fin_state(qp1)
+        self.fsimap.map_fluid_to_solid(qp1[1], sl_control.sub['p'])
+        self.solid.set_control(sl_control)
+
+    def _set_ini_solid_state(self, uva0):
+        self.solid.set_ini_state(uva0)
+
+    _set_fin_solid_state = ExplicitFSIModel._set_fin_solid_state
+
+    def assem_res(self):
+        return bv.concatenate((self.solid.assem_res(), self.fluid.assem_res()))
+
+    def solve_state1(self, ini_state, options=None):
+        prm = dict(FIXEDPOINT_SOLVER_PRM)
+        prm['maximum_iterations'] = 50
+        newton_options = None
+        if options:
+            newton_options = options
+            for key in ('fixedpoint_absolute_tolerance', 'fixedpoint_relative_tolerance',
+                        'fixedpoint_maximum_iterations'):
+                if key in options:
+                    prm[key.replace('fixedpoint_', '')] = options[key]
+            newton_options = {k: v for k, v in options.items() if not k.startswith('fixedpoint_')}
+        x = ini_state.copy()
+        self.set_fin_state(x)
+        k, err0, abs_err, rel_err = 0, None, np.inf, np.inf
+        while True:
+            self._set_fin_fluid_state(x[3:])          # p(n+1) iterate onto the solid
+            uva1, solid_info = self.solid.solve_state1(x[:3], newton_options)
+            self._set_fin_solid_state(uva1)
+            qp1, _ = self.fluid.solve_state1(x[3:], newton_options)
+            x_new = bv.concatenate([uva1, qp1], labels=self.state1.labels)
+            abs_err = (x_new - x).norm()
+            if err0 is None:
+                err0 = abs_err
+            rel_err = abs_err / err0 if err0 > 0 else 0.0
+            x = x_new
+            k += 1
+            if abs_err <= prm['absolute_tolerance'] or rel_err <= prm['relative_tolerance'] \
+                    or k >= prm['maximum_iterations']:
+                break
+        self.set_fin_state(x)
+        return x, {'num_iter': k, 'abs_err': abs_err, 'rel_err': rel_err}
