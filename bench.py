@@ -248,6 +248,79 @@ def workload_config():
     }
 
 
+def run_partition(args, rank, world, local_rank):
+    """BASELINE configs[4]: extruded M5 tetrahedral mesh partitioned over the ranks; local
+    (communication-free) assembly and a fixed number of GMRES iterations with NCCL halo
+    exchange.  Extra measurement (own JSON line), not the driver's default workload."""
+    import torch
+    import torch.distributed as dist
+    from femvf_b200 import meshgen
+    from femvf_b200.distributed import DistributedSolid
+    from femvf_b200.residuals import solid as slr
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    t0 = time.perf_counter()
+    mt2 = meshgen.m5_cb_refined(BASE_H, args.levels2d, renumber=False)
+    nz = max(int(round(args.tets / (3.0 * mt2[0].num_cells()))), 1)
+    mt3 = meshgen.renumber_for_locality(meshgen.extrude_to_tets(mt2, 1.5, nz))
+    res = slr.KelvinVoigt(*mt3)
+    ds = DistributedSolid(res, rank, world, restart=30)
+    setup_s = time.perf_counter() - t0
+    mesh = res.mesh()
+    nn, ne = mesh.num_vertices(), mesh.num_cells()
+    rng = np.random.default_rng(0)
+    prop = dict(rho=np.full(ne, 1.0), eta=rng.uniform(1, 5, ne), emod=rng.uniform(2.5e4, 1e5, ne))
+    N = 3 * nn
+    state = dict(u1=rng.uniform(-1e-4, 1e-4, N), u0=rng.uniform(-1e-4, 1e-4, N),
+                 v0=rng.uniform(-1e-2, 1e-2, N), a0=rng.uniform(-1e2, 1e2, N))
+    p1 = rng.uniform(0, 8e3, nn)
+    scal = np.zeros(10); scal[0] = 0.45; scal[1] = np.inf; scal[2] = 1.0; scal[4] = 1.0
+    ds.upload_global(prop, state, p1, scal)
+    barrier = dist.barrier if world > 1 else None
+    dt = 1e-4
+    ms_asm = time_events(lambda: ds.assemble(dt), args.steps, args.warmup, barrier)
+    b = ds.owned('F').clone()
+    x = torch.empty_like(b)
+    iters = args.gmres_iters
+
+    def solve():
+        return ds.solve(b, x, rtol=0.0, atol=0.0, maxiter=iters)
+    solve()
+    ds.gmres.spmv_count = 0
+    ms_solve = time_events(solve, 1, 0, barrier)
+    t = torch.tensor([ms_asm, ms_solve], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    eng = ds.engine
+    own_nnz = int(9 * (ds.tables['brptr'][ds.part.n_own] - ds.tables['brptr'][0]))
+    line = {
+        'metric': 'partitioned_assembly_dof_per_s', 'unit': 'DOF/s',
+        'value': N * args.steps / (float(t[0]) * 1e-3), 'n_gpus': world, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': float(t[0]) / args.steps,
+        'higher_is_better': True, 'scaling': 'strong', 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': 'BASELINE configs[4]: M5_CB triangles extruded to tetrahedra, '
+                               'vertex ranges partitioned over ranks, owner-computes assembly + '
+                               'GMRES with NCCL halo exchange',
+                   'tets': ne, 'nn': nn, 'dof': N, 'nz': nz,
+                   'rank0': {'owned_nodes': ds.part.n_own, 'ghost_nodes': len(ds.part.ghost_global),
+                             'local_cells': len(ds.part.cell_ids), 'owned_nnz': own_nnz,
+                             'halo_send_bytes_per_spmv': ds.halo.halo_bytes}},
+        'gmres': {'iterations': iters, 'ms_total': float(t[1]),
+                  'iterations_per_s': iters / (float(t[1]) * 1e-3),
+                  'operator_applications': ds.gmres.spmv_count,
+                  'note': 'host-driven loop (one device->host read per reduction); CGS2, '
+                          'restart 30, left block-Jacobi'},
+        'setup_s': setup_s, 'gpu_launches': int(eng.launch_count),
+    }
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -256,6 +329,10 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--levels', type=int, default=REFINE_LEVELS)
     ap.add_argument('--skip-extras', action='store_true')
+    ap.add_argument('--workload', default='assembly', choices=['assembly', 'partition'])
+    ap.add_argument('--tets', type=float, default=5.0e6)
+    ap.add_argument('--levels2d', type=int, default=3)
+    ap.add_argument('--gmres-iters', type=int, default=60)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
 
@@ -265,6 +342,9 @@ def main():
 
     if args.impl == 'reference':
         run_reference(args, rank, world)
+        return
+    if args.workload == 'partition':
+        run_partition(args, rank, world, local_rank)
         return
 
     import torch

@@ -58,6 +58,7 @@ typedef struct vf_problem_desc {
   int32_t max_tile_elems;
   int32_t max_tile_pairs;
   int32_t tile2_threads;
+  int32_t fan_ok;             /* n2e lists are counter-clockwise fans (tables.order_fans_2d) */
   /* 1D fluid + FSI map (models/fsi.py:18-88) */
   int32_t n_fluid, ns, n_fsi;
   const double* s_host;           /* (n_fluid, ns) arclength coordinates */

@@ -25,7 +25,7 @@ extern "C" int hostcheck_assemble(
     const double* u1,
     const double* u0, const double* v0, const double* a0, const double* p1, double dt,
     double* J, double* F) {
-  vf::MeshView m{dim, nn, ne, nfp, xyz, cells, brptr, bcol, n2e_ptr, n2e,
+  vf::MeshView m{dim, nn, ne, nfp, xyz, nullptr, cells, brptr, bcol, n2e_ptr, n2e,
                  n2f_ptr, n2f, pf_cell, pf_opp, bc};
   vf::PropView p{rho, eta, emod, scal, emod_m, nu_m, th_m, contact, membrane, damping};
   vf::StateView s{u1, u0, v0, a0, p1, dt, 0};
@@ -47,7 +47,7 @@ extern "C" int hostcheck_assemble_tile2(
     const double* u0, const double* v0, const double* a0, const double* p1, double dt,
     int ntiles, const int* tile_start, const int* te_ptr, const int* te_elem,
     const unsigned* pair_info, int max_tile_elems, double* J, double* F) {
-  vf::MeshView m{2, nn, ne, nfp, xyz, cells, brptr, bcol, n2e_ptr, n2e,
+  vf::MeshView m{2, nn, ne, nfp, xyz, nullptr, cells, brptr, bcol, n2e_ptr, n2e,
                  n2f_ptr, n2f, pf_cell, pf_opp, bc};
   vf::PropView p{rho, eta, emod, scal, emod_m, nu_m, th_m, contact, membrane, damping};
   vf::StateView s{u1, u0, v0, a0, p1, dt, 0};
@@ -82,14 +82,15 @@ extern "C" int hostcheck_assemble_tile2(
         const unsigned info = pair_info[q];
         const double* rec = recs + (size_t)(info & 0xfffu) * vf::kRec2D;
         const int a = (info >> 12) & 3;
-        for (int c = 0; c < 3; ++c) {
+        vf::D2 w0[3], w1[3];
+        vf::tri_row_fan(rec, a, 0, w0[0], w0[1], w0[2]);
+        vf::tri_row_fan(rec, a, 1, w1[0], w1[1], w1[2]);
+        for (int c = 0; c < 3; ++c) {   // slots are (self, next, prev)
           const int slot = (info >> (14 + 6 * c)) & 63;
-          double b[2][2];
-          vf::tri_block(rec, a, c, b);
-          row0[2 * slot] += b[0][0];
-          row0[2 * slot + 1] += b[0][1];
-          row1[2 * slot] += b[1][0];
-          row1[2 * slot + 1] += b[1][1];
+          row0[2 * slot] += w0[c].x;
+          row0[2 * slot + 1] += w0[c].y;
+          row1[2 * slot] += w1[c].x;
+          row1[2 * slot + 1] += w1[c].y;
         }
         r0 += rec[9 + 2 * a];
         r1 += rec[10 + 2 * a];

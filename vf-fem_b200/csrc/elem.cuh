@@ -362,13 +362,46 @@ struct
   double x, y;
 };
 
-// u1/u0/v0/a0: interleaved nodal vectors; nd: the cell's vertices.  The nodal state is
-// consumed node by node (gradients and the lumped sums are accumulated on the fly) to keep
-// the live register set small.
-VF_HD void tri_record(const double (&x)[3][2], const int (&nd)[3], double emod,
-                      const LameFac& lf, double eta, double rho, const Damping& dp,
-                      const NewmarkCoef& nc, bool is_static, bool with_res, const double* u1,
-                      const double* u0, const double* v0, const double* a0, double* rec) {
+// Nodal state of one vertex as the residual needs it: u1 and the Newmark velocity /
+// acceleration (form.py:1107-1111), each an (x, y) pair.
+struct NodeUVA {
+  D2 u, v, a;
+};
+
+VF_HD NodeUVA node_uva(const NewmarkCoef& nc, bool is_static, const D2& p1, const D2& p0,
+                       const D2& pv, const D2& pa) {
+  NodeUVA r;
+  r.u = p1;
+  if (is_static) {
+    r.v = D2{0.0, 0.0};
+    r.a = D2{0.0, 0.0};
+  } else {
+    r.v = D2{newmark_v(nc, p1.x, p0.x, pv.x, pa.x), newmark_v(nc, p1.y, p0.y, pv.y, pa.y)};
+    r.a = D2{newmark_a(nc, p1.x, p0.x, pv.x, pa.x), newmark_a(nc, p1.y, p0.y, pv.y, pa.y)};
+  }
+  return r;
+}
+
+// Gather a vertex's state from the interleaved global vectors with 16-byte loads.
+VF_HD NodeUVA gather_node_uva(const NewmarkCoef& nc, bool is_static, int node, const double* u1,
+                              const double* u0, const double* v0, const double* a0) {
+  const D2 p1 = reinterpret_cast<const D2*>(u1)[node];
+  D2 p0 = D2{0.0, 0.0}, pv = D2{0.0, 0.0}, pa = D2{0.0, 0.0};
+  if (!is_static) {
+    p0 = reinterpret_cast<const D2*>(u0)[node];
+    pv = reinterpret_cast<const D2*>(v0)[node];
+    pa = reinterpret_cast<const D2*>(a0)[node];
+  }
+  return node_uva(nc, is_static, p1, p0, pv, pa);
+}
+
+// Record of one triangle.  `fetch(a)` returns the NodeUVA of the cell's a-th vertex; the nodal
+// state is consumed vertex by vertex (gradients and lumped sums accumulated on the fly) to
+// keep the live register set small.
+template <class Fetch>
+VF_HD void tri_record_t(const double (&x)[3][2], double emod, const LameFac& lf, double eta,
+                        double rho, const Damping& dp, const NewmarkCoef& nc, bool is_static,
+                        bool with_res, Fetch fetch, double* rec) {
   CellGeo<2> g;
   p1_geometry(x, g);
   const CellCoef cf = cell_coef<2>(emod, lf, eta, rho, g.vol, dp);
@@ -385,28 +418,14 @@ VF_HD void tri_record(const double (&x)[3][2], const int (&nd)[3], double emod,
   double gu[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, gv[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
   double As[2] = {0.0, 0.0}, Aa[3][2];  // lumped sums: massv a + vmass v
   for (int a = 0; a < 3; ++a) {
-    // 16-byte gathers of the node's (x, y) pair from the interleaved vectors
-    const D2 p1 = reinterpret_cast<const D2*>(u1)[nd[a]];
-    D2 p0 = D2{0.0, 0.0}, pv = D2{0.0, 0.0}, pa = D2{0.0, 0.0};
-    if (!is_static) {
-      p0 = reinterpret_cast<const D2*>(u0)[nd[a]];
-      pv = reinterpret_cast<const D2*>(v0)[nd[a]];
-      pa = reinterpret_cast<const D2*>(a0)[nd[a]];
-    }
-    const double w1c[2] = {p1.x, p1.y}, w0c[2] = {p0.x, p0.y}, wvc[2] = {pv.x, pv.y},
-                 wac[2] = {pa.x, pa.y};
+    const NodeUVA s = fetch(a);
+    const double w1c[2] = {s.u.x, s.u.y}, vc[2] = {s.v.x, s.v.y}, ac[2] = {s.a.x, s.a.y};
     for (int c = 0; c < 2; ++c) {
-      const double w1 = w1c[c];
-      double v = 0.0, acc = 0.0;
-      if (!is_static) {
-        v = newmark_v(nc, w1, w0c[c], wvc[c], wac[c]);
-        acc = newmark_a(nc, w1, w0c[c], wvc[c], wac[c]);
-      }
-      gu[c][0] += w1 * g.G[a][0];
-      gu[c][1] += w1 * g.G[a][1];
-      gv[c][0] += v * g.G[a][0];
-      gv[c][1] += v * g.G[a][1];
-      const double lump = cf.massv * acc + cf.vmass * v;
+      gu[c][0] += w1c[c] * g.G[a][0];
+      gu[c][1] += w1c[c] * g.G[a][1];
+      gv[c][0] += vc[c] * g.G[a][0];
+      gv[c][1] += vc[c] * g.G[a][1];
+      const double lump = cf.massv * ac[c] + cf.vmass * vc[c];
       As[c] += lump;
       Aa[a][c] = lump;
     }
@@ -427,6 +446,15 @@ VF_HD void tri_record(const double (&x)[3][2], const int (&nd)[3], double emod,
   r2[7] = D2{r[2][1], 0.0};
 }
 
+// Pointer version: every vertex is gathered from the global vectors.
+VF_HD void tri_record(const double (&x)[3][2], const int (&nd)[3], double emod,
+                      const LameFac& lf, double eta, double rho, const Damping& dp,
+                      const NewmarkCoef& nc, bool is_static, bool with_res, const double* u1,
+                      const double* u0, const double* v0, const double* a0, double* rec) {
+  tri_record_t(x, emod, lf, eta, rho, dp, nc, is_static, with_res,
+               [&](int a) { return gather_node_uva(nc, is_static, nd[a], u1, u0, v0, a0); }, rec);
+}
+
 // Block (a, c) of the cell matrix from a record; identical arithmetic to cell_block<2>.
 VF_HD void tri_block(const double* rec, int a, int c, double (&b)[2][2]) {
   const D2* r2 = reinterpret_cast<const D2*>(rec);
@@ -439,20 +467,51 @@ VF_HD void tri_block(const double* rec, int a, int c, double (&b)[2][2]) {
   b[1][1] = lamv * ga.y * gc.y + mv * gc.y * ga.y + dg;
 }
 
-// Scalar row `comp` of block (a, c) of the cell matrix, from a record; identical arithmetic
-// to cell_block<2>.
-VF_HD void tri_row_block(const double* rec, int a, int c, int comp, double& v0, double& v1) {
+// Scalar row `comp` of the blocks (a, a), (a, next), (a, prev) with next = (a+1)%3,
+// prev = (a+2)%3 (the cell's counter-clockwise order), from a record.
+VF_HD void tri_row_fan(const double* rec, int a, int comp, D2& w_self, D2& w_next, D2& w_prev) {
   const D2* r2 = reinterpret_cast<const D2*>(rec);
-  const D2 ga = r2[a], gc = r2[c], lm = r2[3];
-  const double lamv = lm.x, mv = lm.y;
-  const double gg = ga.x * gc.x + ga.y * gc.y;
-  const double ga_i = comp == 0 ? ga.x : ga.y;
-  const double gc_i = comp == 0 ? gc.x : gc.y;
-  v0 = lamv * ga_i * gc.x + mv * gc_i * ga.x;
-  v1 = lamv * ga_i * gc.y + mv * gc_i * ga.y;
-  const double dg = mv * gg + rec[8] * (a == c ? 2.0 : 1.0);
-  if (comp == 0) v0 += dg;
-  else v1 += dg;
+  const D2 g0 = r2[0], g1 = r2[1], g2 = r2[2], lm = r2[3];
+  const double mass = rec[8];
+  const D2 ga = a == 0 ? g0 : (a == 1 ? g1 : g2);
+  const D2 gn = a == 0 ? g1 : (a == 1 ? g2 : g0);
+  const D2 gp = a == 0 ? g2 : (a == 1 ? g0 : g1);
+  const double A = lm.x * (comp == 0 ? ga.x : ga.y);
+  const double Bx = lm.y * ga.x, By = lm.y * ga.y;
+  const D2 gc[3] = {ga, gn, gp};
+  D2 w[3];
+  for (int c = 0; c < 3; ++c) {
+    const double gc_i = comp == 0 ? gc[c].x : gc[c].y;
+    double w0 = A * gc[c].x + gc_i * Bx;
+    double w1 = A * gc[c].y + gc_i * By;
+    const double dg = gc[c].x * Bx + gc[c].y * By + mass * (c == 0 ? 2.0 : 1.0);
+    if (comp == 0) w0 += dg;
+    else w1 += dg;
+    w[c] = D2{w0, w1};
+  }
+  w_self = w[0];
+  w_next = w[1];
+  w_prev = w[2];
+}
+
+// Scalar row `comp` of the three blocks (a, c = 0..2) of the cell matrix, from a record.
+// Per-pair factors are hoisted (A = lv ga_i, B = mv ga); each block then costs 7 fp64 ops.
+VF_HD void tri_row_blocks(const double* rec, int a, int comp, D2 (&w)[3]) {
+  const D2* r2 = reinterpret_cast<const D2*>(rec);
+  const D2 ga = r2[a], lm = r2[3];
+  const double mass = rec[8];
+  const double A = lm.x * (comp == 0 ? ga.x : ga.y);
+  const double Bx = lm.y * ga.x, By = lm.y * ga.y;
+  for (int c = 0; c < 3; ++c) {
+    const D2 gc = r2[c];
+    const double gc_i = comp == 0 ? gc.x : gc.y;
+    double w0 = A * gc.x + gc_i * Bx;
+    double w1 = A * gc.y + gc_i * By;
+    const double dg = gc.x * Bx + gc.y * By + mass * (a == c ? 2.0 : 1.0);
+    if (comp == 0) w0 += dg;
+    else w1 += dg;
+    w[c] = D2{w0, w1};
+  }
 }
 
 }  // namespace vf

@@ -34,6 +34,7 @@ enum ScalarProp {
 struct MeshView {
   int dim, nn, ne, nfp;
   const double* xyz;    // SoA coordinates: xyz[c*nn + node]
+  const double* xy;     // 2D only: interleaved (x, y) per node for 16-byte gathers (else null)
   const int* cells;     // SoA connectivity: cells[a*ne + e]
   const int* brptr;     // node graph = block CSR pattern of J
   const int* bcol;

@@ -83,7 +83,6 @@ __global__ void asm_tile_kernel(EngineDev E, int member, double dt, int is_stati
 }
 
 
-constexpr int kTile2MaxThreads = 320;
 
 // Two-phase, element-centric tile assembly (triangles).  Replaces the thread-per-node gather
 // for 2D: every cell touching the tile is processed ONCE per CTA.
@@ -101,11 +100,11 @@ constexpr int kTile2MaxThreads = 320;
 // The exterior-facet terms and Dirichlet rows touch O(sqrt(N)) boundary nodes only and are
 // applied afterwards by facet_bc_kernel, which keeps this kernel's register budget small.
 // Shared memory: [records: max_tile_elems x 18][CSR slice][F: 2 x nodes][pair info][brptr][n2e_ptr].
-template <bool JAC, bool RES, bool ROW, int MINB>
-__global__ void __launch_bounds__(kTile2MaxThreads, MINB) asm_tile2_kernel(
-    EngineDev E, int member, double dt, int is_static, const int4* __restrict__ tile_desc,
+template <bool JAC, bool RES, int ROW, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) asm_tile2_kernel(
+    EngineDev E, int member, NewmarkCoef nc_arg, int is_static, const int4* __restrict__ tile_desc,
     const int4* __restrict__ te_quad, const unsigned* __restrict__ pair_info, int max_tile_elems,
-    int tile_max_values, int max_tile_pairs, int max_tile_nodes) {
+    int tile_max_values, int max_tile_pairs, int max_tile_nodes, int dbg_skip) {
   constexpr int D = 2;
   extern __shared__ double smem[];
   double* recs = smem;
@@ -114,6 +113,9 @@ __global__ void __launch_bounds__(kTile2MaxThreads, MINB) asm_tile2_kernel(
   unsigned* s_pair = reinterpret_cast<unsigned*>(tileF + D * max_tile_nodes);
   int* s_brptr = reinterpret_cast<int*>(s_pair + max_tile_pairs);
   int* s_n2e = s_brptr + max_tile_nodes + 1;
+  // nodal data of the tile's own (contiguous) vertices: coordinates and u1 / v_nmk / a_nmk
+  D2* s_xy = reinterpret_cast<D2*>(tileF + D * max_tile_nodes + ((max_tile_pairs + 2 * (max_tile_nodes + 1) + 3) / 4) * 2);
+  NodeUVA* s_uva = reinterpret_cast<NodeUVA*>(s_xy + max_tile_nodes);
   double* mb = E.members + (size_t)member * E.L.stride;
   const Layout& L = E.L;
   const MeshView& m = E.mesh;
@@ -138,10 +140,12 @@ __global__ void __launch_bounds__(kTile2MaxThreads, MINB) asm_tile2_kernel(
   }
   // Lame / Newmark coefficients: a handful of fp64 divisions, done once per CTA
   __shared__ LameFac s_lf;
-  __shared__ NewmarkCoef s_nc;
-  if (threadIdx.x == 0) {
-    s_lf = lame_fac(pv.scal[SC_NU]);
-    s_nc = newmark_coef(dt);
+  if (threadIdx.x == 0) s_lf = lame_fac(pv.scal[SC_NU]);
+  // stage the tile's own vertices with coalesced 16-byte loads; v_nmk / a_nmk are evaluated
+  // once per vertex here instead of once per (cell, vertex) in phase 1
+  for (int n = threadIdx.x; n < nT; n += blockDim.x) {
+    s_xy[n] = reinterpret_cast<const D2*>(m.xy)[i0 + n];
+    if (RES) s_uva[n] = gather_node_uva(nc_arg, is_static != 0, i0 + n, u1, u0, v0, a0);
   }
   // the vertex quads of this thread's cells (issued before the barrier: independent loads)
   int4 quad = make_int4(0, 0, 0, 0);
@@ -152,27 +156,84 @@ __global__ void __launch_bounds__(kTile2MaxThreads, MINB) asm_tile2_kernel(
   // ---- phase 1: one record per cell --------------------------------------------------------
   {
     const LameFac lf = s_lf;
-    const NewmarkCoef nc = s_nc;
+    const NewmarkCoef nc = nc_arg;
     const Damping dp = prop_damping(pv);
-    for (int q = te0 + threadIdx.x; q < te1; q += blockDim.x) {
+    for (int q = te0 + threadIdx.x; q < te1 && !(dbg_skip & 1); q += blockDim.x) {
       if (q != te0 + (int)threadIdx.x) quad = te_quad[q];
       const int e = quad.w;
       const int nd[3] = {quad.x, quad.y, quad.z};
       double x[3][2];
 #pragma unroll
       for (int a = 0; a < 3; ++a) {
-        x[a][0] = m.xyz[nd[a]];
-        x[a][1] = m.xyz[m.nn + nd[a]];
+        const unsigned ln = (unsigned)(nd[a] - i0);
+        const D2 c2 = ln < (unsigned)nT ? s_xy[ln] : reinterpret_cast<const D2*>(m.xy)[nd[a]];
+        x[a][0] = c2.x;
+        x[a][1] = c2.y;
       }
-      tri_record(x, nd, pv.emod[e], lf, pv.eta[e], pv.rho[e], dp, nc, is_static != 0, RES, u1, u0,
-                 v0, a0, recs + (size_t)(q - te0) * kRec2D);
+      tri_record_t(
+          x, pv.emod[e], lf, pv.eta[e], pv.rho[e], dp, nc, is_static != 0, RES,
+          [&](int a) {
+            const unsigned ln = (unsigned)(nd[a] - i0);  // own vertex: shared memory
+            return ln < (unsigned)nT
+                       ? s_uva[ln]
+                       : gather_node_uva(nc, is_static != 0, nd[a], u1, u0, v0, a0);
+          },
+          recs + (size_t)(q - te0) * kRec2D);
     }
   }
   __syncthreads();
 
   // ---- phase 2 ---------------------------------------------------------------------------------
-  if (ROW) {
-    // one thread per scalar row
+  if (dbg_skip & 2) {
+    // measurement aid (VF_DEBUG_SKIP): phase skipped
+  } else if (ROW == 2) {
+    // one thread per scalar row; the row's cells are visited counter-clockwise around the
+    // vertex (tables.order_fans_2d), so every off-diagonal block is the sum of two
+    // CONSECUTIVE cells: it is completed in registers and stored once -- no zero-fill and no
+    // read-modify-write of the shared-memory slice
+    for (int r = threadIdx.x; r < D * nT; r += blockDim.x) {
+      const int n = r >> 1, comp = r & 1;
+      const int b0 = s_brptr[n], deg = s_brptr[n + 1] - b0;
+      double* row = tileJ + D * D * (b0 - bbase) + comp * D * deg;
+      double racc = 0.0;
+      D2 diag = D2{0.0, 0.0}, carry = D2{0.0, 0.0}, first = D2{0.0, 0.0};
+      int slot_first = -1, slot_carry = -2, slot_self = 0;
+      const int qb = s_n2e[n] - pr0, qe = s_n2e[n + 1] - pr0;
+      for (int q = qb; q < qe; ++q) {
+        const unsigned info = s_pair[q];
+        const double* rec = recs + (size_t)(info & 0xfffu) * kRec2D;
+        const int a = (info >> 12) & 3;
+        if (JAC) {
+          D2 ws, wn, wp;
+          tri_row_fan(rec, a, comp, ws, wn, wp);
+          slot_self = (info >> 14) & 63;
+          const int slot_next = (info >> 20) & 63;
+          diag.x += ws.x;
+          diag.y += ws.y;
+          if (q == qb) {
+            first = wn;
+            slot_first = slot_next;
+          } else {
+            *reinterpret_cast<D2*>(row + D * slot_next) = D2{carry.x + wn.x, carry.y + wn.y};
+          }
+          carry = wp;
+          slot_carry = (info >> 26) & 63;
+        }
+        if (RES) racc += rec[9 + 2 * a + comp];
+      }
+      if (JAC && qe > qb) {
+        if (slot_carry == slot_first) {
+          *reinterpret_cast<D2*>(row + D * slot_first) = D2{first.x + carry.x, first.y + carry.y};
+        } else {
+          *reinterpret_cast<D2*>(row + D * slot_first) = first;
+          *reinterpret_cast<D2*>(row + D * slot_carry) = carry;
+        }
+        *reinterpret_cast<D2*>(row + D * slot_self) = diag;
+      }
+      if (RES) tileF[r] = racc;
+    }
+  } else if (ROW == 1) {
+    // one thread per scalar row, read-modify-write accumulation (any cell order)
     for (int r = threadIdx.x; r < D * nT; r += blockDim.x) {
       const int n = r >> 1, comp = r & 1;
       const int b0 = s_brptr[n], deg = s_brptr[n + 1] - b0;
@@ -188,15 +249,15 @@ __global__ void __launch_bounds__(kTile2MaxThreads, MINB) asm_tile2_kernel(
         const double* rec = recs + (size_t)(info & 0xfffu) * kRec2D;
         const int a = (info >> 12) & 3;
         if (JAC) {
+          D2 wv[3];
+          tri_row_fan(rec, a, comp, wv[0], wv[1], wv[2]);  // slots are (self, next, prev)
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
             const int slot = (info >> (14 + 6 * c)) & 63;
-            double w0, w1;
-            tri_row_block(rec, a, c, comp, w0, w1);
             D2* dst = reinterpret_cast<D2*>(row + D * slot);
             D2 cur = *dst;
-            cur.x += w0;
-            cur.y += w1;
+            cur.x += wv[c].x;
+            cur.y += wv[c].y;
             *dst = cur;
           }
         }
@@ -222,8 +283,9 @@ __global__ void __launch_bounds__(kTile2MaxThreads, MINB) asm_tile2_kernel(
         const int a = (info >> 12) & 3;
         if (JAC) {
 #pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            const int slot = (info >> (14 + 6 * c)) & 63;
+          for (int sft = 0; sft < 3; ++sft) {
+            const int slot = (info >> (14 + 6 * sft)) & 63;  // slots are (self, next, prev)
+            const int c = (a + sft) % 3;
             double b[2][2];
             tri_block(rec, a, c, b);
             D2* p0 = reinterpret_cast<D2*>(row0 + D * slot);
@@ -251,6 +313,7 @@ __global__ void __launch_bounds__(kTile2MaxThreads, MINB) asm_tile2_kernel(
   __syncthreads();
 
   // ---- phase 3: coalesced write-out ---------------------------------------------------------------
+  if (dbg_skip & 4) return;
   if (JAC) {
     double2* dst = reinterpret_cast<double2*>(mb + L.off[VF_J] + base);
     const double2* src = reinterpret_cast<const double2*>(tileJ);
@@ -660,6 +723,7 @@ struct vf_engine {
   int* touch_dev;
   int n_touch;
   bool two_phase;
+  bool fan_ok;
   std::vector<int32_t> brptr, bcol;
   int member_threads;
   int64_t launches;
@@ -671,7 +735,7 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct ArenaPlan {
   // byte offsets of the shared tables
-  size_t xyz, cells, brptr, bcol, n2e_ptr, n2e, n2f_ptr, n2f, pf_cell, pf_opp, bc, tile_start, s,
+  size_t xyz, xy, cells, brptr, bcol, n2e_ptr, n2e, n2f_ptr, n2f, pf_cell, pf_opp, bc, tile_start, s,
       fsi_solid, fsi_fluid, fsip_solid, fsip_fluid, te_ptr, te_elem, pair_info, tile_desc, te_quad, touch, members, total;
   Layout L;
   long long nnz;
@@ -693,6 +757,7 @@ ArenaPlan plan_arena(const vf_problem_desc& d) {
   const int n_n2e = d.n2e_ptr_host ? d.n2e_ptr_host[d.nn] : 0;
   const int n_n2f = d.n2f_ptr_host ? d.n2f_ptr_host[d.nn] : 0;
   P.xyz = take(sizeof(double) * d.dim * d.nn);
+  P.xy = take(sizeof(double) * 2 * (d.dim == 2 ? d.nn : 1));
   P.cells = take(sizeof(int) * nen * d.ne);
   P.brptr = take(sizeof(int) * (d.nn + 1));
   P.bcol = take(sizeof(int) * nnzb);
@@ -781,6 +846,15 @@ cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 double* member_array(vf_engine* e, int id, int member) {
   return e->dev.members + (size_t)member * e->dev.L.stride + e->dev.L.off[id];
+}
+
+// dynamic shared memory of asm_tile2_kernel: records, CSR slice, F, index slices (padded to
+// 16 bytes), nodal staging (coordinates + u/v/a: 4 x 16 bytes per own vertex)
+size_t tile2_smem_bytes(const vf_problem_desc& d) {
+  const size_t idx_words = (size_t)d.max_tile_pairs + 2 * ((size_t)d.tile_threads + 1);
+  return sizeof(double) * ((size_t)d.max_tile_elems * kRec2D + d.tile_max_values +
+                           2 * (size_t)d.tile_threads + ((idx_words + 3) / 4) * 2) +
+         64 * (size_t)d.tile_threads;
 }
 
 SolverOpts to_opts(const vf_solver_opts* o) {
@@ -907,6 +981,15 @@ int vf_create(const vf_problem_desc* desc, void* arena_dev, size_t arena_bytes, 
     return cudaMemcpyAsync(A + off, src, bytes, cudaMemcpyHostToDevice, st);
   };
   VF_CUDA(up(P.xyz, d.xyz_host, sizeof(double) * d.dim * d.nn));
+  std::vector<double> xy;
+  if (d.dim == 2) {
+    xy.resize((size_t)2 * d.nn);
+    for (int i = 0; i < d.nn; ++i) {
+      xy[2 * (size_t)i] = d.xyz_host[i];
+      xy[2 * (size_t)i + 1] = d.xyz_host[(size_t)d.nn + i];
+    }
+    VF_CUDA(up(P.xy, xy.data(), sizeof(double) * xy.size()));
+  }
   VF_CUDA(up(P.cells, d.cells_host, sizeof(int) * nen * d.ne));
   VF_CUDA(up(P.brptr, d.brptr_host, sizeof(int) * (d.nn + 1)));
   VF_CUDA(up(P.bcol, d.bcol_host, sizeof(int) * nnzb));
@@ -958,6 +1041,7 @@ int vf_create(const vf_problem_desc* desc, void* arena_dev, size_t arena_bytes, 
   e->desc.te_ptr_host = nullptr; e->desc.te_elem_host = nullptr; e->desc.pair_info_host = nullptr;
   e->desc.tile_desc_host = nullptr; e->desc.te_quad_host = nullptr;
   e->two_phase = two_phase;
+  e->fan_ok = d.fan_ok != 0;
   e->touch_dev = reinterpret_cast<int*>(A + P.touch);
   e->n_touch = (int)touch.size();
   e->te_ptr_dev = reinterpret_cast<int*>(A + P.te_ptr);
@@ -969,6 +1053,7 @@ int vf_create(const vf_problem_desc* desc, void* arena_dev, size_t arena_bytes, 
   EngineDev& E = e->dev;
   E.mesh.dim = d.dim; E.mesh.nn = d.nn; E.mesh.ne = d.ne; E.mesh.nfp = d.nfp;
   E.mesh.xyz = reinterpret_cast<const double*>(A + P.xyz);
+  E.mesh.xy = d.dim == 2 ? reinterpret_cast<const double*>(A + P.xy) : nullptr;
   E.mesh.cells = reinterpret_cast<const int*>(A + P.cells);
   E.mesh.brptr = reinterpret_cast<const int*>(A + P.brptr);
   E.mesh.bcol = reinterpret_cast<const int*>(A + P.bcol);
@@ -1003,22 +1088,24 @@ int vf_create(const vf_problem_desc* desc, void* arena_dev, size_t arena_bytes, 
     VF_CUDA(cudaFuncSetAttribute(asm_tile_kernel<3, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   }
   if (two_phase) {
-    const int smem2 = (int)(sizeof(double) * (d.max_tile_elems * kRec2D + d.tile_max_values +
-                                              2 * d.tile_threads) +
-                            sizeof(int) * (d.max_tile_pairs + 2 * (d.tile_threads + 1)));
+    const int smem2 = (int)tile2_smem_bytes(d);
     if (smem2 > 227 * 1024) {
       delete e;
       return fail("two-phase tile exceeds the 227 KB shared memory of an SM");
     }
 #define VF_SMEM2(K) VF_CUDA(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2))
-    VF_SMEM2((asm_tile2_kernel<true, true, true, 2>));
-    VF_SMEM2((asm_tile2_kernel<true, true, true, 3>));
-    VF_SMEM2((asm_tile2_kernel<true, true, true, 4>));
-    VF_SMEM2((asm_tile2_kernel<true, true, false, 2>));
-    VF_SMEM2((asm_tile2_kernel<true, true, false, 3>));
-    VF_SMEM2((asm_tile2_kernel<true, true, false, 4>));
-    VF_SMEM2((asm_tile2_kernel<true, false, true, 2>));
-    VF_SMEM2((asm_tile2_kernel<false, true, true, 2>));
+#define VF_SMEM2_ALL(J_, R_, ROW_)                          \
+  VF_SMEM2((asm_tile2_kernel<J_, R_, ROW_, 128, 8>));       \
+  VF_SMEM2((asm_tile2_kernel<J_, R_, ROW_, 192, 5>));       \
+  VF_SMEM2((asm_tile2_kernel<J_, R_, ROW_, 320, 3>))
+    VF_SMEM2_ALL(true, true, 0);
+    VF_SMEM2_ALL(true, true, 1);
+    VF_SMEM2_ALL(true, true, 2);
+    VF_SMEM2_ALL(true, false, 0);
+    VF_SMEM2_ALL(true, false, 1);
+    VF_SMEM2_ALL(true, false, 2);
+    VF_SMEM2_ALL(false, true, 1);
+#undef VF_SMEM2_ALL
 #undef VF_SMEM2
   }
   *out = e;
@@ -1088,24 +1175,34 @@ int vf_assemble(vf_engine* e, int member, int flags, double dt, int is_static, v
   const int grid = e->desc.ntiles, block = e->desc.tile_threads;
   if (e->two_phase) {
     const vf_problem_desc& d = e->desc;
-    const size_t smem2 = sizeof(double) * ((size_t)d.max_tile_elems * kRec2D + d.tile_max_values +
-                                           2 * d.tile_threads) +
-                         sizeof(int) * (d.max_tile_pairs + 2 * (d.tile_threads + 1));
-#define VF_LAUNCH_ASM2(J_, R_, ROW_, MB_)                                                          \
-  asm_tile2_kernel<J_, R_, ROW_, MB_><<<grid, d.tile2_threads, smem2, st>>>(                       \
-      e->dev, member, dt, is_static, e->tile_desc_dev, e->te_quad_dev, e->pair_info_dev,          \
-      d.max_tile_elems, d.tile_max_values, d.max_tile_pairs, d.tile_threads)
-    const int v_row = getenv("VF_TILE2_ROW") ? atoi(getenv("VF_TILE2_ROW")) : 1;
-    const int v_minb = getenv("VF_TILE2_MINB") ? atoi(getenv("VF_TILE2_MINB")) : 3;
-    if (jac && res) {
-      if (v_row && v_minb == 2) VF_LAUNCH_ASM2(true, true, true, 2);
-      else if (v_row && v_minb == 3) VF_LAUNCH_ASM2(true, true, true, 3);
-      else if (v_row) VF_LAUNCH_ASM2(true, true, true, 4);
-      else if (v_minb == 2) VF_LAUNCH_ASM2(true, true, false, 2);
-      else if (v_minb == 3) VF_LAUNCH_ASM2(true, true, false, 3);
-      else VF_LAUNCH_ASM2(true, true, false, 4);
-    } else if (jac) VF_LAUNCH_ASM2(true, false, true, 2);
-    else VF_LAUNCH_ASM2(false, true, true, 2);
+    const size_t smem2 = tile2_smem_bytes(d);
+#define VF_LAUNCH_ASM2(J_, R_, ROW_, MT_, MB_)                                                     \
+  asm_tile2_kernel<J_, R_, ROW_, MT_, MB_><<<grid, d.tile2_threads, smem2, st>>>(                  \
+      e->dev, member, newmark_coef(dt), is_static, e->tile_desc_dev, e->te_quad_dev,               \
+      e->pair_info_dev,                                                                            \
+      d.max_tile_elems, d.tile_max_values, d.max_tile_pairs, d.tile_threads, dbg_skip)
+    const int dbg_skip = getenv("VF_DEBUG_SKIP") ? atoi(getenv("VF_DEBUG_SKIP")) : 0;
+    int v_row = getenv("VF_TILE2_ROW") ? atoi(getenv("VF_TILE2_ROW")) : 2;
+    if (v_row == 2 && !e->fan_ok) v_row = 1;
+    // occupancy class by CTA size: small CTAs run many per SM so that their phases overlap
+    const int nt = d.tile2_threads;
+#define VF_ASM2_BY_SIZE(J_, R_, ROW_)                                                              \
+  do {                                                                                            \
+    if (nt <= 128) VF_LAUNCH_ASM2(J_, R_, ROW_, 128, 8);                                          \
+    else if (nt <= 192) VF_LAUNCH_ASM2(J_, R_, ROW_, 192, 5);                                     \
+    else VF_LAUNCH_ASM2(J_, R_, ROW_, 320, 3);                                                    \
+  } while (0)
+#define VF_ASM2_BY_MODE(J_, R_)                                                                    \
+  do {                                                                                            \
+    if (v_row == 2) VF_ASM2_BY_SIZE(J_, R_, 2);                                                   \
+    else if (v_row == 1) VF_ASM2_BY_SIZE(J_, R_, 1);                                              \
+    else VF_ASM2_BY_SIZE(J_, R_, 0);                                                              \
+  } while (0)
+    if (jac && res) VF_ASM2_BY_MODE(true, true);
+    else if (jac) VF_ASM2_BY_MODE(true, false);
+    else VF_ASM2_BY_SIZE(false, true, 1);
+#undef VF_ASM2_BY_MODE
+#undef VF_ASM2_BY_SIZE
 #undef VF_LAUNCH_ASM2
     e->launches += 1;
     VF_CUDA(cudaGetLastError());

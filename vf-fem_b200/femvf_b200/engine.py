@@ -97,8 +97,8 @@ class Engine:
             want = max(tile2['max_tile_elems'], d * nodes_per_tile)
             tile2_threads = int(os.environ.get('VF_TILE2_THREADS', str(-(-want // 32) * 32)))
             smem = 8 * (18 * tile2['max_tile_elems'] + tile_max + d * nodes_per_tile) \
-                + 4 * (tile2['max_tile_pairs'] + 2 * nodes_per_tile + 8)
-            if smem > 200 * 1024 or tile2_threads > 1024:
+                + 4 * (tile2['max_tile_pairs'] + 2 * nodes_per_tile + 8) + 64 * nodes_per_tile
+            if smem > 200 * 1024 or tile2_threads > 320:
                 tile2, tile2_threads = None, 0
         self.tile_info = {'nodes_per_tile': nodes_per_tile, 'ntiles': len(tile_start) - 1,
                           'tile_max_values': tile_max, 'two_phase': tile2 is not None,
@@ -144,7 +144,7 @@ class Engine:
             _ptr(keep.get('te_ptr')), _ptr(keep.get('te_elem')), _ptr(keep.get('pair_info')),
             _ptr(keep.get('tile_desc')), _ptr(keep.get('te_quad')),
             tile2['max_tile_elems'] if tile2 else 0, tile2['max_tile_pairs'] if tile2 else 0,
-            tile2_threads,
+            tile2_threads, int(bool(tables.get('fan_ok', False))),
             self.n_fluid, self.ns, len(fsia_solid), _ptr(s), _ptr(fsia_solid), _ptr(fsia_fluid),
             len(fsip_solid), _ptr(fsip_solid), _ptr(fsip_fluid),
             int(fluid_kind), int(idx_sep), int(bool(contact)), int(bool(membrane)),

@@ -53,6 +53,63 @@ def _csr_from_pairs(keys: np.ndarray, vals: np.ndarray, n: int):
     return np.cumsum(ptr).astype(np.int32), vals.astype(np.int32)
 
 
+def order_fans_2d(cells: np.ndarray, n2e_ptr: np.ndarray, n2e: np.ndarray, nn: int):
+    """
+    Reorder every vertex's adjacent-cell list counter-clockwise around the vertex (cells are
+    positively oriented), so that consecutive cells share the edge (vertex, prev(cell)) ==
+    (vertex, next(next cell)).  Open fans (boundary vertices) start at the cell whose ``next``
+    edge is a boundary edge.  Returns (n2e_reordered, ok); ``ok`` is False when some vertex
+    star is not a single fan (non-manifold vertex), in which case the input order is kept.
+    """
+    n2e_ptr = n2e_ptr.astype(np.int64)
+    npair = len(n2e)
+    e, a = n2e.astype(np.int64) >> 2, n2e.astype(np.int64) & 3
+    node = np.repeat(np.arange(nn), np.diff(n2e_ptr))
+    nxt = cells[e, (a + 1) % 3]
+    prv = cells[e, (a + 2) % 3]
+    # successor of pair q: the pair of the same vertex whose next vertex is prev(q)
+    key_next = node * nn + nxt
+    order = np.argsort(key_next, kind='stable')
+    ks = key_next[order]
+    if np.any(ks[1:] == ks[:-1]):
+        return n2e, False                      # an edge with two cells on the same side
+    want = node * nn + prv
+    pos = np.searchsorted(ks, want)
+    pos_c = np.minimum(pos, npair - 1)
+    has_succ = ks[pos_c] == want
+    succ = np.where(has_succ, order[pos_c], -1)
+    has_pred = np.zeros(npair, dtype=bool)
+    has_pred[succ[has_succ]] = True
+    # start of each fan: the pair without predecessor (open fan) or the first listed (closed)
+    start = n2e_ptr[:-1].copy()
+    nopred = np.nonzero(~has_pred)[0]
+    cnt = np.zeros(nn, dtype=np.int64)
+    np.add.at(cnt, node[nopred], 1)
+    if np.any(cnt > 1):
+        return n2e, False                      # more than one open fan at a vertex
+    start[node[nopred]] = nopred
+    deg = np.diff(n2e_ptr)
+    rank = -np.ones(npair, dtype=np.int64)
+    cur = start.copy()
+    alive = deg > 0
+    for r in range(int(deg.max()) if npair else 0):
+        idx = np.nonzero(alive & (r < deg))[0]
+        c = cur[idx]
+        good = c >= 0
+        if not np.all(good):
+            return n2e, False
+        rank[c] = r
+        cur[idx] = succ[c]
+    if np.any(rank < 0):
+        return n2e, False
+    new_pos = n2e_ptr[node] + rank
+    if len(np.unique(new_pos)) != npair:
+        return n2e, False
+    out = np.empty_like(n2e)
+    out[new_pos] = n2e
+    return out, True
+
+
 def build_tables(coords, cells, pf_cell, pf_opp, fixed_dofs):
     """
     Parameters
@@ -74,6 +131,9 @@ def build_tables(coords, cells, pf_cell, pf_opp, fixed_dofs):
     e_idx = np.repeat(np.arange(ne, dtype=np.int64), nen)
     a_idx = np.tile(np.arange(nen, dtype=np.int64), ne)
     n2e_ptr, n2e = _csr_from_pairs(cells.ravel(), e_idx * 4 + a_idx, nn)
+    fan_ok = False
+    if d == 2:
+        n2e, fan_ok = order_fans_2d(cells, n2e_ptr, n2e, nn)
 
     pf_cell = np.asarray(pf_cell, dtype=np.int64).reshape(-1)
     pf_opp = np.asarray(pf_opp, dtype=np.int64).reshape(-1)
@@ -95,7 +155,7 @@ def build_tables(coords, cells, pf_cell, pf_opp, fixed_dofs):
         'brptr': brptr, 'bcol': bcol, 'rowptr': rowptr, 'colidx': colidx,
         'n2e_ptr': n2e_ptr, 'n2e': n2e, 'n2f_ptr': n2f_ptr, 'n2f': n2f,
         'pf_cell': pf_cell.astype(np.int32), 'pf_opp': pf_opp.astype(np.int32),
-        'bc': bc,
+        'bc': bc, 'fan_ok': bool(fan_ok),
     }
 
 
@@ -129,7 +189,7 @@ def build_tile_elem_tables(T: dict, tile_start: np.ndarray):
     pair_info      : one uint32 per (node, adjacent cell) pair in ``n2e`` order:
                      bits [0,12) index of the cell in its node's tile list, [12,14) local
                      index a of the node in the cell, [14,20) [20,26) [26,32) CSR slots (within
-                     the node's block row) of the cell's three vertices
+                     the node's block row) of the cell's vertices a, (a+1)%3, (a+2)%3
     Returns None when the packing limits (4096 cells per tile, 64 blocks per row) do not hold.
     """
     d, nn, ne = T['dim'], T['nn'], T['ne']
@@ -166,8 +226,8 @@ def build_tile_elem_tables(T: dict, tile_start: np.ndarray):
     # CSR slot of each vertex of the cell in the node's block row
     gkey = np.repeat(np.arange(nn), np.diff(brptr)) * nn + bcol  # sorted globally
     slots = []
-    for c in range(3):
-        col = cells[pe, c]
+    for shift in range(3):   # the pair's own vertex, then next and prev in the cell's CCW order
+        col = cells[pe, (pa + shift) % 3]
         pos = np.searchsorted(gkey, pair_node * nn + col)
         slots.append(pos - brptr[pair_node])
     info = (local.astype(np.uint64) | (pa.astype(np.uint64) << np.uint64(12))
