@@ -405,7 +405,7 @@ def main():
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': dict(workload_config(), nn=nn, ne=ne, dof=N, nnz=nnz,
                        parallelism=f'{world} independent mesh shards, no collective'),
-        'roofline': {'kernel': 'asm_tile2_kernel<true,true> (+ facet_bc_kernel on boundary nodes)', 'bound': 'hbm',
+        'roofline': {'kernel': 'asm_tile2_kernel<true,true,2,320,3> (+ facet_bc_kernel on boundary nodes)', 'bound': 'hbm',
                      'achieved': asm_gbs, 'peak': peak, 'unit': 'GB/s', 'frac': asm_gbs / peak,
                      # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel on
                      # this workload, from the ncu --set full capture summarised in

@@ -325,6 +325,216 @@ __global__ void __launch_bounds__(MAXT, MINB) asm_tile2_kernel(
   }
 }
 
+
+// ---- persistent, software-pipelined variant of the two-phase tile kernel --------------------
+// One CTA per resident slot loops over tiles (tile = blockIdx.x + k * gridDim.x).  All index
+// data and the raw nodal data of tile k+1 are fetched with cp.async (LDGSTS) into the other
+// half of a double-buffered shared-memory input area while tile k is being processed, and the
+// descriptor of tile k+2 travels in registers, so the dependent chain
+// descriptor -> index slices -> nodal gathers no longer sits on the critical path of a CTA.
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+struct Tile3In {       // one half of the input area (pointers into shared memory)
+  int4* quad;          // vertex quads of the tile's cells
+  D2* raw;             // [5][max_nodes]: xy, u1, u0, v0, a0 of the tile's own vertices
+  unsigned* pair;
+  int* brptr;
+  int* n2e;
+};
+
+template <bool JAC, bool RES, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) asm_tile3_kernel(
+    EngineDev E, int member, NewmarkCoef nc, int is_static, const int4* __restrict__ tile_desc,
+    const int4* __restrict__ te_quad, const unsigned* __restrict__ pair_info, int ntiles,
+    int max_tile_elems, int tile_max_values, int max_tile_pairs, int max_tile_nodes) {
+  constexpr int D = 2;
+  extern __shared__ double smem[];
+  double* recs = smem;
+  double* tileJ = recs + (size_t)max_tile_elems * kRec2D;
+  double* tileF = tileJ + tile_max_values;
+  NodeUVA* s_uva = reinterpret_cast<NodeUVA*>(tileF + D * max_tile_nodes);
+  char* in_base = reinterpret_cast<char*>(s_uva + max_tile_nodes);
+  const size_t quad_b = 16 * (size_t)max_tile_elems, raw_b = 80 * (size_t)max_tile_nodes;
+  const size_t pair_b = (4 * (size_t)max_tile_pairs + 15) & ~size_t(15);
+  const size_t ptr_b = (4 * ((size_t)max_tile_nodes + 1) + 15) & ~size_t(15);
+  const size_t in_b = quad_b + raw_b + pair_b + 2 * ptr_b;
+  Tile3In in[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    char* b = in_base + h * in_b;
+    in[h].quad = reinterpret_cast<int4*>(b);
+    in[h].raw = reinterpret_cast<D2*>(b + quad_b);
+    in[h].pair = reinterpret_cast<unsigned*>(b + quad_b + raw_b);
+    in[h].brptr = reinterpret_cast<int*>(b + quad_b + raw_b + pair_b);
+    in[h].n2e = reinterpret_cast<int*>(b + quad_b + raw_b + pair_b + ptr_b);
+  }
+  double* mb = E.members + (size_t)member * E.L.stride;
+  const Layout& L = E.L;
+  const MeshView& m = E.mesh;
+  const PropView pv = member_props<D>(E, mb);
+  const double* u1 = mb + L.off[VF_U1];
+  const double* u0 = is_static ? u1 : mb + L.off[VF_U0];
+  const double* v0 = mb + L.off[VF_V0];
+  const double* a0 = mb + L.off[VF_A0];
+  const D2* gsrc[5] = {reinterpret_cast<const D2*>(m.xy), reinterpret_cast<const D2*>(u1),
+                       reinterpret_cast<const D2*>(u0), reinterpret_cast<const D2*>(v0),
+                       reinterpret_cast<const D2*>(a0)};
+  const int nraw = RES ? 5 : 1;
+
+  auto issue = [&](const int4& d0, const int4& d1, const Tile3In& dst) {
+    const int i0 = d0.x, nT = d0.y - d0.x, te0 = d0.z, ne_t = d0.w - d0.z;
+    const int pr0 = d1.x, npair = d1.y - d1.x;
+    for (int t = threadIdx.x; t < ne_t; t += blockDim.x) cp_async16(dst.quad + t, te_quad + te0 + t);
+    for (int f = 0; f < nraw; ++f)
+      for (int t = threadIdx.x; t < nT; t += blockDim.x)
+        cp_async16(dst.raw + (size_t)f * max_tile_nodes + t, gsrc[f] + i0 + t);
+    for (int t = threadIdx.x; t < npair; t += blockDim.x) cp_async4(dst.pair + t, pair_info + pr0 + t);
+    for (int t = threadIdx.x; t <= nT; t += blockDim.x) {
+      cp_async4(dst.brptr + t, m.brptr + i0 + t);
+      cp_async4(dst.n2e + t, m.n2e_ptr + i0 + t);
+    }
+    cp_async_commit();
+  };
+
+  __shared__ LameFac s_lf;
+  if (threadIdx.x == 0) s_lf = lame_fac(pv.scal[SC_NU]);
+  int tile = blockIdx.x;
+  if (tile >= ntiles) return;
+  int4 c0 = tile_desc[2 * tile], c1 = tile_desc[2 * tile + 1];
+  issue(c0, c1, in[0]);
+  int next = tile + gridDim.x;
+  int4 n0 = c0, n1 = c1;
+  if (next < ntiles) {
+    n0 = tile_desc[2 * next];
+    n1 = tile_desc[2 * next + 1];
+  }
+  const Damping dp = prop_damping(pv);
+
+  for (int k = 0;; ++k) {
+    const Tile3In& I = in[k & 1];
+    cp_async_wait_all();
+    __syncthreads();  // inputs of this tile have landed; the previous tile is fully retired
+    if (next < ntiles) issue(n0, n1, in[(k & 1) ^ 1]);
+    const int next2 = next + gridDim.x;
+    int4 m0 = n0, m1 = n1;
+    if (next2 < ntiles) {  // descriptor of the tile after next: plain loads, consumed next round
+      m0 = tile_desc[2 * next2];
+      m1 = tile_desc[2 * next2 + 1];
+    }
+    const int i0 = c0.x, nT = c0.y - c0.x, ne_t = c0.w - c0.z;
+    const int pr0 = c1.x, bbase = c1.z, bend = c1.w;
+    const size_t base = (size_t)D * D * bbase;
+    const int nvals = D * D * (bend - bbase);
+    const LameFac lf = s_lf;
+
+    // own vertices: v_nmk / a_nmk once per vertex
+    if (RES) {
+      for (int n = threadIdx.x; n < nT; n += blockDim.x)
+        s_uva[n] = node_uva(nc, is_static != 0, I.raw[(size_t)max_tile_nodes + n],
+                            I.raw[2 * (size_t)max_tile_nodes + n],
+                            I.raw[3 * (size_t)max_tile_nodes + n],
+                            I.raw[4 * (size_t)max_tile_nodes + n]);
+      __syncthreads();
+    }
+
+    // ---- phase 1: one record per cell ------------------------------------------------------
+    for (int q = threadIdx.x; q < ne_t; q += blockDim.x) {
+      const int4 quad = I.quad[q];
+      const int e = quad.w;
+      const int nd[3] = {quad.x, quad.y, quad.z};
+      double x[3][2];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const unsigned ln = (unsigned)(nd[a] - i0);
+        const D2 c2 = ln < (unsigned)nT ? I.raw[ln] : reinterpret_cast<const D2*>(m.xy)[nd[a]];
+        x[a][0] = c2.x;
+        x[a][1] = c2.y;
+      }
+      tri_record_t(
+          x, pv.emod[e], lf, pv.eta[e], pv.rho[e], dp, nc, is_static != 0, RES,
+          [&](int a) {
+            const unsigned ln = (unsigned)(nd[a] - i0);
+            return ln < (unsigned)nT
+                       ? s_uva[ln]
+                       : gather_node_uva(nc, is_static != 0, nd[a], u1, u0, v0, a0);
+          },
+          recs + (size_t)q * kRec2D);
+    }
+    __syncthreads();
+
+    // ---- phase 2: one thread per scalar row, cells visited as a counter-clockwise fan -------
+    for (int r = threadIdx.x; r < D * nT; r += blockDim.x) {
+      const int n = r >> 1, comp = r & 1;
+      const int b0 = I.brptr[n], deg = I.brptr[n + 1] - b0;
+      double* row = tileJ + D * D * (b0 - bbase) + comp * D * deg;
+      double racc = 0.0;
+      D2 diag = D2{0.0, 0.0}, carry = D2{0.0, 0.0}, first = D2{0.0, 0.0};
+      int slot_first = -1, slot_carry = -2, slot_self = 0;
+      const int qb = I.n2e[n] - pr0, qe = I.n2e[n + 1] - pr0;
+      for (int q = qb; q < qe; ++q) {
+        const unsigned info = I.pair[q];
+        const double* rec = recs + (size_t)(info & 0xfffu) * kRec2D;
+        const int a = (info >> 12) & 3;
+        if (JAC) {
+          D2 ws, wn, wp;
+          tri_row_fan(rec, a, comp, ws, wn, wp);
+          slot_self = (info >> 14) & 63;
+          const int slot_next = (info >> 20) & 63;
+          diag.x += ws.x;
+          diag.y += ws.y;
+          if (q == qb) {
+            first = wn;
+            slot_first = slot_next;
+          } else {
+            *reinterpret_cast<D2*>(row + D * slot_next) = D2{carry.x + wn.x, carry.y + wn.y};
+          }
+          carry = wp;
+          slot_carry = (info >> 26) & 63;
+        }
+        if (RES) racc += rec[9 + 2 * a + comp];
+      }
+      if (JAC && qe > qb) {
+        if (slot_carry == slot_first) {
+          *reinterpret_cast<D2*>(row + D * slot_first) = D2{first.x + carry.x, first.y + carry.y};
+        } else {
+          *reinterpret_cast<D2*>(row + D * slot_first) = first;
+          *reinterpret_cast<D2*>(row + D * slot_carry) = carry;
+        }
+        *reinterpret_cast<D2*>(row + D * slot_self) = diag;
+      }
+      if (RES) tileF[r] = racc;
+    }
+    __syncthreads();
+
+    // ---- phase 3: coalesced write-out -----------------------------------------------------------
+    if (JAC) {
+      double2* dst = reinterpret_cast<double2*>(mb + L.off[VF_J] + base);
+      const double2* src = reinterpret_cast<const double2*>(tileJ);
+      for (int t = threadIdx.x; t < nvals / 2; t += blockDim.x) __stcs(dst + t, src[t]);
+    }
+    if (RES) {
+      double* F = mb + L.off[VF_F] + (size_t)D * i0;
+      for (int t = threadIdx.x; t < D * nT; t += blockDim.x) F[t] = tileF[t];
+    }
+    if (next >= ntiles) break;
+    c0 = n0;
+    c1 = n1;
+    n0 = m0;
+    n1 = m1;
+    tile = next;
+    next = next2;
+  }
+}
+
 // Exterior-facet terms (follower pressure, contact, membrane) and Dirichlet rows of the
 // boundary nodes, applied in place to the rows the tile kernel has written.  One thread owns
 // one node: private rows, fixed order, no atomics.
@@ -857,6 +1067,15 @@ size_t tile2_smem_bytes(const vf_problem_desc& d) {
          64 * (size_t)d.tile_threads;
 }
 
+size_t tile3_smem_bytes(const vf_problem_desc& d) {
+  const size_t mn = d.tile_threads;  // >= nodes per tile
+  const size_t quad_b = 16 * (size_t)d.max_tile_elems, raw_b = 80 * mn;
+  const size_t pair_b = (4 * (size_t)d.max_tile_pairs + 15) & ~size_t(15);
+  const size_t ptr_b = (4 * (mn + 1) + 15) & ~size_t(15);
+  return sizeof(double) * ((size_t)d.max_tile_elems * kRec2D + d.tile_max_values + 2 * mn) +
+         48 * mn + 2 * (quad_b + raw_b + pair_b + 2 * ptr_b);
+}
+
 SolverOpts to_opts(const vf_solver_opts* o) {
   SolverOpts s;
   if (o) {
@@ -1181,6 +1400,40 @@ int vf_assemble(vf_engine* e, int member, int flags, double dt, int is_static, v
       e->dev, member, newmark_coef(dt), is_static, e->tile_desc_dev, e->te_quad_dev,               \
       e->pair_info_dev,                                                                            \
       d.max_tile_elems, d.tile_max_values, d.max_tile_pairs, d.tile_threads, dbg_skip)
+    bool done3 = false;
+    // the persistent cp.async-pipelined variant measured slower than the plain kernel (fewer
+    // resident CTAs; profiles/README.md) and is off unless VF_TILE3=1
+    const int use_t3 = getenv("VF_TILE3") ? atoi(getenv("VF_TILE3")) : 0;
+    if (use_t3 && e->fan_ok && tile3_smem_bytes(d) <= 227 * 1024) {
+      const size_t smem3 = tile3_smem_bytes(d);
+      const int nt3 = d.tile2_threads;
+      const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (227 * 1024) / (smem3 + 1024)));
+#define VF_LAUNCH_ASM3(J_, R_, MT_, MB_)                                                           \
+  do {                                                                                            \
+    VF_CUDA(cudaFuncSetAttribute(asm_tile3_kernel<J_, R_, MT_, MB_>,                              \
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));       \
+    const int g3 = std::min(grid, 148 * std::min(per_sm, MB_));                                   \
+    asm_tile3_kernel<J_, R_, MT_, MB_><<<g3, nt3, smem3, st>>>(                                   \
+        e->dev, member, newmark_coef(dt), is_static, e->tile_desc_dev, e->te_quad_dev,           \
+        e->pair_info_dev, grid, d.max_tile_elems, d.tile_max_values, d.max_tile_pairs,           \
+        d.tile_threads);                                                                          \
+  } while (0)
+#define VF_ASM3_BY_SIZE(J_, R_)                                                                    \
+  do {                                                                                            \
+    if (nt3 <= 128) VF_LAUNCH_ASM3(J_, R_, 128, 8);                                               \
+    else if (nt3 <= 224) VF_LAUNCH_ASM3(J_, R_, 224, 4);                                          \
+    else VF_LAUNCH_ASM3(J_, R_, 320, 3);                                                          \
+  } while (0)
+      if (jac && res) VF_ASM3_BY_SIZE(true, true);
+      else if (jac) VF_ASM3_BY_SIZE(true, false);
+      else VF_ASM3_BY_SIZE(false, true);
+#undef VF_ASM3_BY_SIZE
+#undef VF_LAUNCH_ASM3
+      e->launches += 1;
+      VF_CUDA(cudaGetLastError());
+      done3 = true;
+    }
+    if (!done3) {
     const int dbg_skip = getenv("VF_DEBUG_SKIP") ? atoi(getenv("VF_DEBUG_SKIP")) : 0;
     int v_row = getenv("VF_TILE2_ROW") ? atoi(getenv("VF_TILE2_ROW")) : 2;
     if (v_row == 2 && !e->fan_ok) v_row = 1;
@@ -1206,6 +1459,7 @@ int vf_assemble(vf_engine* e, int member, int flags, double dt, int is_static, v
 #undef VF_LAUNCH_ASM2
     e->launches += 1;
     VF_CUDA(cudaGetLastError());
+    }
     if (e->n_touch > 0) {
       const int fb = 128, fg = (e->n_touch + fb - 1) / fb;
       if (jac && res)
