@@ -671,6 +671,38 @@ __global__ void apply_block_jacobi_kernel(const double* __restrict__ Dinv,
 
 // partial[b][j] = sum over the block's chunk of V_j[i] w[i]; fixed-order reductions so the
 // result is bit-reproducible; a second kernel adds the partials in block order.
+
+// Thread-per-node gather writing the node's block row straight to the global CSR array (no
+// shared-memory slice).  Used for tetrahedra, where a block row is ~1 KB: staging it in shared
+// memory caps the resident threads at ~200 per SM, while here occupancy is bounded by
+// registers only.  Rows are private to their thread, so the accumulation is still
+// deterministic; the read-modify-write traffic stays in L1/L2.
+template <int D, bool JAC, bool RES>
+__global__ void __launch_bounds__(128, 3)
+asm_node_global_kernel(EngineDev E, int member, double dt, int is_static) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= E.mesh.nn) return;
+  double* mb = E.members + (size_t)member * E.L.stride;
+  const Layout& L = E.L;
+  PropView pv = member_props<D>(E, mb);
+  StateView sv;
+  sv.u1 = mb + L.off[VF_U1];
+  sv.u0 = is_static ? sv.u1 : mb + L.off[VF_U0];
+  sv.v0 = mb + L.off[VF_V0];
+  sv.a0 = mb + L.off[VF_A0];
+  sv.p1 = mb + L.off[VF_P1];
+  sv.dt = dt;
+  sv.is_static = is_static;
+  double res[D];
+  assemble_node<D, JAC, RES>(i, E.mesh, pv, sv,
+                             JAC ? mb + L.off[VF_J] + (size_t)D * D * E.mesh.brptr[i] : nullptr, res);
+  if (RES) {
+    double* F = mb + L.off[VF_F];
+#pragma unroll
+    for (int c = 0; c < D; ++c) F[D * i + c] = res[c];
+  }
+}
+
 constexpr int kDotBlock = 256;
 __global__ void multidot_partial_kernel(const double* __restrict__ V, size_t ldv, int nvec,
                                         const double* __restrict__ w, size_t n,
@@ -1471,6 +1503,15 @@ int vf_assemble(vf_engine* e, int member, int flags, double dt, int is_static, v
       e->launches += 1;
       VF_CUDA(cudaGetLastError());
     }
+    return 0;
+  }
+  if (e->desc.dim == 3 && !(getenv("VF_TET_SMEM") && atoi(getenv("VF_TET_SMEM")))) {
+    const int nb = 128, ng = (e->desc.nn + nb - 1) / nb;
+    if (jac && res) asm_node_global_kernel<3, true, true><<<ng, nb, 0, st>>>(e->dev, member, dt, is_static);
+    else if (jac) asm_node_global_kernel<3, true, false><<<ng, nb, 0, st>>>(e->dev, member, dt, is_static);
+    else asm_node_global_kernel<3, false, true><<<ng, nb, 0, st>>>(e->dev, member, dt, is_static);
+    e->launches += 1;
+    VF_CUDA(cudaGetLastError());
     return 0;
   }
   const size_t smem = jac ? (size_t)e->desc.tile_max_values * sizeof(double) : 0;

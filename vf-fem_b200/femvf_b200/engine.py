@@ -162,6 +162,7 @@ class Engine:
         self._h = handle
         self.nnz = int(self._lib.vf_nnz(self._h))
         self._views = {}
+        self._pinned = {}
 
     # --- plumbing -------------------------------------------------------------------
     def _stream(self):
@@ -202,9 +203,18 @@ class Engine:
         check(self._lib.vf_upload(self._h, ARRAY_IDS[name], member, _ptr(a), a.size,
                                   self._stream()))
 
-    def download(self, name: str, member: int = 0) -> np.ndarray:
+    def download(self, name: str, member: int = 0, pinned: bool = False) -> np.ndarray:
+        """Device -> host copy of a named array.  ``pinned=True`` returns a view of a cached
+        page-locked staging buffer (valid until the next pinned download of that array): large
+        results such as the CSR values then move at full PCIe rate."""
         v = self.view(name, member)
-        out = np.empty(v.numel(), dtype=np.float64)
+        if pinned:
+            key = (name, member)
+            if key not in self._pinned:
+                self._pinned[key] = torch.empty(v.numel(), dtype=torch.float64, pin_memory=True)
+            out = self._pinned[key].numpy()
+        else:
+            out = np.empty(v.numel(), dtype=np.float64)
         check(self._lib.vf_download(self._h, ARRAY_IDS[name], member, _ptr(out), out.size,
                                     self._stream()))
         return out

@@ -158,6 +158,13 @@ class FenicsModel(BaseTransientModel):
         self._engine: Optional[Engine] = None
         self._engine_provider = None
         self._member = 0
+        # Host -> device synchronisation policy.  The reference mutates host vectors freely, so
+        # by default every device call re-uploads state, control and properties.  With
+        # ``trust_setters = True`` only the groups changed through set_ini_state /
+        # set_fin_state / set_control / set_prop / dt since the last device call are uploaded
+        # (in-place edits of the BlockVectors then need ``mark_dirty()``).
+        self.trust_setters = False
+        self._dirty = {'prop': True, 'state0': True, 'state1': True, 'control': True}
         self.set_prop(self.prop)
 
     # --- engine management -----------------------------------------------------------
@@ -199,16 +206,24 @@ class FenicsModel(BaseTransientModel):
     def dt(self, value):
         self.residual.form['time/dt'].vector()[:] = value
 
+    def mark_dirty(self, *groups):
+        for g in (groups or self._dirty.keys()):
+            self._dirty[g] = True
+
     def set_ini_state(self, state):
         self.state0[:] = state
+        self._dirty['state0'] = True
 
     def set_fin_state(self, state):
         self.state1[:] = state
+        self._dirty['state1'] = True
 
     def set_control(self, p1):
         self.control[:] = p1
+        self._dirty['control'] = True
 
     def set_prop(self, prop):
+        self._dirty['prop'] = True
         for key, value in prop.sub_items():
             self.residual.form['prop/' + key].vector()[:] = np.ravel(value) \
                 if np.size(value) > 1 else np.ravel(value)[0]
@@ -248,8 +263,20 @@ class FenicsModel(BaseTransientModel):
         e.upload('p1', self.control['p'], m)
 
     def _push_all(self):
-        self._push_prop(getattr(self, '_ymid', 0.0))
-        self._push_state()
+        e, m = self.engine, self._member
+        every = not self.trust_setters
+        if every or self._dirty['prop']:
+            self._push_prop(getattr(self, '_ymid', 0.0))
+        if every or self._dirty['state0']:
+            for name, vec in zip(('u0', 'v0', 'a0'), self.state0.vecs):
+                e.upload(name, vec, m)
+        if every or self._dirty['state1']:
+            for name, vec in zip(('u1', 'v1', 'a1'), self.state1.vecs):
+                e.upload(name, vec, m)
+        if every or self._dirty['control']:
+            e.upload('p1', self.control['p'], m)
+        for g in self._dirty:
+            self._dirty[g] = False
 
     # --- residual and sensitivities -----------------------------------------------------
     def assem_res(self):
@@ -270,7 +297,7 @@ class FenicsModel(BaseTransientModel):
     def _assem_jac_uu(self, is_static: bool = False) -> sp.csr_matrix:
         self._push_all()
         self.engine.assemble(self._member, res=False, jac=True, dt=self.dt, is_static=is_static)
-        vals = self.engine.download('J', self._member)
+        vals = self.engine.download('J', self._member, pinned=self.trust_setters)
         rowptr, colidx = self.csr_pattern()
         N = self.state0['u'].size
         return sp.csr_matrix((vals, colidx, rowptr), shape=(N, N))
