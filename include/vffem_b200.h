@@ -53,10 +53,13 @@ typedef struct vf_problem_desc {
   const int32_t* te_ptr_host;     /* (ntiles+1) */
   const int32_t* te_elem_host;    /* (te_ptr[ntiles]) */
   const uint32_t* pair_info_host; /* (n2e_ptr[nn]) */
-  const int32_t* tile_desc_host;  /* (ntiles, 8): i0 i1 te0 te1 pair0 pair1 blk0 blk1 */
-  const int32_t* te_quad_host;    /* (te_ptr[ntiles], 4): the cell's 3 vertices + cell id */
+  const int32_t* tile_desc_host;  /* (ntiles, 8): i0 te0 pair0 blk0 halo0 nT|nH<<16 ncell|npair<<16 nblk */
+  const int32_t* te_quad_host;    /* (te_ptr[ntiles], 4): local slots of the cell's 3 vertices + cell id */
+  const int32_t* tile_halo_host;  /* (n_tile_halo) halo vertices of the tiles, ascending per tile */
   int32_t max_tile_elems;
   int32_t max_tile_pairs;
+  int32_t n_tile_halo;
+  int32_t max_tile_verts;     /* max own + halo vertices of a tile */
   int32_t tile2_threads;
   int32_t fan_ok;             /* n2e lists are counter-clockwise fans (tables.order_fans_2d) */
   /* 1D fluid + FSI map (models/fsi.py:18-88) */

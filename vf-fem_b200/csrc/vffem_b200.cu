@@ -100,85 +100,121 @@ __global__ void asm_tile_kernel(EngineDev E, int member, double dt, int is_stati
 // The exterior-facet terms and Dirichlet rows touch O(sqrt(N)) boundary nodes only and are
 // applied afterwards by facet_bc_kernel, which keeps this kernel's register budget small.
 // Shared memory: [records: max_tile_elems x 18][CSR slice][F: 2 x nodes][pair info][brptr][n2e_ptr].
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ int4 ldg_nc_v4(const int4* p) {
+  int4 r;
+  asm volatile("ld.global.nc.v4.s32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ double ldg_nc_f64(const double* p) {
+  double r;
+  asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(r) : "l"(p));
+  return r;
+}
+
 template <bool JAC, bool RES, int ROW, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) asm_tile2_kernel(
     EngineDev E, int member, NewmarkCoef nc_arg, int is_static, const int4* __restrict__ tile_desc,
-    const int4* __restrict__ te_quad, const unsigned* __restrict__ pair_info, int max_tile_elems,
-    int tile_max_values, int max_tile_pairs, int max_tile_nodes, int dbg_skip) {
+    const int4* __restrict__ te_quad, const unsigned* __restrict__ pair_info,
+    const int* __restrict__ tile_halo, int max_tile_elems, int tile_max_values,
+    int max_tile_pairs, int max_tile_nodes, int max_tile_verts, int dbg_skip) {
   constexpr int D = 2;
   extern __shared__ double smem[];
   double* recs = smem;
+  // region A: the CSR slice (phases 2-3) aliases the nodal staging area (phases 0-1)
   double* tileJ = recs + (size_t)max_tile_elems * kRec2D;
-  double* tileF = tileJ + tile_max_values;
+  D2* s_xy = reinterpret_cast<D2*>(tileJ);
+  NodeUVA* s_uva = reinterpret_cast<NodeUVA*>(s_xy + max_tile_verts);
+  const size_t region_a = max((size_t)tile_max_values, (size_t)8 * max_tile_verts);
+  double* tileF = tileJ + region_a;
   unsigned* s_pair = reinterpret_cast<unsigned*>(tileF + D * max_tile_nodes);
   int* s_brptr = reinterpret_cast<int*>(s_pair + max_tile_pairs);
   int* s_n2e = s_brptr + max_tile_nodes + 1;
-  // nodal data of the tile's own (contiguous) vertices: coordinates and u1 / v_nmk / a_nmk
-  D2* s_xy = reinterpret_cast<D2*>(tileF + D * max_tile_nodes + ((max_tile_pairs + 2 * (max_tile_nodes + 1) + 3) / 4) * 2);
-  NodeUVA* s_uva = reinterpret_cast<NodeUVA*>(s_xy + max_tile_nodes);
   double* mb = E.members + (size_t)member * E.L.stride;
   const Layout& L = E.L;
   const MeshView& m = E.mesh;
 
-  // ---- phase 0: descriptor, then independent index loads -------------------------------------
+  // ---- phase 0: descriptor, then every load of the tile in one dependent round ---------------
   const int4 d0 = tile_desc[2 * blockIdx.x], d1 = tile_desc[2 * blockIdx.x + 1];
-  const int i0 = d0.x, i1 = d0.y, te0 = d0.z, te1 = d0.w;
-  const int pr0 = d1.x, pr1 = d1.y, bbase = d1.z, bend = d1.w;
-  const int nT = i1 - i0;
+  const int i0 = d0.x, te0 = d0.y, pr0 = d0.z, bbase = d0.w;
+  const int h0 = d1.x, nT = d1.y & 0xffff, nH = (int)((unsigned)d1.y >> 16);
+  const int nte = d1.z & 0xffff, npr = (int)((unsigned)d1.z >> 16);
+  const int nV = nT + nH;
   const size_t base = (size_t)D * D * bbase;
-  const int nvals = D * D * (bend - bbase);
+  const int nvals = D * D * d1.w;
   const PropView pv = member_props<D>(E, mb);
   const double* u1 = mb + L.off[VF_U1];
   const double* u0 = is_static ? u1 : mb + L.off[VF_U0];
   const double* v0 = mb + L.off[VF_V0];
   const double* a0 = mb + L.off[VF_A0];
 
-  for (int t = threadIdx.x; t < pr1 - pr0; t += blockDim.x) s_pair[t] = pair_info[pr0 + t];
+  // this thread's first cell (volatile load: issued here, not sunk below the barrier)
+  int4 quad = make_int4(0, 0, 0, 0);
+  const bool have = (int)threadIdx.x < nte;
+  if (have) quad = ldg_nc_v4(te_quad + te0 + threadIdx.x);
+  // index slices: asynchronous global->shared copies, no registers, waited for at the barrier
+  for (int t = threadIdx.x; t < npr; t += blockDim.x) cp_async4(s_pair + t, pair_info + pr0 + t);
   for (int t = threadIdx.x; t <= nT; t += blockDim.x) {
-    s_brptr[t] = m.brptr[i0 + t];
-    s_n2e[t] = m.n2e_ptr[i0 + t];
+    cp_async4(s_brptr + t, m.brptr + i0 + t);
+    cp_async4(s_n2e + t, m.n2e_ptr + i0 + t);
   }
+  cp_async_commit();
   // Lame / Newmark coefficients: a handful of fp64 divisions, done once per CTA
   __shared__ LameFac s_lf;
-  if (threadIdx.x == 0) s_lf = lame_fac(pv.scal[SC_NU]);
-  // stage the tile's own vertices with coalesced 16-byte loads; v_nmk / a_nmk are evaluated
-  // once per vertex here instead of once per (cell, vertex) in phase 1
-  for (int n = threadIdx.x; n < nT; n += blockDim.x) {
-    s_xy[n] = reinterpret_cast<const D2*>(m.xy)[i0 + n];
-    if (RES) s_uva[n] = gather_node_uva(nc_arg, is_static != 0, i0 + n, u1, u0, v0, a0);
+  if (threadIdx.x == blockDim.x - 1) s_lf = lame_fac(pv.scal[SC_NU]);
+  // stage the tile's vertices -- its own contiguous range, then the halo vertices of its
+  // cells -- with 16-byte loads; v_nmk / a_nmk are evaluated once per vertex here instead of
+  // once per (cell, vertex) in phase 1, and phase 1 reads shared memory only
+  for (int t = threadIdx.x; t < nV; t += blockDim.x) {
+    const int vtx = t < nT ? i0 + t : tile_halo[h0 + t - nT];
+    s_xy[t] = reinterpret_cast<const D2*>(m.xy)[vtx];
+    if (RES) s_uva[t] = gather_node_uva(nc_arg, is_static != 0, vtx, u1, u0, v0, a0);
   }
-  // the vertex quads of this thread's cells (issued before the barrier: independent loads)
-  int4 quad = make_int4(0, 0, 0, 0);
-  const bool have = te0 + (int)threadIdx.x < te1;
-  if (have) quad = te_quad[te0 + threadIdx.x];
+  // the quad has arrived by now: the cell's material data, also before the barrier
+  double emod_e = 0.0, eta_e = 0.0, rho_e = 0.0;
+  if (have) {
+    emod_e = ldg_nc_f64(pv.emod + quad.w);
+    eta_e = ldg_nc_f64(pv.eta + quad.w);
+    rho_e = ldg_nc_f64(pv.rho + quad.w);
+  }
+  cp_async_wait_all();
   __syncthreads();
 
-  // ---- phase 1: one record per cell --------------------------------------------------------
+  // ---- phase 1: one record per cell, from shared memory ----------------------------------------
   {
     const LameFac lf = s_lf;
     const NewmarkCoef nc = nc_arg;
     const Damping dp = prop_damping(pv);
-    for (int q = te0 + threadIdx.x; q < te1 && !(dbg_skip & 1); q += blockDim.x) {
-      if (q != te0 + (int)threadIdx.x) quad = te_quad[q];
-      const int e = quad.w;
-      const int nd[3] = {quad.x, quad.y, quad.z};
+    for (int q = threadIdx.x; q < nte && !(dbg_skip & 1); q += blockDim.x) {
+      if (q != (int)threadIdx.x) {
+        quad = te_quad[te0 + q];
+        emod_e = pv.emod[quad.w];
+        eta_e = pv.eta[quad.w];
+        rho_e = pv.rho[quad.w];
+      }
+      const int nd[3] = {quad.x, quad.y, quad.z};  // local slots in the staged vertex list
       double x[3][2];
 #pragma unroll
       for (int a = 0; a < 3; ++a) {
-        const unsigned ln = (unsigned)(nd[a] - i0);
-        const D2 c2 = ln < (unsigned)nT ? s_xy[ln] : reinterpret_cast<const D2*>(m.xy)[nd[a]];
+        const D2 c2 = s_xy[nd[a]];
         x[a][0] = c2.x;
         x[a][1] = c2.y;
       }
       tri_record_t(
-          x, pv.emod[e], lf, pv.eta[e], pv.rho[e], dp, nc, is_static != 0, RES,
-          [&](int a) {
-            const unsigned ln = (unsigned)(nd[a] - i0);  // own vertex: shared memory
-            return ln < (unsigned)nT
-                       ? s_uva[ln]
-                       : gather_node_uva(nc, is_static != 0, nd[a], u1, u0, v0, a0);
-          },
-          recs + (size_t)(q - te0) * kRec2D);
+          x, emod_e, lf, eta_e, rho_e, dp, nc, is_static != 0, RES,
+          [&](int a) { return s_uva[nd[a]]; }, recs + (size_t)q * kRec2D);
     }
   }
   __syncthreads();
@@ -326,218 +362,6 @@ __global__ void __launch_bounds__(MAXT, MINB) asm_tile2_kernel(
 }
 
 
-// ---- persistent, software-pipelined variant of the two-phase tile kernel --------------------
-// One CTA per resident slot loops over tiles (tile = blockIdx.x + k * gridDim.x).  All index
-// data and the raw nodal data of tile k+1 are fetched with cp.async (LDGSTS) into the other
-// half of a double-buffered shared-memory input area while tile k is being processed, and the
-// descriptor of tile k+2 travels in registers, so the dependent chain
-// descriptor -> index slices -> nodal gathers no longer sits on the critical path of a CTA.
-__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src));
-}
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
-struct Tile3In {       // one half of the input area (pointers into shared memory)
-  int4* quad;          // vertex quads of the tile's cells
-  D2* raw;             // [5][max_nodes]: xy, u1, u0, v0, a0 of the tile's own vertices
-  unsigned* pair;
-  int* brptr;
-  int* n2e;
-};
-
-template <bool JAC, bool RES, int MAXT, int MINB>
-__global__ void __launch_bounds__(MAXT, MINB) asm_tile3_kernel(
-    EngineDev E, int member, NewmarkCoef nc, int is_static, const int4* __restrict__ tile_desc,
-    const int4* __restrict__ te_quad, const unsigned* __restrict__ pair_info, int ntiles,
-    int max_tile_elems, int tile_max_values, int max_tile_pairs, int max_tile_nodes) {
-  constexpr int D = 2;
-  extern __shared__ double smem[];
-  double* recs = smem;
-  double* tileJ = recs + (size_t)max_tile_elems * kRec2D;
-  double* tileF = tileJ + tile_max_values;
-  NodeUVA* s_uva = reinterpret_cast<NodeUVA*>(tileF + D * max_tile_nodes);
-  char* in_base = reinterpret_cast<char*>(s_uva + max_tile_nodes);
-  const size_t quad_b = 16 * (size_t)max_tile_elems, raw_b = 80 * (size_t)max_tile_nodes;
-  const size_t pair_b = (4 * (size_t)max_tile_pairs + 15) & ~size_t(15);
-  const size_t ptr_b = (4 * ((size_t)max_tile_nodes + 1) + 15) & ~size_t(15);
-  const size_t in_b = quad_b + raw_b + pair_b + 2 * ptr_b;
-  Tile3In in[2];
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    char* b = in_base + h * in_b;
-    in[h].quad = reinterpret_cast<int4*>(b);
-    in[h].raw = reinterpret_cast<D2*>(b + quad_b);
-    in[h].pair = reinterpret_cast<unsigned*>(b + quad_b + raw_b);
-    in[h].brptr = reinterpret_cast<int*>(b + quad_b + raw_b + pair_b);
-    in[h].n2e = reinterpret_cast<int*>(b + quad_b + raw_b + pair_b + ptr_b);
-  }
-  double* mb = E.members + (size_t)member * E.L.stride;
-  const Layout& L = E.L;
-  const MeshView& m = E.mesh;
-  const PropView pv = member_props<D>(E, mb);
-  const double* u1 = mb + L.off[VF_U1];
-  const double* u0 = is_static ? u1 : mb + L.off[VF_U0];
-  const double* v0 = mb + L.off[VF_V0];
-  const double* a0 = mb + L.off[VF_A0];
-  const D2* gsrc[5] = {reinterpret_cast<const D2*>(m.xy), reinterpret_cast<const D2*>(u1),
-                       reinterpret_cast<const D2*>(u0), reinterpret_cast<const D2*>(v0),
-                       reinterpret_cast<const D2*>(a0)};
-  const int nraw = RES ? 5 : 1;
-
-  auto issue = [&](const int4& d0, const int4& d1, const Tile3In& dst) {
-    const int i0 = d0.x, nT = d0.y - d0.x, te0 = d0.z, ne_t = d0.w - d0.z;
-    const int pr0 = d1.x, npair = d1.y - d1.x;
-    for (int t = threadIdx.x; t < ne_t; t += blockDim.x) cp_async16(dst.quad + t, te_quad + te0 + t);
-    for (int f = 0; f < nraw; ++f)
-      for (int t = threadIdx.x; t < nT; t += blockDim.x)
-        cp_async16(dst.raw + (size_t)f * max_tile_nodes + t, gsrc[f] + i0 + t);
-    for (int t = threadIdx.x; t < npair; t += blockDim.x) cp_async4(dst.pair + t, pair_info + pr0 + t);
-    for (int t = threadIdx.x; t <= nT; t += blockDim.x) {
-      cp_async4(dst.brptr + t, m.brptr + i0 + t);
-      cp_async4(dst.n2e + t, m.n2e_ptr + i0 + t);
-    }
-    cp_async_commit();
-  };
-
-  __shared__ LameFac s_lf;
-  if (threadIdx.x == 0) s_lf = lame_fac(pv.scal[SC_NU]);
-  int tile = blockIdx.x;
-  if (tile >= ntiles) return;
-  int4 c0 = tile_desc[2 * tile], c1 = tile_desc[2 * tile + 1];
-  issue(c0, c1, in[0]);
-  int next = tile + gridDim.x;
-  int4 n0 = c0, n1 = c1;
-  if (next < ntiles) {
-    n0 = tile_desc[2 * next];
-    n1 = tile_desc[2 * next + 1];
-  }
-  const Damping dp = prop_damping(pv);
-
-  for (int k = 0;; ++k) {
-    const Tile3In& I = in[k & 1];
-    cp_async_wait_all();
-    __syncthreads();  // inputs of this tile have landed; the previous tile is fully retired
-    if (next < ntiles) issue(n0, n1, in[(k & 1) ^ 1]);
-    const int next2 = next + gridDim.x;
-    int4 m0 = n0, m1 = n1;
-    if (next2 < ntiles) {  // descriptor of the tile after next: plain loads, consumed next round
-      m0 = tile_desc[2 * next2];
-      m1 = tile_desc[2 * next2 + 1];
-    }
-    const int i0 = c0.x, nT = c0.y - c0.x, ne_t = c0.w - c0.z;
-    const int pr0 = c1.x, bbase = c1.z, bend = c1.w;
-    const size_t base = (size_t)D * D * bbase;
-    const int nvals = D * D * (bend - bbase);
-    const LameFac lf = s_lf;
-
-    // own vertices: v_nmk / a_nmk once per vertex
-    if (RES) {
-      for (int n = threadIdx.x; n < nT; n += blockDim.x)
-        s_uva[n] = node_uva(nc, is_static != 0, I.raw[(size_t)max_tile_nodes + n],
-                            I.raw[2 * (size_t)max_tile_nodes + n],
-                            I.raw[3 * (size_t)max_tile_nodes + n],
-                            I.raw[4 * (size_t)max_tile_nodes + n]);
-      __syncthreads();
-    }
-
-    // ---- phase 1: one record per cell ------------------------------------------------------
-    for (int q = threadIdx.x; q < ne_t; q += blockDim.x) {
-      const int4 quad = I.quad[q];
-      const int e = quad.w;
-      const int nd[3] = {quad.x, quad.y, quad.z};
-      double x[3][2];
-#pragma unroll
-      for (int a = 0; a < 3; ++a) {
-        const unsigned ln = (unsigned)(nd[a] - i0);
-        const D2 c2 = ln < (unsigned)nT ? I.raw[ln] : reinterpret_cast<const D2*>(m.xy)[nd[a]];
-        x[a][0] = c2.x;
-        x[a][1] = c2.y;
-      }
-      tri_record_t(
-          x, pv.emod[e], lf, pv.eta[e], pv.rho[e], dp, nc, is_static != 0, RES,
-          [&](int a) {
-            const unsigned ln = (unsigned)(nd[a] - i0);
-            return ln < (unsigned)nT
-                       ? s_uva[ln]
-                       : gather_node_uva(nc, is_static != 0, nd[a], u1, u0, v0, a0);
-          },
-          recs + (size_t)q * kRec2D);
-    }
-    __syncthreads();
-
-    // ---- phase 2: one thread per scalar row, cells visited as a counter-clockwise fan -------
-    for (int r = threadIdx.x; r < D * nT; r += blockDim.x) {
-      const int n = r >> 1, comp = r & 1;
-      const int b0 = I.brptr[n], deg = I.brptr[n + 1] - b0;
-      double* row = tileJ + D * D * (b0 - bbase) + comp * D * deg;
-      double racc = 0.0;
-      D2 diag = D2{0.0, 0.0}, carry = D2{0.0, 0.0}, first = D2{0.0, 0.0};
-      int slot_first = -1, slot_carry = -2, slot_self = 0;
-      const int qb = I.n2e[n] - pr0, qe = I.n2e[n + 1] - pr0;
-      for (int q = qb; q < qe; ++q) {
-        const unsigned info = I.pair[q];
-        const double* rec = recs + (size_t)(info & 0xfffu) * kRec2D;
-        const int a = (info >> 12) & 3;
-        if (JAC) {
-          D2 ws, wn, wp;
-          tri_row_fan(rec, a, comp, ws, wn, wp);
-          slot_self = (info >> 14) & 63;
-          const int slot_next = (info >> 20) & 63;
-          diag.x += ws.x;
-          diag.y += ws.y;
-          if (q == qb) {
-            first = wn;
-            slot_first = slot_next;
-          } else {
-            *reinterpret_cast<D2*>(row + D * slot_next) = D2{carry.x + wn.x, carry.y + wn.y};
-          }
-          carry = wp;
-          slot_carry = (info >> 26) & 63;
-        }
-        if (RES) racc += rec[9 + 2 * a + comp];
-      }
-      if (JAC && qe > qb) {
-        if (slot_carry == slot_first) {
-          *reinterpret_cast<D2*>(row + D * slot_first) = D2{first.x + carry.x, first.y + carry.y};
-        } else {
-          *reinterpret_cast<D2*>(row + D * slot_first) = first;
-          *reinterpret_cast<D2*>(row + D * slot_carry) = carry;
-        }
-        *reinterpret_cast<D2*>(row + D * slot_self) = diag;
-      }
-      if (RES) tileF[r] = racc;
-    }
-    __syncthreads();
-
-    // ---- phase 3: coalesced write-out -----------------------------------------------------------
-    if (JAC) {
-      double2* dst = reinterpret_cast<double2*>(mb + L.off[VF_J] + base);
-      const double2* src = reinterpret_cast<const double2*>(tileJ);
-      for (int t = threadIdx.x; t < nvals / 2; t += blockDim.x) __stcs(dst + t, src[t]);
-    }
-    if (RES) {
-      double* F = mb + L.off[VF_F] + (size_t)D * i0;
-      for (int t = threadIdx.x; t < D * nT; t += blockDim.x) F[t] = tileF[t];
-    }
-    if (next >= ntiles) break;
-    c0 = n0;
-    c1 = n1;
-    n0 = m0;
-    n1 = m1;
-    tile = next;
-    next = next2;
-  }
-}
-
-// Exterior-facet terms (follower pressure, contact, membrane) and Dirichlet rows of the
-// boundary nodes, applied in place to the rows the tile kernel has written.  One thread owns
-// one node: private rows, fixed order, no atomics.
 template <int D, bool JAC, bool RES>
 __global__ void facet_bc_kernel(EngineDev E, int member, double dt, int is_static,
                                 const int* __restrict__ touch_nodes, int n_touch) {
@@ -962,6 +786,7 @@ struct vf_engine {
   unsigned* pair_info_dev;
   int4* tile_desc_dev;
   int4* te_quad_dev;
+  int* tile_halo_dev;
   int* touch_dev;
   int n_touch;
   bool two_phase;
@@ -978,7 +803,7 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 struct ArenaPlan {
   // byte offsets of the shared tables
   size_t xyz, xy, cells, brptr, bcol, n2e_ptr, n2e, n2f_ptr, n2f, pf_cell, pf_opp, bc, tile_start, s,
-      fsi_solid, fsi_fluid, fsip_solid, fsip_fluid, te_ptr, te_elem, pair_info, tile_desc, te_quad, touch, members, total;
+      fsi_solid, fsi_fluid, fsip_solid, fsip_fluid, te_ptr, te_elem, pair_info, tile_desc, te_quad, tile_halo, touch, members, total;
   Layout L;
   long long nnz;
   int N;
@@ -1022,6 +847,7 @@ ArenaPlan plan_arena(const vf_problem_desc& d) {
   P.pair_info = take(sizeof(unsigned) * std::max(d.te_ptr_host ? n_n2e : 0, 1));
   P.tile_desc = take(sizeof(int) * 8 * (d.te_ptr_host ? d.ntiles : 1));
   P.te_quad = take(sizeof(int) * 4 * std::max(n_te, 1));
+  P.tile_halo = take(sizeof(int) * std::max(d.te_ptr_host ? d.n_tile_halo : 0, 1));
   P.touch = take(sizeof(int) * std::max(d.nn, 1));
   P.members = o;
 
@@ -1090,22 +916,13 @@ double* member_array(vf_engine* e, int id, int member) {
   return e->dev.members + (size_t)member * e->dev.L.stride + e->dev.L.off[id];
 }
 
-// dynamic shared memory of asm_tile2_kernel: records, CSR slice, F, index slices (padded to
-// 16 bytes), nodal staging (coordinates + u/v/a: 4 x 16 bytes per own vertex)
+// dynamic shared memory of asm_tile2_kernel: records, region A (CSR slice aliasing the nodal
+// staging: coordinates + u/v/a = 64 bytes per own or halo vertex), F, index slices
 size_t tile2_smem_bytes(const vf_problem_desc& d) {
   const size_t idx_words = (size_t)d.max_tile_pairs + 2 * ((size_t)d.tile_threads + 1);
-  return sizeof(double) * ((size_t)d.max_tile_elems * kRec2D + d.tile_max_values +
-                           2 * (size_t)d.tile_threads + ((idx_words + 3) / 4) * 2) +
-         64 * (size_t)d.tile_threads;
-}
-
-size_t tile3_smem_bytes(const vf_problem_desc& d) {
-  const size_t mn = d.tile_threads;  // >= nodes per tile
-  const size_t quad_b = 16 * (size_t)d.max_tile_elems, raw_b = 80 * mn;
-  const size_t pair_b = (4 * (size_t)d.max_tile_pairs + 15) & ~size_t(15);
-  const size_t ptr_b = (4 * (mn + 1) + 15) & ~size_t(15);
-  return sizeof(double) * ((size_t)d.max_tile_elems * kRec2D + d.tile_max_values + 2 * mn) +
-         48 * mn + 2 * (quad_b + raw_b + pair_b + 2 * ptr_b);
+  const size_t region_a = std::max((size_t)d.tile_max_values, (size_t)8 * d.max_tile_verts);
+  return sizeof(double) * ((size_t)d.max_tile_elems * kRec2D + region_a +
+                           2 * (size_t)d.tile_threads + ((idx_words + 3) / 4) * 2);
 }
 
 SolverOpts to_opts(const vf_solver_opts* o) {
@@ -1258,7 +1075,8 @@ int vf_create(const vf_problem_desc* desc, void* arena_dev, size_t arena_bytes, 
   VF_CUDA(up(P.fsip_solid, d.fsip_solid_host, sizeof(int) * d.n_fsip));
   VF_CUDA(up(P.fsip_fluid, d.fsip_fluid_host, sizeof(int) * d.n_fsip));
   const bool two_phase = d.te_ptr_host && d.te_elem_host && d.pair_info_host &&
-                         d.tile_desc_host && d.te_quad_host && d.dim == 2 && d.tile2_threads > 0;
+                         d.tile_desc_host && d.te_quad_host && d.tile_halo_host && d.dim == 2 &&
+                         d.tile2_threads > 0;
   std::vector<int> touch;
   for (int i = 0; i < d.nn; ++i) {
     bool t = d.n2f_ptr_host[i + 1] > d.n2f_ptr_host[i];
@@ -1272,6 +1090,7 @@ int vf_create(const vf_problem_desc* desc, void* arena_dev, size_t arena_bytes, 
     VF_CUDA(up(P.pair_info, d.pair_info_host, sizeof(unsigned) * n_n2e));
     VF_CUDA(up(P.tile_desc, d.tile_desc_host, sizeof(int) * 8 * d.ntiles));
     VF_CUDA(up(P.te_quad, d.te_quad_host, sizeof(int) * 4 * d.te_ptr_host[d.ntiles]));
+    VF_CUDA(up(P.tile_halo, d.tile_halo_host, sizeof(int) * d.n_tile_halo));
   }
   VF_CUDA(cudaStreamSynchronize(st));
 
@@ -1291,6 +1110,7 @@ int vf_create(const vf_problem_desc* desc, void* arena_dev, size_t arena_bytes, 
   e->desc.fsip_solid_host = nullptr; e->desc.fsip_fluid_host = nullptr;
   e->desc.te_ptr_host = nullptr; e->desc.te_elem_host = nullptr; e->desc.pair_info_host = nullptr;
   e->desc.tile_desc_host = nullptr; e->desc.te_quad_host = nullptr;
+  e->desc.tile_halo_host = nullptr;
   e->two_phase = two_phase;
   e->fan_ok = d.fan_ok != 0;
   e->touch_dev = reinterpret_cast<int*>(A + P.touch);
@@ -1300,6 +1120,7 @@ int vf_create(const vf_problem_desc* desc, void* arena_dev, size_t arena_bytes, 
   e->pair_info_dev = reinterpret_cast<unsigned*>(A + P.pair_info);
   e->tile_desc_dev = reinterpret_cast<int4*>(A + P.tile_desc);
   e->te_quad_dev = reinterpret_cast<int4*>(A + P.te_quad);
+  e->tile_halo_dev = reinterpret_cast<int*>(A + P.tile_halo);
 
   EngineDev& E = e->dev;
   E.mesh.dim = d.dim; E.mesh.nn = d.nn; E.mesh.ne = d.ne; E.mesh.nfp = d.nfp;
@@ -1430,42 +1251,8 @@ int vf_assemble(vf_engine* e, int member, int flags, double dt, int is_static, v
 #define VF_LAUNCH_ASM2(J_, R_, ROW_, MT_, MB_)                                                     \
   asm_tile2_kernel<J_, R_, ROW_, MT_, MB_><<<grid, d.tile2_threads, smem2, st>>>(                  \
       e->dev, member, newmark_coef(dt), is_static, e->tile_desc_dev, e->te_quad_dev,               \
-      e->pair_info_dev,                                                                            \
-      d.max_tile_elems, d.tile_max_values, d.max_tile_pairs, d.tile_threads, dbg_skip)
-    bool done3 = false;
-    // the persistent cp.async-pipelined variant measured slower than the plain kernel (fewer
-    // resident CTAs; profiles/README.md) and is off unless VF_TILE3=1
-    const int use_t3 = getenv("VF_TILE3") ? atoi(getenv("VF_TILE3")) : 0;
-    if (use_t3 && e->fan_ok && tile3_smem_bytes(d) <= 227 * 1024) {
-      const size_t smem3 = tile3_smem_bytes(d);
-      const int nt3 = d.tile2_threads;
-      const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (227 * 1024) / (smem3 + 1024)));
-#define VF_LAUNCH_ASM3(J_, R_, MT_, MB_)                                                           \
-  do {                                                                                            \
-    VF_CUDA(cudaFuncSetAttribute(asm_tile3_kernel<J_, R_, MT_, MB_>,                              \
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));       \
-    const int g3 = std::min(grid, 148 * std::min(per_sm, MB_));                                   \
-    asm_tile3_kernel<J_, R_, MT_, MB_><<<g3, nt3, smem3, st>>>(                                   \
-        e->dev, member, newmark_coef(dt), is_static, e->tile_desc_dev, e->te_quad_dev,           \
-        e->pair_info_dev, grid, d.max_tile_elems, d.tile_max_values, d.max_tile_pairs,           \
-        d.tile_threads);                                                                          \
-  } while (0)
-#define VF_ASM3_BY_SIZE(J_, R_)                                                                    \
-  do {                                                                                            \
-    if (nt3 <= 128) VF_LAUNCH_ASM3(J_, R_, 128, 8);                                               \
-    else if (nt3 <= 224) VF_LAUNCH_ASM3(J_, R_, 224, 4);                                          \
-    else VF_LAUNCH_ASM3(J_, R_, 320, 3);                                                          \
-  } while (0)
-      if (jac && res) VF_ASM3_BY_SIZE(true, true);
-      else if (jac) VF_ASM3_BY_SIZE(true, false);
-      else VF_ASM3_BY_SIZE(false, true);
-#undef VF_ASM3_BY_SIZE
-#undef VF_LAUNCH_ASM3
-      e->launches += 1;
-      VF_CUDA(cudaGetLastError());
-      done3 = true;
-    }
-    if (!done3) {
+      e->pair_info_dev, e->tile_halo_dev, d.max_tile_elems, d.tile_max_values, d.max_tile_pairs,   \
+      d.tile_threads, d.max_tile_verts, dbg_skip)
     const int dbg_skip = getenv("VF_DEBUG_SKIP") ? atoi(getenv("VF_DEBUG_SKIP")) : 0;
     int v_row = getenv("VF_TILE2_ROW") ? atoi(getenv("VF_TILE2_ROW")) : 2;
     if (v_row == 2 && !e->fan_ok) v_row = 1;
@@ -1491,7 +1278,6 @@ int vf_assemble(vf_engine* e, int member, int flags, double dt, int is_static, v
 #undef VF_LAUNCH_ASM2
     e->launches += 1;
     VF_CUDA(cudaGetLastError());
-    }
     if (e->n_touch > 0) {
       const int fb = 128, fg = (e->n_touch + fb - 1) / fb;
       if (jac && res)

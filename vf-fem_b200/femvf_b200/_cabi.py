@@ -31,8 +31,9 @@ class ProblemDesc(C.Structure):
         ('ntiles', C.c_int32), ('tile_max_values', C.c_int32), ('tile_threads', C.c_int32),
         ('te_ptr_host', C.c_void_p), ('te_elem_host', C.c_void_p),
         ('pair_info_host', C.c_void_p), ('tile_desc_host', C.c_void_p),
-        ('te_quad_host', C.c_void_p),
+        ('te_quad_host', C.c_void_p), ('tile_halo_host', C.c_void_p),
         ('max_tile_elems', C.c_int32), ('max_tile_pairs', C.c_int32),
+        ('n_tile_halo', C.c_int32), ('max_tile_verts', C.c_int32),
         ('tile2_threads', C.c_int32), ('fan_ok', C.c_int32),
         ('n_fluid', C.c_int32), ('ns', C.c_int32), ('n_fsi', C.c_int32),
         ('s_host', C.c_void_p), ('fsi_solid_host', C.c_void_p), ('fsi_fluid_host', C.c_void_p),

@@ -96,13 +96,15 @@ class Engine:
         if tile2 is not None:
             want = max(tile2['max_tile_elems'], d * nodes_per_tile)
             tile2_threads = int(os.environ.get('VF_TILE2_THREADS', str(-(-want // 32) * 32)))
-            smem = 8 * (18 * tile2['max_tile_elems'] + tile_max + d * nodes_per_tile) \
-                + 4 * (tile2['max_tile_pairs'] + 2 * nodes_per_tile + 8) + 64 * nodes_per_tile
+            smem = 8 * (18 * tile2['max_tile_elems'] + max(tile_max, 8 * tile2['max_tile_verts'])
+                        + d * nodes_per_tile) \
+                + 4 * (tile2['max_tile_pairs'] + 2 * nodes_per_tile + 8)
             if smem > 200 * 1024 or tile2_threads > 320:
                 tile2, tile2_threads = None, 0
         self.tile_info = {'nodes_per_tile': nodes_per_tile, 'ntiles': len(tile_start) - 1,
                           'tile_max_values': tile_max, 'two_phase': tile2 is not None,
                           'max_tile_elems': tile2['max_tile_elems'] if tile2 else 0,
+                          'max_tile_verts': tile2['max_tile_verts'] if tile2 else 0,
                           'tile2_threads': tile2_threads}
 
         if s is None:
@@ -134,7 +136,7 @@ class Engine:
         if tile2 is not None:
             keep.update(te_ptr=tile2['te_ptr'], te_elem=tile2['te_elem'],
                         pair_info=tile2['pair_info'], tile_desc=tile2['tile_desc'],
-                        te_quad=tile2['te_quad'])
+                        te_quad=tile2['te_quad'], tile_halo=tile2['tile_halo'])
         desc = ProblemDesc(
             d, self.nn, self.ne, tables['nfp'],
             _ptr(keep['xyz']), _ptr(keep['cells']), _ptr(keep['brptr']), _ptr(keep['bcol']),
@@ -142,8 +144,9 @@ class Engine:
             _ptr(keep['pf_cell']), _ptr(keep['pf_opp']), _ptr(keep['bc']),
             _ptr(tile_start), len(tile_start) - 1, tile_max, tile_threads,
             _ptr(keep.get('te_ptr')), _ptr(keep.get('te_elem')), _ptr(keep.get('pair_info')),
-            _ptr(keep.get('tile_desc')), _ptr(keep.get('te_quad')),
+            _ptr(keep.get('tile_desc')), _ptr(keep.get('te_quad')), _ptr(keep.get('tile_halo')),
             tile2['max_tile_elems'] if tile2 else 0, tile2['max_tile_pairs'] if tile2 else 0,
+            tile2['n_tile_halo'] if tile2 else 0, tile2['max_tile_verts'] if tile2 else 0,
             tile2_threads, int(bool(tables.get('fan_ok', False))),
             self.n_fluid, self.ns, len(fsia_solid), _ptr(s), _ptr(fsia_solid), _ptr(fsia_fluid),
             len(fsip_solid), _ptr(fsip_solid), _ptr(fsip_fluid),

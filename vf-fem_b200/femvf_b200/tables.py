@@ -186,6 +186,10 @@ def build_tile_elem_tables(T: dict, tile_start: np.ndarray):
     Tables of the two-phase tile assembly kernel (``asm_tile2_kernel``, triangles only).
 
     te_ptr/te_elem : cells touching each node tile (owned + halo), ascending
+    te_quad        : per (tile, cell): the LOCAL slots of the cell's 3 vertices in the tile's
+                     staged vertex list (own vertices first, then ``tile_halo``) + the cell id
+    tile_halo      : halo vertices (global ids) of each tile, ascending per tile
+    tile_desc      : 8 int32 per tile (see below)
     pair_info      : one uint32 per (node, adjacent cell) pair in ``n2e`` order:
                      bits [0,12) index of the cell in its node's tile list, [12,14) local
                      index a of the node in the cell, [14,20) [20,26) [26,32) CSR slots (within
@@ -234,26 +238,52 @@ def build_tile_elem_tables(T: dict, tile_start: np.ndarray):
             | (slots[0].astype(np.uint64) << np.uint64(14))
             | (slots[1].astype(np.uint64) << np.uint64(20))
             | (slots[2].astype(np.uint64) << np.uint64(26)))
-    # flat per-tile descriptor and per-(tile, cell) vertex quads: everything a CTA needs is
-    # addressable after ONE dependent load (the descriptor), instead of a chain
-    # tile_start -> te_ptr -> te_elem -> cells
+    # halo vertices of each tile: vertices of the tile's cells outside its own node range,
+    # ascending per tile.  The kernel stages own + halo vertices in shared memory, so a cell
+    # addresses its vertices by LOCAL slot: own vertex v -> v - i0, halo -> nT + rank in the list
     ts = tile_start.astype(np.int64)
-    desc = np.zeros((ntiles, 8), dtype=np.int32)
-    desc[:, 0] = ts[:-1]
-    desc[:, 1] = ts[1:]
-    desc[:, 2] = te_ptr[:-1]
-    desc[:, 3] = te_ptr[1:]
-    desc[:, 4] = n2e_ptr[ts[:-1]]
-    desc[:, 5] = n2e_ptr[ts[1:]]
-    desc[:, 6] = brptr[ts[:-1]]
-    desc[:, 7] = brptr[ts[1:]]
+    tcells = cells[te_elem]                                   # (n_te, 3) global vertex ids
+    vkey = np.unique((te_tile[:, None] * nn + tcells).ravel())
+    vtile, vvert = vkey // nn, vkey % nn
+    is_halo = tile_of_node[vvert] != vtile
+    hkey = vkey[is_halo]                                      # sorted by tile, then vertex
+    th_ptr = np.zeros(ntiles + 1, dtype=np.int64)
+    np.add.at(th_ptr, vtile[is_halo] + 1, 1)
+    th_ptr = np.cumsum(th_ptr)
+    tile_halo = vvert[is_halo].astype(np.int32)
+    nown = np.diff(ts)
+    own = tile_of_node[tcells] == te_tile[:, None]
+    slot_own = tcells - ts[te_tile][:, None]
+    slot_halo = (np.searchsorted(hkey, te_tile[:, None] * nn + tcells)
+                 - th_ptr[te_tile][:, None] + nown[te_tile][:, None])
     te_quad = np.empty((len(te_elem), 4), dtype=np.int32)
-    te_quad[:, :3] = cells[te_elem]
+    te_quad[:, :3] = np.where(own, slot_own, slot_halo)
     te_quad[:, 3] = te_elem
-    max_tile_pairs = int(np.max(desc[:, 5] - desc[:, 4]))
+    # flat per-tile descriptor: everything a CTA needs is addressable after ONE dependent load,
+    # instead of a chain tile_start -> te_ptr -> te_elem -> cells.  Eight int32:
+    #   i0, te0, pair0, blk0, halo0, nT | nH << 16, n_cells | n_pairs << 16, n_blocks
+    npairs = n2e_ptr[ts[1:]] - n2e_ptr[ts[:-1]]
+    ncell = np.diff(te_ptr)
+    nhalo = np.diff(th_ptr)
+    if np.max(npairs) >= 65536 or np.max(nown + nhalo) >= 32768:
+        return None
+    desc = np.zeros((ntiles, 8), dtype=np.int64)
+    desc[:, 0] = ts[:-1]
+    desc[:, 1] = te_ptr[:-1]
+    desc[:, 2] = n2e_ptr[ts[:-1]]
+    desc[:, 3] = brptr[ts[:-1]]
+    desc[:, 4] = th_ptr[:-1]
+    desc[:, 5] = nown | (nhalo << 16)
+    desc[:, 6] = ncell | (npairs << 16)
+    desc[:, 7] = brptr[ts[1:]] - brptr[ts[:-1]]
+    desc = desc.astype(np.uint32).view(np.int32)
+    max_tile_pairs = int(np.max(npairs))
+    max_tile_verts = int(np.max(nown + nhalo))
     return {
         'te_ptr': te_ptr.astype(np.int32), 'te_elem': te_elem,
         'pair_info': info.astype(np.uint32), 'max_tile_elems': max_tile_elems,
         'tile_desc': np.ascontiguousarray(desc), 'te_quad': np.ascontiguousarray(te_quad),
         'max_tile_pairs': max_tile_pairs,
+        'tile_halo': tile_halo if len(tile_halo) else np.zeros(1, np.int32),
+        'n_tile_halo': int(len(tile_halo)), 'max_tile_verts': max_tile_verts,
     }
