@@ -11,8 +11,8 @@ levels = int(sys.argv[1]) if len(sys.argv) > 1 else 7
 model = bench.build_big_model(levels, 0)
 T = model.assembly_tables
 configs = []
-for tn, t3 in itertools.product((48, 64, 80, 96, 128), (1, 0)):
-    configs.append(dict(VF_TILE2='1', VF_TILE_NODES=str(tn), VF_TILE3=str(t3)))
+for tn in (40, 48, 56, 64, 72, 80, 88, 96, 104, 112, 128):
+    configs.append(dict(VF_TILE2='1', VF_TILE_NODES=str(tn)))
 configs.append(dict(VF_TILE2='0', VF_TILE_NODES='128'))
 for cfg in configs:
     os.environ.update(cfg)

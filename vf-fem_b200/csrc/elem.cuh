@@ -471,22 +471,26 @@ VF_HD void tri_block(const double* rec, int a, int c, double (&b)[2][2]) {
 // prev = (a+2)%3 (the cell's counter-clockwise order), from a record.
 VF_HD void tri_row_fan(const double* rec, int a, int comp, D2& w_self, D2& w_next, D2& w_prev) {
   const D2* r2 = reinterpret_cast<const D2*>(rec);
-  const D2 g0 = r2[0], g1 = r2[1], g2 = r2[2], lm = r2[3];
+  // (a+1)%3 and (a+2)%3 from nibble tables: the three gradients are fetched by address, not
+  // loaded all and permuted in registers
+  const int nx = (0x021 >> (4 * a)) & 3, pv = (0x102 >> (4 * a)) & 3;
+  const D2 lm = r2[3];
   const double mass = rec[8];
-  const D2 ga = a == 0 ? g0 : (a == 1 ? g1 : g2);
-  const D2 gn = a == 0 ? g1 : (a == 1 ? g2 : g0);
-  const D2 gp = a == 0 ? g2 : (a == 1 ? g0 : g1);
+  const D2 gc[3] = {r2[a], r2[nx], r2[pv]};
+  const D2 ga = gc[0];
   const double A = lm.x * (comp == 0 ? ga.x : ga.y);
   const double Bx = lm.y * ga.x, By = lm.y * ga.y;
-  const D2 gc[3] = {ga, gn, gp};
+  // the diagonal term goes to entry `comp` of the row: e0 * dg is exact (e0 is 0 or 1), so the
+  // multiply-add rounds once like the plain addition it replaces
+  const double e0 = comp == 0 ? 1.0 : 0.0, e1 = 1.0 - e0;
   D2 w[3];
   for (int c = 0; c < 3; ++c) {
     const double gc_i = comp == 0 ? gc[c].x : gc[c].y;
     double w0 = A * gc[c].x + gc_i * Bx;
     double w1 = A * gc[c].y + gc_i * By;
     const double dg = gc[c].x * Bx + gc[c].y * By + mass * (c == 0 ? 2.0 : 1.0);
-    if (comp == 0) w0 += dg;
-    else w1 += dg;
+    w0 = e0 * dg + w0;
+    w1 = e1 * dg + w1;
     w[c] = D2{w0, w1};
   }
   w_self = w[0];

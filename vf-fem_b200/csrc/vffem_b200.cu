@@ -146,6 +146,13 @@ __global__ void __launch_bounds__(MAXT, MINB) asm_tile2_kernel(
   const Layout& L = E.L;
   const MeshView& m = E.mesh;
 
+#ifdef VF_PHASE_PROF  // -DVF_PHASE_PROF + VF_DEBUG_SKIP=32: per-phase cycle counts into info[8..15]
+  const bool prof = (dbg_skip & 32) && threadIdx.x == 0;
+  long long tk0 = prof ? clock64() : 0, tk1 = 0, tk2 = 0, tk3 = 0, ta = 0, tb = 0, tc = 0;
+#define VF_PROBE(x) x
+#else
+#define VF_PROBE(x)
+#endif
   // ---- phase 0: descriptor, then every load of the tile in one dependent round ---------------
   const int4 d0 = tile_desc[2 * blockIdx.x], d1 = tile_desc[2 * blockIdx.x + 1];
   const int i0 = d0.x, te0 = d0.y, pr0 = d0.z, bbase = d0.w;
@@ -160,6 +167,7 @@ __global__ void __launch_bounds__(MAXT, MINB) asm_tile2_kernel(
   const double* v0 = mb + L.off[VF_V0];
   const double* a0 = mb + L.off[VF_A0];
 
+  VF_PROBE(if (prof) ta = clock64() + (i0 & 0);)
   // this thread's first cell (volatile load: issued here, not sunk below the barrier)
   int4 quad = make_int4(0, 0, 0, 0);
   const bool have = (int)threadIdx.x < nte;
@@ -179,9 +187,15 @@ __global__ void __launch_bounds__(MAXT, MINB) asm_tile2_kernel(
   // once per (cell, vertex) in phase 1, and phase 1 reads shared memory only
   for (int t = threadIdx.x; t < nV; t += blockDim.x) {
     const int vtx = t < nT ? i0 + t : tile_halo[h0 + t - nT];
-    s_xy[t] = reinterpret_cast<const D2*>(m.xy)[vtx];
-    if (RES) s_uva[t] = gather_node_uva(nc_arg, is_static != 0, vtx, u1, u0, v0, a0);
+    // all global loads first, then the shared-memory stores: a store in between would order
+    // the (generic-pointer) loads behind it and cost a second round trip
+    const D2 c2 = reinterpret_cast<const D2*>(m.xy)[vtx];
+    NodeUVA s3;
+    if (RES) s3 = gather_node_uva(nc_arg, is_static != 0, vtx, u1, u0, v0, a0);
+    s_xy[t] = c2;
+    if (RES) s_uva[t] = s3;
   }
+  VF_PROBE(if (prof) tb = clock64();)
   // the quad has arrived by now: the cell's material data, also before the barrier
   double emod_e = 0.0, eta_e = 0.0, rho_e = 0.0;
   if (have) {
@@ -190,7 +204,9 @@ __global__ void __launch_bounds__(MAXT, MINB) asm_tile2_kernel(
     rho_e = ldg_nc_f64(pv.rho + quad.w);
   }
   cp_async_wait_all();
+  VF_PROBE(if (prof) tc = clock64() + (__double_as_longlong(emod_e) & 0);)
   __syncthreads();
+  VF_PROBE(if (prof) tk1 = clock64();)
 
   // ---- phase 1: one record per cell, from shared memory ----------------------------------------
   {
@@ -218,6 +234,7 @@ __global__ void __launch_bounds__(MAXT, MINB) asm_tile2_kernel(
     }
   }
   __syncthreads();
+  VF_PROBE(if (prof) tk2 = clock64();)
 
   // ---- phase 2 ---------------------------------------------------------------------------------
   if (dbg_skip & 2) {
@@ -231,40 +248,48 @@ __global__ void __launch_bounds__(MAXT, MINB) asm_tile2_kernel(
       const int n = r >> 1, comp = r & 1;
       const int b0 = s_brptr[n], deg = s_brptr[n + 1] - b0;
       double* row = tileJ + D * D * (b0 - bbase) + comp * D * deg;
-      double racc = 0.0;
-      D2 diag = D2{0.0, 0.0}, carry = D2{0.0, 0.0}, first = D2{0.0, 0.0};
-      int slot_first = -1, slot_carry = -2, slot_self = 0;
       const int qb = s_n2e[n] - pr0, qe = s_n2e[n + 1] - pr0;
-      for (int q = qb; q < qe; ++q) {
-        const unsigned info = s_pair[q];
+      double racc = 0.0;
+      if (qe > qb) {
+        // first cell of the fan (peeled): nothing to complete yet
+        unsigned info = s_pair[qb];
         const double* rec = recs + (size_t)(info & 0xfffu) * kRec2D;
-        const int a = (info >> 12) & 3;
+        int a = (info >> 12) & 3;
+        D2 diag = D2{0.0, 0.0}, carry = D2{0.0, 0.0}, first = D2{0.0, 0.0};
+        int slot_first = 0, slot_carry = 0;
         if (JAC) {
-          D2 ws, wn, wp;
-          tri_row_fan(rec, a, comp, ws, wn, wp);
-          slot_self = (info >> 14) & 63;
-          const int slot_next = (info >> 20) & 63;
-          diag.x += ws.x;
-          diag.y += ws.y;
-          if (q == qb) {
-            first = wn;
-            slot_first = slot_next;
-          } else {
-            *reinterpret_cast<D2*>(row + D * slot_next) = D2{carry.x + wn.x, carry.y + wn.y};
-          }
-          carry = wp;
+          D2 wn;
+          tri_row_fan(rec, a, comp, diag, wn, carry);
+          first = wn;
+          slot_first = (info >> 20) & 63;
           slot_carry = (info >> 26) & 63;
         }
-        if (RES) racc += rec[9 + 2 * a + comp];
-      }
-      if (JAC && qe > qb) {
-        if (slot_carry == slot_first) {
-          *reinterpret_cast<D2*>(row + D * slot_first) = D2{first.x + carry.x, first.y + carry.y};
-        } else {
-          *reinterpret_cast<D2*>(row + D * slot_first) = first;
-          *reinterpret_cast<D2*>(row + D * slot_carry) = carry;
+        if (RES) racc = rec[9 + 2 * a + comp];
+        for (int q = qb + 1; q < qe; ++q) {
+          info = s_pair[q];
+          rec = recs + (size_t)(info & 0xfffu) * kRec2D;
+          a = (info >> 12) & 3;
+          if (JAC) {
+            D2 ws, wn, wp;
+            tri_row_fan(rec, a, comp, ws, wn, wp);
+            diag.x += ws.x;
+            diag.y += ws.y;
+            *reinterpret_cast<D2*>(row + D * ((info >> 20) & 63)) =
+                D2{carry.x + wn.x, carry.y + wn.y};
+            carry = wp;
+            slot_carry = (info >> 26) & 63;
+          }
+          if (RES) racc += rec[9 + 2 * a + comp];
         }
-        *reinterpret_cast<D2*>(row + D * slot_self) = diag;
+        if (JAC) {
+          if (slot_carry == slot_first) {  // closed fan: the last cell meets the first
+            *reinterpret_cast<D2*>(row + D * slot_first) = D2{first.x + carry.x, first.y + carry.y};
+          } else {
+            *reinterpret_cast<D2*>(row + D * slot_first) = first;
+            *reinterpret_cast<D2*>(row + D * slot_carry) = carry;
+          }
+          *reinterpret_cast<D2*>(row + D * ((info >> 14) & 63)) = diag;
+        }
       }
       if (RES) tileF[r] = racc;
     }
@@ -347,6 +372,7 @@ __global__ void __launch_bounds__(MAXT, MINB) asm_tile2_kernel(
     }
   }
   __syncthreads();
+  VF_PROBE(if (prof) tk3 = clock64();)
 
   // ---- phase 3: coalesced write-out ---------------------------------------------------------------
   if (dbg_skip & 4) return;
@@ -359,6 +385,21 @@ __global__ void __launch_bounds__(MAXT, MINB) asm_tile2_kernel(
     double* F = mb + L.off[VF_F] + (size_t)D * i0;
     for (int t = threadIdx.x; t < D * nT; t += blockDim.x) F[t] = tileF[t];
   }
+#ifdef VF_PHASE_PROF
+  if (prof) {
+    const long long tk4 = clock64();
+    double* info = mb + L.off[VF_INFO];
+    atomicAdd(info + 8, (double)(tk1 - tk0));
+    atomicAdd(info + 9, (double)(tk2 - tk1));
+    atomicAdd(info + 10, (double)(tk3 - tk2));
+    atomicAdd(info + 11, (double)(tk4 - tk3));
+    atomicAdd(info + 12, 1.0);
+    atomicAdd(info + 13, (double)(ta - tk0));
+    atomicAdd(info + 14, (double)(tb - ta));
+    atomicAdd(info + 15, (double)(tc - tb));
+  }
+#endif
+#undef VF_PROBE
 }
 
 
@@ -1169,6 +1210,7 @@ int vf_create(const vf_problem_desc* desc, void* arena_dev, size_t arena_bytes, 
 #define VF_SMEM2_ALL(J_, R_, ROW_)                          \
   VF_SMEM2((asm_tile2_kernel<J_, R_, ROW_, 128, 8>));       \
   VF_SMEM2((asm_tile2_kernel<J_, R_, ROW_, 192, 5>));       \
+  VF_SMEM2((asm_tile2_kernel<J_, R_, ROW_, 256, 4>));       \
   VF_SMEM2((asm_tile2_kernel<J_, R_, ROW_, 320, 3>))
     VF_SMEM2_ALL(true, true, 0);
     VF_SMEM2_ALL(true, true, 1);
@@ -1262,6 +1304,7 @@ int vf_assemble(vf_engine* e, int member, int flags, double dt, int is_static, v
   do {                                                                                            \
     if (nt <= 128) VF_LAUNCH_ASM2(J_, R_, ROW_, 128, 8);                                          \
     else if (nt <= 192) VF_LAUNCH_ASM2(J_, R_, ROW_, 192, 5);                                     \
+    else if (nt <= 256) VF_LAUNCH_ASM2(J_, R_, ROW_, 256, 4);                                     \
     else VF_LAUNCH_ASM2(J_, R_, ROW_, 320, 3);                                                    \
   } while (0)
 #define VF_ASM2_BY_MODE(J_, R_)                                                                    \

@@ -11,7 +11,9 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), 'lib', 'libvffem_b200.so')
+# VF_LIB_PATH: developer aid for A/B timing of two builds of the same library
+LIB_PATH = os.environ.get('VF_LIB_PATH') or \
+    os.path.join(os.path.dirname(_HERE), 'lib', 'libvffem_b200.so')
 
 c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)
