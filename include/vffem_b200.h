@@ -53,7 +53,7 @@ typedef struct vf_problem_desc {
   const int32_t* te_ptr_host;     /* (ntiles+1) */
   const int32_t* te_elem_host;    /* (te_ptr[ntiles]) */
   const uint32_t* pair_info_host; /* (n2e_ptr[nn]) */
-  const int32_t* tile_desc_host;  /* (ntiles, 8): i0 te0 pair0 blk0 halo0 nT|nH<<16 ncell|npair<<16 nblk */
+  const int32_t* tile_desc_host;  /* (ntiles, 12): i0 te0 pair0 blk0 halo0 nT|nH<<16 ncell|npair<<16 nblk cell_lo cell_cnt 0 0 */
   const int32_t* te_quad_host;    /* (te_ptr[ntiles], 4): local slots of the cell's 3 vertices + cell id */
   const int32_t* tile_halo_host;  /* (n_tile_halo) halo vertices of the tiles, ascending per tile */
   int32_t max_tile_elems;

@@ -118,6 +118,9 @@ __device__ __forceinline__ int4 ldg_nc_v4(const int4* p) {
                : "l"(p));
   return r;
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
 __device__ __forceinline__ double ldg_nc_f64(const double* p) {
   double r;
   asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(r) : "l"(p));
@@ -129,7 +132,7 @@ __global__ void __launch_bounds__(MAXT, MINB) asm_tile2_kernel(
     EngineDev E, int member, NewmarkCoef nc_arg, int is_static, const int4* __restrict__ tile_desc,
     const int4* __restrict__ te_quad, const unsigned* __restrict__ pair_info,
     const int* __restrict__ tile_halo, int max_tile_elems, int tile_max_values,
-    int max_tile_pairs, int max_tile_nodes, int max_tile_verts, int dbg_skip) {
+    int max_tile_pairs, int max_tile_nodes, int max_tile_verts, int pf_dist, int dbg_skip) {
   constexpr int D = 2;
   extern __shared__ double smem[];
   double* recs = smem;
@@ -154,7 +157,7 @@ __global__ void __launch_bounds__(MAXT, MINB) asm_tile2_kernel(
 #define VF_PROBE(x)
 #endif
   // ---- phase 0: descriptor, then every load of the tile in one dependent round ---------------
-  const int4 d0 = tile_desc[2 * blockIdx.x], d1 = tile_desc[2 * blockIdx.x + 1];
+  const int4 d0 = tile_desc[3 * blockIdx.x], d1 = tile_desc[3 * blockIdx.x + 1];
   const int i0 = d0.x, te0 = d0.y, pr0 = d0.z, bbase = d0.w;
   const int h0 = d1.x, nT = d1.y & 0xffff, nH = (int)((unsigned)d1.y >> 16);
   const int nte = d1.z & 0xffff, npr = (int)((unsigned)d1.z >> 16);
@@ -178,6 +181,13 @@ __global__ void __launch_bounds__(MAXT, MINB) asm_tile2_kernel(
     cp_async4(s_brptr + t, m.brptr + i0 + t);
     cp_async4(s_n2e + t, m.n2e_ptr + i0 + t);
   }
+  // descriptor of the tile `pf_dist` CTAs ahead: its inputs are pulled into L2 by this CTA's
+  // idle threads during phase 2, so that the later CTA's three dependent round trips hit L2
+  __shared__ int s_far[12];
+  const int far = blockIdx.x + pf_dist;
+  const bool pf = pf_dist > 0 && far < (int)gridDim.x;
+  if (pf && threadIdx.x < 12)
+    cp_async4(s_far + threadIdx.x, reinterpret_cast<const int*>(tile_desc) + 12 * far + threadIdx.x);
   cp_async_commit();
   // Lame / Newmark coefficients: a handful of fp64 divisions, done once per CTA
   __shared__ LameFac s_lf;
@@ -292,6 +302,55 @@ __global__ void __launch_bounds__(MAXT, MINB) asm_tile2_kernel(
         }
       }
       if (RES) tileF[r] = racc;
+    }
+    if (pf) {
+      // threads without a row (or all, when every thread has one) share the far tile's lines
+      const int idle0 = ((D * nT + 31) / 32) * 32;
+      const bool some_idle = idle0 + 32 <= (int)blockDim.x;
+      const int k = some_idle ? (int)threadIdx.x - idle0 : (int)threadIdx.x;
+      const int nk = some_idle ? (int)blockDim.x - idle0 : (int)blockDim.x;
+      if (k >= 0) {
+        const int f_i0 = s_far[0], f_te0 = s_far[1], f_pr0 = s_far[2], f_h0 = s_far[4];
+        const int f_nT = s_far[5] & 0xffff, f_nH = (int)((unsigned)s_far[5] >> 16);
+        const int f_nte = s_far[6] & 0xffff, f_npr = (int)((unsigned)s_far[6] >> 16);
+        const int f_e0 = s_far[8], f_en = s_far[9];
+        auto pull = [&](const void* p, int nbytes) {
+          const char* c = reinterpret_cast<const char*>(p);
+          for (int off = k * 128; off < nbytes; off += nk * 128) prefetch_l2(c + off);
+        };
+        pull(te_quad + f_te0, 16 * f_nte);
+        pull(pair_info + f_pr0, 4 * f_npr);
+        pull(tile_halo + f_h0, 4 * f_nH);
+        pull(m.brptr + f_i0, 4 * (f_nT + 1));
+        pull(m.n2e_ptr + f_i0, 4 * (f_nT + 1));
+        pull(m.xy + D * f_i0, 16 * f_nT);
+        if (RES) {
+          pull(u1 + D * f_i0, 16 * f_nT);
+          if (!is_static) {
+            pull(u0 + D * f_i0, 16 * f_nT);
+            pull(v0 + D * f_i0, 16 * f_nT);
+            pull(a0 + D * f_i0, 16 * f_nT);
+          }
+        }
+        if (!(dbg_skip & 64)) {
+          // nodal data of the far tile's halo vertices (gathered: one line per vertex and array)
+          for (int h = k; h < f_nH; h += nk) {
+            const int v = tile_halo[f_h0 + h];
+            prefetch_l2(m.xy + D * v);
+            if (RES) {
+              prefetch_l2(u1 + D * v);
+              if (!is_static) {
+                prefetch_l2(u0 + D * v);
+                prefetch_l2(v0 + D * v);
+                prefetch_l2(a0 + D * v);
+              }
+            }
+          }
+        }
+        pull(pv.emod + f_e0, 8 * f_en);
+        pull(pv.eta + f_e0, 8 * f_en);
+        pull(pv.rho + f_e0, 8 * f_en);
+      }
     }
   } else if (ROW == 1) {
     // one thread per scalar row, read-modify-write accumulation (any cell order)
@@ -886,7 +945,7 @@ ArenaPlan plan_arena(const vf_problem_desc& d) {
   P.te_ptr = take(sizeof(int) * (d.ntiles + 1));
   P.te_elem = take(sizeof(int) * std::max(n_te, 1));
   P.pair_info = take(sizeof(unsigned) * std::max(d.te_ptr_host ? n_n2e : 0, 1));
-  P.tile_desc = take(sizeof(int) * 8 * (d.te_ptr_host ? d.ntiles : 1));
+  P.tile_desc = take(sizeof(int) * 12 * (d.te_ptr_host ? d.ntiles : 1));
   P.te_quad = take(sizeof(int) * 4 * std::max(n_te, 1));
   P.tile_halo = take(sizeof(int) * std::max(d.te_ptr_host ? d.n_tile_halo : 0, 1));
   P.touch = take(sizeof(int) * std::max(d.nn, 1));
@@ -1129,7 +1188,7 @@ int vf_create(const vf_problem_desc* desc, void* arena_dev, size_t arena_bytes, 
     VF_CUDA(up(P.te_ptr, d.te_ptr_host, sizeof(int) * (d.ntiles + 1)));
     VF_CUDA(up(P.te_elem, d.te_elem_host, sizeof(int) * d.te_ptr_host[d.ntiles]));
     VF_CUDA(up(P.pair_info, d.pair_info_host, sizeof(unsigned) * n_n2e));
-    VF_CUDA(up(P.tile_desc, d.tile_desc_host, sizeof(int) * 8 * d.ntiles));
+    VF_CUDA(up(P.tile_desc, d.tile_desc_host, sizeof(int) * 12 * d.ntiles));
     VF_CUDA(up(P.te_quad, d.te_quad_host, sizeof(int) * 4 * d.te_ptr_host[d.ntiles]));
     VF_CUDA(up(P.tile_halo, d.tile_halo_host, sizeof(int) * d.n_tile_halo));
   }
@@ -1294,8 +1353,11 @@ int vf_assemble(vf_engine* e, int member, int flags, double dt, int is_static, v
   asm_tile2_kernel<J_, R_, ROW_, MT_, MB_><<<grid, d.tile2_threads, smem2, st>>>(                  \
       e->dev, member, newmark_coef(dt), is_static, e->tile_desc_dev, e->te_quad_dev,               \
       e->pair_info_dev, e->tile_halo_dev, d.max_tile_elems, d.tile_max_values, d.max_tile_pairs,   \
-      d.tile_threads, d.max_tile_verts, dbg_skip)
+      d.tile_threads, d.max_tile_verts, pf_dist, dbg_skip)
     const int dbg_skip = getenv("VF_DEBUG_SKIP") ? atoi(getenv("VF_DEBUG_SKIP")) : 0;
+    // L2 prefetch distance in tiles: one wave of resident CTAs (148 SMs x 3 CTAs; measured flat
+    // between one and two waves, worse below and far above: profiles/README.md)
+    const int pf_dist = getenv("VF_PF_DIST") ? atoi(getenv("VF_PF_DIST")) : 3 * 148;
     int v_row = getenv("VF_TILE2_ROW") ? atoi(getenv("VF_TILE2_ROW")) : 2;
     if (v_row == 2 && !e->fan_ok) v_row = 1;
     // occupancy class by CTA size: small CTAs run many per SM so that their phases overlap

@@ -260,14 +260,26 @@ def build_tile_elem_tables(T: dict, tile_start: np.ndarray):
     te_quad[:, :3] = np.where(own, slot_own, slot_halo)
     te_quad[:, 3] = te_elem
     # flat per-tile descriptor: everything a CTA needs is addressable after ONE dependent load,
-    # instead of a chain tile_start -> te_ptr -> te_elem -> cells.  Eight int32:
+    # instead of a chain tile_start -> te_ptr -> te_elem -> cells.  Twelve int32 (8-11: prefetch hint):
     #   i0, te0, pair0, blk0, halo0, nT | nH << 16, n_cells | n_pairs << 16, n_blocks
     npairs = n2e_ptr[ts[1:]] - n2e_ptr[ts[:-1]]
     ncell = np.diff(te_ptr)
     nhalo = np.diff(th_ptr)
     if np.max(npairs) >= 65536 or np.max(nown + nhalo) >= 32768:
         return None
-    desc = np.zeros((ntiles, 8), dtype=np.int64)
+    # window between the 10% and 90% quantile of the tile's (ascending) cell ids: where the
+    # material data of the bulk of its cells lives.  Only an L2 prefetch hint (descriptor
+    # words 8 and 9)
+    es = te_elem.astype(np.int64)
+    n_b = np.diff(te_ptr)
+    lo_i = te_ptr[:-1] + n_b // 10
+    hi_i = te_ptr[:-1] + np.maximum(n_b - n_b // 10 - 1, 0)
+    e_lo = es[lo_i]
+    e_cnt = es[hi_i] - es[lo_i] + 1
+    e_cnt = np.minimum(e_cnt, 4 * np.diff(te_ptr))   # a sparse window is not worth fetching
+    desc = np.zeros((ntiles, 12), dtype=np.int64)
+    desc[:, 8] = e_lo
+    desc[:, 9] = e_cnt
     desc[:, 0] = ts[:-1]
     desc[:, 1] = te_ptr[:-1]
     desc[:, 2] = n2e_ptr[ts[:-1]]
