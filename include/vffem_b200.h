@@ -166,6 +166,12 @@ int vf_multi_axpy(vf_engine* e, const double* V_dev, size_t ldv, int nvec, const
 int vf_axpby(vf_engine* e, double alpha, const double* x_dev, double beta, double* y_dev, size_t n,
              void* stream);
 
+/* Nodal Newmark residuals F_v = v1 - newmark_v(u1, u0, v0, a0, dt), F_a = a1 - newmark_a(...)
+ * of FenicsModel.assem_res (models/transient.py:374-377, equations/newmark.py:8-73), from the
+ * member's device-resident state.  fv, fa: device, N doubles. */
+int vf_newmark_residual(vf_engine* e, int member, double dt, double* fv_dev, double* fa_dev,
+                        void* stream);
+
 /* Solve J_uu x = b with the block-Jacobi preconditioned GMRES that stands in for the PETSc
  * LU of dfn.solve(A, x, b, 'petsc') (transient.py:487).  b, x: device, N doubles.
  * info_host[0] = iterations, [1] = final residual norm, [2] = ||b||. */

@@ -60,7 +60,18 @@ def test_assembly_parity(torch_cuda, mesh_name, variant):
 
     res = model.assem_res()
     assert np.max(np.abs(res['u'] - F_ref)) <= TOL * np.max(np.abs(F_ref))
-    J = model.assem_dres_dstate1().sub['u', 'state/u1']
+    # nodal Newmark residuals (transient.py:374-377), computed on the device
+    from femvf_b200.equations import newmark
+    v1, a1 = np.asarray(s1['v']), np.asarray(s1['a'])
+    rv_ref = v1 - newmark.newmark_v(u1, u0, v0, a0, dt)
+    ra_ref = a1 - newmark.newmark_a(u1, u0, v0, a0, dt)
+    assert np.max(np.abs(res['v'] - rv_ref)) <= TOL * np.max(np.abs(rv_ref))
+    assert np.max(np.abs(res['a'] - ra_ref)) <= TOL * np.max(np.abs(ra_ref))
+    dres = model.assem_dres_dstate1()
+    J = dres.sub['u', 'state/u1']
+    dv = dres.sub['v', 'state/u1']
+    assert np.allclose(dv.diagonal(), -newmark.newmark_v_du1(dt), rtol=0, atol=0)
+    assert np.allclose(dres.sub['a', 'state/a1'].diagonal(), 1.0, rtol=0, atol=0)
     # CSR sparsity pattern bit-exact
     assert np.array_equal(J.indptr, J_ref.indptr)
     assert np.array_equal(J.indices, J_ref.indices)

@@ -683,6 +683,26 @@ __global__ void axpby_kernel(double alpha, const double* __restrict__ x, double 
     y[i] = alpha * x[i] + (beta == 0.0 ? 0.0 : beta * y[i]);
 }
 
+// Nodal Newmark residuals F_v = v1 - v_nmk(u1, u0, v0, a0), F_a = a1 - a_nmk(...)
+// (transient.py:374-377): streaming, 6 reads + 2 writes per DOF.
+__global__ void newmark_res_kernel(EngineDev E, int member, NewmarkCoef nc, double* fv,
+                                   double* fa) {
+  const double* mb = E.members + (size_t)member * E.L.stride;
+  const double* u1 = mb + E.L.off[VF_U1];
+  const double* v1 = mb + E.L.off[VF_V1];
+  const double* a1 = mb + E.L.off[VF_A1];
+  const double* u0 = mb + E.L.off[VF_U0];
+  const double* v0 = mb + E.L.off[VF_V0];
+  const double* a0 = mb + E.L.off[VF_A0];
+  const size_t n = (size_t)E.mesh.dim * E.mesh.nn;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const double u = u1[i], p0 = u0[i], pv = v0[i], pa = a0[i];
+    fv[i] = v1[i] - newmark_v(nc, u, p0, pv, pa);
+    fa[i] = a1[i] - newmark_a(nc, u, p0, pv, pa);
+  }
+}
+
 __global__ void fluid_kernel(EngineDev E, int member0) {
   double* mb = E.members + (size_t)(member0 + blockIdx.x) * E.L.stride;
   const Layout& L = E.L;
@@ -1527,6 +1547,22 @@ int vf_axpby(vf_engine* e, double alpha, const double* x_dev, double beta, doubl
   const int block = 256;
   const int grid = (int)std::min<size_t>(148 * 8, (n + block - 1) / block);
   axpby_kernel<<<grid, block, 0, st>>>(alpha, x_dev, beta, y_dev, n);
+  e->launches += 1;
+  VF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int vf_newmark_residual(vf_engine* e, int member, double dt, double* fv_dev, double* fa_dev,
+                        void* stream) {
+  if (!e) return fail("null engine");
+  if (member < 0 || member >= e->desc.n_members) return fail("member out of range");
+  if (!fv_dev || !fa_dev) return fail("null output");
+  if (!(dt > 0.0)) return fail("dt must be positive");
+  const size_t n = (size_t)e->desc.dim * e->desc.nn;
+  const int block = 256;
+  const int grid = (int)std::min<size_t>(148 * 8, (n + block - 1) / block);
+  newmark_res_kernel<<<grid, block, 0, as_stream(stream)>>>(e->dev, member, newmark_coef(dt),
+                                                             fv_dev, fa_dev);
   e->launches += 1;
   VF_CUDA(cudaGetLastError());
   return 0;

@@ -166,12 +166,20 @@ class Engine:
         self.nnz = int(self._lib.vf_nnz(self._h))
         self._views = {}
         self._pinned = {}
+        self._pinned_up = {}
+        self._registered = {}
 
     # --- plumbing -------------------------------------------------------------------
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def __del__(self):
+        for key in list(getattr(self, '_registered', {})):
+            try:
+                torch.cuda.cudart().cudaHostUnregister(key)
+            except Exception:
+                pass
+            self._registered.pop(key, None)
         h = getattr(self, '_h', None)
         if h is not None and h.value:
             self._lib.vf_destroy(h)
@@ -199,10 +207,36 @@ class Engine:
         flat = self.arena.view(torch.float64)
         return torch.as_strided(flat, (self.n_members, cnt.value), (stride, 1), off0.value // 8)
 
-    def upload(self, name: str, value, member: int = 0):
-        v = self.view(name, member)
-        a = np.empty(v.numel(), dtype=np.float64)
-        a[:] = np.ravel(value) if np.ndim(value) else value
+    def _page_lock(self, arr: np.ndarray) -> bool:
+        """cudaHostRegister a caller-owned array once (the engine keeps it alive)."""
+        key = arr.ctypes.data
+        hit = self._registered.get(key)
+        if hit is not None:
+            return hit[1] >= arr.nbytes
+        rc = torch.cuda.cudart().cudaHostRegister(key, arr.nbytes, 0)
+        ok = int(rc) == 0
+        if ok:
+            self._registered[key] = (arr, arr.nbytes)
+        return ok
+
+    def upload(self, name: str, value, member: int = 0, persistent: bool = False):
+        """Host -> device copy of a named array (scalars are broadcast).  Large arrays move at
+        PCIe DMA rate: ``persistent=True`` page-locks the caller's own (long-lived, contiguous
+        float64) array in place; otherwise they are staged through a cached pinned buffer."""
+        n = self.view(name, member).numel()
+        a = None
+        if n * 8 >= (1 << 20):
+            if persistent and isinstance(value, np.ndarray) and value.dtype == np.float64 \
+                    and value.flags.c_contiguous and value.size == n and self._page_lock(value):
+                a = value
+            else:
+                if name not in self._pinned_up:
+                    self._pinned_up[name] = torch.empty(n, dtype=torch.float64, pin_memory=True)
+                a = self._pinned_up[name].numpy()
+                a[:] = np.ravel(value) if np.ndim(value) else value
+        else:
+            a = np.empty(n, dtype=np.float64)
+            a[:] = np.ravel(value) if np.ndim(value) else value
         check(self._lib.vf_upload(self._h, ARRAY_IDS[name], member, _ptr(a), a.size,
                                   self._stream()))
 
@@ -274,6 +308,23 @@ class Engine:
     def axpby(self, alpha: float, x: torch.Tensor, beta: float, y: torch.Tensor, n: int):
         check(self._lib.vf_axpby(self._h, float(alpha), x.data_ptr(), float(beta), y.data_ptr(),
                                  int(n), self._stream()))
+
+    def newmark_residual(self, dt: float, member: int = 0, pinned: bool = False):
+        """Host copies of F_v, F_a (``transient.py:374-377``) computed on the device from the
+        member's resident state.  ``pinned=True``: views of cached page-locked buffers."""
+        if not hasattr(self, '_nmk_dev'):
+            self._nmk_dev = torch.empty((2, self.N), dtype=torch.float64, device=self.device)
+        d = self._nmk_dev
+        check(self._lib.vf_newmark_residual(self._h, member, float(dt), d[0].data_ptr(),
+                                            d[1].data_ptr(), self._stream()))
+        if pinned:
+            if not hasattr(self, '_nmk_host'):
+                self._nmk_host = torch.empty((2, self.N), dtype=torch.float64, pin_memory=True)
+            h = self._nmk_host
+        else:
+            h = torch.empty((2, self.N), dtype=torch.float64)
+        h.copy_(d)
+        return h[0].numpy(), h[1].numpy()
 
     def linear_solve(self, b: torch.Tensor, x: torch.Tensor, member: int = 0, options=None):
         info = np.zeros(3)

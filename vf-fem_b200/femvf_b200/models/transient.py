@@ -162,7 +162,9 @@ class FenicsModel(BaseTransientModel):
         # by default every device call re-uploads state, control and properties.  With
         # ``trust_setters = True`` only the groups changed through set_ini_state /
         # set_fin_state / set_control / set_prop / dt since the last device call are uploaded
-        # (in-place edits of the BlockVectors then need ``mark_dirty()``).
+        # (in-place edits of the BlockVectors then need ``mark_dirty()``), and large results
+        # (F, J values, the constant Jacobian blocks) are returned as views of cached
+        # page-locked buffers that the next call of the same method overwrites.
         self.trust_setters = False
         self._dirty = {'prop': True, 'state0': True, 'state1': True, 'control': True}
         self.set_prop(self.prop)
@@ -267,12 +269,13 @@ class FenicsModel(BaseTransientModel):
         every = not self.trust_setters
         if every or self._dirty['prop']:
             self._push_prop(getattr(self, '_ymid', 0.0))
+        lock = self.trust_setters  # the model's own state vectors are page-locked in place
         if every or self._dirty['state0']:
             for name, vec in zip(('u0', 'v0', 'a0'), self.state0.vecs):
-                e.upload(name, vec, m)
+                e.upload(name, vec, m, persistent=lock)
         if every or self._dirty['state1']:
             for name, vec in zip(('u1', 'v1', 'a1'), self.state1.vecs):
-                e.upload(name, vec, m)
+                e.upload(name, vec, m, persistent=lock)
         if every or self._dirty['control']:
             e.upload('p1', self.control['p'], m)
         for g in self._dirty:
@@ -283,10 +286,9 @@ class FenicsModel(BaseTransientModel):
         """``transient.py:363-382``: F_u by device assembly; F_v, F_a nodal; BCs on F_u."""
         self._push_all()
         self.engine.assemble(self._member, res=True, jac=False, dt=self.dt)
-        res_u = self.engine.download('F', self._member)
-        u1, v1, a1 = self.state1.sub_blocks
-        res_v = v1 - newmark.newmark_v(u1, *self.state0.sub_blocks, self.dt)
-        res_a = a1 - newmark.newmark_a(u1, *self.state0.sub_blocks, self.dt)
+        res_u = self.engine.download('F', self._member, pinned=self.trust_setters)
+        res_v, res_a = self.engine.newmark_residual(self.dt, self._member,
+                                                    pinned=self.trust_setters)
         return BlockVector([res_u, res_v, res_a], labels=(self.FORM_KEYS,))
 
     def csr_pattern(self):
@@ -306,12 +308,19 @@ class FenicsModel(BaseTransientModel):
         """``transient.py:384-406``: block Jacobian labelled (FORM_KEYS, STATE1_KEYS)."""
         N = self.state0['u'].size
         dt = self.dt
-        eye = sp.identity(N, format='csr')
-        zero = sp.csr_matrix((N, N))
+        # the constant blocks depend on (N, dt) only: built once per time step size
+        const = getattr(self, '_jac_const_blocks', None)
+        if const is None or const[0] != (N, dt) or not self.trust_setters:
+            eye = sp.identity(N, format='csr')
+            zero = sp.csr_matrix((N, N))
+            const = ((N, dt), eye, zero, -newmark.newmark_v_du1(dt) * eye,
+                     -newmark.newmark_a_du1(dt) * eye)
+            self._jac_const_blocks = const
+        _, eye, zero, dv_du, da_du = const
         mats = [
             self._assem_jac_uu(), zero, zero,
-            -newmark.newmark_v_du1(dt) * eye, eye, zero,
-            -newmark.newmark_a_du1(dt) * eye, zero, eye,
+            dv_du, eye, zero,
+            da_du, zero, eye,
         ]
         return BlockMatrix(mats, (3, 3), (self.FORM_KEYS, self.STATE1_KEYS))
 
