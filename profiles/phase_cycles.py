@@ -1,5 +1,5 @@
 import sys, os
-sys.path.insert(0, 'vf-fem_b200'); sys.path.insert(0, 'tests'); sys.path.insert(0, '.')
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path[:0] = [ROOT, os.path.join(ROOT, 'vf-fem_b200'), os.path.join(ROOT, 'tests')]
 import numpy as np, torch
 import bench
 os.environ['VF_DEBUG_SKIP'] = '32'
