@@ -310,8 +310,8 @@ def run_partition(args, rank, world, local_rank):
         'gmres': {'iterations': iters, 'ms_total': float(t[1]),
                   'iterations_per_s': iters / (float(t[1]) * 1e-3),
                   'operator_applications': ds.gmres.spmv_count,
-                  'note': 'host-driven loop (one device->host read per reduction); CGS2, '
-                          'restart 30, left block-Jacobi'},
+                  'note': 'host-launched, device-resident Arnoldi data (one device->host read per 8 '
+                          'iterations); CGS2, restart 30, left block-Jacobi'},
         'setup_s': setup_s, 'gpu_launches': int(eng.launch_count),
     }
     if rank == 0:

@@ -628,27 +628,35 @@ asm_node_global_kernel(EngineDev E, int member, double dt, int is_static) {
 }
 
 constexpr int kDotBlock = 256;
-__global__ void multidot_partial_kernel(const double* __restrict__ V, size_t ldv, int nvec,
-                                        const double* __restrict__ w, size_t n,
-                                        double* __restrict__ partial) {
-  __shared__ double red[kDotBlock / 32];
-  const size_t chunk = (n + gridDim.x - 1) / gridDim.x;
-  const size_t lo = (size_t)blockIdx.x * chunk;
-  const size_t hi = lo + chunk < n ? lo + chunk : n;
+// Partial dot products of w with NV (<= nvec) Krylov vectors in ONE pass over the data: each
+// thread keeps the NV accumulators of its elements in registers (w is read once, every V_j
+// once, coalesced), then the block reduces them in a fixed order (deterministic).
+template <int NV>
+__global__ void __launch_bounds__(kDotBlock) multidot_partial_kernel(
+    const double* __restrict__ V, size_t ldv, int nvec, const double* __restrict__ w, size_t n,
+    double* __restrict__ partial) {
+  __shared__ double red[kDotBlock / 32][NV];
+  double acc[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) acc[j] = 0.0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const double wi = w[i];
+#pragma unroll
+    for (int j = 0; j < NV; ++j)
+      if (j < nvec) acc[j] += V[(size_t)j * ldv + i] * wi;
+  }
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (int j = 0; j < nvec; ++j) {
-    const double* vj = V + (size_t)j * ldv;
-    double s = 0.0;
-    for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) s += vj[i] * w[i];
-    s = warp_sum(s);
-    if (lane == 0) red[wid] = s;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double t = 0.0;
-      for (int q = 0; q < kDotBlock / 32; ++q) t += red[q];
-      partial[(size_t)blockIdx.x * nvec + j] = t;
-    }
-    __syncthreads();
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const double s = warp_sum(acc[j]);
+    if (lane == 0) red[wid][j] = s;
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < nvec; j += blockDim.x) {
+    double t = 0.0;
+    for (int q = 0; q < kDotBlock / 32; ++q) t += red[q][j];
+    partial[(size_t)blockIdx.x * nvec + j] = t;
   }
 }
 
@@ -673,6 +681,17 @@ __global__ void multi_axpy_kernel(const double* __restrict__ V, size_t ldv, int 
     for (int j = 0; j < nvec; ++j) s += hs[j] * V[(size_t)j * ldv + i];
     w[i] -= s;
   }
+}
+
+// y = x / sqrt(*s2) with the scalar read from device memory (0 when *s2 == 0): normalises a
+// Krylov vector by a norm that never visits the host
+__global__ void scale_rsqrt_kernel(const double* __restrict__ x, const double* __restrict__ s2,
+                                   double* __restrict__ y, size_t n) {
+  const double v = *s2;
+  const double f = v > 0.0 ? 1.0 / sqrt(v) : 0.0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x)
+    y[i] = f * x[i];
 }
 
 // y = alpha x + beta y
@@ -1519,9 +1538,22 @@ int vf_multidot(vf_engine* e, const double* V_dev, size_t ldv, int nvec, const d
   int nblocks = (int)std::min<size_t>(148 * 4, (n + 2047) / 2048);
   nblocks = std::max(nblocks, 1);
   if (scratch_count < (size_t)nblocks * nvec) return fail("vf_multidot: scratch too small");
-  multidot_partial_kernel<<<nblocks, kDotBlock, 0, st>>>(V_dev, ldv, nvec, w_dev, n, scratch_dev);
-  multidot_final_kernel<<<(nvec + 63) / 64, 64, 0, st>>>(scratch_dev, nblocks, nvec, out_dev);
-  e->launches += 2;
+  // vectors are processed in groups of at most 32 (register accumulators)
+  for (int j0 = 0; j0 < nvec; j0 += 32) {
+    const int nv = std::min(32, nvec - j0);
+    const double* Vg = V_dev + (size_t)j0 * ldv;
+    double* part = scratch_dev + (size_t)j0 * nblocks;
+    if (nv <= 4)
+      multidot_partial_kernel<4><<<nblocks, kDotBlock, 0, st>>>(Vg, ldv, nv, w_dev, n, part);
+    else if (nv <= 8)
+      multidot_partial_kernel<8><<<nblocks, kDotBlock, 0, st>>>(Vg, ldv, nv, w_dev, n, part);
+    else if (nv <= 16)
+      multidot_partial_kernel<16><<<nblocks, kDotBlock, 0, st>>>(Vg, ldv, nv, w_dev, n, part);
+    else
+      multidot_partial_kernel<32><<<nblocks, kDotBlock, 0, st>>>(Vg, ldv, nv, w_dev, n, part);
+    multidot_final_kernel<<<(nv + 63) / 64, 64, 0, st>>>(part, nblocks, nv, out_dev + j0);
+    e->launches += 2;
+  }
   VF_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1547,6 +1579,18 @@ int vf_axpby(vf_engine* e, double alpha, const double* x_dev, double beta, doubl
   const int block = 256;
   const int grid = (int)std::min<size_t>(148 * 8, (n + block - 1) / block);
   axpby_kernel<<<grid, block, 0, st>>>(alpha, x_dev, beta, y_dev, n);
+  e->launches += 1;
+  VF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int vf_scale_rsqrt(vf_engine* e, const double* x_dev, const double* s2_dev, double* y_dev,
+                   size_t n, void* stream) {
+  if (!e) return fail("null engine");
+  if (n == 0) return 0;
+  const int block = 256;
+  const int grid = (int)std::min<size_t>(148 * 8, (n + block - 1) / block);
+  scale_rsqrt_kernel<<<grid, block, 0, as_stream(stream)>>>(x_dev, s2_dev, y_dev, n);
   e->launches += 1;
   VF_CUDA(cudaGetLastError());
   return 0;

@@ -147,7 +147,8 @@ class GridGMRES:
     """
     Left block-Jacobi preconditioned restarted GMRES(m) with CGS2 over the rows owned by this
     rank.  Host-side control flow (as PETSc's KSP), device kernels for every O(N) operation,
-    one halo exchange per operator application and one small all-reduce per reduction.
+    one halo exchange per operator application and one small all-reduce per reduction; the
+    host reads results back only every few iterations (see ``solve``).
     """
 
     def __init__(self, engine, n_own_nodes: int, halo: Optional[HaloPlan] = None,
@@ -167,8 +168,15 @@ class GridGMRES:
         self.w = torch.zeros(self.nown, dtype=f64, device=dev)
         self.t = torch.zeros(self.nown, dtype=f64, device=dev)
         self.h = torch.zeros(restart + 2, dtype=f64, device=dev)
+        # per-iteration device record: [h (pass 1) | h (pass 2) | ||w||^2]
+        self.Hd = torch.zeros((restart, 2 * (restart + 1) + 1), dtype=f64, device=dev)
         self.scratch = torch.zeros(592 * (restart + 2), dtype=f64, device=dev)
         self.distributed = halo is not None and halo.part.world > 1
+        import os
+        want = os.environ.get('VF_GMRES_GRAPH')
+        self.use_graphs = (not self.distributed and str(dev).startswith('cuda')) \
+            if want is None else want == '1'
+        self._graphs = {}
         self.spmv_count = 0
 
     def _allreduce(self, t: torch.Tensor):
@@ -196,9 +204,53 @@ class GridGMRES:
         self._allreduce(out)
         return float(torch.sqrt(out)[0].item())
 
+    def _arnoldi_steps(self, k: int, kend: int):
+        e, m, n, V, w, Hd = self.e, self.m, self.nown, self.V, self.w, self.Hd
+        for j in range(k, kend):
+            row = Hd[j]
+            h1, h2, nrm2 = row[:j + 1], row[m + 1:m + 2 + j], row[2 * m + 2:2 * m + 3]
+            self.apply(V[j], w)
+            e.multidot(V, j + 1, w, n, h1, self.scratch)
+            self._allreduce(h1)
+            e.multi_axpy(V, j + 1, h1, w, n)
+            e.multidot(V, j + 1, w, n, h2, self.scratch)
+            self._allreduce(h2)
+            e.multi_axpy(V, j + 1, h2, w, n)
+            e.multidot(w.view(1, -1), 1, w, n, nrm2, self.scratch)
+            self._allreduce(nrm2)
+            e.scale_rsqrt(w, nrm2, V[j + 1], n)
+
+    def _arnoldi_block(self, k: int, kend: int):
+        """Arnoldi iterations k..kend-1 on the device.  On a single rank the block's launch
+        sequence (about 15 small kernels per iteration, all on fixed buffers) is captured once
+        into a CUDA graph and replayed, which removes the per-launch host cost."""
+        if not self.use_graphs:
+            self._arnoldi_steps(k, kend)
+            return
+        key = (k, kend)
+        g = self._graphs.get(key)
+        if g is None:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            count = self.spmv_count
+            with torch.cuda.graph(g):
+                self._arnoldi_steps(k, kend)
+            self.spmv_count = count
+            self._graphs[key] = g
+        g.replay()
+        self.spmv_count += kend - k
+
     def solve(self, b_own: torch.Tensor, x_own: torch.Tensor, rtol: float = 1e-12,
-              atol: float = 0.0, maxiter: int = 2000):
-        """Solve J x = b on the owned rows; ``x_own`` is overwritten (initial guess 0)."""
+              atol: float = 0.0, maxiter: int = 2000, check_every: int = 8):
+        """
+        Solve J x = b on the owned rows; ``x_own`` is overwritten (initial guess 0).
+
+        The Arnoldi loop is asynchronous: the Hessenberg column (both CGS passes) and the
+        squared norm of every iteration stay in device memory, the new basis vector is
+        normalised by ``vf_scale_rsqrt`` from that device scalar, and the host reads them back
+        (one copy) only every ``check_every`` iterations to advance the Givens recurrence and
+        test convergence.  Iterations computed past the converged one are discarded.
+        """
         e, m, n = self.e, self.m, self.nown
         e.block_jacobi_setup(0, self.n_own)
         x_own.zero_()
@@ -213,6 +265,7 @@ class GridGMRES:
         iters = 0
         first = True
         H = np.zeros((m + 1, m))
+        Hd = self.Hd                                    # (m, 2 (m+1) + 1) device rows
         while True:
             if not first:
                 self.apply(x_own, w)                    # w = Dinv J x
@@ -230,34 +283,34 @@ class GridGMRES:
             cs, sn = np.zeros(m), np.zeros(m)
             k, resid = 0, beta
             done = False
+            Hd.zero_()
             while k < m and not done:
-                self.apply(V[k], w)
-                h1 = self.dots(k + 1, w).clone()
-                e.multi_axpy(V, k + 1, h1, w, n)
-                h2 = self.dots(k + 1, w).clone()
-                e.multi_axpy(V, k + 1, h2, w, n)
-                hk1 = self.norm(w)
-                hc = (h1 + h2).cpu().numpy()
-                col = np.zeros(m + 1)
-                col[:k + 1] = hc
-                for j in range(k):
-                    t0 = cs[j] * col[j] + sn[j] * col[j + 1]
-                    col[j + 1] = -sn[j] * col[j] + cs[j] * col[j + 1]
-                    col[j] = t0
-                denom = np.hypot(col[k], hk1)
-                c, s_ = (1.0, 0.0) if denom == 0 else (col[k] / denom, hk1 / denom)
-                cs[k], sn[k] = c, s_
-                col[k] = c * col[k] + s_ * hk1
-                g[k + 1] = -s_ * g[k]
-                g[k] = c * g[k]
-                H[:, k] = col
-                resid = abs(g[k + 1])
-                iters += 1
-                if hk1 > 0:
-                    e.axpby(1.0 / hk1, w, 0.0, V[k + 1], n)
-                k += 1
-                if resid <= tol or iters >= maxiter or hk1 == 0:
-                    done = True
+                kend = min(k + check_every, m, k + max(maxiter - iters, 1))
+                self._arnoldi_block(k, kend)            # device only, no host read
+                blk = Hd[k:kend].cpu().numpy()          # the only synchronisation of the block
+                k0 = k
+                for j in range(k0, kend):
+                    r = blk[j - k0]
+                    hk1 = float(np.sqrt(max(r[2 * m + 2], 0.0)))
+                    col = np.zeros(m + 1)
+                    col[:j + 1] = r[:j + 1] + r[m + 1:m + 2 + j]
+                    for i in range(j):
+                        t0 = cs[i] * col[i] + sn[i] * col[i + 1]
+                        col[i + 1] = -sn[i] * col[i] + cs[i] * col[i + 1]
+                        col[i] = t0
+                    denom = np.hypot(col[j], hk1)
+                    c, s_ = (1.0, 0.0) if denom == 0 else (col[j] / denom, hk1 / denom)
+                    cs[j], sn[j] = c, s_
+                    col[j] = c * col[j] + s_ * hk1
+                    g[j + 1] = -s_ * g[j]
+                    g[j] = c * g[j]
+                    H[:, j] = col
+                    resid = abs(g[j + 1])
+                    iters += 1
+                    k = j + 1
+                    if resid <= tol or iters >= maxiter or hk1 == 0:
+                        done = True
+                        break
             y = np.linalg.solve(np.triu(H[:k, :k]), g[:k]) if k else np.zeros(0)
             yd = torch.as_tensor(-y, device=x_own.device)
             e.multi_axpy(V, k, yd, x_own, n)            # x += V y

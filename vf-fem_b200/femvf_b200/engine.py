@@ -309,6 +309,11 @@ class Engine:
         check(self._lib.vf_axpby(self._h, float(alpha), x.data_ptr(), float(beta), y.data_ptr(),
                                  int(n), self._stream()))
 
+    def scale_rsqrt(self, x: torch.Tensor, s2: torch.Tensor, y: torch.Tensor, n: int):
+        """y = x / sqrt(s2[0]) with the scalar read on the device."""
+        check(self._lib.vf_scale_rsqrt(self._h, x.data_ptr(), s2.data_ptr(), y.data_ptr(), int(n),
+                                       self._stream()))
+
     def newmark_residual(self, dt: float, member: int = 0, pinned: bool = False):
         """Host copies of F_v, F_a (``transient.py:374-377``) computed on the device from the
         member's resident state.  ``pinned=True``: views of cached page-locked buffers."""
