@@ -166,10 +166,12 @@ int vf_multi_axpy(vf_engine* e, const double* V_dev, size_t ldv, int nvec, const
 int vf_axpby(vf_engine* e, double alpha, const double* x_dev, double beta, double* y_dev, size_t n,
              void* stream);
 
-/* y = x / sqrt(*s2_dev): Krylov-vector normalisation with the squared norm left on the device
- * by vf_multidot (KSPGMRES's VecNormalize without the host round trip). */
-int vf_scale_rsqrt(vf_engine* e, const double* x_dev, const double* s2_dev, double* y_dev,
-                   size_t n, void* stream);
+/* y = x / sqrt(s), s = *s2_dev - sum_{i<nsub} sub_dev[i]^2, all read on the device; s is also
+ * stored to *s_out_dev when non-null (must not alias s2_dev).  Krylov-vector normalisation
+ * with the squared norm left on the device by vf_multidot (KSPGMRES's VecNormalize without the
+ * host round trip); the subtraction is the norm update of the second Gram-Schmidt pass. */
+int vf_scale_rsqrt(vf_engine* e, const double* x_dev, const double* s2_dev, const double* sub_dev,
+                   int nsub, double* s_out_dev, double* y_dev, size_t n, void* stream);
 
 /* Nodal Newmark residuals F_v = v1 - newmark_v(u1, u0, v0, a0, dt), F_a = a1 - newmark_a(...)
  * of FenicsModel.assem_res (models/transient.py:374-377, equations/newmark.py:8-73), from the

@@ -207,7 +207,11 @@ def test_grid_gmres_host_logic_with_stub_engine():
         def multidot(self, V, nvec, w, n, out, scratch): out.copy_(V[:nvec] @ w)
         def multi_axpy(self, V, nvec, h, w, n): w.sub_(V[:nvec].T @ h)
         def axpby(self, alpha, x, beta, y, n): y.copy_(alpha * x + beta * y)
-        def scale_rsqrt(self, x, s2, y, n): y.copy_(x / torch.sqrt(s2[0]))
+        def scale_rsqrt(self, x, s2, y, n, sub=None, s_out=None):
+            s = s2[0] - (torch.dot(sub, sub) if sub is not None else 0.0)
+            if s_out is not None:
+                s_out[0] = s
+            y.copy_(x / torch.sqrt(s))
 
     rng = np.random.default_rng(0)
     n = 60

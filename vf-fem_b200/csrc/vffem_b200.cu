@@ -683,15 +683,19 @@ __global__ void multi_axpy_kernel(const double* __restrict__ V, size_t ldv, int 
   }
 }
 
-// y = x / sqrt(*s2) with the scalar read from device memory (0 when *s2 == 0): normalises a
-// Krylov vector by a norm that never visits the host
-__global__ void scale_rsqrt_kernel(const double* __restrict__ x, const double* __restrict__ s2,
-                                   double* __restrict__ y, size_t n) {
-  const double v = *s2;
+// y = x / sqrt(s) with s = *s2 - sum_i sub[i]^2 read from device memory (y = 0 when s <= 0):
+// normalises a Krylov vector by a norm that never visits the host.  The subtraction is the
+// Pythagorean update of the second Gram-Schmidt pass; s is also stored to *s_out for the host.
+__global__ void scale_rsqrt_kernel(const double* x, const double* __restrict__ s2,
+                                   const double* __restrict__ sub, int nsub, double* s_out,
+                                   double* y, size_t n) {  // y may alias x
+  double v = *s2;
+  for (int i = 0; i < nsub; ++i) v -= sub[i] * sub[i];
   const double f = v > 0.0 ? 1.0 / sqrt(v) : 0.0;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (size_t)gridDim.x * blockDim.x)
     y[i] = f * x[i];
+  if (s_out && blockIdx.x == 0 && threadIdx.x == 0) *s_out = v;
 }
 
 // y = alpha x + beta y
@@ -1584,13 +1588,16 @@ int vf_axpby(vf_engine* e, double alpha, const double* x_dev, double beta, doubl
   return 0;
 }
 
-int vf_scale_rsqrt(vf_engine* e, const double* x_dev, const double* s2_dev, double* y_dev,
-                   size_t n, void* stream) {
+int vf_scale_rsqrt(vf_engine* e, const double* x_dev, const double* s2_dev, const double* sub_dev,
+                   int nsub, double* s_out_dev, double* y_dev, size_t n, void* stream) {
   if (!e) return fail("null engine");
   if (n == 0) return 0;
+  if (nsub < 0 || (nsub > 0 && !sub_dev)) return fail("vf_scale_rsqrt: bad subtraction list");
+  if (s_out_dev == s2_dev) return fail("vf_scale_rsqrt: s_out must not alias s2");
   const int block = 256;
   const int grid = (int)std::min<size_t>(148 * 8, (n + block - 1) / block);
-  scale_rsqrt_kernel<<<grid, block, 0, as_stream(stream)>>>(x_dev, s2_dev, y_dev, n);
+  scale_rsqrt_kernel<<<grid, block, 0, as_stream(stream)>>>(x_dev, s2_dev, sub_dev, nsub,
+                                                             s_out_dev, y_dev, n);
   e->launches += 1;
   VF_CUDA(cudaGetLastError());
   return 0;

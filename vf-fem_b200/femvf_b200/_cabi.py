@@ -114,8 +114,8 @@ def load_library() -> C.CDLL:
                                   C.c_void_p, C.c_size_t, C.c_void_p]
     lib.vf_axpby.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_double, C.c_void_p,
                              C.c_size_t, C.c_void_p]
-    lib.vf_scale_rsqrt.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
-                                   C.c_void_p]
+    lib.vf_scale_rsqrt.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                   C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     lib.vf_newmark_residual.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p,
                                         C.c_void_p]
     lib.vf_linear_solve.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,

@@ -205,20 +205,23 @@ class GridGMRES:
         return float(torch.sqrt(out)[0].item())
 
     def _arnoldi_steps(self, k: int, kend: int):
-        e, m, n, V, w, Hd = self.e, self.m, self.nown, self.V, self.w, self.Hd
+        e, m, n, V, Hd = self.e, self.m, self.nown, self.V, self.Hd
         for j in range(k, kend):
             row = Hd[j]
             h1, h2, nrm2 = row[:j + 1], row[m + 1:m + 2 + j], row[2 * m + 2:2 * m + 3]
+            # the new vector is built in place in V[j+1], so that ONE multidot (and one
+            # all-reduce) of the second pass returns both V_i.w (i <= j) and w.w
+            w = V[j + 1]
             self.apply(V[j], w)
             e.multidot(V, j + 1, w, n, h1, self.scratch)
             self._allreduce(h1)
             e.multi_axpy(V, j + 1, h1, w, n)
-            e.multidot(V, j + 1, w, n, h2, self.scratch)
-            self._allreduce(h2)
+            h2n = row[m + 1:m + 3 + j]                  # [h2 (j+1 entries) | w.w before pass 2]
+            e.multidot(V, j + 2, w, n, h2n, self.scratch)
+            self._allreduce(h2n)
             e.multi_axpy(V, j + 1, h2, w, n)
-            e.multidot(w.view(1, -1), 1, w, n, nrm2, self.scratch)
-            self._allreduce(nrm2)
-            e.scale_rsqrt(w, nrm2, V[j + 1], n)
+            # ||w - V h2||^2 = w.w - |h2|^2 (V orthonormal, h2 = O(eps |w|): no cancellation)
+            e.scale_rsqrt(w, h2n[j + 1:j + 2], w, n, sub=h2, s_out=nrm2)
 
     def _arnoldi_block(self, k: int, kend: int):
         """Arnoldi iterations k..kend-1 on the device.  On a single rank the block's launch

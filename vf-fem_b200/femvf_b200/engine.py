@@ -309,10 +309,15 @@ class Engine:
         check(self._lib.vf_axpby(self._h, float(alpha), x.data_ptr(), float(beta), y.data_ptr(),
                                  int(n), self._stream()))
 
-    def scale_rsqrt(self, x: torch.Tensor, s2: torch.Tensor, y: torch.Tensor, n: int):
-        """y = x / sqrt(s2[0]) with the scalar read on the device."""
-        check(self._lib.vf_scale_rsqrt(self._h, x.data_ptr(), s2.data_ptr(), y.data_ptr(), int(n),
-                                       self._stream()))
+    def scale_rsqrt(self, x: torch.Tensor, s2: torch.Tensor, y: torch.Tensor, n: int,
+                    sub: Optional[torch.Tensor] = None, s_out: Optional[torch.Tensor] = None):
+        """y = x / sqrt(s2[0] - sum(sub**2)), scalars read on the device; the radicand is
+        stored to ``s_out[0]`` when given."""
+        check(self._lib.vf_scale_rsqrt(
+            self._h, x.data_ptr(), s2.data_ptr(), sub.data_ptr() if sub is not None else None,
+            int(sub.numel()) if sub is not None else 0,
+            s_out.data_ptr() if s_out is not None else None, y.data_ptr(), int(n),
+            self._stream()))
 
     def newmark_residual(self, dt: float, member: int = 0, pinned: bool = False):
         """Host copies of F_v, F_a (``transient.py:374-377``) computed on the device from the
