@@ -134,6 +134,8 @@ __global__ void __launch_bounds__(MAXT, MINB) asm_tile2_kernel(
     const int* __restrict__ tile_halo, int max_tile_elems, int tile_max_values,
     int max_tile_pairs, int max_tile_nodes, int max_tile_verts, int pf_dist, int dbg_skip) {
   constexpr int D = 2;
+  constexpr int kThreads = MAXT;  // always launched with exactly MAXT threads: loop strides
+                                  // and trip counts are compile-time constants
   extern __shared__ double smem[];
   double* recs = smem;
   // region A: the CSR slice (phases 2-3) aliases the nodal staging area (phases 0-1)
@@ -176,8 +178,8 @@ __global__ void __launch_bounds__(MAXT, MINB) asm_tile2_kernel(
   const bool have = (int)threadIdx.x < nte;
   if (have) quad = ldg_nc_v4(te_quad + te0 + threadIdx.x);
   // index slices: asynchronous global->shared copies, no registers, waited for at the barrier
-  for (int t = threadIdx.x; t < npr; t += blockDim.x) cp_async4(s_pair + t, pair_info + pr0 + t);
-  for (int t = threadIdx.x; t <= nT; t += blockDim.x) {
+  for (int t = threadIdx.x; t < npr; t += kThreads) cp_async4(s_pair + t, pair_info + pr0 + t);
+  for (int t = threadIdx.x; t <= nT; t += kThreads) {
     cp_async4(s_brptr + t, m.brptr + i0 + t);
     cp_async4(s_n2e + t, m.n2e_ptr + i0 + t);
   }
@@ -191,11 +193,11 @@ __global__ void __launch_bounds__(MAXT, MINB) asm_tile2_kernel(
   cp_async_commit();
   // Lame / Newmark coefficients: a handful of fp64 divisions, done once per CTA
   __shared__ LameFac s_lf;
-  if (threadIdx.x == blockDim.x - 1) s_lf = lame_fac(pv.scal[SC_NU]);
+  if (threadIdx.x == kThreads - 1) s_lf = lame_fac(pv.scal[SC_NU]);
   // stage the tile's vertices -- its own contiguous range, then the halo vertices of its
   // cells -- with 16-byte loads; v_nmk / a_nmk are evaluated once per vertex here instead of
   // once per (cell, vertex) in phase 1, and phase 1 reads shared memory only
-  for (int t = threadIdx.x; t < nV; t += blockDim.x) {
+  for (int t = threadIdx.x; t < nV; t += kThreads) {
     const int vtx = t < nT ? i0 + t : tile_halo[h0 + t - nT];
     // all global loads first, then the shared-memory stores: a store in between would order
     // the (generic-pointer) loads behind it and cost a second round trip
@@ -223,7 +225,7 @@ __global__ void __launch_bounds__(MAXT, MINB) asm_tile2_kernel(
     const LameFac lf = s_lf;
     const NewmarkCoef nc = nc_arg;
     const Damping dp = prop_damping(pv);
-    for (int q = threadIdx.x; q < nte && !(dbg_skip & 1); q += blockDim.x) {
+    for (int q = threadIdx.x; q < nte && !(dbg_skip & 1); q += kThreads) {
       if (q != (int)threadIdx.x) {
         quad = te_quad[te0 + q];
         emod_e = pv.emod[quad.w];
@@ -254,7 +256,7 @@ __global__ void __launch_bounds__(MAXT, MINB) asm_tile2_kernel(
     // vertex (tables.order_fans_2d), so every off-diagonal block is the sum of two
     // CONSECUTIVE cells: it is completed in registers and stored once -- no zero-fill and no
     // read-modify-write of the shared-memory slice
-    for (int r = threadIdx.x; r < D * nT; r += blockDim.x) {
+    for (int r = threadIdx.x; r < D * nT; r += kThreads) {
       const int n = r >> 1, comp = r & 1;
       const int b0 = s_brptr[n], deg = s_brptr[n + 1] - b0;
       double* row = tileJ + D * D * (b0 - bbase) + comp * D * deg;
@@ -306,9 +308,9 @@ __global__ void __launch_bounds__(MAXT, MINB) asm_tile2_kernel(
     if (pf) {
       // threads without a row (or all, when every thread has one) share the far tile's lines
       const int idle0 = ((D * nT + 31) / 32) * 32;
-      const bool some_idle = idle0 + 32 <= (int)blockDim.x;
+      const bool some_idle = idle0 + 32 <= (int)kThreads;
       const int k = some_idle ? (int)threadIdx.x - idle0 : (int)threadIdx.x;
-      const int nk = some_idle ? (int)blockDim.x - idle0 : (int)blockDim.x;
+      const int nk = some_idle ? (int)kThreads - idle0 : (int)kThreads;
       if (k >= 0) {
         const int f_i0 = s_far[0], f_te0 = s_far[1], f_pr0 = s_far[2], f_h0 = s_far[4];
         const int f_nT = s_far[5] & 0xffff, f_nH = (int)((unsigned)s_far[5] >> 16);
@@ -354,7 +356,7 @@ __global__ void __launch_bounds__(MAXT, MINB) asm_tile2_kernel(
     }
   } else if (ROW == 1) {
     // one thread per scalar row, read-modify-write accumulation (any cell order)
-    for (int r = threadIdx.x; r < D * nT; r += blockDim.x) {
+    for (int r = threadIdx.x; r < D * nT; r += kThreads) {
       const int n = r >> 1, comp = r & 1;
       const int b0 = s_brptr[n], deg = s_brptr[n + 1] - b0;
       double* row = tileJ + D * D * (b0 - bbase) + comp * D * deg;
@@ -387,7 +389,7 @@ __global__ void __launch_bounds__(MAXT, MINB) asm_tile2_kernel(
     }
   } else {
     // one thread per node (both scalar rows of its block row)
-    for (int n = threadIdx.x; n < nT; n += blockDim.x) {
+    for (int n = threadIdx.x; n < nT; n += kThreads) {
       const int b0 = s_brptr[n], deg = s_brptr[n + 1] - b0;
       double* row0 = tileJ + D * D * (b0 - bbase);
       double* row1 = row0 + D * deg;
@@ -438,11 +440,11 @@ __global__ void __launch_bounds__(MAXT, MINB) asm_tile2_kernel(
   if (JAC) {
     double2* dst = reinterpret_cast<double2*>(mb + L.off[VF_J] + base);
     const double2* src = reinterpret_cast<const double2*>(tileJ);
-    for (int t = threadIdx.x; t < nvals / 2; t += blockDim.x) __stcs(dst + t, src[t]);
+    for (int t = threadIdx.x; t < nvals / 2; t += kThreads) __stcs(dst + t, src[t]);
   }
   if (RES) {
     double* F = mb + L.off[VF_F] + (size_t)D * i0;
-    for (int t = threadIdx.x; t < D * nT; t += blockDim.x) F[t] = tileF[t];
+    for (int t = threadIdx.x; t < D * nT; t += kThreads) F[t] = tileF[t];
   }
 #ifdef VF_PHASE_PROF
   if (prof) {
@@ -1393,7 +1395,7 @@ int vf_assemble(vf_engine* e, int member, int flags, double dt, int is_static, v
     const vf_problem_desc& d = e->desc;
     const size_t smem2 = tile2_smem_bytes(d);
 #define VF_LAUNCH_ASM2(J_, R_, ROW_, MT_, MB_)                                                     \
-  asm_tile2_kernel<J_, R_, ROW_, MT_, MB_><<<grid, d.tile2_threads, smem2, st>>>(                  \
+  asm_tile2_kernel<J_, R_, ROW_, MT_, MB_><<<grid, MT_, smem2, st>>>(                  \
       e->dev, member, newmark_coef(dt), is_static, e->tile_desc_dev, e->te_quad_dev,               \
       e->pair_info_dev, e->tile_halo_dev, d.max_tile_elems, d.tile_max_values, d.max_tile_pairs,   \
       d.tile_threads, d.max_tile_verts, pf_dist, dbg_skip)
