@@ -96,3 +96,66 @@ def test_assembly_parity(torch_cuda, mesh_name, variant):
     x_ref = spla.splu(J_ref.tocsc()).solve(b)
     err = np.linalg.norm(st.cpu().numpy() - x_ref) / np.linalg.norm(x_ref)
     assert err < 1e-9, (err, info)
+
+
+def _assemble_and_compare(model, rng, contact=False, membrane=False):
+    prob = oracle_problem(model.residual)
+    N = prob.N
+    prop = random_solid_prop(prob, rng, membrane=membrane)
+    mprop = model.prop.copy()
+    set_model_prop(mprop, prop)
+    model.set_prop(mprop)
+    u1, u0, v0, a0 = random_state(N, rng)
+    p1 = rng.uniform(0, 8e3, prob.nn)
+    dt = 1e-4
+    model.dt = dt
+    s0 = model.state0.copy(); s0['u'][:] = u0; s0['v'][:] = v0; s0['a'][:] = a0
+    s1 = model.state1.copy(); s1['u'][:] = u1
+    model.set_ini_state(s0); model.set_fin_state(s1)
+    ctl = model.control.copy(); ctl['p'][:] = p1
+    model.set_control(ctl)
+    so = om.SolidOracle(prob, contact=contact, membrane=membrane)
+    F_ref = so.res(u1, (u0, v0, a0), dt, prop, p1)
+    J_ref = so.jac(u1, dt, prop, p1)
+    res = model.assem_res()
+    assert np.max(np.abs(res['u'] - F_ref)) <= TOL * np.max(np.abs(F_ref))
+    J = model.assem_dres_dstate1().sub['u', 'state/u1']
+    assert np.array_equal(J.indptr, J_ref.indptr)
+    assert np.array_equal(J.indices, J_ref.indices)
+    assert rel_row_err(J.data, J_ref) <= TOL
+    return model
+
+
+@pytest.mark.parametrize('tile_nodes', ['24', '48', '64', '96'])
+def test_assembly_parity_many_tiles(torch_cuda, monkeypatch, tile_nodes):
+    """Entry-wise parity on a mesh of ~90-350 tiles (Morton-ordered M5_CB refined 3x, 15.7 k
+    triangles): exercises the per-tile halo lists, local vertex slots, the L2 prefetch of the
+    far tile and every launch-bounds variant of the tile kernel (128/192/256/320 threads)."""
+    from femvf_b200 import meshgen
+    from femvf_b200.models import transient
+    from femvf_b200.residuals import solid as slr
+    monkeypatch.setenv('VF_TILE_NODES', tile_nodes)
+    monkeypatch.setenv('VF_PF_DIST', '7')          # a far tile that exists on a small grid
+    mt = meshgen.m5_cb_refined(0.05, 3)
+    model = transient.FenicsModel(slr.KelvinVoigt(*mt))
+    _assemble_and_compare(model, np.random.default_rng(int(tile_nodes)))
+    info = model.engine.tile_info
+    assert info['two_phase'] and info['ntiles'] >= 80
+    assert info['nodes_per_tile'] == int(tile_nodes)
+
+
+def test_assembly_parity_degenerate_meshes(torch_cuda):
+    """Smallest inputs: two triangles; a mesh with no Dirichlet and no pressure facets."""
+    from femvf_b200 import mesh as M
+    from femvf_b200.models import transient
+    from femvf_b200.residuals import solid as slr
+    rng = np.random.default_rng(5)
+    mt = M.fixture_mesh_tuple(M.unit_square_mesh(1, 1))
+    _assemble_and_compare(transient.FenicsModel(slr.KelvinVoigt(*mt)), rng)
+    # strip every facet tag: free-floating body, no traction
+    mesh, mfs, labels = M.fixture_mesh_tuple(M.unit_square_mesh(4, 3))
+    mfs[1].array()[:] = 7          # neither 'fixed' (1) nor 'pressure' (0)
+    model = transient.FenicsModel(slr.KelvinVoigt(mesh, mfs, labels))
+    assert len(model.residual.fixed_dofs()) == 0
+    assert len(model.residual.pressure_facets()[0]) == 0
+    _assemble_and_compare(model, rng)

@@ -137,7 +137,8 @@ def m5_cb_mesh(h: float = 0.05):
     tri = Delaunay(pts)
     cells = tri.simplices.astype(np.int64)
     x = pts[cells]
-    area = 0.5 * np.abs(np.cross(x[:, 1] - x[:, 0], x[:, 2] - x[:, 0]))
+    e1, e2 = x[:, 1] - x[:, 0], x[:, 2] - x[:, 0]
+    area = 0.5 * np.abs(e1[:, 0] * e2[:, 1] - e1[:, 1] * e2[:, 0])
     cen = x.mean(axis=1)
     good = (area > 1e-6 * h * h) & _points_in_polygon(cen, bpts)
     cells = cells[good]
