@@ -166,6 +166,13 @@ int vf_multi_axpy(vf_engine* e, const double* V_dev, size_t ldv, int nvec, const
 int vf_axpby(vf_engine* e, double alpha, const double* x_dev, double beta, double* y_dev, size_t n,
              void* stream);
 
+/* Glottal-width time series (postprocess/solid.py:487-501 MeanGlottalWidth evaluated by
+ * postprocess/base.py:138-161 TimeSeries over a StateFile): out[t] = min over the fluid area
+ * vector obtained from the stored displacement u_hist[t] (nt rows of ldu >= N doubles, device)
+ * through the FSI area map, using the member's ymid and current fluid area as the base. */
+int vf_glottal_width_series(vf_engine* e, int member, int nt, const double* u_hist_dev, size_t ldu,
+                            double* out_dev, void* stream);
+
 /* y = x / sqrt(s), s = *s2_dev - sum_{i<nsub} sub_dev[i]^2, all read on the device; s is also
  * stored to *s_out_dev when non-null (must not alias s2_dev).  Krylov-vector normalisation
  * with the squared norm left on the device by vf_multidot (KSPGMRES's VecNormalize without the

@@ -728,6 +728,39 @@ __global__ void newmark_res_kernel(EngineDev E, int member, NewmarkCoef nc, doub
   }
 }
 
+// Minimum fluid area ("glottal width", postprocess/solid.py:487-501) of a batch of stored
+// displacement states: one CTA per state.  The area vector starts from the member's current
+// fluid area (entries no solid DOF maps to keep their value), the mapped entries are
+// 2 (ymid - y) of the deformed surface (transient.py:836-848), then a block-wide minimum.
+template <int D>
+__global__ void glottal_width_series_kernel(EngineDev E, int member, const double* __restrict__ u_hist,
+                                            size_t ldu, double* __restrict__ out) {
+  extern __shared__ double s_area[];
+  __shared__ double s_red[32];
+  const double* mb = E.members + (size_t)member * E.L.stride;
+  const double* base = mb + E.L.off[VF_AREA];
+  const double ymid = (mb + E.L.off[VF_SCAL])[SC_YMID];
+  const double* u = u_hist + (size_t)blockIdx.x * ldu;
+  const int na = E.n_fluid * E.ns;
+  for (int k = threadIdx.x; k < na; k += blockDim.x) s_area[k] = base[k];
+  __syncthreads();
+  for (int k = threadIdx.x; k < E.n_fsi; k += blockDim.x) {
+    const int i = E.fsi_solid[k];
+    const double y = E.mesh.xyz[(size_t)1 * E.mesh.nn + i] + u[D * i + 1];
+    s_area[E.fsi_fluid[k]] = 2.0 * (ymid - y);
+  }
+  __syncthreads();
+  double mn = INFINITY;
+  for (int k = threadIdx.x; k < na; k += blockDim.x) mn = fmin(mn, s_area[k]);
+  for (int o = 16; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = mn;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int q = 1; q < (int)(blockDim.x >> 5); ++q) mn = fmin(mn, s_red[q]);
+    out[blockIdx.x] = mn;
+  }
+}
+
 __global__ void fluid_kernel(EngineDev E, int member0) {
   double* mb = E.members + (size_t)(member0 + blockIdx.x) * E.L.stride;
   const Layout& L = E.L;
@@ -1585,6 +1618,27 @@ int vf_axpby(vf_engine* e, double alpha, const double* x_dev, double beta, doubl
   const int block = 256;
   const int grid = (int)std::min<size_t>(148 * 8, (n + block - 1) / block);
   axpby_kernel<<<grid, block, 0, st>>>(alpha, x_dev, beta, y_dev, n);
+  e->launches += 1;
+  VF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int vf_glottal_width_series(vf_engine* e, int member, int nt, const double* u_hist_dev, size_t ldu,
+                            double* out_dev, void* stream) {
+  if (!e) return fail("null engine");
+  if (member < 0 || member >= e->desc.n_members) return fail("member out of range");
+  if (nt <= 0) return 0;
+  if (!u_hist_dev || !out_dev) return fail("null argument");
+  const int na = e->desc.n_fluid * e->desc.ns;
+  if (na <= 0) return fail("vf_glottal_width_series: the engine has no fluid");
+  const size_t smem = sizeof(double) * na;
+  if (smem > 48 * 1024) return fail("vf_glottal_width_series: fluid mesh too large");
+  if (ldu < (size_t)e->desc.dim * e->desc.nn) return fail("vf_glottal_width_series: ldu < N");
+  cudaStream_t st = as_stream(stream);
+  if (e->desc.dim == 2)
+    glottal_width_series_kernel<2><<<nt, 128, smem, st>>>(e->dev, member, u_hist_dev, ldu, out_dev);
+  else
+    glottal_width_series_kernel<3><<<nt, 128, smem, st>>>(e->dev, member, u_hist_dev, ldu, out_dev);
   e->launches += 1;
   VF_CUDA(cudaGetLastError());
   return 0;

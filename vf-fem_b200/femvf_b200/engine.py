@@ -309,6 +309,15 @@ class Engine:
         check(self._lib.vf_axpby(self._h, float(alpha), x.data_ptr(), float(beta), y.data_ptr(),
                                  int(n), self._stream()))
 
+    def glottal_width_series(self, u_hist: np.ndarray, member: int = 0) -> np.ndarray:
+        """min fluid area of every stored displacement state (rows of ``u_hist``, host)."""
+        u_hist = np.ascontiguousarray(u_hist, dtype=np.float64).reshape(-1, self.N)
+        ud = torch.as_tensor(u_hist).to(self.device)
+        out = torch.empty(u_hist.shape[0], dtype=torch.float64, device=self.device)
+        check(self._lib.vf_glottal_width_series(self._h, member, u_hist.shape[0], ud.data_ptr(),
+                                                self.N, out.data_ptr(), self._stream()))
+        return out.cpu().numpy()
+
     def scale_rsqrt(self, x: torch.Tensor, s2: torch.Tensor, y: torch.Tensor, n: int,
                     sub: Optional[torch.Tensor] = None, s_out: Optional[torch.Tensor] = None):
         """y = x / sqrt(s2[0] - sum(sub**2)), scalars read on the device; the radicand is
