@@ -144,6 +144,22 @@ int64_t vf_nnz(const vf_engine* e);
  * (models/assemblyutils.py:49-50, transient.py:379-380, 398-399). */
 int vf_assemble(vf_engine* e, int member, int flags, double dt, int is_static, void* stream);
 
+/* The state0 sensitivities of FenicsModel.assem_dres_dstate0 (models/transient.py:408-421:
+ * assemble_derivative(form, 'state/u0' | 'state/v0' | 'state/a0'), no bc.apply).  F_u depends on
+ * state0 only through v_nmk, a_nmk, so each block is a mix of the matrices the Jacobian is made
+ * of: VF_J := coef4[0] K + coef4[1] C + coef4[2] M + coef4[3] K_p on the Jacobian's CSR pattern,
+ * C = dF_u/dv1, M = dF_u/da1; Dirichlet rows only when apply_bc != 0. */
+int vf_assemble_mix(vf_engine* e, int member, double dt, const double* coef4, int apply_bc,
+                    void* stream);
+
+/* FenicsModel.assem_dres_dcontrol (models/transient.py:423-435): dF_u/dp1 of the follower
+ * pressure term.  One (dim x 1) block per ordered pair (a, b) of vertices of every pressure
+ * facet, written as nfp * dim * dim blocks of dim doubles to out_dev in the order
+ * facet-major, a, b (local facet vertex order = parent cell order without the opposite
+ * vertex); rows_host / cols_host (optional, nfp*dim*dim each) receive the vertex a and b. */
+int vf_pressure_control_blocks(vf_engine* e, int member, double* out_dev, int32_t* rows_host,
+                               int32_t* cols_host, void* stream);
+
 /* y = J_uu x for `member` (PETSc MatMult; transient.py:488-489).  x, y: device, N doubles. */
 int vf_spmv(vf_engine* e, int member, const double* x_dev, double* y_dev, void* stream);
 

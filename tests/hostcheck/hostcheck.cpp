@@ -28,7 +28,7 @@ extern "C" int hostcheck_assemble(
   vf::MeshView m{dim, nn, ne, nfp, xyz, nullptr, cells, brptr, bcol, n2e_ptr, n2e,
                  n2f_ptr, n2f, pf_cell, pf_opp, bc};
   vf::PropView p{rho, eta, emod, scal, emod_m, nu_m, th_m, contact, membrane, damping};
-  vf::StateView s{u1, u0, v0, a0, p1, dt, 0};
+  vf::StateView s{u1, u0, v0, a0, p1, dt, 0, vf::jac_mix_du1(vf::newmark_coef(dt), false)};
   if (dim == 2) run<2>(m, p, s, J, F);
   else if (dim == 3) run<3>(m, p, s, J, F);
   else return 1;
@@ -50,7 +50,7 @@ extern "C" int hostcheck_assemble_tile2(
   vf::MeshView m{2, nn, ne, nfp, xyz, nullptr, cells, brptr, bcol, n2e_ptr, n2e,
                  n2f_ptr, n2f, pf_cell, pf_opp, bc};
   vf::PropView p{rho, eta, emod, scal, emod_m, nu_m, th_m, contact, membrane, damping};
-  vf::StateView s{u1, u0, v0, a0, p1, dt, 0};
+  vf::StateView s{u1, u0, v0, a0, p1, dt, 0, vf::jac_mix_du1(vf::newmark_coef(dt), false)};
   const vf::LameFac lf = vf::lame_fac(scal[vf::SC_NU]);
   const vf::NewmarkCoef nc = vf::newmark_coef(dt);
   // 16-byte aligned like the shared-memory buffer of the kernel

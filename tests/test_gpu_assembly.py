@@ -159,3 +159,76 @@ def test_assembly_parity_degenerate_meshes(torch_cuda):
     assert len(model.residual.fixed_dofs()) == 0
     assert len(model.residual.pressure_facets()[0]) == 0
     _assemble_and_compare(model, rng)
+
+
+@pytest.mark.parametrize('mesh_name', ['m5', 'cube332'])
+@pytest.mark.parametrize('variant', ['kv', 'rayleigh'])
+def test_state0_and_control_sensitivities(torch_cuda, mesh_name, variant):
+    """assem_dres_dstate0 / assem_dres_dcontrol (transient.py:408-435).  F_u is affine in
+    (u0, v0, a0) and linear in p1, so a finite difference of the ORACLE residual is exact to
+    round-off and pins every block without new oracle code."""
+    from femvf_b200.equations import newmark
+    from femvf_b200.models import transient
+    from femvf_b200.residuals import solid as slr
+    rng = np.random.default_rng(11)
+    mt = mesh_tuples()[mesh_name]()
+    Residual = slr.Rayleigh if variant == 'rayleigh' else slr.KelvinVoigt
+    model = transient.FenicsModel(Residual(*mt))
+    prob = oracle_problem(model.residual)
+    N = prob.N
+    prop = random_solid_prop(prob, rng)
+    if variant == 'rayleigh':
+        del prop['eta']
+        prop.update(rayleigh_m=12.5, rayleigh_k=4e-5)
+    mprop = model.prop.copy()
+    set_model_prop(mprop, prop)
+    model.set_prop(mprop)
+    u1, u0, v0, a0 = random_state(N, rng)
+    p1 = rng.uniform(0, 8e3, prob.nn)
+    dt = 1e-4
+    model.dt = dt
+    s0 = model.state0.copy(); s0['u'][:] = u0; s0['v'][:] = v0; s0['a'][:] = a0
+    s1 = model.state1.copy(); s1['u'][:] = u1
+    model.set_ini_state(s0); model.set_fin_state(s1)
+    ctl = model.control.copy(); ctl['p'][:] = p1
+    model.set_control(ctl)
+    so = om.SolidOracle(prob, contact=False, membrane=False)
+
+    def F(u0_, v0_, a0_, p_):
+        # raw residual rows: the reference applies no Dirichlet condition to these blocks, so
+        # compare on the free rows and check the fixed rows separately below
+        return so.res(u1, (u0_, v0_, a0_), dt, prop, p_)
+    free = np.ones(N, dtype=bool)
+    free[model.residual.fixed_dofs()] = False
+    base = F(u0, v0, a0, p1)
+    d0 = model.assem_dres_dstate0()
+    scales = {'u': 1e-2, 'v': 1.0, 'a': 1e3}
+    for key, args in (('u', 0), ('v', 1), ('a', 2)):
+        dx = rng.uniform(-1, 1, N) * scales[key]
+        pert = [u0, v0, a0]
+        pert[args] = pert[args] + dx
+        fd = F(pert[0], pert[1], pert[2], p1) - base
+        A = d0.sub['u', 'state/' + key + '0']
+        got = A @ dx
+        ref_scale = np.max(np.abs(fd))
+        assert np.max(np.abs(got[free] - fd[free])) <= 1e-9 * ref_scale, key
+        # pattern is the Jacobian's pattern
+        J = model.assem_dres_dstate1().sub['u', 'state/u1']
+        assert np.array_equal(A.indptr, J.indptr) and np.array_equal(A.indices, J.indices)
+    # nodal blocks: F_v = v1 - v_nmk, F_a = a1 - a_nmk
+    assert np.all(d0.sub['v', 'state/u0'].diagonal() == -newmark.newmark_v_du0(dt))
+    assert np.all(d0.sub['v', 'state/v0'].diagonal() == -newmark.newmark_v_dv0(dt))
+    assert np.all(d0.sub['a', 'state/a0'].diagonal() == -newmark.newmark_a_da0(dt))
+    # Dirichlet rows are NOT identity rows here (bc.apply is commented out, transient.py:415)
+    fixed = model.residual.fixed_dofs()
+    if len(fixed):
+        A = d0.sub['u', 'state/a0']
+        assert np.any(A[fixed].toarray() != 0.0)
+
+    dc = model.assem_dres_dcontrol()
+    B = dc.sub['u', 'control/p1'] if 'control/p1' in dc.labels[1] else dc.sub['u', 0]
+    dp = rng.uniform(-1e3, 1e3, prob.nn)
+    fd = F(u0, v0, a0, p1 + dp) - base
+    got = B @ dp
+    assert np.max(np.abs(got[free] - fd[free])) <= 1e-9 * np.max(np.abs(fd))
+    assert B.shape == (N, prob.nn)

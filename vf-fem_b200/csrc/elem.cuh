@@ -62,6 +62,24 @@ VF_HD double newmark_a(const NewmarkCoef& c, double u1, double u0, double v0, do
   return c.ca * (u1 - u0 - c.dt * v0) - c.c_a0a * a0;
 }
 
+// Weights of the matrices that make up a Jacobian-like assembly:
+//   k K + c C + m M + p K_p, with Dirichlet rows applied when bc != 0.
+// d F_u / d u1 is (1, cv, ca, 1, bc) (App. A.3); the state0 sensitivities (transient.py:408-421)
+// are other mixes of the same matrices (C = d F_u / d v1, M = d F_u / d a1) without BCs.
+struct JacMix {
+  double k, c, m, p;
+  int bc;
+};
+VF_HD JacMix jac_mix_du1(const NewmarkCoef& nc, bool is_static) {
+  JacMix x;
+  x.k = 1.0;
+  x.c = is_static ? 0.0 : nc.cv;
+  x.m = is_static ? 0.0 : nc.ca;
+  x.p = 1.0;
+  x.bc = 1;
+  return x;
+}
+
 // Lame factors per unit modulus: lambda = emod * lam_fac, mu = emod * mu_fac
 // (uflcontinuum.py:22-23); nu is a constant, so the divisions are done once.
 struct LameFac {
@@ -162,12 +180,13 @@ VF_HD CellCoef cell_coef(double emod, const LameFac& lf, double eta, double rho,
 
 // Block (a, c) of d F_u / d u1 from the cell integrals: 4M/dt^2 + 2C/dt + K  (App. A.3).
 template <int D>
-VF_HD void cell_block(const CellGeo<D>& g, const CellCoef& cf, double cv, double ca, int a,
+VF_HD void cell_block(const CellGeo<D>& g, const CellCoef& cf, const JacMix& mix, int a,
                       int c, double (&blk)[D][D]) {
+  const double cv = mix.c, ca = mix.m;
   double gg = 0.0;
   for (int i = 0; i < D; ++i) gg += g.G[a][i] * g.G[c][i];
-  const double lv = cf.lamv + cv * cf.vlam;
-  const double mv = cf.muv + cv * cf.vmu;
+  const double lv = mix.k * cf.lamv + cv * cf.vlam;  // (mix.k == 1 reproduces lamv exactly)
+  const double mv = mix.k * cf.muv + cv * cf.vmu;
   for (int i = 0; i < D; ++i)
     for (int j = 0; j < D; ++j)
       blk[i][j] = lv * g.G[a][i] * g.G[c][j] + mv * g.G[c][i] * g.G[a][j];
@@ -400,16 +419,15 @@ VF_HD NodeUVA gather_node_uva(const NewmarkCoef& nc, bool is_static, int node, c
 // keep the live register set small.
 template <class Fetch>
 VF_HD void tri_record_t(const double (&x)[3][2], double emod, const LameFac& lf, double eta,
-                        double rho, const Damping& dp, const NewmarkCoef& nc, bool is_static,
-                        bool with_res, Fetch fetch, double* rec) {
+                        double rho, const Damping& dp, const JacMix& mix, bool with_res,
+                        Fetch fetch, double* rec) {
   CellGeo<2> g;
   p1_geometry(x, g);
   const CellCoef cf = cell_coef<2>(emod, lf, eta, rho, g.vol, dp);
-  const double cv = is_static ? 0.0 : nc.cv;
-  const double ca = is_static ? 0.0 : nc.ca;
+  const double cv = mix.c, ca = mix.m;
   D2* r2 = reinterpret_cast<D2*>(rec);  // 16-byte stores
   for (int a = 0; a < 3; ++a) r2[a] = D2{g.G[a][0], g.G[a][1]};
-  r2[3] = D2{cf.lamv + cv * cf.vlam, cf.muv + cv * cf.vmu};
+  r2[3] = D2{mix.k * cf.lamv + cv * cf.vlam, mix.k * cf.muv + cv * cf.vmu};
   const double mass_blk = ca * cf.massv + cv * cf.vmass;
   if (!with_res) {
     r2[4] = D2{mass_blk, 0.0};
@@ -451,7 +469,7 @@ VF_HD void tri_record(const double (&x)[3][2], const int (&nd)[3], double emod,
                       const LameFac& lf, double eta, double rho, const Damping& dp,
                       const NewmarkCoef& nc, bool is_static, bool with_res, const double* u1,
                       const double* u0, const double* v0, const double* a0, double* rec) {
-  tri_record_t(x, emod, lf, eta, rho, dp, nc, is_static, with_res,
+  tri_record_t(x, emod, lf, eta, rho, dp, jac_mix_du1(nc, is_static), with_res,
                [&](int a) { return gather_node_uva(nc, is_static, nd[a], u1, u0, v0, a0); }, rec);
 }
 

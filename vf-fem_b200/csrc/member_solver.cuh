@@ -530,6 +530,7 @@ __device__ void blk_solve_solid(const EngineDev& E, double* mb, const SolverWork
   sv.p1 = mb + L.off[VF_P1];
   sv.dt = dt;
   sv.is_static = opt.is_static;
+  sv.mix = jac_mix_du1(newmark_coef(sv.dt), opt.is_static != 0);
 
   int k = 0;
   double r0 = 0.0, abs_err = 0.0, rel_err = 0.0;

@@ -76,6 +76,7 @@ struct StateView {
   const double* p1;  // nodal pressure control (nn)
   double dt;
   int is_static;  // static.py:105-124: u0 == u1, v0 = a0 = 0 -> no inertia / damping
+  JacMix mix;     // matrix weights of the Jacobian-like output (jac_mix_du1 for d F_u / d u1)
 };
 
 VF_HD int find_slot(const int* bcol_i, int deg, int node) {
@@ -145,7 +146,7 @@ VF_HD void assemble_node_facets_bc(int i, const MeshView& m, const PropView& p,
         for (int b = 0; b <= D; ++b) {
           double dc[D][D];
           dcof_normal(gu, N, g.G[b], dc);
-          add_block<D>(rowblk, ld, find_slot(bcol_i, deg, nd[b]), dc, pw);
+          add_block<D>(rowblk, ld, find_slot(bcol_i, deg, nd[b]), dc, pw * s.mix.p);
         }
       }
       if (p.contact) {
@@ -163,7 +164,7 @@ VF_HD void assemble_node_facets_bc(int i, const MeshView& m, const PropView& p,
             const double dp = contact_dpressure(gap, kc);
             const int slot = find_slot(bcol_i, deg, nd[b]);
             for (int k = 0; k < D; ++k)
-              rowblk[k * ld + slot * D + k] -= mab * dp * p.scal[SC_NCONTACT + k];
+              rowblk[k * ld + slot * D + k] -= s.mix.k * mab * dp * p.scal[SC_NCONTACT + k];
           }
         }
       }
@@ -196,7 +197,7 @@ VF_HD void assemble_node_facets_bc(int i, const MeshView& m, const PropView& p,
               blk[k][j] = sacc;
             }
           }
-          add_block<D>(rowblk, ld, find_slot(bcol_i, deg, nd[b]), blk, w);
+          add_block<D>(rowblk, ld, find_slot(bcol_i, deg, nd[b]), blk, w * s.mix.k);
         }
       }
     }
@@ -206,7 +207,7 @@ VF_HD void assemble_node_facets_bc(int i, const MeshView& m, const PropView& p,
   const int self = find_slot(bcol_i, deg, i);
   for (int a = 0; a < D; ++a) {
     if (m.bc[D * i + a]) {
-      if (JAC) {
+      if (JAC && s.mix.bc) {
         for (int t = 0; t < ld; ++t) rowblk[a * ld + t] = 0.0;
         rowblk[a * ld + self * D + a] = 1.0;
       }
@@ -230,8 +231,6 @@ VF_HD void assemble_node(int i, const MeshView& m, const PropView& p, const Stat
   const LameFac lf = lame_fac(p.scal[SC_NU]);
   const Damping dp = prop_damping(p);
   const NewmarkCoef nc = newmark_coef(s.dt);
-  const double cv = s.is_static ? 0.0 : nc.cv;
-  const double ca = s.is_static ? 0.0 : nc.ca;
 
   // ---- cell integrals --------------------------------------------------------
   for (int t = m.n2e_ptr[i]; t < m.n2e_ptr[i + 1]; ++t) {
@@ -246,7 +245,7 @@ VF_HD void assemble_node(int i, const MeshView& m, const PropView& p, const Stat
     if (JAC) {
       for (int c = 0; c <= D; ++c) {
         double blk[D][D];
-        cell_block<D>(g, cf, cv, ca, a, c, blk);
+        cell_block<D>(g, cf, s.mix, a, c, blk);
         add_block<D>(rowblk, ld, find_slot(bcol_i, deg, nd[c]), blk, 1.0);
       }
     }

@@ -40,7 +40,7 @@ static int fail(const std::string& msg) {
 // ---- grid-wide kernels (single large mesh) ----------------------------------------------
 
 template <int D, bool JAC, bool RES>
-__global__ void asm_tile_kernel(EngineDev E, int member, double dt, int is_static,
+__global__ void asm_tile_kernel(EngineDev E, int member, double dt, int is_static, JacMix mix,
                                 const int* __restrict__ tile_start) {
   extern __shared__ double tile[];
   double* mb = E.members + (size_t)member * E.L.stride;
@@ -59,6 +59,8 @@ __global__ void asm_tile_kernel(EngineDev E, int member, double dt, int is_stati
     sv.p1 = mb + L.off[VF_P1];
     sv.dt = dt;
     sv.is_static = is_static;
+  sv.mix = mix;
+    sv.mix = mix;
     double res[D];
     double* rowblk = JAC ? tile + ((size_t)D * D * E.mesh.brptr[i] - base) : nullptr;
     assemble_node<D, JAC, RES>(i, E.mesh, pv, sv, rowblk, res);
@@ -129,7 +131,8 @@ __device__ __forceinline__ double ldg_nc_f64(const double* p) {
 
 template <bool JAC, bool RES, int ROW, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) asm_tile2_kernel(
-    EngineDev E, int member, NewmarkCoef nc_arg, int is_static, const int4* __restrict__ tile_desc,
+    EngineDev E, int member, NewmarkCoef nc_arg, int is_static, JacMix mix,
+    const int4* __restrict__ tile_desc,
     const int4* __restrict__ te_quad, const unsigned* __restrict__ pair_info,
     const int* __restrict__ tile_halo, int max_tile_elems, int tile_max_values,
     int max_tile_pairs, int max_tile_nodes, int max_tile_verts, int pf_dist, int dbg_skip) {
@@ -223,7 +226,6 @@ __global__ void __launch_bounds__(MAXT, MINB) asm_tile2_kernel(
   // ---- phase 1: one record per cell, from shared memory ----------------------------------------
   {
     const LameFac lf = s_lf;
-    const NewmarkCoef nc = nc_arg;
     const Damping dp = prop_damping(pv);
     for (int q = threadIdx.x; q < nte && !(dbg_skip & 1); q += kThreads) {
       if (q != (int)threadIdx.x) {
@@ -241,7 +243,7 @@ __global__ void __launch_bounds__(MAXT, MINB) asm_tile2_kernel(
         x[a][1] = c2.y;
       }
       tri_record_t(
-          x, emod_e, lf, eta_e, rho_e, dp, nc, is_static != 0, RES,
+          x, emod_e, lf, eta_e, rho_e, dp, mix, RES,
           [&](int a) { return s_uva[nd[a]]; }, recs + (size_t)q * kRec2D);
     }
   }
@@ -465,7 +467,7 @@ __global__ void __launch_bounds__(MAXT, MINB) asm_tile2_kernel(
 
 
 template <int D, bool JAC, bool RES>
-__global__ void facet_bc_kernel(EngineDev E, int member, double dt, int is_static,
+__global__ void facet_bc_kernel(EngineDev E, int member, double dt, int is_static, JacMix mix,
                                 const int* __restrict__ touch_nodes, int n_touch) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_touch) return;
@@ -481,6 +483,7 @@ __global__ void facet_bc_kernel(EngineDev E, int member, double dt, int is_stati
   sv.p1 = mb + L.off[VF_P1];
   sv.dt = dt;
   sv.is_static = is_static;
+  sv.mix = mix;
   double* F = mb + L.off[VF_F];
   double res[D];
 #pragma unroll
@@ -605,7 +608,7 @@ __global__ void apply_block_jacobi_kernel(const double* __restrict__ Dinv,
 // deterministic; the read-modify-write traffic stays in L1/L2.
 template <int D, bool JAC, bool RES>
 __global__ void __launch_bounds__(128, 3)
-asm_node_global_kernel(EngineDev E, int member, double dt, int is_static) {
+asm_node_global_kernel(EngineDev E, int member, double dt, int is_static, JacMix mix) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= E.mesh.nn) return;
   double* mb = E.members + (size_t)member * E.L.stride;
@@ -619,6 +622,7 @@ asm_node_global_kernel(EngineDev E, int member, double dt, int is_static) {
   sv.p1 = mb + L.off[VF_P1];
   sv.dt = dt;
   sv.is_static = is_static;
+  sv.mix = mix;
   double res[D];
   assemble_node<D, JAC, RES>(i, E.mesh, pv, sv,
                              JAC ? mb + L.off[VF_J] + (size_t)D * D * E.mesh.brptr[i] : nullptr, res);
@@ -706,6 +710,45 @@ __global__ void axpby_kernel(double alpha, const double* __restrict__ x, double 
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (size_t)gridDim.x * blockDim.x)
     y[i] = alpha * x[i] + (beta == 0.0 ? 0.0 : beta * y[i]);
+}
+
+// d F_u / d p1 (transient.py:423-435): thread per pressure facet.  res_a += mw (1 + delta_ab)
+// p_b cof(F) N for facet vertices a, b (assemble_node_facets_bc), so the (a, b) block is
+// mw (1 + delta_ab) cof(F) N.  Dirichlet rows are not touched (the reference applies none).
+template <int D>
+__global__ void pressure_control_kernel(EngineDev E, int member, double* __restrict__ out) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= E.mesh.nfp) return;
+  const MeshView& m = E.mesh;
+  const double* mb = E.members + (size_t)member * E.L.stride;
+  const double* u1 = mb + E.L.off[VF_U1];
+  const int e = m.pf_cell[f], o = m.pf_opp[f];
+  int nd[D + 1];
+  double x[D + 1][D];
+  load_cell<D>(m, e, nd, x);
+  CellGeo<D> g;
+  p1_geometry(x, g);
+  double N[D], meas;
+  facet_geometry<D>(g, o, N, meas);
+  double U[D + 1][D], gu[D][D];
+  gather_vec<D>(u1, nd, U);
+  grad_u<D>(g, U, gu);
+  const double mw = meas / double(D * (D + 1));
+  double c[D];
+  cof_normal(gu, N, c);
+  double* dst = out + (size_t)f * D * D * D;
+  int ia = 0;
+  for (int a = 0; a <= D; ++a) {
+    if (a == o) continue;
+    int ib = 0;
+    for (int b = 0; b <= D; ++b) {
+      if (b == o) continue;
+      const double w = mw * (a == b ? 2.0 : 1.0);
+      for (int k = 0; k < D; ++k) dst[(ia * D + ib) * D + k] = w * c[k];
+      ++ib;
+    }
+    ++ia;
+  }
 }
 
 // Nodal Newmark residuals F_v = v1 - v_nmk(u1, u0, v0, a0), F_a = a1 - a_nmk(...)
@@ -970,6 +1013,7 @@ struct vf_engine {
   bool two_phase;
   bool fan_ok;
   std::vector<int32_t> brptr, bcol;
+  std::vector<int32_t> pf_nodes;  // (nfp, dim): vertices of every pressure facet, parent-cell order
   int member_threads;
   int64_t launches;
 };
@@ -1279,6 +1323,13 @@ int vf_create(const vf_problem_desc* desc, void* arena_dev, size_t arena_bytes, 
   e->launches = 0;
   e->brptr.assign(d.brptr_host, d.brptr_host + d.nn + 1);
   e->bcol.assign(d.bcol_host, d.bcol_host + nnzb);
+  e->pf_nodes.resize((size_t)d.nfp * d.dim);
+  for (int f = 0; f < d.nfp; ++f) {
+    int k = 0;
+    for (int a = 0; a <= d.dim; ++a)
+      if (a != d.pf_opp_host[f])
+        e->pf_nodes[(size_t)f * d.dim + k++] = d.cells_host[(size_t)a * d.ne + d.pf_cell_host[f]];
+  }
   // host pointers of the descriptor are not retained
   e->desc.xyz_host = nullptr; e->desc.cells_host = nullptr; e->desc.brptr_host = nullptr;
   e->desc.bcol_host = nullptr; e->desc.n2e_ptr_host = nullptr; e->desc.n2e_host = nullptr;
@@ -1417,8 +1468,33 @@ int vf_csr_pattern(const vf_engine* e, int32_t* rowptr, int32_t* colidx) {
   return 0;
 }
 
+namespace {
+int assemble_impl(vf_engine* e, int member, int flags, double dt, int is_static, const JacMix& mix,
+                  void* stream);
+}
+
 int vf_assemble(vf_engine* e, int member, int flags, double dt, int is_static, void* stream) {
   if (!e) return fail("null engine");
+  return assemble_impl(e, member, flags, dt, is_static,
+                       jac_mix_du1(newmark_coef(dt), is_static != 0), stream);
+}
+
+int vf_assemble_mix(vf_engine* e, int member, double dt, const double* coef4, int apply_bc,
+                    void* stream) {
+  if (!e) return fail("null engine");
+  if (!coef4) return fail("null coefficient array");
+  JacMix mix;
+  mix.k = coef4[0];
+  mix.c = coef4[1];
+  mix.m = coef4[2];
+  mix.p = coef4[3];
+  mix.bc = apply_bc ? 1 : 0;
+  return assemble_impl(e, member, 2, dt, 0, mix, stream);
+}
+
+namespace {
+int assemble_impl(vf_engine* e, int member, int flags, double dt, int is_static, const JacMix& mix,
+                  void* stream) {
   if (member < 0 || member >= e->desc.n_members) return fail("member out of range");
   const bool res = flags & 1, jac = flags & 2;
   if (!res && !jac) return 0;
@@ -1429,7 +1505,7 @@ int vf_assemble(vf_engine* e, int member, int flags, double dt, int is_static, v
     const size_t smem2 = tile2_smem_bytes(d);
 #define VF_LAUNCH_ASM2(J_, R_, ROW_, MT_, MB_)                                                     \
   asm_tile2_kernel<J_, R_, ROW_, MT_, MB_><<<grid, MT_, smem2, st>>>(                  \
-      e->dev, member, newmark_coef(dt), is_static, e->tile_desc_dev, e->te_quad_dev,               \
+      e->dev, member, newmark_coef(dt), is_static, mix, e->tile_desc_dev, e->te_quad_dev,          \
       e->pair_info_dev, e->tile_halo_dev, d.max_tile_elems, d.tile_max_values, d.max_tile_pairs,   \
       d.tile_threads, d.max_tile_verts, pf_dist, dbg_skip)
     const int dbg_skip = getenv("VF_DEBUG_SKIP") ? atoi(getenv("VF_DEBUG_SKIP")) : 0;
@@ -1464,11 +1540,11 @@ int vf_assemble(vf_engine* e, int member, int flags, double dt, int is_static, v
     if (e->n_touch > 0) {
       const int fb = 128, fg = (e->n_touch + fb - 1) / fb;
       if (jac && res)
-        facet_bc_kernel<2, true, true><<<fg, fb, 0, st>>>(e->dev, member, dt, is_static, e->touch_dev, e->n_touch);
+        facet_bc_kernel<2, true, true><<<fg, fb, 0, st>>>(e->dev, member, dt, is_static, mix, e->touch_dev, e->n_touch);
       else if (jac)
-        facet_bc_kernel<2, true, false><<<fg, fb, 0, st>>>(e->dev, member, dt, is_static, e->touch_dev, e->n_touch);
+        facet_bc_kernel<2, true, false><<<fg, fb, 0, st>>>(e->dev, member, dt, is_static, mix, e->touch_dev, e->n_touch);
       else
-        facet_bc_kernel<2, false, true><<<fg, fb, 0, st>>>(e->dev, member, dt, is_static, e->touch_dev, e->n_touch);
+        facet_bc_kernel<2, false, true><<<fg, fb, 0, st>>>(e->dev, member, dt, is_static, mix, e->touch_dev, e->n_touch);
       e->launches += 1;
       VF_CUDA(cudaGetLastError());
     }
@@ -1476,9 +1552,9 @@ int vf_assemble(vf_engine* e, int member, int flags, double dt, int is_static, v
   }
   if (e->desc.dim == 3 && !(getenv("VF_TET_SMEM") && atoi(getenv("VF_TET_SMEM")))) {
     const int nb = 128, ng = (e->desc.nn + nb - 1) / nb;
-    if (jac && res) asm_node_global_kernel<3, true, true><<<ng, nb, 0, st>>>(e->dev, member, dt, is_static);
-    else if (jac) asm_node_global_kernel<3, true, false><<<ng, nb, 0, st>>>(e->dev, member, dt, is_static);
-    else asm_node_global_kernel<3, false, true><<<ng, nb, 0, st>>>(e->dev, member, dt, is_static);
+    if (jac && res) asm_node_global_kernel<3, true, true><<<ng, nb, 0, st>>>(e->dev, member, dt, is_static, mix);
+    else if (jac) asm_node_global_kernel<3, true, false><<<ng, nb, 0, st>>>(e->dev, member, dt, is_static, mix);
+    else asm_node_global_kernel<3, false, true><<<ng, nb, 0, st>>>(e->dev, member, dt, is_static, mix);
     e->launches += 1;
     VF_CUDA(cudaGetLastError());
     return 0;
@@ -1486,13 +1562,13 @@ int vf_assemble(vf_engine* e, int member, int flags, double dt, int is_static, v
   const size_t smem = jac ? (size_t)e->desc.tile_max_values * sizeof(double) : 0;
 #define VF_LAUNCH_ASM(D)                                                                          \
   if (jac && res)                                                                                 \
-    asm_tile_kernel<D, true, true><<<grid, block, smem, st>>>(e->dev, member, dt, is_static,      \
+    asm_tile_kernel<D, true, true><<<grid, block, smem, st>>>(e->dev, member, dt, is_static, mix, \
                                                               e->tile_start_dev);                 \
   else if (jac)                                                                                   \
-    asm_tile_kernel<D, true, false><<<grid, block, smem, st>>>(e->dev, member, dt, is_static,     \
+    asm_tile_kernel<D, true, false><<<grid, block, smem, st>>>(e->dev, member, dt, is_static, mix, \
                                                                e->tile_start_dev);                \
   else                                                                                            \
-    asm_tile_kernel<D, false, true><<<grid, block, 0, st>>>(e->dev, member, dt, is_static,        \
+    asm_tile_kernel<D, false, true><<<grid, block, 0, st>>>(e->dev, member, dt, is_static, mix, \
                                                             e->tile_start_dev);
   if (e->desc.dim == 2) {
     VF_LAUNCH_ASM(2)
@@ -1504,6 +1580,7 @@ int vf_assemble(vf_engine* e, int member, int flags, double dt, int is_static, v
   VF_CUDA(cudaGetLastError());
   return 0;
 }
+}  // namespace
 
 int vf_spmv_rows(vf_engine* e, int member, const double* x_dev, double* y_dev, int node0,
                  int node1, void* stream) {
@@ -1618,6 +1695,31 @@ int vf_axpby(vf_engine* e, double alpha, const double* x_dev, double beta, doubl
   const int block = 256;
   const int grid = (int)std::min<size_t>(148 * 8, (n + block - 1) / block);
   axpby_kernel<<<grid, block, 0, st>>>(alpha, x_dev, beta, y_dev, n);
+  e->launches += 1;
+  VF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int vf_pressure_control_blocks(vf_engine* e, int member, double* out_dev, int32_t* rows_host,
+                               int32_t* cols_host, void* stream) {
+  if (!e) return fail("null engine");
+  if (member < 0 || member >= e->desc.n_members) return fail("member out of range");
+  const int nfp = e->desc.nfp, d = e->desc.dim;
+  if (rows_host || cols_host) {
+    if (!rows_host || !cols_host) return fail("rows_host and cols_host go together");
+    if (e->pf_nodes.size() != (size_t)nfp * d) return fail("facet vertex table missing");
+    for (int f = 0; f < nfp; ++f)
+      for (int a = 0; a < d; ++a)
+        for (int b = 0; b < d; ++b) {
+          rows_host[((size_t)f * d + a) * d + b] = e->pf_nodes[(size_t)f * d + a];
+          cols_host[((size_t)f * d + a) * d + b] = e->pf_nodes[(size_t)f * d + b];
+        }
+  }
+  if (nfp == 0) return 0;
+  if (!out_dev) return fail("null output");
+  const int block = 128, grid = (nfp + block - 1) / block;
+  if (d == 2) pressure_control_kernel<2><<<grid, block, 0, as_stream(stream)>>>(e->dev, member, out_dev);
+  else pressure_control_kernel<3><<<grid, block, 0, as_stream(stream)>>>(e->dev, member, out_dev);
   e->launches += 1;
   VF_CUDA(cudaGetLastError());
   return 0;

@@ -71,6 +71,7 @@ EXPORTED_SYMBOLS = [
     'vf_integrate_host', 'vf_launch_count', 'vf_spmv_rows', 'vf_block_jacobi_setup',
     'vf_block_jacobi_apply', 'vf_multidot', 'vf_multi_axpy', 'vf_axpby',
     'vf_newmark_residual', 'vf_scale_rsqrt', 'vf_glottal_width_series',
+    'vf_assemble_mix', 'vf_pressure_control_blocks',
 ]
 
 _lib = None
@@ -116,6 +117,10 @@ def load_library() -> C.CDLL:
                              C.c_size_t, C.c_void_p]
     lib.vf_scale_rsqrt.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                    C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.vf_assemble_mix.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_int,
+                                    C.c_void_p]
+    lib.vf_pressure_control_blocks.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                               C.c_void_p, C.c_void_p]
     lib.vf_glottal_width_series.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t,
                                             C.c_void_p, C.c_void_p]
     lib.vf_newmark_residual.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p,

@@ -78,6 +78,7 @@ class Engine:
         d = tables['dim']
         self.dim, self.nn, self.ne = d, tables['nn'], tables['ne']
         self.N = d * self.nn
+        self.nfp = int(tables['nfp'])
         self.n_members = int(n_members)
 
         import os
@@ -275,6 +276,25 @@ class Engine:
         flags = (1 if res else 0) | (2 if jac else 0)
         check(self._lib.vf_assemble(self._h, member, flags, float(dt), int(is_static),
                                     self._stream()))
+
+    def assemble_mix(self, coef4, dt: float, member: int = 0, apply_bc: bool = False):
+        """J := coef4 . (K, C, M, K_p) on the Jacobian's pattern (``vf_assemble_mix``)."""
+        c = np.ascontiguousarray(coef4, dtype=np.float64)
+        assert c.size == 4
+        check(self._lib.vf_assemble_mix(self._h, member, float(dt), _ptr(c), int(apply_bc),
+                                        self._stream()))
+
+    def pressure_control_blocks(self, member: int = 0):
+        """(rows, cols, blocks): vertex pairs (a, b) of the pressure facets and the (dim,)
+        blocks d F_u[a] / d p1[b] (``vf_pressure_control_blocks``)."""
+        d = self.dim
+        n = self.nfp * d * d
+        rows = np.zeros(n, dtype=np.int32)
+        cols = np.zeros(n, dtype=np.int32)
+        out = torch.zeros(max(n * d, 1), dtype=torch.float64, device=self.device)
+        check(self._lib.vf_pressure_control_blocks(self._h, member, out.data_ptr(), _ptr(rows),
+                                                   _ptr(cols), self._stream()))
+        return rows, cols, out[:n * d].cpu().numpy().reshape(n, d)
 
     def spmv(self, x: torch.Tensor, y: torch.Tensor, member: int = 0):
         assert x.dtype == torch.float64 and y.dtype == torch.float64

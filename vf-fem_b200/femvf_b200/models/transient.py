@@ -86,10 +86,10 @@ class BaseTransientModel:
     def assem_res(self) -> BlockVec:
         raise NotImplementedError(f"Subclass {type(self)} must implement this function")
 
-    def assem_dres_dstate0(self):
+    def assem_dres_dstate1(self):
         raise NotImplementedError(f"Subclass {type(self)} must implement this function")
 
-    def assem_dres_dstate1(self):
+    def assem_dres_dstate0(self):
         raise NotImplementedError(f"Subclass {type(self)} must implement this function")
 
     def assem_dres_dcontrol(self):
@@ -325,12 +325,44 @@ class FenicsModel(BaseTransientModel):
         return BlockMatrix(mats, (3, 3), (self.FORM_KEYS, self.STATE1_KEYS))
 
     def assem_dres_dstate0(self):
-        raise NotImplementedError(
-            "state0 sensitivities are a listed next step (SURVEY.md section 8f-4)")
+        """``transient.py:408-421``: block matrix labelled (FORM_KEYS, STATE0_KEYS); as in the
+        reference no Dirichlet condition is applied.  F_u depends on state0 only through
+        v_nmk and a_nmk, so with C = dF_u/dv1 and M = dF_u/da1
+        ``dF_u/dx0 = C dv_nmk/dx0 + M da_nmk/dx0`` -- one device assembly per block with the
+        corresponding weights of (K, C, M, K_p).  The v, a rows are the nodal Newmark
+        relations."""
+        N = self.state0['u'].size
+        dt = self.dt
+        self._push_all()
+        rowptr, colidx = self.csr_pattern()
+        eye = sp.identity(N, format='csr')
+        cv_c = {'u': newmark.newmark_v_du0(dt), 'v': newmark.newmark_v_dv0(dt),
+                'a': newmark.newmark_v_da0(dt)}
+        ca_c = {'u': newmark.newmark_a_du0(dt), 'v': newmark.newmark_a_dv0(dt),
+                'a': newmark.newmark_a_da0(dt)}
+        mats = {}
+        for key in ('u', 'v', 'a'):
+            self.engine.assemble_mix((0.0, cv_c[key], ca_c[key], 0.0), dt, self._member)
+            vals = self.engine.download('J', self._member)
+            mats['u', key] = sp.csr_matrix((vals, colidx, rowptr), shape=(N, N))
+            mats['v', key] = -cv_c[key] * eye        # F_v = v1 - v_nmk(u1, u0, v0, a0)
+            mats['a', key] = -ca_c[key] * eye
+        flat = [mats[r, c] for r in self.FORM_KEYS for c in ('u', 'v', 'a')]
+        return BlockMatrix(flat, (3, 3), (self.FORM_KEYS, self.STATE0_KEYS))
 
     def assem_dres_dcontrol(self):
-        raise NotImplementedError(
-            "control sensitivities are a listed next step (SURVEY.md section 8f-4)")
+        """``transient.py:423-435``: (FORM_KEYS, CONTROL_KEYS); only dF_u/dp1 is non-zero (the
+        follower pressure is linear in the nodal pressure)."""
+        N = self.state0['u'].size
+        nn = self.control['p'].size
+        d = N // nn
+        self._push_all()
+        rows, cols, blocks = self.engine.pressure_control_blocks(self._member)
+        ii = (d * rows[:, None] + np.arange(d)[None, :]).ravel()
+        jj = np.repeat(cols, d)
+        dfu_dp = sp.coo_matrix((blocks.ravel(), (ii, jj)), shape=(N, nn)).tocsr()
+        zero = sp.csr_matrix((N, nn))
+        return BlockMatrix([dfu_dp, zero, zero], (3, 1), (self.FORM_KEYS, self.CONTROL_KEYS))
 
     def assem_dres_dprops(self):
         raise NotImplementedError("Not implemented yet!")  # transient.py:437-438
