@@ -17,7 +17,7 @@ torch.cuda.synchronize(); print('forward steps/s', 297 / (time.perf_counter() - 
 fm.push_to_device()
 ms = bench.time_events(lambda: fm.engine.integrate(np.full(99, 1e-4), np.array([[[8e3], [0.0]]]), None, False, True), 3, 1) / 3
 print('device-only 99 steps ms', ms, 'steps/s', 99 / ms * 1e3)
-info = fm.engine.download('info'); print('cycles/step: asm %.0f spmv %.0f orth %.0f givens %.0f tail %.0f fluid %.0f total %.0f' % tuple(info[8:15] / 99))
+info = fm.engine.download('info'); print('cycles/step: asm %.0f spmv %.0f orth %.0f givens %.0f tail %.0f fluid %.0f total %.0f; inverse total %.0f; gmres its %s' % (*tuple(info[8:15] / 99), info[15], info[3]))
 B = int(os.environ.get('B', '1024'))
 runner = EnsembleRunner(fm, B)
 rng = np.random.default_rng(0)

@@ -279,3 +279,26 @@ def test_implicit_coupling_matches_oracle():
         ref = hist[-1][k]
         assert np.max(np.abs(fin[key] - ref)) <= 1e-7 * np.max(np.abs(ref)), key
     assert info['num_iter'] == infos[-1]['num_iter'] and info['num_iter'] > 1
+
+
+def test_dense_inverse_preconditioner_opt_in(monkeypatch):
+    """The experimental dense-inverse preconditioner (VF_DENSE_PREC=1) must give the same
+    trajectory as the default polynomial one to solver tolerance (it only changes how the
+    Newton linear systems are solved)."""
+    import numpy as np
+    import bench
+    from femvf_b200 import forward
+    times = 1e-4 * np.arange(12)
+    out = {}
+    for flag in ('0', '1'):
+        monkeypatch.setenv('VF_DENSE_PREC', flag)
+        fm = bench.fsi_model()
+        state0, control, prop = bench.config1_args(fm)
+        fin, info = forward.integrate(fm, None, state0, [control], prop, times, write=False)
+        out[flag] = (np.asarray(fin['u']).copy(), float(np.asarray(fin['q'])[0]),
+                     fm.engine.download('info')[3])
+    u0, q0, it0 = out['0']
+    u1, q1, it1 = out['1']
+    assert np.max(np.abs(u1 - u0)) <= 1e-8 * np.max(np.abs(u0))
+    assert abs(q1 - q0) <= 1e-8 * abs(q0)
+    assert it1 < it0          # fewer Krylov iterations with the inverse

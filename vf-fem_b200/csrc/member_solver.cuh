@@ -32,6 +32,7 @@ struct Layout {
   size_t off[32];   // offsets (doubles) of the public arrays inside a member block
   size_t cnt[32];
   size_t Dinv, V, w, z, H, cs, sn, g, y, xk;  // solver workspace
+  size_t Pinv, pstate;  // dense inverse preconditioner (N x N, transposed) and its state
   size_t stride;    // member block size (doubles)
 };
 
@@ -47,7 +48,7 @@ struct SolverOpts {
 struct EngineDev {
   MeshView mesh;
   int d, N, n_fluid, ns, n_fsi, n_fsip, fluid_kind, idx_sep, contact, membrane, damping,
-      restart;
+      restart, dense;  // dense != 0: the member blocks carry Pinv
   long long nnz;
   const double* s;
   const int* fsi_solid;   // area gather map (unique fluid DOFs)
@@ -109,6 +110,7 @@ __device__ __forceinline__ void blk_spmv(const EngineDev& E, const double* __res
 // DOF) fits entirely, so a Krylov iteration never leaves the SM.
 struct SolverWork {
   double *J, *F, *dx, *Dinv, *V, *w, *z, *t, *H, *cs, *sn, *g, *y;
+  double *P, *pstate;  // dense inverse (global memory) and {dt it was built for, refresh flag}
 };
 
 __device__ __forceinline__ SolverWork make_work(const EngineDev& E, double* mb, double* dsm,
@@ -128,6 +130,8 @@ __device__ __forceinline__ SolverWork make_work(const EngineDev& E, double* mb, 
   W.sn = mb + L.sn;
   W.g = mb + L.g;
   W.y = mb + L.y;
+  W.P = E.dense ? mb + L.Pinv : nullptr;
+  W.pstate = E.dense ? mb + L.pstate : nullptr;
   size_t o = 0;
   auto take = [&](size_t n) {
     double* p = dsm + o;
@@ -287,6 +291,78 @@ __device__ __forceinline__ double blk_project_out(const double* V, int N, int nv
   return p2;
 }
 
+// ---- dense inverse preconditioner ---------------------------------------------------
+// For the small systems this kernel is built for (one CTA per member, N of a few hundred) the
+// Newton matrix barely changes from step to step: K, C, M are constant and only the follower
+// pressure / contact blocks move.  Its inverse is therefore formed ONCE per launch (in-CTA
+// Gauss-Jordan, N^3 fused multiply-adds, no pivoting: the matrix is a Dirichlet-row-modified
+// SPD matrix plus a small perturbation) and reused as the left preconditioner of GMRES, which
+// then converges in one to three iterations instead of ten with the polynomial
+// preconditioner.  This is the sparse-LU stand-in for PETSc's direct solve at these sizes
+// (transient.py:487).  The inverse is stored transposed, so a mat-vec reads it coalesced.
+constexpr int kMaxDenseN = 1024;
+
+// P := (J^T)^{-1} = (J^{-1})^T, row-major N x N in global memory.  s_row / s_col: N doubles each.
+template <int D>
+__device__ void blk_dense_inverse(const EngineDev& E, const double* __restrict__ J, double* P,
+                                  double* s_row, double* s_col) {
+  const int N = E.N;
+  const size_t NN = (size_t)N * N;
+  for (size_t t = threadIdx.x; t < NN; t += blockDim.x) P[t] = 0.0;
+  __syncthreads();
+  // scatter the CSR values transposed: P[col][row] = J[row][col]
+  for (int r = threadIdx.x; r < N; r += blockDim.x) {
+    const int i = r / D, a = r - i * D;
+    const int b0 = E.mesh.brptr[i], deg = E.mesh.brptr[i + 1] - b0;
+    const double* row = J + (size_t)D * D * b0 + (size_t)a * D * deg;
+    for (int k = 0; k < deg; ++k) {
+      const int j = E.mesh.bcol[b0 + k];
+#pragma unroll
+      for (int c = 0; c < D; ++c) P[(size_t)(D * j + c) * N + r] = row[k * D + c];
+    }
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int k = 0; k < N; ++k) {
+    // stage the pivot row and column
+    for (int t = threadIdx.x; t < N; t += blockDim.x) {
+      s_row[t] = P[(size_t)k * N + t];
+      s_col[t] = P[(size_t)t * N + k];
+    }
+    __syncthreads();
+    const double piv = 1.0 / s_row[k];
+    // in-place Gauss-Jordan step: warps take rows, lanes take columns (coalesced)
+    for (int i = wid; i < N; i += nw) {
+      double* Pi = P + (size_t)i * N;
+      if (i == k) {
+        for (int j = lane; j < N; j += 32) Pi[j] = (j == k) ? piv : s_row[j] * piv;
+      } else {
+        const double f = s_col[i] * piv;
+        for (int j = lane; j < N; j += 32) Pi[j] = (j == k) ? -f : Pi[j] - f * s_row[j];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// out = J^{-1} r with the transposed inverse: out[t] = sum_j P[j][t] r[j]
+__device__ __forceinline__ void blk_dense_mv(const double* __restrict__ P, int N,
+                                             const double* __restrict__ r,
+                                             double* __restrict__ out) {
+  for (int t = threadIdx.x; t < N; t += blockDim.x) {
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int j = 0;
+    for (; j + 3 < N; j += 4) {
+      s0 += P[(size_t)j * N + t] * r[j];
+      s1 += P[(size_t)(j + 1) * N + t] * r[j + 1];
+      s2 += P[(size_t)(j + 2) * N + t] * r[j + 2];
+      s3 += P[(size_t)(j + 3) * N + t] * r[j + 3];
+    }
+    for (; j < N; ++j) s0 += P[(size_t)j * N + t] * r[j];
+    out[t] = (s0 + s1) + (s2 + s3);
+  }
+}
+
 // w = M^{-1} J v with M^{-1} = (I + N + ... + N^p) D^{-1}, N = I - D^{-1} J: the block-Jacobi
 // preconditioner accelerated by a truncated Neumann series (M^{-1} J = I - N^{p+1}).  For the
 // mass-dominated Newmark Jacobian the spectral radius of N is ~0.6, so p = 3 shrinks the
@@ -295,6 +371,13 @@ __device__ __forceinline__ double blk_project_out(const double* V, int N, int nv
 template <int D>
 __device__ __forceinline__ void blk_apply_op(const EngineDev& E, const SolverWork& W, int p,
                                              const double* v, double* w) {
+  if (p < 0) {
+    blk_spmv<D>(E, W.J, v, W.t);
+    __syncthreads();
+    blk_dense_mv(W.P, E.N, W.t, w);
+    __syncthreads();
+    return;
+  }
   if (p == 0) {
     blk_spmv_prec<D>(E, W.J, W.Dinv, v, w);
     __syncthreads();
@@ -319,6 +402,11 @@ __device__ __forceinline__ void blk_apply_op(const EngineDev& E, const SolverWor
 template <int D>
 __device__ __forceinline__ void blk_apply_prec(const EngineDev& E, const SolverWork& W, int p,
                                                const double* r, double* out) {
+  if (p < 0) {
+    blk_dense_mv(W.P, E.N, r, out);
+    __syncthreads();
+    return;
+  }
   blk_apply_dinv<D>(E, W.Dinv, r, out);  // z0 = D^{-1} r
   __syncthreads();
   if (p == 0) return;
@@ -343,7 +431,7 @@ __device__ __forceinline__ void blk_apply_prec(const EngineDev& E, const SolverW
 template <int D>
 __device__ int blk_gmres(const EngineDev& E, const SolverWork& W, const double* b, double* x,
                          const SolverOpts& opt, BlockShared& sh, double* resid_out,
-                         double* bnorm_out) {
+                         double* bnorm_out, bool dense = false) {
   const int N = E.N;
   const int m = E.restart;
   const double* J = W.J;
@@ -359,7 +447,7 @@ __device__ int blk_gmres(const EngineDev& E, const SolverWork& W, const double* 
   // r0 = M^{-1} b  (x0 = 0)
   // static problems have no mass term: the spectral radius of N approaches (or exceeds) 1 and
   // the Neumann acceleration does not pay, so it is only used for the transient Jacobian
-  int pdeg = opt.is_static ? 0 : opt.poly_degree;
+  int pdeg = dense ? -1 : (opt.is_static ? 0 : opt.poly_degree);
   for (int t = threadIdx.x; t < N; t += blockDim.x) x[t] = 0.0;
   __syncthreads();
   blk_apply_prec<D>(E, W, pdeg, b, w);
@@ -378,9 +466,10 @@ __device__ int blk_gmres(const EngineDev& E, const SolverWork& W, const double* 
   bool first = true;
   while (true) {
     if (!first) {
-      if (pdeg > 0) {
+      if (pdeg != 0) {
         // a full cycle did not converge: the Neumann series is not contracting for this
-        // matrix -- fall back to plain block-Jacobi (norms are re-based on the new M)
+        // matrix (or the dense inverse is stale beyond repair) -- fall back to plain
+        // block-Jacobi (norms are re-based on the new M)
         pdeg = 0;
         __syncthreads();
         blk_apply_prec<D>(E, W, 0, b, w);
@@ -513,7 +602,7 @@ __device__ __forceinline__ PropView member_props(const EngineDev& E, double* mb)
 // then v1, a1 from the Newmark relations (App. C, Q2).
 template <int D>
 __device__ void blk_solve_solid(const EngineDev& E, double* mb, const SolverWork& W, double dt,
-                                const SolverOpts& opt, BlockShared& sh) {
+                                const SolverOpts& opt, BlockShared& sh, bool allow_dense) {
   const Layout& L = E.L;
   const int N = E.N, nn = E.mesh.nn;
   double* u1 = mb + L.off[VF_U1];
@@ -567,7 +656,27 @@ __device__ void blk_solve_solid(const EngineDev& E, double* mb, const SolverWork
     __syncthreads();
     blk_compute_dinv<D>(E, Jv, W.Dinv);
     __syncthreads();
-    gm_iters += blk_gmres<D>(E, W, F, dx, opt, sh, &gm_resid, &gm_bnorm);
+    bool dense = false;
+    if (W.P && allow_dense) {
+      // (re)build the inverse when there is none for this dt / mode, or the last solve with it
+      // needed more than a few iterations (the matrix has drifted: contact, large pressure)
+      const double key = opt.is_static ? -1.0 : dt;
+      if (W.pstate[0] != key || W.pstate[1] != 0.0) {
+        const long long tp = clock64();
+        __syncthreads();
+        blk_dense_inverse<D>(E, Jv, W.P, W.w, W.z);
+        if (threadIdx.x == 0) {
+          W.pstate[0] = key;
+          W.pstate[1] = 0.0;
+          sh.cyc[7] += clock64() - tp;
+        }
+        __syncthreads();
+      }
+      dense = true;
+    }
+    const int its = blk_gmres<D>(E, W, F, dx, opt, sh, &gm_resid, &gm_bnorm, dense);
+    gm_iters += its;
+    if (dense && its > 4 && threadIdx.x == 0) W.pstate[1] = 1.0;
     __syncthreads();
     for (int t = threadIdx.x; t < N; t += blockDim.x) u1[t] -= dx[t];
     __syncthreads();

@@ -891,11 +891,17 @@ member_kernel(EngineDev E, int member0, int mode, int nsteps, const double* __re
   // single solves keep the member's global J / F / dx (they are API-visible results)
   const SolverWork W = make_work(E, mb, dsm, mode == MODE_INTEGRATE ? smem_flags : 0);
   if (threadIdx.x < 8) sh.cyc[threadIdx.x] = 0;
+  // the dense inverse never outlives a launch: results then depend on the inputs of this
+  // launch only (properties may have been rewritten in between), and ensemble members and
+  // single runs take the same path
+  if (threadIdx.x == 0 && W.pstate) W.pstate[1] = 1.0;
   const long long t_start = clock64();
   __syncthreads();
 
   if (mode == MODE_SOLVE_SOLID) {
-    blk_solve_solid<D>(E, mb, W, dt_single, opt, sh);
+    // a single transient solve is cheaper with the polynomial preconditioner than one
+    // inversion; the stiff static problem (no mass term) is where the inverse pays
+    blk_solve_solid<D>(E, mb, W, dt_single, opt, sh, opt.is_static != 0);
     return;
   }
   if (mode == MODE_LINEAR_SOLVE) {
@@ -963,7 +969,7 @@ member_kernel(EngineDev E, int member0, int mode, int nsteps, const double* __re
     for (int k = threadIdx.x; k < E.n_fsip; k += blockDim.x) p1[E.fsip_solid[k]] = p0[E.fsip_fluid[k]];
     __syncthreads();
 
-    blk_solve_solid<D>(E, mb, W, dt, opt, sh);
+    blk_solve_solid<D>(E, mb, W, dt, opt, sh, true);
     const long long tf = clock64();
     blk_fluid<D>(E, mb, sh);
     if (threadIdx.x == 0) sh.cyc[5] += clock64() - tf;
@@ -983,6 +989,7 @@ member_kernel(EngineDev E, int member0, int mode, int nsteps, const double* __re
     double* info = mb + L.off[VF_INFO];
     for (int q = 0; q < 6; ++q) info[8 + q] = double(sh.cyc[q]);
     info[14] = double(clock64() - t_start);
+    info[15] = double(sh.cyc[7]);  // dense-inverse builds
   }
 }
 
@@ -1021,6 +1028,19 @@ struct vf_engine {
 namespace {
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Dense inverse preconditioner of the member solver (member_solver.cuh): experimental, OFF unless
+// VF_DENSE_PREC=1.  Measured on config 1 (N = 296): GMRES drops from 10 to 4 iterations per
+// solve, but the in-CTA Gauss-Jordan costs 21 ms per launch (N^3 updates through L2, latency
+// bound) and a mat-vec with the 700 KB inverse 22 k cycles (L2 bandwidth of one SM), so the
+// 99-step run is 2.4x SLOWER than with the polynomial preconditioner (profiles/README.md).
+inline bool dense_prec_enabled(const vf_problem_desc& d) {
+  const char* env = getenv("VF_DENSE_PREC");
+  if (!env || atoi(env) == 0) return false;
+  const size_t N = (size_t)d.dim * d.nn;
+  if (N > (size_t)kMaxDenseN) return false;
+  return N * N * sizeof(double) * (size_t)d.n_members <= (size_t)24 << 30;
+}
 
 struct ArenaPlan {
   // byte offsets of the shared tables
@@ -1111,6 +1131,12 @@ ArenaPlan plan_arena(const vf_problem_desc& d) {
   L.g = mtake(mr + 1);
   L.y = mtake(mr);
   L.xk = mtake(N);
+  L.Pinv = 0;
+  L.pstate = 0;
+  if (dense_prec_enabled(d)) {
+    L.Pinv = mtake(N * N);
+    L.pstate = mtake(2);
+  }
   L.stride = align_up(m, 32);
   P.total = P.members + sizeof(double) * L.stride * (size_t)d.n_members;
   return P;
@@ -1368,6 +1394,7 @@ int vf_create(const vf_problem_desc* desc, void* arena_dev, size_t arena_bytes, 
   E.d = d.dim; E.N = P.N; E.n_fluid = d.n_fluid; E.ns = d.ns; E.n_fsi = d.n_fsi;
   E.fluid_kind = d.fluid_kind; E.idx_sep = d.idx_sep; E.contact = d.contact;
   E.membrane = d.membrane; E.damping = d.damping; E.restart = d.gmres_restart; E.nnz = P.nnz;
+  E.dense = dense_prec_enabled(d) ? 1 : 0;
   E.s = reinterpret_cast<const double*>(A + P.s);
   E.fsi_solid = reinterpret_cast<const int*>(A + P.fsi_solid);
   E.fsi_fluid = reinterpret_cast<const int*>(A + P.fsi_fluid);
