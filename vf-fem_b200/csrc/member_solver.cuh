@@ -24,6 +24,10 @@
 namespace vf {
 
 constexpr int kMaxRestart = 128;
+constexpr int kMaxDenseN = 1024;  // dense inverse preconditioner: largest system
+constexpr int kDenseNb = 8;       // ... and the pivot block of its Gauss-Jordan
+// leading dimension of the fp32 inverse: rows padded to 128 bytes for aligned float4 loads
+__host__ __device__ __forceinline__ int dense_ldp(int N) { return (N + 31) & ~31; }
 constexpr int kInfoCount = 16;
 enum InfoSlot { INFO_NUM_ITER = 0, INFO_ABS_ERR = 1, INFO_REL_ERR = 2, INFO_GMRES_ITERS = 3,
                 INFO_GMRES_RESID = 4, INFO_MIN_AREA = 5, INFO_BNORM = 6 };
@@ -32,7 +36,8 @@ struct Layout {
   size_t off[32];   // offsets (doubles) of the public arrays inside a member block
   size_t cnt[32];
   size_t Dinv, V, w, z, H, cs, sn, g, y, xk;  // solver workspace
-  size_t Pinv, pstate;  // dense inverse preconditioner (N x N, transposed) and its state
+  size_t Pinv, Pf, Pscr, pstate;  // dense inverse preconditioner: fp64 work matrix, fp32
+                                  // transposed inverse, mat-vec scratch, state
   size_t stride;    // member block size (doubles)
 };
 
@@ -69,6 +74,7 @@ struct BlockShared {
   double g[kMaxRestart + 2];   // they must not live in global memory
   double y[kMaxRestart + 2];
   double bc[8];  // broadcast scalars
+  double B[kDenseNb][kDenseNb + 1];  // pivot block of the blocked Gauss-Jordan
   long long cyc[8];  // cycle counters: 0 assembly 1 spmv 2 dots+update 3 givens 4 solve tail 5 fluid 6 total
 };
 
@@ -110,7 +116,9 @@ __device__ __forceinline__ void blk_spmv(const EngineDev& E, const double* __res
 // DOF) fits entirely, so a Krylov iteration never leaves the SM.
 struct SolverWork {
   double *J, *F, *dx, *Dinv, *V, *w, *z, *t, *H, *cs, *sn, *g, *y;
-  double *P, *pstate;  // dense inverse (global memory) and {dt it was built for, refresh flag}
+  double *P, *pstate;  // dense fp64 work matrix (global) and {dt it was built for, refresh flag}
+  float* Pf;           // transposed fp32 inverse
+  double* Pscr;        // (warps x N) partial sums of the dense mat-vec
 };
 
 __device__ __forceinline__ SolverWork make_work(const EngineDev& E, double* mb, double* dsm,
@@ -131,6 +139,8 @@ __device__ __forceinline__ SolverWork make_work(const EngineDev& E, double* mb, 
   W.g = mb + L.g;
   W.y = mb + L.y;
   W.P = E.dense ? mb + L.Pinv : nullptr;
+  W.Pf = E.dense ? reinterpret_cast<float*>(mb + L.Pf) : nullptr;
+  W.Pscr = E.dense ? mb + L.Pscr : nullptr;
   W.pstate = E.dense ? mb + L.pstate : nullptr;
   size_t o = 0;
   auto take = [&](size_t n) {
@@ -294,23 +304,123 @@ __device__ __forceinline__ double blk_project_out(const double* V, int N, int nv
 // ---- dense inverse preconditioner ---------------------------------------------------
 // For the small systems this kernel is built for (one CTA per member, N of a few hundred) the
 // Newton matrix barely changes from step to step: K, C, M are constant and only the follower
-// pressure / contact blocks move.  Its inverse is therefore formed ONCE per launch (in-CTA
-// Gauss-Jordan, N^3 fused multiply-adds, no pivoting: the matrix is a Dirichlet-row-modified
-// SPD matrix plus a small perturbation) and reused as the left preconditioner of GMRES, which
-// then converges in one to three iterations instead of ten with the polynomial
-// preconditioner.  This is the sparse-LU stand-in for PETSc's direct solve at these sizes
-// (transient.py:487).  The inverse is stored transposed, so a mat-vec reads it coalesced.
-constexpr int kMaxDenseN = 1024;
+// pressure / contact blocks move.  Its inverse is therefore formed ONCE per launch and reused
+// as the left preconditioner of GMRES, which then converges in a few iterations instead of
+// ten with the polynomial preconditioner.  This is the sparse-LU stand-in for PETSc's direct
+// solve at these sizes (transient.py:487).
+//   * inversion: in-place BLOCKED Gauss-Jordan in fp64 on a dense work matrix in global
+//     memory (L2): pivots are eliminated kDenseNb at a time, the pivot rows and columns are
+//     staged in shared memory, and every other entry is read and written once per block with
+//     kDenseNb fused multiply-adds in between (N^3 flops, N^3 / kDenseNb * 16 bytes of L2
+//     traffic).  No pivoting: the matrix is a Dirichlet-row-modified SPD matrix plus a small
+//     perturbation.
+//   * application: the inverse is kept TRANSPOSED in fp32 (it is only a preconditioner; GMRES
+//     still converges the fp64 system to its tolerance), warps split the summation range,
+//     lanes own output entries (coalesced 4-byte loads, several independent loads in flight),
+//     partial sums meet in a small global scratch.
 
-// P := (J^T)^{-1} = (J^{-1})^T, row-major N x N in global memory.  s_row / s_col: N doubles each.
+// A := inverse of the matrix held in A (row-major N x N, global).  rows/cols: shared (or
+// global) panels of kDenseNb * N doubles each.
+__device__ void blk_block_gauss_jordan(double* A, int N, double* rows, double* cols,
+                                       double (&B)[kDenseNb][kDenseNb + 1]) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int k0 = 0; k0 < N; k0 += kDenseNb) {
+    const int nb = min(kDenseNb, N - k0);
+    // 1. stage the pivot rows and the (old) pivot columns
+    for (int t = threadIdx.x; t < N; t += blockDim.x)
+      for (int p = 0; p < nb; ++p) {
+        rows[p * N + t] = A[(size_t)(k0 + p) * N + t];
+        cols[p * N + t] = A[(size_t)t * N + k0 + p];
+      }
+    __syncthreads();
+    // 2. B = A11^{-1} (nb x nb), unblocked Gauss-Jordan by one thread on a tiny matrix
+    if (threadIdx.x == 0) {
+      for (int p = 0; p < nb; ++p)
+        for (int q = 0; q < nb; ++q) B[p][q] = rows[p * N + k0 + q];
+      for (int k = 0; k < nb; ++k) {
+        const double piv = 1.0 / B[k][k];
+        for (int q = 0; q < nb; ++q) B[k][q] = (q == k) ? piv : B[k][q] * piv;
+        for (int p = 0; p < nb; ++p) {
+          if (p == k) continue;
+          const double f = B[p][k];
+          for (int q = 0; q < nb; ++q) B[p][q] = (q == k) ? -f * piv : B[p][q] - f * B[k][q];
+        }
+      }
+    }
+    __syncthreads();
+    // 3. new pivot rows A12' = B A12 (columns outside the block), A11' = B; thread per column
+    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+      double r[kDenseNb];
+      for (int p = 0; p < nb; ++p) r[p] = rows[p * N + j];
+      const bool inblk = j >= k0 && j < k0 + nb;
+      for (int p = 0; p < nb; ++p) {
+        double v;
+        if (inblk) {
+          v = B[p][j - k0];
+        } else {
+          v = 0.0;
+          for (int q = 0; q < nb; ++q) v += B[p][q] * r[q];
+        }
+        rows[p * N + j] = v;
+        A[(size_t)(k0 + p) * N + j] = v;
+      }
+    }
+    // 4. new pivot columns A21' = -A21 B (rows outside the block); thread per row.  The OLD
+    //    columns stay in shared memory for the rank-nb update
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+      if (i >= k0 && i < k0 + nb) continue;
+      double c[kDenseNb];
+      for (int p = 0; p < nb; ++p) c[p] = cols[p * N + i];
+      for (int q = 0; q < nb; ++q) {
+        double v = 0.0;
+        for (int p = 0; p < nb; ++p) v -= c[p] * B[p][q];
+        A[(size_t)i * N + k0 + q] = v;
+      }
+    }
+    __syncthreads();
+    // 5. A22 -= A21 A12': warps take groups of 4 rows, lanes take columns; the rows' column
+    //    entries sit in registers, the new pivot rows come from shared memory, and the 4 loads
+    //    of a column chunk are independent (latency of the L2 round trip is overlapped)
+    for (int i0 = 4 * wid; i0 < N; i0 += 4 * nw) {
+      double c[4][kDenseNb];
+      bool live[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u;
+        live[u] = i < N && !(i >= k0 && i < k0 + nb);
+#pragma unroll
+        for (int p = 0; p < kDenseNb; ++p) c[u][p] = (live[u] && p < nb) ? cols[p * N + i] : 0.0;
+      }
+      for (int j = lane; j < N; j += 32) {
+        if (j >= k0 && j < k0 + nb) continue;
+        double v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = live[u] ? A[(size_t)(i0 + u) * N + j] : 0.0;
+#pragma unroll
+        for (int p = 0; p < kDenseNb; ++p) {
+          const double rp = p < nb ? rows[p * N + j] : 0.0;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) v[u] -= c[u][p] * rp;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (live[u]) A[(size_t)(i0 + u) * N + j] = v[u];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// Pf := float((J^{-1})^T), N x N row-major.  A: fp64 work matrix (N x N, global).
 template <int D>
-__device__ void blk_dense_inverse(const EngineDev& E, const double* __restrict__ J, double* P,
-                                  double* s_row, double* s_col) {
+__device__ void blk_dense_inverse(const EngineDev& E, const double* __restrict__ J, double* A,
+                                  float* Pf, double* rows, double* cols,
+                                  double (&B)[kDenseNb][kDenseNb + 1]) {
   const int N = E.N;
   const size_t NN = (size_t)N * N;
-  for (size_t t = threadIdx.x; t < NN; t += blockDim.x) P[t] = 0.0;
+  for (size_t t = threadIdx.x; t < NN; t += blockDim.x) A[t] = 0.0;
   __syncthreads();
-  // scatter the CSR values transposed: P[col][row] = J[row][col]
+  // scatter the CSR values transposed: A[col][row] = J[row][col], so that A^{-1} = (J^{-1})^T
   for (int r = threadIdx.x; r < N; r += blockDim.x) {
     const int i = r / D, a = r - i * D;
     const int b0 = E.mesh.brptr[i], deg = E.mesh.brptr[i + 1] - b0;
@@ -318,48 +428,73 @@ __device__ void blk_dense_inverse(const EngineDev& E, const double* __restrict__
     for (int k = 0; k < deg; ++k) {
       const int j = E.mesh.bcol[b0 + k];
 #pragma unroll
-      for (int c = 0; c < D; ++c) P[(size_t)(D * j + c) * N + r] = row[k * D + c];
+      for (int c = 0; c < D; ++c) A[(size_t)(D * j + c) * N + r] = row[k * D + c];
     }
   }
   __syncthreads();
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int k = 0; k < N; ++k) {
-    // stage the pivot row and column
-    for (int t = threadIdx.x; t < N; t += blockDim.x) {
-      s_row[t] = P[(size_t)k * N + t];
-      s_col[t] = P[(size_t)t * N + k];
-    }
-    __syncthreads();
-    const double piv = 1.0 / s_row[k];
-    // in-place Gauss-Jordan step: warps take rows, lanes take columns (coalesced)
-    for (int i = wid; i < N; i += nw) {
-      double* Pi = P + (size_t)i * N;
-      if (i == k) {
-        for (int j = lane; j < N; j += 32) Pi[j] = (j == k) ? piv : s_row[j] * piv;
-      } else {
-        const double f = s_col[i] * piv;
-        for (int j = lane; j < N; j += 32) Pi[j] = (j == k) ? -f : Pi[j] - f * s_row[j];
-      }
-    }
-    __syncthreads();
-  }
+  blk_block_gauss_jordan(A, N, rows, cols, B);
+  const int ldp = dense_ldp(N);
+  for (int i = threadIdx.x >> 5; i < N; i += blockDim.x >> 5)
+    for (int j = threadIdx.x & 31; j < ldp; j += 32)
+      Pf[(size_t)i * ldp + j] = j < N ? (float)A[(size_t)i * N + j] : 0.0f;
+  __syncthreads();
 }
 
-// out = J^{-1} r with the transposed inverse: out[t] = sum_j P[j][t] r[j]
-__device__ __forceinline__ void blk_dense_mv(const double* __restrict__ P, int N,
-                                             const double* __restrict__ r,
+// out = J^{-1} r with the transposed fp32 inverse: out[t] = sum_j Pf[j][t] r[j].
+// One SM reaches its L2 bandwidth only with tens of KB in flight: every lane owns 4
+// consecutive outputs per 128-entry chunk (16-byte loads), two chunks and four rows are
+// unrolled, i.e. 8 independent 512-byte warp loads per iteration.
+// scratch: (warps x ldp) doubles in global memory.
+__device__ __forceinline__ void blk_dense_mv(const float* __restrict__ Pf, int N,
+                                             const double* __restrict__ r, double* scratch,
                                              double* __restrict__ out) {
-  for (int t = threadIdx.x; t < N; t += blockDim.x) {
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    int j = 0;
-    for (; j + 3 < N; j += 4) {
-      s0 += P[(size_t)j * N + t] * r[j];
-      s1 += P[(size_t)(j + 1) * N + t] * r[j + 1];
-      s2 += P[(size_t)(j + 2) * N + t] * r[j + 2];
-      s3 += P[(size_t)(j + 3) * N + t] * r[j + 3];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int ldp = dense_ldp(N);
+  const int per = (N + nw - 1) / nw;
+  const int j0 = wid * per, j1 = min(N, j0 + per);
+  for (int c0 = 0; c0 < ldp; c0 += 256) {        // two chunks of 128 outputs per pass
+    const int ta = c0 + 4 * lane, tb = c0 + 128 + 4 * lane;
+    const bool ha = ta < ldp, hb = tb < ldp;
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0, b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+    int j = j0;
+    for (; j + 3 < j1; j += 4) {
+      float4 xa[4], xb[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float* row = Pf + (size_t)(j + u) * ldp;
+        xa[u] = ha ? *reinterpret_cast<const float4*>(row + ta) : make_float4(0, 0, 0, 0);
+        xb[u] = hb ? *reinterpret_cast<const float4*>(row + tb) : make_float4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const double rj = r[j + u];
+        a0 += (double)xa[u].x * rj; a1 += (double)xa[u].y * rj;
+        a2 += (double)xa[u].z * rj; a3 += (double)xa[u].w * rj;
+        b0 += (double)xb[u].x * rj; b1 += (double)xb[u].y * rj;
+        b2 += (double)xb[u].z * rj; b3 += (double)xb[u].w * rj;
+      }
     }
-    for (; j < N; ++j) s0 += P[(size_t)j * N + t] * r[j];
-    out[t] = (s0 + s1) + (s2 + s3);
+    for (; j < j1; ++j) {
+      const float* row = Pf + (size_t)j * ldp;
+      const double rj = r[j];
+      if (ha) {
+        const float4 x = *reinterpret_cast<const float4*>(row + ta);
+        a0 += (double)x.x * rj; a1 += (double)x.y * rj; a2 += (double)x.z * rj; a3 += (double)x.w * rj;
+      }
+      if (hb) {
+        const float4 x = *reinterpret_cast<const float4*>(row + tb);
+        b0 += (double)x.x * rj; b1 += (double)x.y * rj; b2 += (double)x.z * rj; b3 += (double)x.w * rj;
+      }
+    }
+    double* sc = scratch + (size_t)wid * ldp;
+    if (ha) { sc[ta] = a0; sc[ta + 1] = a1; sc[ta + 2] = a2; sc[ta + 3] = a3; }
+    if (hb) { sc[tb] = b0; sc[tb + 1] = b1; sc[tb + 2] = b2; sc[tb + 3] = b3; }
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < N; t += blockDim.x) {
+    double s = 0.0;
+    for (int w = 0; w < nw; ++w) s += scratch[(size_t)w * ldp + t];
+    out[t] = s;
   }
 }
 
@@ -374,7 +509,7 @@ __device__ __forceinline__ void blk_apply_op(const EngineDev& E, const SolverWor
   if (p < 0) {
     blk_spmv<D>(E, W.J, v, W.t);
     __syncthreads();
-    blk_dense_mv(W.P, E.N, W.t, w);
+    blk_dense_mv(W.Pf, E.N, W.t, W.Pscr, w);
     __syncthreads();
     return;
   }
@@ -403,7 +538,7 @@ template <int D>
 __device__ __forceinline__ void blk_apply_prec(const EngineDev& E, const SolverWork& W, int p,
                                                const double* r, double* out) {
   if (p < 0) {
-    blk_dense_mv(W.P, E.N, r, out);
+    blk_dense_mv(W.Pf, E.N, r, W.Pscr, out);
     __syncthreads();
     return;
   }
@@ -661,10 +796,11 @@ __device__ void blk_solve_solid(const EngineDev& E, double* mb, const SolverWork
       // (re)build the inverse when there is none for this dt / mode, or the last solve with it
       // needed more than a few iterations (the matrix has drifted: contact, large pressure)
       const double key = opt.is_static ? -1.0 : dt;
-      if (W.pstate[0] != key || W.pstate[1] != 0.0) {
+      // (time steps from np.diff(times) differ in the last bits: compare with a tolerance)
+      if (!(fabs(W.pstate[0] - key) <= 1e-6 * fabs(key)) || W.pstate[1] != 0.0) {
         const long long tp = clock64();
         __syncthreads();
-        blk_dense_inverse<D>(E, Jv, W.P, W.w, W.z);
+        blk_dense_inverse<D>(E, Jv, W.P, W.Pf, W.V, W.V + (size_t)kDenseNb * N, sh.B);
         if (threadIdx.x == 0) {
           W.pstate[0] = key;
           W.pstate[1] = 0.0;

@@ -1030,15 +1030,18 @@ namespace {
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // Dense inverse preconditioner of the member solver (member_solver.cuh): experimental, OFF unless
-// VF_DENSE_PREC=1.  Measured on config 1 (N = 296): GMRES drops from 10 to 4 iterations per
-// solve, but the in-CTA Gauss-Jordan costs 21 ms per launch (N^3 updates through L2, latency
-// bound) and a mat-vec with the 700 KB inverse 22 k cycles (L2 bandwidth of one SM), so the
-// 99-step run is 2.4x SLOWER than with the polynomial preconditioner (profiles/README.md).
+// VF_DENSE_PREC=1.  Measured on config 1 (N = 296, profiles/README.md): GMRES drops from 10 to 4
+// iterations per solve and a step from 263 k to 193 k cycles, but the blocked in-CTA
+// Gauss-Jordan costs 5.2 M cycles per launch (one SM's L2 path), so a 99-step launch ends up 5 %
+// slower and the 1024-member ensemble 23 % slower; it pays only for launches of many hundred
+// steps of a single simulation.
 inline bool dense_prec_enabled(const vf_problem_desc& d) {
   const char* env = getenv("VF_DENSE_PREC");
   if (!env || atoi(env) == 0) return false;
   const size_t N = (size_t)d.dim * d.nn;
   if (N > (size_t)kMaxDenseN) return false;
+  // the pivot panels (2 * kDenseNb * N doubles) live in the Krylov basis storage
+  if ((size_t)d.gmres_restart + 1 < 2 * (size_t)kDenseNb) return false;
   return N * N * sizeof(double) * (size_t)d.n_members <= (size_t)24 << 30;
 }
 
@@ -1133,8 +1136,13 @@ ArenaPlan plan_arena(const vf_problem_desc& d) {
   L.xk = mtake(N);
   L.Pinv = 0;
   L.pstate = 0;
+  L.Pf = 0;
+  L.Pscr = 0;
   if (dense_prec_enabled(d)) {
     L.Pinv = mtake(N * N);
+    const size_t ldp = (size_t)dense_ldp((int)N);
+    L.Pf = mtake((N * ldp + 1) / 2);   // fp32, rows padded to 128 bytes
+    L.Pscr = mtake(32 * ldp);          // up to 32 warps
     L.pstate = mtake(2);
   }
   L.stride = align_up(m, 32);
