@@ -1,6 +1,6 @@
 # scratch driver: forward + ensemble timing
 import sys, time, os
-sys.path.insert(0, 'vf-fem_b200'); sys.path.insert(0, 'tests'); sys.path.insert(0, '.')
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path[:0] = [ROOT, os.path.join(ROOT, 'vf-fem_b200'), os.path.join(ROOT, 'tests')]
 import numpy as np, torch
 import bench
 from femvf_b200 import forward

@@ -1213,8 +1213,15 @@ int launch_member(vf_engine* e, int member0, int count, int mode, int nsteps, co
   // place the solver working set in shared memory when it fits (time loop only)
   int flags = 0;
   size_t smem = 0;
+  int per_sm = 1;
   if (mode == MODE_INTEGRATE) {
-    const size_t N = e->dev.N, budget = 200 * 1024;
+    // resident CTAs per SM wanted for ensembles (VF_MEMBER_PER_SM, default 2): the shared
+    // memory budget of one CTA shrinks accordingly and the plan below keeps what fits
+    static const char* env_k = getenv("VF_MEMBER_PER_SM");
+    per_sm = env_k ? std::min(std::max(atoi(env_k), 1), 4) : 2;
+    if (count <= 148) per_sm = 1;
+    const size_t N = e->dev.N;
+    const size_t budget = per_sm == 1 ? 200 * 1024 : (227 * 1024) / per_sm - 2048;
     auto pad = [](size_t n) { return (n + 1) & ~size_t(1); };
     const size_t small = 8 * (5 * pad(N) + pad((size_t)e->desc.nn * D * D));
     const size_t basis = 8 * pad((size_t)(e->dev.restart + 1) * N);
@@ -1238,9 +1245,10 @@ int launch_member(vf_engine* e, int member0, int count, int mode, int nsteps, co
   } while (0)
   // two resident CTAs per SM when the working set leaves room for it and there are enough
   // members to use them (ensembles); one fat CTA otherwise
-  const bool two_per_sm = count > 148 && smem <= 100 * 1024;
   if (e->member_threads == 256) {
-    if (two_per_sm) VF_LAUNCH_MEMBER(256, 2);
+    if (per_sm >= 4) VF_LAUNCH_MEMBER(256, 4);
+    else if (per_sm == 3) VF_LAUNCH_MEMBER(256, 3);
+    else if (per_sm == 2) VF_LAUNCH_MEMBER(256, 2);
     else VF_LAUNCH_MEMBER(256, 1);
   } else {
     VF_LAUNCH_MEMBER(512, 1);
