@@ -129,7 +129,7 @@ __device__ __forceinline__ double ldg_nc_f64(const double* p) {
   return r;
 }
 
-template <bool JAC, bool RES, int ROW, int MAXT, int MINB>
+template <bool JAC, bool RES, int ROW, int MAXT, int MINB, bool DIRECT = false>
 __global__ void __launch_bounds__(MAXT, MINB) asm_tile2_kernel(
     EngineDev E, int member, NewmarkCoef nc_arg, int is_static, JacMix mix,
     const int4* __restrict__ tile_desc,
@@ -145,7 +145,9 @@ __global__ void __launch_bounds__(MAXT, MINB) asm_tile2_kernel(
   double* tileJ = recs + (size_t)max_tile_elems * kRec2D;
   D2* s_xy = reinterpret_cast<D2*>(tileJ);
   NodeUVA* s_uva = reinterpret_cast<NodeUVA*>(s_xy + max_tile_verts);
-  const size_t region_a = max((size_t)tile_max_values, (size_t)8 * max_tile_verts);
+  // DIRECT: phase 2 stores its rows straight to HBM, the region only holds the staging area
+  const size_t region_a = DIRECT ? (size_t)8 * max_tile_verts
+                                 : max((size_t)tile_max_values, (size_t)8 * max_tile_verts);
   double* tileF = tileJ + region_a;
   unsigned* s_pair = reinterpret_cast<unsigned*>(tileF + D * max_tile_nodes);
   int* s_brptr = reinterpret_cast<int*>(s_pair + max_tile_pairs);
@@ -261,7 +263,8 @@ __global__ void __launch_bounds__(MAXT, MINB) asm_tile2_kernel(
     for (int r = threadIdx.x; r < D * nT; r += kThreads) {
       const int n = r >> 1, comp = r & 1;
       const int b0 = s_brptr[n], deg = s_brptr[n + 1] - b0;
-      double* row = tileJ + D * D * (b0 - bbase) + comp * D * deg;
+      double* row = (DIRECT ? mb + L.off[VF_J] + base : tileJ) + D * D * (b0 - bbase) +
+                    comp * D * deg;
       const int qb = s_n2e[n] - pr0, qe = s_n2e[n + 1] - pr0;
       double racc = 0.0;
       if (qe > qb) {
@@ -439,7 +442,7 @@ __global__ void __launch_bounds__(MAXT, MINB) asm_tile2_kernel(
 
   // ---- phase 3: coalesced write-out ---------------------------------------------------------------
   if (dbg_skip & 4) return;
-  if (JAC) {
+  if (JAC && !DIRECT) {
     double2* dst = reinterpret_cast<double2*>(mb + L.off[VF_J] + base);
     const double2* src = reinterpret_cast<const double2*>(tileJ);
     for (int t = threadIdx.x; t < nvals / 2; t += kThreads) __stcs(dst + t, src[t]);
@@ -1174,9 +1177,10 @@ double* member_array(vf_engine* e, int id, int member) {
 
 // dynamic shared memory of asm_tile2_kernel: records, region A (CSR slice aliasing the nodal
 // staging: coordinates + u/v/a = 64 bytes per own or halo vertex), F, index slices
-size_t tile2_smem_bytes(const vf_problem_desc& d) {
+size_t tile2_smem_bytes(const vf_problem_desc& d, bool direct = false) {
   const size_t idx_words = (size_t)d.max_tile_pairs + 2 * ((size_t)d.tile_threads + 1);
-  const size_t region_a = std::max((size_t)d.tile_max_values, (size_t)8 * d.max_tile_verts);
+  const size_t region_a = direct ? (size_t)8 * d.max_tile_verts
+                                 : std::max((size_t)d.tile_max_values, (size_t)8 * d.max_tile_verts);
   return sizeof(double) * ((size_t)d.max_tile_elems * kRec2D + region_a +
                            2 * (size_t)d.tile_threads + ((idx_words + 3) / 4) * 2);
 }
@@ -1572,6 +1576,29 @@ int assemble_impl(vf_engine* e, int member, int flags, double dt, int is_static,
     else if (v_row == 1) VF_ASM2_BY_SIZE(J_, R_, 1);                                              \
     else VF_ASM2_BY_SIZE(J_, R_, 0);                                                              \
   } while (0)
+    // Default for the fan-ordered path: rows are stored straight to HBM from phase 2 (every
+    // 16-byte entry once; L2 merges the sectors), so no CSR slice is kept in shared memory and
+    // 4 CTAs of 256 threads fit per SM (measured 0.4015 -> 0.3751 ms with 80-node tiles;
+    // VF_TILE2_DIRECT=0 restores the staged write-out)
+    static const char* env_direct = getenv("VF_TILE2_DIRECT");
+    if (!(env_direct && atoi(env_direct) == 0) && jac && v_row == 2 && nt <= 320) {
+      const size_t smem_d = tile2_smem_bytes(d, true);
+#define VF_LAUNCH_ASM2D(R_, MT_, MB_)                                                              \
+  do {                                                                                            \
+    VF_CUDA(cudaFuncSetAttribute(asm_tile2_kernel<true, R_, 2, MT_, MB_, true>,                   \
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d));      \
+    asm_tile2_kernel<true, R_, 2, MT_, MB_, true><<<grid, MT_, smem_d, st>>>(                     \
+        e->dev, member, newmark_coef(dt), is_static, mix, e->tile_desc_dev, e->te_quad_dev,       \
+        e->pair_info_dev, e->tile_halo_dev, d.max_tile_elems, d.tile_max_values,                  \
+        d.max_tile_pairs, d.tile_threads, d.max_tile_verts, pf_dist, dbg_skip);                   \
+  } while (0)
+      if (nt <= 256) {
+        if (res) VF_LAUNCH_ASM2D(true, 256, 4); else VF_LAUNCH_ASM2D(false, 256, 4);
+      } else {
+        if (res) VF_LAUNCH_ASM2D(true, 320, 3); else VF_LAUNCH_ASM2D(false, 320, 3);
+      }
+#undef VF_LAUNCH_ASM2D
+    } else
     if (jac && res) VF_ASM2_BY_MODE(true, true);
     else if (jac) VF_ASM2_BY_MODE(true, false);
     else VF_ASM2_BY_SIZE(false, true, 1);

@@ -83,7 +83,7 @@ class Engine:
 
         import os
         if d == 2:
-            nodes_per_tile = int(os.environ.get('VF_TILE_NODES', '96'))
+            nodes_per_tile = int(os.environ.get('VF_TILE_NODES', '80'))
             max_vals, tile_threads = 64 * nodes_per_tile, max(nodes_per_tile, 32)
         else:
             nodes_per_tile, max_vals, tile_threads = 64, 12288, 64
