@@ -405,12 +405,12 @@ def main():
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': dict(workload_config(), nn=nn, ne=ne, dof=N, nnz=nnz,
                        parallelism=f'{world} independent mesh shards, no collective'),
-        'roofline': {'kernel': 'asm_tile2_kernel<true,true,2,320,3> (+ facet_bc_kernel on boundary nodes)', 'bound': 'hbm',
+        'roofline': {'kernel': 'asm_tile2_kernel<true,true,2,256,4,direct> (+ facet_bc_kernel on boundary nodes)', 'bound': 'hbm',
                      'achieved': asm_gbs, 'peak': peak, 'unit': 'GB/s', 'frac': asm_gbs / peak,
                      # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel on
                      # this workload, from the ncu --set full capture summarised in
                      # profiles/r1_ncu_full_asm2_final.csv (not re-measured in this run)
-                     'traffic': 855090432 if args.levels == REFINE_LEVELS else None,
+                     'traffic': 855256832 if args.levels == REFINE_LEVELS else None,
                      'algorithmic_bytes': B_asm, 'peak_source': peak_src},
         'spmv': {'kernel': 'spmv_kernel<2,8>', 'bound': 'hbm', 'achieved': spmv_gbs,
                  'peak': peak, 'unit': 'GB/s', 'frac': spmv_gbs / peak,
