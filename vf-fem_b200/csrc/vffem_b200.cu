@@ -904,7 +904,7 @@ member_kernel(EngineDev E, int member0, int mode, int nsteps, const double* __re
   if (mode == MODE_SOLVE_SOLID) {
     // a single transient solve is cheaper with the polynomial preconditioner than one
     // inversion; the stiff static problem (no mass term) is where the inverse pays
-    blk_solve_solid<D>(E, mb, W, dt_single, opt, sh, opt.is_static != 0);
+    blk_solve_solid<D>(E, mb, W, dt_single, opt, sh, opt.is_static != 0 || E.dense == 2);
     return;
   }
   if (mode == MODE_LINEAR_SOLVE) {
@@ -972,7 +972,7 @@ member_kernel(EngineDev E, int member0, int mode, int nsteps, const double* __re
     for (int k = threadIdx.x; k < E.n_fsip; k += blockDim.x) p1[E.fsip_solid[k]] = p0[E.fsip_fluid[k]];
     __syncthreads();
 
-    blk_solve_solid<D>(E, mb, W, dt, opt, sh, true);
+    blk_solve_solid<D>(E, mb, W, dt, opt, sh, E.dense == 2);
     const long long tf = clock64();
     blk_fluid<D>(E, mb, sh);
     if (threadIdx.x == 0) sh.cyc[5] += clock64() - tf;
@@ -1032,21 +1032,27 @@ namespace {
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-// Dense inverse preconditioner of the member solver (member_solver.cuh): experimental, OFF unless
-// VF_DENSE_PREC=1.  Measured on config 1 (N = 296, profiles/README.md): GMRES drops from 10 to 4
-// iterations per solve and a step from 263 k to 193 k cycles, but the blocked in-CTA
-// Gauss-Jordan costs 5.2 M cycles per launch (one SM's L2 path), so a 99-step launch ends up 5 %
-// slower and the 1024-member ensemble 23 % slower; it pays only for launches of many hundred
-// steps of a single simulation.
-inline bool dense_prec_enabled(const vf_problem_desc& d) {
+// Dense inverse preconditioner of the member solver (member_solver.cuh).  Returns 0 (off), 1 (used
+// for static solves only: the default) or 2 (also in the time loop: VF_DENSE_PREC=1).
+// Measured on config 1/2 (N = 296, profiles/README.md):
+//   * static solve with contact (no mass term, stiff): 2326 -> 11 GMRES iterations,
+//     18.2 -> 3.8 ms: this is the PETSc-LU stand-in, on by default when the storage is small;
+//   * transient steps: 10 -> 4 iterations and 263 k -> 193 k cycles per step, but the blocked
+//     in-CTA Gauss-Jordan costs 5.2 M cycles per launch (one SM's L2 path), so a 99-step launch
+//     is 5 % slower and the 1024-member ensemble 23 % slower: opt-in only.
+inline int dense_prec_mode(const vf_problem_desc& d) {
   const char* env = getenv("VF_DENSE_PREC");
-  if (!env || atoi(env) == 0) return false;
+  const int want = env ? atoi(env) : -1;
+  if (want == 0) return 0;
   const size_t N = (size_t)d.dim * d.nn;
-  if (N > (size_t)kMaxDenseN) return false;
+  if (N > (size_t)kMaxDenseN) return 0;
   // the pivot panels (2 * kDenseNb * N doubles) live in the Krylov basis storage
-  if ((size_t)d.gmres_restart + 1 < 2 * (size_t)kDenseNb) return false;
-  return N * N * sizeof(double) * (size_t)d.n_members <= (size_t)24 << 30;
+  if ((size_t)d.gmres_restart + 1 < 2 * (size_t)kDenseNb) return 0;
+  const size_t bytes = 12 * N * N * (size_t)d.n_members;
+  if (want == 1) return bytes <= ((size_t)24 << 30) ? 2 : 0;
+  return bytes <= ((size_t)2 << 30) ? 1 : 0;
 }
+inline bool dense_prec_enabled(const vf_problem_desc& d) { return dense_prec_mode(d) != 0; }
 
 struct ArenaPlan {
   // byte offsets of the shared tables
@@ -1414,7 +1420,7 @@ int vf_create(const vf_problem_desc* desc, void* arena_dev, size_t arena_bytes, 
   E.d = d.dim; E.N = P.N; E.n_fluid = d.n_fluid; E.ns = d.ns; E.n_fsi = d.n_fsi;
   E.fluid_kind = d.fluid_kind; E.idx_sep = d.idx_sep; E.contact = d.contact;
   E.membrane = d.membrane; E.damping = d.damping; E.restart = d.gmres_restart; E.nnz = P.nnz;
-  E.dense = dense_prec_enabled(d) ? 1 : 0;
+  E.dense = dense_prec_mode(d);
   E.s = reinterpret_cast<const double*>(A + P.s);
   E.fsi_solid = reinterpret_cast<const int*>(A + P.fsi_solid);
   E.fsi_fluid = reinterpret_cast<const int*>(A + P.fsi_fluid);
