@@ -176,7 +176,8 @@ def test_3d_coupled_steps_match_oracle():
 
 
 def test_ensemble_members_and_host_entry_point():
-    """Members with identical inputs reproduce the single simulation bit for bit; the
+    """Members with identical inputs reproduce each other bit for bit and the single simulation
+    to solver tolerance; the
     host-buffer entry point equals the device-resident one; different members differ."""
     from femvf_b200.ensemble import EnsembleRunner
     model = build_fsi('m5')
@@ -198,9 +199,14 @@ def test_ensemble_members_and_host_entry_point():
     model.push_to_device()
     states, _ = model.device_integrate(dts, [control])
     ref = states[-1]
-    for b in (0, 1, 2, 4):
-        assert np.array_equal(fin[b], ref), b
-    assert not np.array_equal(fin[3], ref)
+    # members with identical inputs are bit-identical to each other; the single simulation
+    # runs on its own engine, whose time loop preconditions GMRES differently (dense inverse
+    # for single simulations, polynomial for ensembles), so it agrees to solver tolerance
+    for b in (1, 2, 4):
+        assert np.array_equal(fin[b], fin[0]), b
+    scale = np.max(np.abs(ref))
+    assert np.max(np.abs(fin[0] - ref)) <= 1e-9 * scale
+    assert np.max(np.abs(fin[3] - ref)) > 1e-6 * scale
     # device-resident path gives the same numbers
     runner.upload_members(ini, emod, eta)
     hs, hi = runner.run_device(dts, ctl, store_states=True)

@@ -792,27 +792,77 @@ __device__ void blk_solve_solid(const EngineDev& E, double* mb, const SolverWork
     blk_compute_dinv<D>(E, Jv, W.Dinv);
     __syncthreads();
     bool dense = false;
-    if (W.P && allow_dense) {
-      // (re)build the inverse when there is none for this dt / mode, or the last solve with it
-      // needed more than a few iterations (the matrix has drifted: contact, large pressure)
-      const double key = opt.is_static ? -1.0 : dt;
-      // (time steps from np.diff(times) differ in the last bits: compare with a tolerance)
-      if (!(fabs(W.pstate[0] - key) <= 1e-6 * fabs(key)) || W.pstate[1] != 0.0) {
+    if (W.P && allow_dense && opt.is_static) {
+      // static solve: the inverse of the actual Newton matrix, rebuilt at the first solve of
+      // every launch (member_kernel raises pstate[1]) and whenever the last solve with it needed
+      // more than a few iterations (contact has changed the matrix)
+      if (W.pstate[0] != -1.0 || W.pstate[1] != 0.0) {
         const long long tp = clock64();
         __syncthreads();
         blk_dense_inverse<D>(E, Jv, W.P, W.Pf, W.V, W.V + (size_t)kDenseNb * N, sh.B);
         if (threadIdx.x == 0) {
-          W.pstate[0] = key;
+          W.pstate[0] = -1.0;
           W.pstate[1] = 0.0;
+          W.pstate[2] = 0.0;  // the transient inverse (below) is gone
           sh.cyc[7] += clock64() - tp;
         }
+        __syncthreads();
+      }
+      dense = true;
+    } else if (W.P && allow_dense) {
+      // time loop: the inverse of the STATE-INDEPENDENT part ca M + cv C + K (+ membrane) with
+      // Dirichlet rows -- a pure function of (dt, properties), so it survives launches and the
+      // trajectory does not depend on when it was built.  It is validated once per launch by a
+      // checksum of the properties and rebuilt when that or dt changes.
+      bool fresh = sh.bc[6] != 0.0 && fabs(W.pstate[2] - dt) <= 1e-6 * dt;
+      if (!fresh) {
+        double cpart = 0.0;
+        for (int e = threadIdx.x; e < E.mesh.ne; e += blockDim.x) {
+          const double we = 1.0 + 1e-3 * e;
+          cpart += we * (pv.emod[e] + 0.5 * pv.eta[e] + 0.25 * pv.rho[e]);
+          if (pv.membrane) cpart += we * (pv.emod_m[e] + 0.5 * pv.nu_m[e] + 0.25 * pv.th_m[e]);
+        }
+        double chk = block_sum(cpart, sh);
+        for (int q = 0; q < SC_COUNT; ++q) {
+          const double v = pv.scal[q];
+          if (v == v && fabs(v) < 1e300) chk += (q + 1) * v;  // (ycontact may be +-inf)
+        }
+        const bool ok = W.pstate[3] == chk && fabs(W.pstate[2] - dt) <= 1e-6 * dt &&
+                        W.pstate[0] != -1.0;
+        __syncthreads();
+        if (!ok) {
+          const long long tp = clock64();
+          StateView sc = sv;
+          sc.mix.p = 0.0;
+          PropView pc = pv;
+          pc.contact = 0;
+          for (int i = threadIdx.x; i < nn; i += blockDim.x) {
+            double res[D];
+            assemble_node<D, true, false>(i, E.mesh, pc, sc, Jv + (size_t)D * D * E.mesh.brptr[i], res);
+          }
+          __syncthreads();
+          blk_dense_inverse<D>(E, Jv, W.P, W.Pf, W.V, W.V + (size_t)kDenseNb * N, sh.B);
+          // put the actual Newton matrix back
+          for (int i = threadIdx.x; i < nn; i += blockDim.x) {
+            double res[D];
+            assemble_node<D, true, false>(i, E.mesh, pv, sv, Jv + (size_t)D * D * E.mesh.brptr[i], res);
+          }
+          __syncthreads();
+          if (threadIdx.x == 0) {
+            W.pstate[0] = 0.0;
+            W.pstate[2] = dt;
+            W.pstate[3] = chk;
+            sh.cyc[7] += clock64() - tp;
+          }
+        }
+        if (threadIdx.x == 0) sh.bc[6] = 1.0;
         __syncthreads();
       }
       dense = true;
     }
     const int its = blk_gmres<D>(E, W, F, dx, opt, sh, &gm_resid, &gm_bnorm, dense);
     gm_iters += its;
-    if (dense && its > 4 && threadIdx.x == 0) W.pstate[1] = 1.0;
+    if (dense && opt.is_static && its > 4 && threadIdx.x == 0) W.pstate[1] = 1.0;
     __syncthreads();
     for (int t = threadIdx.x; t < N; t += blockDim.x) u1[t] -= dx[t];
     __syncthreads();

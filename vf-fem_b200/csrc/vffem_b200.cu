@@ -898,6 +898,7 @@ member_kernel(EngineDev E, int member0, int mode, int nsteps, const double* __re
   // launch only (properties may have been rewritten in between), and ensemble members and
   // single runs take the same path
   if (threadIdx.x == 0 && W.pstate) W.pstate[1] = 1.0;
+  if (threadIdx.x == 0) sh.bc[6] = 0.0;  // transient inverse not validated in this launch yet
   const long long t_start = clock64();
   __syncthreads();
 
@@ -1037,9 +1038,10 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 // Measured on config 1/2 (N = 296, profiles/README.md):
 //   * static solve with contact (no mass term, stiff): 2326 -> 11 GMRES iterations,
 //     18.2 -> 3.8 ms: this is the PETSc-LU stand-in, on by default when the storage is small;
-//   * transient steps: 10 -> 4 iterations and 263 k -> 193 k cycles per step, but the blocked
-//     in-CTA Gauss-Jordan costs 5.2 M cycles per launch (one SM's L2 path), so a 99-step launch
-//     is 5 % slower and the 1024-member ensemble 23 % slower: opt-in only.
+//   * transient steps (inverse of the state-independent part, kept across launches): 10 -> 6
+//     iterations, but one mat-vec with the 350 KB fp32 inverse costs ~24 k cycles on ONE SM
+//     (L2 -> SM at ~15 B/clk with 8 warps) against ~10 k for the degree-3 polynomial step out
+//     of shared memory: 5.9 k vs 7.1 k steps/s on the same box.  Opt-in only.
 inline int dense_prec_mode(const vf_problem_desc& d) {
   const char* env = getenv("VF_DENSE_PREC");
   const int want = env ? atoi(env) : -1;
@@ -1152,7 +1154,7 @@ ArenaPlan plan_arena(const vf_problem_desc& d) {
     const size_t ldp = (size_t)dense_ldp((int)N);
     L.Pf = mtake((N * ldp + 1) / 2);   // fp32, rows padded to 128 bytes
     L.Pscr = mtake(32 * ldp);          // up to 32 warps
-    L.pstate = mtake(2);
+    L.pstate = mtake(4);
   }
   L.stride = align_up(m, 32);
   P.total = P.members + sizeof(double) * L.stride * (size_t)d.n_members;
