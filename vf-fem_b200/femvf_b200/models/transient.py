@@ -675,8 +675,13 @@ class ExplicitFSIModel(BaseTransientFSIModel):
         Returns (states, infos): host arrays (nsteps+1, state_size) and (nsteps+1, 4).
         """
         n_fluid = self.engine.n_fluid
-        ctl = np.array([[np.broadcast_to(c['psub'], (n_fluid,)),
-                         np.broadcast_to(c['psup'], (n_fluid,))] for c in controls])
+        # (steps usually share one control object: expand each distinct object once)
+        rows = {}
+        for c in controls:
+            if id(c) not in rows:
+                rows[id(c)] = np.array([np.broadcast_to(c['psub'], (n_fluid,)),
+                                        np.broadcast_to(c['psup'], (n_fluid,))])
+        ctl = np.array([rows[id(c)] for c in controls])
         hs, hi = self.engine.integrate(dts, ctl, options, store_states=True, store_info=True)
         return hs[0].cpu().numpy(), hi[0].cpu().numpy()
 
