@@ -503,7 +503,7 @@ __global__ void facet_bc_kernel(EngineDev E, int member, double dt, int is_stati
 template <int D, int LANES>
 __global__ void spmv_kernel(MeshView m, const double* __restrict__ J,
                             const double* __restrict__ x, double* __restrict__ y, int node0,
-                            int node1) {
+                            int node1, size_t pf_bytes) {
   const int gt = blockIdx.x * blockDim.x + threadIdx.x;
   const int node = node0 + gt / LANES;
   const int lane = gt % LANES;
@@ -514,6 +514,27 @@ __global__ void spmv_kernel(MeshView m, const double* __restrict__ J,
   if (valid) {
     const int b0 = m.brptr[node], deg = m.brptr[node + 1] - b0;
     const double* blk = J + (size_t)D * D * b0;
+    if (pf_bytes > 0) {
+      // J, bcol and brptr are contiguous streams consumed in block order: every thread asks L2
+      // for the line a fixed distance ahead of the one it is about to read, so the union of the
+      // requests is the stream itself, shifted -- later CTAs then find their three dependent
+      // loads (brptr -> bcol -> values) in L2 instead of paying three DRAM round trips
+      const size_t vend = (size_t)D * D * m.brptr[m.nn] * sizeof(double);
+      const size_t voff = (size_t)((const char*)(blk + D * lane) - (const char*)J) + pf_bytes;
+      if (lane < deg) {
+#pragma unroll
+        for (int a = 0; a < D; ++a) {   // one request per scalar row of the block row
+          const size_t o = voff + (size_t)a * D * deg * sizeof(double);
+          if (o < vend) prefetch_l2((const char*)J + o);
+        }
+      }
+      if (lane == 0) {
+        const size_t ahead = pf_bytes / (D * D * sizeof(double));   // blocks
+        if ((size_t)b0 + ahead < (size_t)m.brptr[m.nn]) prefetch_l2(m.bcol + b0 + ahead);
+        const size_t nahead = ahead / 7;                             // nodes (7 blocks per row)
+        if ((size_t)node + nahead < (size_t)m.nn) prefetch_l2(m.brptr + node + nahead);
+      }
+    }
     for (int k = lane; k < deg; k += LANES) {
       const int j = __ldg(m.bcol + b0 + k);
       if (D == 2) {
@@ -1670,14 +1691,21 @@ int vf_spmv_rows(vf_engine* e, int member, const double* x_dev, double* y_dev, i
   const double* J = member_array(e, VF_J, member);
   const int nrows = node1 - node0;
   const int block = 256;
+  // L2 prefetch distance of the value stream (VF_SPMV_PF_MB; 0 disables).  Measured on the
+  // 5.6e7-nnz matrix: 0 -> 0.1536, 4 MB -> 0.1471, 16 MB -> 0.1495, 64 MB -> 0.1707 ms; only
+  // worth it when the matrix does not sit in L2 anyway
+  static const char* env_pf = getenv("VF_SPMV_PF_MB");
+  const size_t pf_mb = env_pf ? (size_t)std::max(atoi(env_pf), 0) : 4;
+  const size_t jbytes = (size_t)e->dev.nnz * sizeof(double);
+  const size_t pf_bytes = jbytes > ((size_t)64 << 20) ? pf_mb << 20 : 0;
   if (e->desc.dim == 2) {
     constexpr int LN = 8;
     const int grid = (int)(((size_t)nrows * LN + block - 1) / block);
-    spmv_kernel<2, LN><<<grid, block, 0, st>>>(e->dev.mesh, J, x_dev, y_dev, node0, node1);
+    spmv_kernel<2, LN><<<grid, block, 0, st>>>(e->dev.mesh, J, x_dev, y_dev, node0, node1, pf_bytes);
   } else {
     constexpr int LN = 16;
     const int grid = (int)(((size_t)nrows * LN + block - 1) / block);
-    spmv_kernel<3, LN><<<grid, block, 0, st>>>(e->dev.mesh, J, x_dev, y_dev, node0, node1);
+    spmv_kernel<3, LN><<<grid, block, 0, st>>>(e->dev.mesh, J, x_dev, y_dev, node0, node1, pf_bytes);
   }
   e->launches += 1;
   VF_CUDA(cudaGetLastError());
