@@ -62,6 +62,9 @@ typedef struct vf_problem_desc {
   int32_t max_tile_verts;     /* max own + halo vertices of a tile */
   int32_t tile2_threads;
   int32_t fan_ok;             /* n2e lists are counter-clockwise fans (tables.order_fans_2d) */
+  /* pair_info of ONE tile covering the whole mesh (cell index = cell id; needs ne < 4096): lets
+   * the per-member time-loop kernel assemble by records too.  NULL disables. */
+  const uint32_t* gpair_host;     /* (n2e_ptr[nn]) */
   /* 1D fluid + FSI map (models/fsi.py:18-88) */
   int32_t n_fluid, ns, n_fsi;
   const double* s_host;           /* (n_fluid, ns) arclength coordinates */

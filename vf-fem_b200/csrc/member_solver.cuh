@@ -60,6 +60,11 @@ struct EngineDev {
   const int* fsi_fluid;
   const int* fsip_solid;  // pressure scatter map (unique solid DOFs)
   const int* fsip_fluid;
+  // record-based in-CTA assembly (triangles, < 4096 cells): packed (node, cell) pair info with
+  // GLOBAL cell ids (tables.build_tile_elem_tables over one tile), nodes with facet / BC work
+  const unsigned* gpair;
+  const int* touch;
+  int n_touch;
   double* members;
   Layout L;
 };
@@ -735,6 +740,91 @@ __device__ __forceinline__ PropView member_props(const EngineDev& E, double* mb)
 
 // FenicsModel.solve_state1: Newton on F_u(u1) = 0 starting from the guess held in VF_U1,
 // then v1, a1 from the Newmark relations (App. C, Q2).
+// Residual (+ Jacobian) of the whole member mesh by the two-phase record algorithm of
+// asm_tile2_kernel, inside the CTA: one 144-byte record per cell (thread per cell), then one
+// thread per scalar row walks the vertex fan and completes its CSR row / residual entry from
+// the records, then the boundary nodes add facet terms and Dirichlet rows.  Every cell's
+// geometry, material and Newmark arithmetic is done once instead of once per adjacent vertex.
+// recs: ne * kRec2D doubles (the Krylov basis storage, idle during assembly).
+template <bool JAC>
+__device__ void blk_assemble_records(const EngineDev& E, const PropView& pv, const StateView& sv,
+                                     double* recs, double* Jv, double* F) {
+  constexpr int D = 2;
+  const MeshView& m = E.mesh;
+  const NewmarkCoef nc = newmark_coef(sv.dt);
+  const LameFac lf = lame_fac(pv.scal[SC_NU]);
+  const Damping dp = prop_damping(pv);
+  const bool is_static = sv.is_static != 0;
+  for (int e = threadIdx.x; e < m.ne; e += blockDim.x) {
+    int nd[3];
+    double x[3][2];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      nd[a] = m.cells[(size_t)a * m.ne + e];
+      const D2 c2 = reinterpret_cast<const D2*>(m.xy)[nd[a]];
+      x[a][0] = c2.x;
+      x[a][1] = c2.y;
+    }
+    tri_record(x, nd, pv.emod[e], lf, pv.eta[e], pv.rho[e], dp, nc, is_static, true, sv.u1, sv.u0,
+               sv.v0, sv.a0, recs + (size_t)e * kRec2D);
+  }
+  __syncthreads();
+  for (int r = threadIdx.x; r < E.N; r += blockDim.x) {
+    const int n = r >> 1, comp = r & 1;
+    const int b0 = m.brptr[n], deg = m.brptr[n + 1] - b0;
+    double* row = Jv + (size_t)D * D * b0 + comp * D * deg;
+    const int qb = m.n2e_ptr[n], qe = m.n2e_ptr[n + 1];
+    double racc = 0.0;
+    if (qe > qb) {
+      unsigned info = E.gpair[qb];
+      const double* rec = recs + (size_t)(info & 0xfffu) * kRec2D;
+      int a = (info >> 12) & 3;
+      D2 diag = D2{0.0, 0.0}, carry = D2{0.0, 0.0}, first = D2{0.0, 0.0};
+      int slot_first = 0, slot_carry = 0;
+      if (JAC) {
+        tri_row_fan(rec, a, comp, diag, first, carry);
+        slot_first = (info >> 20) & 63;
+        slot_carry = (info >> 26) & 63;
+      }
+      racc = rec[9 + 2 * a + comp];
+      for (int q = qb + 1; q < qe; ++q) {
+        info = E.gpair[q];
+        rec = recs + (size_t)(info & 0xfffu) * kRec2D;
+        a = (info >> 12) & 3;
+        if (JAC) {
+          D2 ws, wn, wp;
+          tri_row_fan(rec, a, comp, ws, wn, wp);
+          diag.x += ws.x;
+          diag.y += ws.y;
+          *reinterpret_cast<D2*>(row + D * ((info >> 20) & 63)) = D2{carry.x + wn.x, carry.y + wn.y};
+          carry = wp;
+          slot_carry = (info >> 26) & 63;
+        }
+        racc += rec[9 + 2 * a + comp];
+      }
+      if (JAC) {
+        if (slot_carry == slot_first) {
+          *reinterpret_cast<D2*>(row + D * slot_first) = D2{first.x + carry.x, first.y + carry.y};
+        } else {
+          *reinterpret_cast<D2*>(row + D * slot_first) = first;
+          *reinterpret_cast<D2*>(row + D * slot_carry) = carry;
+        }
+        *reinterpret_cast<D2*>(row + D * ((info >> 14) & 63)) = diag;
+      }
+    }
+    F[r] = racc;
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < E.n_touch; t += blockDim.x) {
+    const int i = E.touch[t];
+    double res[D] = {F[D * i], F[D * i + 1]};
+    assemble_node_facets_bc<D, JAC, true>(i, m, pv, sv, Jv + (size_t)D * D * m.brptr[i], res);
+    F[D * i] = res[0];
+    F[D * i + 1] = res[1];
+  }
+  __syncthreads();
+}
+
 template <int D>
 __device__ void blk_solve_solid(const EngineDev& E, double* mb, const SolverWork& W, double dt,
                                 const SolverOpts& opt, BlockShared& sh, bool allow_dense) {
@@ -756,6 +846,9 @@ __device__ void blk_solve_solid(const EngineDev& E, double* mb, const SolverWork
   sv.is_static = opt.is_static;
   sv.mix = jac_mix_du1(newmark_coef(sv.dt), opt.is_static != 0);
 
+  // record-based assembly when the tables exist and the records fit the Krylov basis storage
+  const bool use_records = E.gpair != nullptr &&
+                           (size_t)E.mesh.ne * kRec2D <= (size_t)(E.restart + 1) * N;
   int k = 0;
   double r0 = 0.0, abs_err = 0.0, rel_err = 0.0;
   int gm_iters = 0;
@@ -764,15 +857,21 @@ __device__ void blk_solve_solid(const EngineDev& E, double* mb, const SolverWork
     // residual (and, in the first iteration, the Jacobian in the same sweep)
     const long long ta = clock64();
     double part = 0.0;
-    for (int i = threadIdx.x; i < nn; i += blockDim.x) {
-      double res[D];
-      if (k == 0)
-        assemble_node<D, true, true>(i, E.mesh, pv, sv, Jv + (size_t)D * D * E.mesh.brptr[i], res);
-      else
-        assemble_node<D, false, true>(i, E.mesh, pv, sv, nullptr, res);
-      for (int c = 0; c < D; ++c) {
-        F[D * i + c] = res[c];
-        part += res[c] * res[c];
+    if (D == 2 && use_records) {
+      if (k == 0) blk_assemble_records<true>(E, pv, sv, W.V, Jv, F);
+      else blk_assemble_records<false>(E, pv, sv, W.V, Jv, F);
+      for (int t = threadIdx.x; t < N; t += blockDim.x) part += F[t] * F[t];
+    } else {
+      for (int i = threadIdx.x; i < nn; i += blockDim.x) {
+        double res[D];
+        if (k == 0)
+          assemble_node<D, true, true>(i, E.mesh, pv, sv, Jv + (size_t)D * D * E.mesh.brptr[i], res);
+        else
+          assemble_node<D, false, true>(i, E.mesh, pv, sv, nullptr, res);
+        for (int c = 0; c < D; ++c) {
+          F[D * i + c] = res[c];
+          part += res[c] * res[c];
+        }
       }
     }
     abs_err = sqrt(block_sum(part, sh));
@@ -783,9 +882,13 @@ __device__ void blk_solve_solid(const EngineDev& E, double* mb, const SolverWork
         k >= opt.newton_max_iter)
       break;
     if (k > 0) {
-      for (int i = threadIdx.x; i < nn; i += blockDim.x) {
-        double res[D];
-        assemble_node<D, true, false>(i, E.mesh, pv, sv, Jv + (size_t)D * D * E.mesh.brptr[i], res);
+      if (D == 2 && use_records) {
+        blk_assemble_records<true>(E, pv, sv, W.V, Jv, F);   // (F is rewritten identically)
+      } else {
+        for (int i = threadIdx.x; i < nn; i += blockDim.x) {
+          double res[D];
+          assemble_node<D, true, false>(i, E.mesh, pv, sv, Jv + (size_t)D * D * E.mesh.brptr[i], res);
+        }
       }
     }
     __syncthreads();

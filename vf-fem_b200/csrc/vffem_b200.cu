@@ -1080,7 +1080,7 @@ inline bool dense_prec_enabled(const vf_problem_desc& d) { return dense_prec_mod
 struct ArenaPlan {
   // byte offsets of the shared tables
   size_t xyz, xy, cells, brptr, bcol, n2e_ptr, n2e, n2f_ptr, n2f, pf_cell, pf_opp, bc, tile_start, s,
-      fsi_solid, fsi_fluid, fsip_solid, fsip_fluid, te_ptr, te_elem, pair_info, tile_desc, te_quad, tile_halo, touch, members, total;
+      fsi_solid, fsi_fluid, fsip_solid, fsip_fluid, te_ptr, te_elem, pair_info, tile_desc, te_quad, tile_halo, touch, gpair, members, total;
   Layout L;
   long long nnz;
   int N;
@@ -1126,6 +1126,7 @@ ArenaPlan plan_arena(const vf_problem_desc& d) {
   P.te_quad = take(sizeof(int) * 4 * std::max(n_te, 1));
   P.tile_halo = take(sizeof(int) * std::max(d.te_ptr_host ? d.n_tile_halo : 0, 1));
   P.touch = take(sizeof(int) * std::max(d.nn, 1));
+  P.gpair = take(sizeof(unsigned) * std::max(d.gpair_host ? n_n2e : 0, 1));
   P.members = o;
 
   // member block (offsets in doubles, each array aligned to 16 doubles = 128 B)
@@ -1381,6 +1382,7 @@ int vf_create(const vf_problem_desc* desc, void* arena_dev, size_t arena_bytes, 
     if (t) touch.push_back(i);
   }
   VF_CUDA(up(P.touch, touch.data(), sizeof(int) * touch.size()));
+  if (d.gpair_host) VF_CUDA(up(P.gpair, d.gpair_host, sizeof(unsigned) * n_n2e));
   if (two_phase) {
     VF_CUDA(up(P.te_ptr, d.te_ptr_host, sizeof(int) * (d.ntiles + 1)));
     VF_CUDA(up(P.te_elem, d.te_elem_host, sizeof(int) * d.te_ptr_host[d.ntiles]));
@@ -1415,6 +1417,7 @@ int vf_create(const vf_problem_desc* desc, void* arena_dev, size_t arena_bytes, 
   e->desc.te_ptr_host = nullptr; e->desc.te_elem_host = nullptr; e->desc.pair_info_host = nullptr;
   e->desc.tile_desc_host = nullptr; e->desc.te_quad_host = nullptr;
   e->desc.tile_halo_host = nullptr;
+  e->desc.gpair_host = nullptr;
   e->two_phase = two_phase;
   e->fan_ok = d.fan_ok != 0;
   e->touch_dev = reinterpret_cast<int*>(A + P.touch);
@@ -1444,6 +1447,13 @@ int vf_create(const vf_problem_desc* desc, void* arena_dev, size_t arena_bytes, 
   E.fluid_kind = d.fluid_kind; E.idx_sep = d.idx_sep; E.contact = d.contact;
   E.membrane = d.membrane; E.damping = d.damping; E.restart = d.gmres_restart; E.nnz = P.nnz;
   E.dense = dense_prec_mode(d);
+  // record-based in-CTA assembly: 2D, fan-ordered adjacency, cell index fits the packed word
+  const char* env_rec = getenv("VF_MEMBER_RECORDS");
+  const bool rec_on = !(env_rec && atoi(env_rec) == 0);
+  E.gpair = (rec_on && d.gpair_host && d.dim == 2 && d.fan_ok && d.ne < 4096)
+                ? reinterpret_cast<const unsigned*>(A + P.gpair) : nullptr;
+  E.touch = reinterpret_cast<const int*>(A + P.touch);
+  E.n_touch = (int)touch.size();
   E.s = reinterpret_cast<const double*>(A + P.s);
   E.fsi_solid = reinterpret_cast<const int*>(A + P.fsi_solid);
   E.fsi_fluid = reinterpret_cast<const int*>(A + P.fsi_fluid);

@@ -37,6 +37,7 @@ class ProblemDesc(C.Structure):
         ('max_tile_elems', C.c_int32), ('max_tile_pairs', C.c_int32),
         ('n_tile_halo', C.c_int32), ('max_tile_verts', C.c_int32),
         ('tile2_threads', C.c_int32), ('fan_ok', C.c_int32),
+        ('gpair_host', C.c_void_p),
         ('n_fluid', C.c_int32), ('ns', C.c_int32), ('n_fsi', C.c_int32),
         ('s_host', C.c_void_p), ('fsi_solid_host', C.c_void_p), ('fsi_fluid_host', C.c_void_p),
         ('n_fsip', C.c_int32), ('fsip_solid_host', C.c_void_p), ('fsip_fluid_host', C.c_void_p),

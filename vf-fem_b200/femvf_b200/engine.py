@@ -134,6 +134,12 @@ class Engine:
         keep = dict(tables)
         keep.update(tile_start=tile_start, s=s, fsi_solid=fsia_solid, fsi_fluid=fsia_fluid,
                     fsip_solid=fsip_solid, fsip_fluid=fsip_fluid)
+        # pair info of one tile spanning the whole mesh: record-based assembly inside the
+        # per-member time-loop kernel (small meshes only: the cell index is packed in 12 bits)
+        if d == 2 and self.ne < 4096 and tables.get('fan_ok', False):
+            whole = _tables.build_tile_elem_tables(tables, np.array([0, self.nn], dtype=np.int32))
+            if whole is not None:
+                keep['gpair'] = np.ascontiguousarray(whole['pair_info'])
         if tile2 is not None:
             keep.update(te_ptr=tile2['te_ptr'], te_elem=tile2['te_elem'],
                         pair_info=tile2['pair_info'], tile_desc=tile2['tile_desc'],
@@ -149,6 +155,7 @@ class Engine:
             tile2['max_tile_elems'] if tile2 else 0, tile2['max_tile_pairs'] if tile2 else 0,
             tile2['n_tile_halo'] if tile2 else 0, tile2['max_tile_verts'] if tile2 else 0,
             tile2_threads, int(bool(tables.get('fan_ok', False))),
+            _ptr(keep.get('gpair')),
             self.n_fluid, self.ns, len(fsia_solid), _ptr(s), _ptr(fsia_solid), _ptr(fsia_fluid),
             len(fsip_solid), _ptr(fsip_solid), _ptr(fsip_fluid),
             int(fluid_kind), int(idx_sep), int(bool(contact)), int(bool(membrane)),
