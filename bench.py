@@ -447,7 +447,7 @@ def main():
                      # profiles/r1_ncu_full_asm2_final.csv (not re-measured in this run)
                      'traffic': 855256832 if args.levels == REFINE_LEVELS else None,
                      'algorithmic_bytes': B_asm, 'peak_source': peak_src},
-        'spmv': {'kernel': 'spmv_kernel<2,8>', 'bound': 'hbm', 'achieved': spmv_gbs,
+        'spmv': {'kernel': 'spmv_kernel<2,4>', 'bound': 'hbm', 'achieved': spmv_gbs,
                  'peak': peak, 'unit': 'GB/s', 'frac': spmv_gbs / peak,
                  'algorithmic_bytes': B_spmv, 'ms': ms_spmv / n_spmv},
         'clocks': clocks,

@@ -1709,13 +1709,42 @@ int vf_spmv_rows(vf_engine* e, int member, const double* x_dev, double* y_dev, i
   const size_t jbytes = (size_t)e->dev.nnz * sizeof(double);
   const size_t pf_bytes = jbytes > ((size_t)64 << 20) ? pf_mb << 20 : 0;
   if (e->desc.dim == 2) {
-    constexpr int LN = 8;
-    const int grid = (int)(((size_t)nrows * LN + block - 1) / block);
-    spmv_kernel<2, LN><<<grid, block, 0, st>>>(e->dev.mesh, J, x_dev, y_dev, node0, node1, pf_bytes);
+    // lanes per node block row (VF_SPMV_LANES).  Triangles have ~7 blocks per row; measured on
+    // the 5.6e7-nnz matrix: 1 -> 0.405, 2 -> 0.195, 4 -> 0.1345, 8 -> 0.1476, 16 -> 0.270 ms
+    static const char* env_ln = getenv("VF_SPMV_LANES");
+    const int ln = env_ln ? atoi(env_ln) : 4;
+    if (ln == 2) {
+      const int grid = (int)(((size_t)nrows * 2 + block - 1) / block);
+      spmv_kernel<2, 2><<<grid, block, 0, st>>>(e->dev.mesh, J, x_dev, y_dev, node0, node1, pf_bytes);
+    } else if (ln == 1) {
+      const int grid = (int)(((size_t)nrows + block - 1) / block);
+      spmv_kernel<2, 1><<<grid, block, 0, st>>>(e->dev.mesh, J, x_dev, y_dev, node0, node1, pf_bytes);
+    } else if (ln == 4) {
+      const int grid = (int)(((size_t)nrows * 4 + block - 1) / block);
+      spmv_kernel<2, 4><<<grid, block, 0, st>>>(e->dev.mesh, J, x_dev, y_dev, node0, node1, pf_bytes);
+    } else if (ln == 16) {
+      const int grid = (int)(((size_t)nrows * 16 + block - 1) / block);
+      spmv_kernel<2, 16><<<grid, block, 0, st>>>(e->dev.mesh, J, x_dev, y_dev, node0, node1, pf_bytes);
+    } else {
+      constexpr int LN = 8;
+      const int grid = (int)(((size_t)nrows * LN + block - 1) / block);
+      spmv_kernel<2, LN><<<grid, block, 0, st>>>(e->dev.mesh, J, x_dev, y_dev, node0, node1, pf_bytes);
+    }
   } else {
-    constexpr int LN = 16;
-    const int grid = (int)(((size_t)nrows * LN + block - 1) / block);
-    spmv_kernel<3, LN><<<grid, block, 0, st>>>(e->dev.mesh, J, x_dev, y_dev, node0, node1, pf_bytes);
+    // tetrahedra: ~15 blocks per row (VF_SPMV_LANES3)
+    static const char* env_l3 = getenv("VF_SPMV_LANES3");
+    const int l3 = env_l3 ? atoi(env_l3) : 16;
+    if (l3 == 8) {
+      const int grid = (int)(((size_t)nrows * 8 + block - 1) / block);
+      spmv_kernel<3, 8><<<grid, block, 0, st>>>(e->dev.mesh, J, x_dev, y_dev, node0, node1, pf_bytes);
+    } else if (l3 == 4) {
+      const int grid = (int)(((size_t)nrows * 4 + block - 1) / block);
+      spmv_kernel<3, 4><<<grid, block, 0, st>>>(e->dev.mesh, J, x_dev, y_dev, node0, node1, pf_bytes);
+    } else {
+      constexpr int LN = 16;
+      const int grid = (int)(((size_t)nrows * LN + block - 1) / block);
+      spmv_kernel<3, LN><<<grid, block, 0, st>>>(e->dev.mesh, J, x_dev, y_dev, node0, node1, pf_bytes);
+    }
   }
   e->launches += 1;
   VF_CUDA(cudaGetLastError());
