@@ -172,7 +172,8 @@ __device__ __forceinline__ SolverWork make_work(const EngineDev& E, double* mb, 
 template <int D>
 __device__ __forceinline__ void blk_spmv_prec(const EngineDev& E, const double* __restrict__ J,
                                               const double* __restrict__ Dinv,
-                                              const double* __restrict__ x, double* __restrict__ y) {
+                                              const double* __restrict__ x, double* __restrict__ y,
+                                              const double* __restrict__ tcomb = nullptr) {
   for (int i = threadIdx.x; i < E.mesh.nn; i += blockDim.x) {
     const int b0 = E.mesh.brptr[i], deg = E.mesh.brptr[i + 1] - b0;
     const double* blk = J + (size_t)D * D * b0;
@@ -195,7 +196,8 @@ __device__ __forceinline__ void blk_spmv_prec(const EngineDev& E, const double* 
       double t = 0.0;
 #pragma unroll
       for (int c = 0; c < D; ++c) t += o[a * D + c] * acc[c];
-      y[D * i + a] = t;
+      // tcomb: the Neumann recurrence y = tcomb + x - D^{-1} J x in the same sweep
+      y[D * i + a] = tcomb ? tcomb[D * i + a] + x[D * i + a] - t : t;
     }
   }
 }
@@ -530,9 +532,7 @@ __device__ __forceinline__ void blk_apply_op(const EngineDev& E, const SolverWor
   for (int q = 0; q < p; ++q) {
     // ping-pong between z and w so that the last term lands in w and dst never aliases cur
     double* dst = ((p - q) & 1) ? w : W.z;
-    blk_spmv_prec<D>(E, W.J, W.Dinv, cur, dst);
-    __syncthreads();
-    for (int i = threadIdx.x; i < E.N; i += blockDim.x) dst[i] = t[i] + cur[i] - dst[i];
+    blk_spmv_prec<D>(E, W.J, W.Dinv, cur, dst, t);  // dst = t + cur - D^{-1} J cur
     __syncthreads();
     cur = dst;
   }
