@@ -660,19 +660,31 @@ __device__ int blk_gmres(const EngineDev& E, const SolverWork& W, const double* 
       long long t2 = clock64();
       if (threadIdx.x == 0) {
         // Hessenberg column, previous Givens rotations, new rotation
+        // the running pair (a, b) of the column stays in registers and the operands of the
+        // next rotation are fetched before the store of the current one: one thread, one
+        // dependent chain -- only the multiply-adds remain on it
         double* hc = H + (size_t)k * ldh;
-        for (int j = 0; j <= k; ++j) hc[j] = sh.h[j] + sh.h2[j];
+        double a = sh.h[0] + sh.h2[0];
+        double cj = cs[0], sj = sn[0];
+        double b = k > 0 ? sh.h[1] + sh.h2[1] : 0.0;
         for (int j = 0; j < k; ++j) {
-          const double t0 = cs[j] * hc[j] + sn[j] * hc[j + 1];
-          hc[j + 1] = -sn[j] * hc[j] + cs[j] * hc[j + 1];
+          const double cn = cs[j + 1], sn_next = sn[j + 1];       // (index k is rewritten below)
+          const double bn = j + 2 <= k ? sh.h[j + 2] + sh.h2[j + 2] : 0.0;
+          const double t0 = cj * a + sj * b;
+          const double b2 = -sj * a + cj * b;
           hc[j] = t0;
+          a = b2;
+          b = bn;
+          cj = cn;
+          sj = sn_next;
         }
-        const double denom = sqrt(hc[k] * hc[k] + hk1 * hk1);
-        const double c = (denom == 0.0) ? 1.0 : hc[k] / denom;
+        const double hkk = a;
+        const double denom = sqrt(hkk * hkk + hk1 * hk1);
+        const double c = (denom == 0.0) ? 1.0 : hkk / denom;
         const double s = (denom == 0.0) ? 0.0 : hk1 / denom;
         cs[k] = c;
         sn[k] = s;
-        hc[k] = c * hc[k] + s * hk1;
+        hc[k] = c * hkk + s * hk1;
         g[k + 1] = -s * g[k];
         g[k] = c * g[k];
         sh.bc[0] = fabs(g[k + 1]);
