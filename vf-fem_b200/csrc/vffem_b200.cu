@@ -1341,6 +1341,17 @@ int vf_create(const vf_problem_desc* desc, void* arena_dev, size_t arena_bytes, 
   const int n_n2e = d.n2e_ptr_host[d.nn];
   const int n_n2f = d.n2f_ptr_host[d.nn];
 
+  {
+    // vf_integrate_host stages through cudaMallocAsync: keep freed blocks in the device's default
+    // pool instead of returning them to the driver at every synchronisation point
+    int dev = 0;
+    cudaMemPool_t pool;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    (void)cudaGetLastError();
+  }
   VF_CUDA(cudaMemsetAsync(A, 0, P.total, st));
   auto up = [&](size_t off, const void* src, size_t bytes) -> cudaError_t {
     if (bytes == 0) return cudaSuccess;
