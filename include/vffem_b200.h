@@ -147,6 +147,18 @@ int64_t vf_nnz(const vf_engine* e);
  * (models/assemblyutils.py:49-50, transient.py:379-380, 398-399). */
 int vf_assemble(vf_engine* e, int member, int flags, double dt, int is_static, void* stream);
 
+/* Tables of the node-centric fan assembly kernel (triangles whose vertex stars are single
+ * counter-clockwise fans; femvf_b200/tables.py build_fan_tables).  Once set, vf_assemble /
+ * vf_assemble_mix run asm_fan_kernel: one thread per vertex walks its fan and stores its two CSR
+ * rows directly.  Still the same dfn.assemble call sites (models/assemblyutils.py:49-50).
+ *   desc_host (ntiles, 8) int32: i0, nT | nH << 16, halo0, ring0, rows, cell_lo, cell_cnt, 0
+ *   ring_host (n_ring, 2) uint32: per tile rows x tile_nodes entries (header row + ring rows)
+ *   halo_host (n_halo) int32: ring vertices outside each tile's own node range
+ * The tables are copied into a device allocation owned by the engine. */
+int vf_set_fan_tables(vf_engine* e, int tile_nodes, int ntiles, const int32_t* desc_host,
+                      const uint32_t* ring_host, size_t n_ring, const int32_t* halo_host,
+                      size_t n_halo, int max_verts, int max_rows, void* stream);
+
 /* The state0 sensitivities of FenicsModel.assem_dres_dstate0 (models/transient.py:408-421:
  * assemble_derivative(form, 'state/u0' | 'state/v0' | 'state/a0'), no bc.apply).  F_u depends on
  * state0 only through v_nmk, a_nmk, so each block is a mix of the matrices the Jacobian is made

@@ -5,6 +5,7 @@
 #include <cstdlib>
 using std::sqrt; using std::fabs; using std::isinf;
 #include "../../vf-fem_b200/csrc/node_assembly.cuh"
+#include "../../vf-fem_b200/csrc/fan_assembly.cuh"
 
 template <int D>
 static void run(const vf::MeshView& m, const vf::PropView& p, const vf::StateView& s,
@@ -100,6 +101,72 @@ extern "C" int hostcheck_assemble_tile2(
     }
   }
   free(recs);
+  for (int i = 0; i < nn; ++i) {
+    bool touch = n2f_ptr[i + 1] > n2f_ptr[i] || bc[2 * i] || bc[2 * i + 1];
+    if (!touch) continue;
+    double res[2] = {F[2 * i], F[2 * i + 1]};
+    vf::assemble_node_facets_bc<2, true, true>(i, m, p, s, J + 4 * (size_t)brptr[i], res);
+    F[2 * i] = res[0];
+    F[2 * i + 1] = res[1];
+  }
+  return 0;
+}
+
+// CPU emulation of asm_fan_kernel + facet_bc_kernel (node-centric fan assembly, triangles): the
+// same device function (fan_walk_node) driven by the product's fan tables, tile by tile, with
+// the staged vertex list (own vertices, then the tile's halo) rebuilt like the kernel does.
+extern "C" int hostcheck_assemble_fan(
+    int nn, int ne, int nfp, const double* xyz, const int* cells, const int* brptr,
+    const int* bcol, const int* n2e_ptr, const int* n2e, const int* n2f_ptr, const int* n2f,
+    const int* pf_cell, const int* pf_opp, const unsigned char* bc, const double* rho,
+    const double* eta, const double* emod, const double* scal, const double* emod_m,
+    const double* nu_m, const double* th_m, int contact, int membrane, int damping,
+    const double* u1, const double* u0, const double* v0, const double* a0, const double* p1,
+    double dt, int is_static, int tile_nodes, int ntiles, const int* desc, const unsigned* ring,
+    const int* halo, int max_verts, int rows_s, double* J, double* F) {
+  vf::MeshView m{2, nn, ne, nfp, xyz, nullptr, cells, brptr, bcol, n2e_ptr, n2e,
+                 n2f_ptr, n2f, pf_cell, pf_opp, bc};
+  vf::PropView p{rho, eta, emod, scal, emod_m, nu_m, th_m, contact, membrane, damping};
+  const vf::NewmarkCoef nc = vf::newmark_coef(dt);
+  const vf::JacMix mix = vf::jac_mix_du1(nc, is_static != 0);
+  vf::StateView s{u1, is_static ? u1 : u0, v0, a0, p1, dt, is_static, mix};
+  const vf::FanCoef fc = vf::fan_coef(vf::lame_fac(scal[vf::SC_NU]), vf::prop_damping(p), mix);
+  const int TN = tile_nodes;
+  vf::D2* sxy = new vf::D2[max_verts];
+  vf::NodeUVA* suva = new vf::NodeUVA[max_verts];
+  for (int t = 0; t < ntiles; ++t) {
+    const int* d = desc + 8 * t;
+    const int i0 = d[0], nT = d[1] & 0xffff, nH = (int)((unsigned)d[1] >> 16);
+    const int h0 = d[2], ring0 = d[3], rows = d[4];
+    if (nT + nH > max_verts) return 2;
+    for (int k = 0; k < nT + nH; ++k) {
+      const int v = k < nT ? i0 + k : halo[h0 + k - nT];
+      sxy[k] = vf::D2{xyz[v], xyz[nn + v]};
+      suva[k] = vf::gather_node_uva(nc, is_static != 0, v, u1, s.u0, v0, a0);
+    }
+    const unsigned* ring_t = ring + 2 * (size_t)ring0;
+    (void)rows_s;
+    for (int k = 0; k < nT; ++k) {
+      auto ringf = [&](int r) {
+        if (r >= rows) std::abort();
+        const unsigned* w = ring_t + 2 * ((size_t)r * TN + k);
+        return vf::FanEntry{w[0], w[1]};
+      };
+      auto vxy = [&](int sl) { return sxy[sl]; };
+      auto vuva = [&](int sl, vf::D2& u, vf::D2& v, vf::D2& a) {
+        u = suva[sl].u; v = suva[sl].v; a = suva[sl].a;
+      };
+      auto mat = [&](unsigned e, double& em, double& et, double& rh) {
+        em = emod[e]; et = eta[e]; rh = rho[e];
+      };
+      double res[2];
+      vf::fan_walk_node<true, true>(k, ringf, vxy, vuva, mat, fc, J, res);
+      F[2 * (i0 + k)] = res[0];
+      F[2 * (i0 + k) + 1] = res[1];
+    }
+  }
+  delete[] sxy;
+  delete[] suva;
   for (int i = 0; i < nn; ++i) {
     bool touch = n2f_ptr[i + 1] > n2f_ptr[i] || bc[2 * i] || bc[2 * i + 1];
     if (!touch) continue;

@@ -1,0 +1,1017 @@
+// Residual + Jacobian assembly kernels and their C-ABI entry points (vf_assemble,
+// vf_assemble_mix, vf_set_fan_tables, vf_pressure_control_blocks, vf_newmark_residual).
+// See DESIGN.md section 5 for the roofline of each kernel.
+#include "engine_internal.h"
+#include "dev_util.cuh"
+#include "fan_assembly.cuh"
+
+namespace vf {
+
+template <int D, bool JAC, bool RES>
+__global__ void asm_tile_kernel(EngineDev E, int member, double dt, int is_static, JacMix mix,
+                                const int* __restrict__ tile_start) {
+  extern __shared__ double tile[];
+  double* mb = E.members + (size_t)member * E.L.stride;
+  const Layout& L = E.L;
+  const int i0 = tile_start[blockIdx.x], i1 = tile_start[blockIdx.x + 1];
+  const size_t base = (size_t)D * D * E.mesh.brptr[i0];
+  const int nvals = int((size_t)D * D * E.mesh.brptr[i1] - base);
+  const int i = i0 + threadIdx.x;
+  if (i < i1) {
+    PropView pv = member_props<D>(E, mb);
+    StateView sv;
+    sv.u1 = mb + L.off[VF_U1];
+    sv.u0 = is_static ? sv.u1 : mb + L.off[VF_U0];
+    sv.v0 = mb + L.off[VF_V0];
+    sv.a0 = mb + L.off[VF_A0];
+    sv.p1 = mb + L.off[VF_P1];
+    sv.dt = dt;
+    sv.is_static = is_static;
+  sv.mix = mix;
+    sv.mix = mix;
+    double res[D];
+    double* rowblk = JAC ? tile + ((size_t)D * D * E.mesh.brptr[i] - base) : nullptr;
+    assemble_node<D, JAC, RES>(i, E.mesh, pv, sv, rowblk, res);
+    if (RES) {
+      double* F = mb + L.off[VF_F];
+#pragma unroll
+      for (int c = 0; c < D; ++c) F[D * i + c] = res[c];
+    }
+  }
+  if (JAC) {
+    __syncthreads();
+    double* Jg = mb + L.off[VF_J] + base;
+    if (D == 2) {
+      // base and nvals are multiples of 4 doubles: 16-byte vector stores, fully coalesced
+      double2* dst = reinterpret_cast<double2*>(Jg);
+      const double2* src = reinterpret_cast<const double2*>(tile);
+      for (int t = threadIdx.x; t < nvals / 2; t += blockDim.x) dst[t] = src[t];
+    } else {
+      for (int t = threadIdx.x; t < nvals; t += blockDim.x) Jg[t] = tile[t];
+    }
+  }
+}
+
+
+
+// Two-phase, element-centric tile assembly (triangles).  Replaces the thread-per-node gather
+// for 2D: every cell touching the tile is processed ONCE per CTA.
+//   phase 0  one 32-byte tile descriptor, then all index data of the tile (vertex quads,
+//            packed pair info, slices of brptr / n2e_ptr) is fetched with independent,
+//            coalesced loads -- a single dependent round trip instead of the chain
+//            tile_start -> te_ptr -> te_elem -> cells -> nodal data
+//   phase 1  thread per cell: 16-byte nodal gathers, geometry + material + cell residual
+//            -> one 144-byte record in shared memory
+//   phase 2  thread per scalar row (or per node) of the tile: walks the row's (node, cell)
+//            pairs in the fixed n2e order, reads the records, and accumulates its CSR row
+//            slice in shared memory (rows are private to their thread: no atomics,
+//            bit-reproducible, same summation order as assemble_node)
+//   phase 3  the tile's CSR slice and residual entries are streamed out with coalesced stores
+// The exterior-facet terms and Dirichlet rows touch O(sqrt(N)) boundary nodes only and are
+// applied afterwards by facet_bc_kernel, which keeps this kernel's register budget small.
+// Shared memory: [records: max_tile_elems x 18][CSR slice][F: 2 x nodes][pair info][brptr][n2e_ptr].
+
+template <bool JAC, bool RES, int ROW, int MAXT, int MINB, bool DIRECT = false>
+__global__ void __launch_bounds__(MAXT, MINB) asm_tile2_kernel(
+    EngineDev E, int member, NewmarkCoef nc_arg, int is_static, JacMix mix,
+    const int4* __restrict__ tile_desc,
+    const int4* __restrict__ te_quad, const unsigned* __restrict__ pair_info,
+    const int* __restrict__ tile_halo, int max_tile_elems, int tile_max_values,
+    int max_tile_pairs, int max_tile_nodes, int max_tile_verts, int pf_dist, int dbg_skip) {
+  constexpr int D = 2;
+  constexpr int kThreads = MAXT;  // always launched with exactly MAXT threads: loop strides
+                                  // and trip counts are compile-time constants
+  extern __shared__ double smem[];
+  double* recs = smem;
+  // region A: the CSR slice (phases 2-3) aliases the nodal staging area (phases 0-1)
+  double* tileJ = recs + (size_t)max_tile_elems * kRec2D;
+  D2* s_xy = reinterpret_cast<D2*>(tileJ);
+  NodeUVA* s_uva = reinterpret_cast<NodeUVA*>(s_xy + max_tile_verts);
+  // DIRECT: phase 2 stores its rows straight to HBM, the region only holds the staging area
+  const size_t region_a = DIRECT ? (size_t)8 * max_tile_verts
+                                 : max((size_t)tile_max_values, (size_t)8 * max_tile_verts);
+  double* tileF = tileJ + region_a;
+  unsigned* s_pair = reinterpret_cast<unsigned*>(tileF + D * max_tile_nodes);
+  int* s_brptr = reinterpret_cast<int*>(s_pair + max_tile_pairs);
+  int* s_n2e = s_brptr + max_tile_nodes + 1;
+  double* mb = E.members + (size_t)member * E.L.stride;
+  const Layout& L = E.L;
+  const MeshView& m = E.mesh;
+
+#ifdef VF_PHASE_PROF  // -DVF_PHASE_PROF + VF_DEBUG_SKIP=32: per-phase cycle counts into info[8..15]
+  const bool prof = (dbg_skip & 32) && threadIdx.x == 0;
+  long long tk0 = prof ? clock64() : 0, tk1 = 0, tk2 = 0, tk3 = 0, ta = 0, tb = 0, tc = 0;
+#define VF_PROBE(x) x
+#else
+#define VF_PROBE(x)
+#endif
+  // ---- phase 0: descriptor, then every load of the tile in one dependent round ---------------
+  const int4 d0 = tile_desc[3 * blockIdx.x], d1 = tile_desc[3 * blockIdx.x + 1];
+  const int i0 = d0.x, te0 = d0.y, pr0 = d0.z, bbase = d0.w;
+  const int h0 = d1.x, nT = d1.y & 0xffff, nH = (int)((unsigned)d1.y >> 16);
+  const int nte = d1.z & 0xffff, npr = (int)((unsigned)d1.z >> 16);
+  const int nV = nT + nH;
+  const size_t base = (size_t)D * D * bbase;
+  const int nvals = D * D * d1.w;
+  const PropView pv = member_props<D>(E, mb);
+  const double* u1 = mb + L.off[VF_U1];
+  const double* u0 = is_static ? u1 : mb + L.off[VF_U0];
+  const double* v0 = mb + L.off[VF_V0];
+  const double* a0 = mb + L.off[VF_A0];
+
+  VF_PROBE(if (prof) ta = clock64() + (i0 & 0);)
+  // this thread's first cell (volatile load: issued here, not sunk below the barrier)
+  int4 quad = make_int4(0, 0, 0, 0);
+  const bool have = (int)threadIdx.x < nte;
+  if (have) quad = ldg_nc_v4(te_quad + te0 + threadIdx.x);
+  // index slices: asynchronous global->shared copies, no registers, waited for at the barrier
+  for (int t = threadIdx.x; t < npr; t += kThreads) cp_async4(s_pair + t, pair_info + pr0 + t);
+  for (int t = threadIdx.x; t <= nT; t += kThreads) {
+    cp_async4(s_brptr + t, m.brptr + i0 + t);
+    cp_async4(s_n2e + t, m.n2e_ptr + i0 + t);
+  }
+  // descriptor of the tile `pf_dist` CTAs ahead: its inputs are pulled into L2 by this CTA's
+  // idle threads during phase 2, so that the later CTA's three dependent round trips hit L2
+  __shared__ int s_far[12];
+  const int far = blockIdx.x + pf_dist;
+  const bool pf = pf_dist > 0 && far < (int)gridDim.x;
+  if (pf && threadIdx.x < 12)
+    cp_async4(s_far + threadIdx.x, reinterpret_cast<const int*>(tile_desc) + 12 * far + threadIdx.x);
+  cp_async_commit();
+  // Lame / Newmark coefficients: a handful of fp64 divisions, done once per CTA
+  __shared__ LameFac s_lf;
+  if (threadIdx.x == kThreads - 1) s_lf = lame_fac(pv.scal[SC_NU]);
+  // stage the tile's vertices -- its own contiguous range, then the halo vertices of its
+  // cells -- with 16-byte loads; v_nmk / a_nmk are evaluated once per vertex here instead of
+  // once per (cell, vertex) in phase 1, and phase 1 reads shared memory only
+  for (int t = threadIdx.x; t < nV; t += kThreads) {
+    const int vtx = t < nT ? i0 + t : tile_halo[h0 + t - nT];
+    // all global loads first, then the shared-memory stores: a store in between would order
+    // the (generic-pointer) loads behind it and cost a second round trip
+    const D2 c2 = reinterpret_cast<const D2*>(m.xy)[vtx];
+    NodeUVA s3;
+    if (RES) s3 = gather_node_uva(nc_arg, is_static != 0, vtx, u1, u0, v0, a0);
+    s_xy[t] = c2;
+    if (RES) s_uva[t] = s3;
+  }
+  VF_PROBE(if (prof) tb = clock64();)
+  // the quad has arrived by now: the cell's material data, also before the barrier
+  double emod_e = 0.0, eta_e = 0.0, rho_e = 0.0;
+  if (have) {
+    emod_e = ldg_nc_f64(pv.emod + quad.w);
+    eta_e = ldg_nc_f64(pv.eta + quad.w);
+    rho_e = ldg_nc_f64(pv.rho + quad.w);
+  }
+  cp_async_wait_all();
+  VF_PROBE(if (prof) tc = clock64() + (__double_as_longlong(emod_e) & 0);)
+  __syncthreads();
+  VF_PROBE(if (prof) tk1 = clock64();)
+
+  // ---- phase 1: one record per cell, from shared memory ----------------------------------------
+  {
+    const LameFac lf = s_lf;
+    const Damping dp = prop_damping(pv);
+    for (int q = threadIdx.x; q < nte && !(dbg_skip & 1); q += kThreads) {
+      if (q != (int)threadIdx.x) {
+        quad = te_quad[te0 + q];
+        emod_e = pv.emod[quad.w];
+        eta_e = pv.eta[quad.w];
+        rho_e = pv.rho[quad.w];
+      }
+      const int nd[3] = {quad.x, quad.y, quad.z};  // local slots in the staged vertex list
+      double x[3][2];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const D2 c2 = s_xy[nd[a]];
+        x[a][0] = c2.x;
+        x[a][1] = c2.y;
+      }
+      tri_record_t(
+          x, emod_e, lf, eta_e, rho_e, dp, mix, RES,
+          [&](int a) { return s_uva[nd[a]]; }, recs + (size_t)q * kRec2D);
+    }
+  }
+  __syncthreads();
+  VF_PROBE(if (prof) tk2 = clock64();)
+
+  // ---- phase 2 ---------------------------------------------------------------------------------
+  if (dbg_skip & 2) {
+    // measurement aid (VF_DEBUG_SKIP): phase skipped
+  } else if (ROW == 2) {
+    // one thread per scalar row; the row's cells are visited counter-clockwise around the
+    // vertex (tables.order_fans_2d), so every off-diagonal block is the sum of two
+    // CONSECUTIVE cells: it is completed in registers and stored once -- no zero-fill and no
+    // read-modify-write of the shared-memory slice
+    for (int r = threadIdx.x; r < D * nT; r += kThreads) {
+      const int n = r >> 1, comp = r & 1;
+      const int b0 = s_brptr[n], deg = s_brptr[n + 1] - b0;
+      double* row = (DIRECT ? mb + L.off[VF_J] + base : tileJ) + D * D * (b0 - bbase) +
+                    comp * D * deg;
+      const int qb = s_n2e[n] - pr0, qe = s_n2e[n + 1] - pr0;
+      double racc = 0.0;
+      if (qe > qb) {
+        // first cell of the fan (peeled): nothing to complete yet
+        unsigned info = s_pair[qb];
+        const double* rec = recs + (size_t)(info & 0xfffu) * kRec2D;
+        int a = (info >> 12) & 3;
+        D2 diag = D2{0.0, 0.0}, carry = D2{0.0, 0.0}, first = D2{0.0, 0.0};
+        int slot_first = 0, slot_carry = 0;
+        if (JAC) {
+          D2 wn;
+          tri_row_fan(rec, a, comp, diag, wn, carry);
+          first = wn;
+          slot_first = (info >> 20) & 63;
+          slot_carry = (info >> 26) & 63;
+        }
+        if (RES) racc = rec[9 + 2 * a + comp];
+        for (int q = qb + 1; q < qe; ++q) {
+          info = s_pair[q];
+          rec = recs + (size_t)(info & 0xfffu) * kRec2D;
+          a = (info >> 12) & 3;
+          if (JAC) {
+            D2 ws, wn, wp;
+            tri_row_fan(rec, a, comp, ws, wn, wp);
+            diag.x += ws.x;
+            diag.y += ws.y;
+            *reinterpret_cast<D2*>(row + D * ((info >> 20) & 63)) =
+                D2{carry.x + wn.x, carry.y + wn.y};
+            carry = wp;
+            slot_carry = (info >> 26) & 63;
+          }
+          if (RES) racc += rec[9 + 2 * a + comp];
+        }
+        if (JAC) {
+          if (slot_carry == slot_first) {  // closed fan: the last cell meets the first
+            *reinterpret_cast<D2*>(row + D * slot_first) = D2{first.x + carry.x, first.y + carry.y};
+          } else {
+            *reinterpret_cast<D2*>(row + D * slot_first) = first;
+            *reinterpret_cast<D2*>(row + D * slot_carry) = carry;
+          }
+          *reinterpret_cast<D2*>(row + D * ((info >> 14) & 63)) = diag;
+        }
+      }
+      if (RES) tileF[r] = racc;
+    }
+    if (pf) {
+      // threads without a row (or all, when every thread has one) share the far tile's lines
+      const int idle0 = ((D * nT + 31) / 32) * 32;
+      const bool some_idle = idle0 + 32 <= (int)kThreads;
+      const int k = some_idle ? (int)threadIdx.x - idle0 : (int)threadIdx.x;
+      const int nk = some_idle ? (int)kThreads - idle0 : (int)kThreads;
+      if (k >= 0) {
+        const int f_i0 = s_far[0], f_te0 = s_far[1], f_pr0 = s_far[2], f_h0 = s_far[4];
+        const int f_nT = s_far[5] & 0xffff, f_nH = (int)((unsigned)s_far[5] >> 16);
+        const int f_nte = s_far[6] & 0xffff, f_npr = (int)((unsigned)s_far[6] >> 16);
+        const int f_e0 = s_far[8], f_en = s_far[9];
+        auto pull = [&](const void* p, int nbytes) {
+          const char* c = reinterpret_cast<const char*>(p);
+          for (int off = k * 128; off < nbytes; off += nk * 128) prefetch_l2(c + off);
+        };
+        pull(te_quad + f_te0, 16 * f_nte);
+        pull(pair_info + f_pr0, 4 * f_npr);
+        pull(tile_halo + f_h0, 4 * f_nH);
+        pull(m.brptr + f_i0, 4 * (f_nT + 1));
+        pull(m.n2e_ptr + f_i0, 4 * (f_nT + 1));
+        pull(m.xy + D * f_i0, 16 * f_nT);
+        if (RES) {
+          pull(u1 + D * f_i0, 16 * f_nT);
+          if (!is_static) {
+            pull(u0 + D * f_i0, 16 * f_nT);
+            pull(v0 + D * f_i0, 16 * f_nT);
+            pull(a0 + D * f_i0, 16 * f_nT);
+          }
+        }
+        if (!(dbg_skip & 64)) {
+          // nodal data of the far tile's halo vertices (gathered: one line per vertex and array)
+          for (int h = k; h < f_nH; h += nk) {
+            const int v = tile_halo[f_h0 + h];
+            prefetch_l2(m.xy + D * v);
+            if (RES) {
+              prefetch_l2(u1 + D * v);
+              if (!is_static) {
+                prefetch_l2(u0 + D * v);
+                prefetch_l2(v0 + D * v);
+                prefetch_l2(a0 + D * v);
+              }
+            }
+          }
+        }
+        pull(pv.emod + f_e0, 8 * f_en);
+        pull(pv.eta + f_e0, 8 * f_en);
+        pull(pv.rho + f_e0, 8 * f_en);
+      }
+    }
+  } else if (ROW == 1) {
+    // one thread per scalar row, read-modify-write accumulation (any cell order)
+    for (int r = threadIdx.x; r < D * nT; r += kThreads) {
+      const int n = r >> 1, comp = r & 1;
+      const int b0 = s_brptr[n], deg = s_brptr[n + 1] - b0;
+      double* row = tileJ + D * D * (b0 - bbase) + comp * D * deg;
+      if (JAC) {
+        const D2 z = D2{0.0, 0.0};
+        for (int t = 0; t < deg; ++t) reinterpret_cast<D2*>(row)[t] = z;
+      }
+      double racc = 0.0;
+      const int qe = s_n2e[n + 1] - pr0;
+      for (int q = s_n2e[n] - pr0; q < qe; ++q) {
+        const unsigned info = s_pair[q];
+        const double* rec = recs + (size_t)(info & 0xfffu) * kRec2D;
+        const int a = (info >> 12) & 3;
+        if (JAC) {
+          D2 wv[3];
+          tri_row_fan(rec, a, comp, wv[0], wv[1], wv[2]);  // slots are (self, next, prev)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const int slot = (info >> (14 + 6 * c)) & 63;
+            D2* dst = reinterpret_cast<D2*>(row + D * slot);
+            D2 cur = *dst;
+            cur.x += wv[c].x;
+            cur.y += wv[c].y;
+            *dst = cur;
+          }
+        }
+        if (RES) racc += rec[9 + 2 * a + comp];
+      }
+      if (RES) tileF[r] = racc;
+    }
+  } else {
+    // one thread per node (both scalar rows of its block row)
+    for (int n = threadIdx.x; n < nT; n += kThreads) {
+      const int b0 = s_brptr[n], deg = s_brptr[n + 1] - b0;
+      double* row0 = tileJ + D * D * (b0 - bbase);
+      double* row1 = row0 + D * deg;
+      if (JAC) {
+        const D2 z = D2{0.0, 0.0};
+        for (int t = 0; t < D * deg; ++t) reinterpret_cast<D2*>(row0)[t] = z;
+      }
+      double r0 = 0.0, r1 = 0.0;
+      const int qe = s_n2e[n + 1] - pr0;
+      for (int q = s_n2e[n] - pr0; q < qe; ++q) {
+        const unsigned info = s_pair[q];
+        const double* rec = recs + (size_t)(info & 0xfffu) * kRec2D;
+        const int a = (info >> 12) & 3;
+        if (JAC) {
+#pragma unroll
+          for (int sft = 0; sft < 3; ++sft) {
+            const int slot = (info >> (14 + 6 * sft)) & 63;  // slots are (self, next, prev)
+            const int c = (a + sft) % 3;
+            double b[2][2];
+            tri_block(rec, a, c, b);
+            D2* p0 = reinterpret_cast<D2*>(row0 + D * slot);
+            D2* p1 = reinterpret_cast<D2*>(row1 + D * slot);
+            D2 c0 = *p0, c1 = *p1;
+            c0.x += b[0][0];
+            c0.y += b[0][1];
+            c1.x += b[1][0];
+            c1.y += b[1][1];
+            *p0 = c0;
+            *p1 = c1;
+          }
+        }
+        if (RES) {
+          r0 += rec[9 + 2 * a];
+          r1 += rec[10 + 2 * a];
+        }
+      }
+      if (RES) {
+        tileF[D * n] = r0;
+        tileF[D * n + 1] = r1;
+      }
+    }
+  }
+  __syncthreads();
+  VF_PROBE(if (prof) tk3 = clock64();)
+
+  // ---- phase 3: coalesced write-out ---------------------------------------------------------------
+  if (dbg_skip & 4) return;
+  if (JAC && !DIRECT) {
+    double2* dst = reinterpret_cast<double2*>(mb + L.off[VF_J] + base);
+    const double2* src = reinterpret_cast<const double2*>(tileJ);
+    for (int t = threadIdx.x; t < nvals / 2; t += kThreads) __stcs(dst + t, src[t]);
+  }
+  if (RES) {
+    double* F = mb + L.off[VF_F] + (size_t)D * i0;
+    for (int t = threadIdx.x; t < D * nT; t += kThreads) F[t] = tileF[t];
+  }
+#ifdef VF_PHASE_PROF
+  if (prof) {
+    const long long tk4 = clock64();
+    double* info = mb + L.off[VF_INFO];
+    atomicAdd(info + 8, (double)(tk1 - tk0));
+    atomicAdd(info + 9, (double)(tk2 - tk1));
+    atomicAdd(info + 10, (double)(tk3 - tk2));
+    atomicAdd(info + 11, (double)(tk4 - tk3));
+    atomicAdd(info + 12, 1.0);
+    atomicAdd(info + 13, (double)(ta - tk0));
+    atomicAdd(info + 14, (double)(tb - ta));
+    atomicAdd(info + 15, (double)(tc - tb));
+  }
+#endif
+#undef VF_PROBE
+}
+
+
+
+// ---- node-centric fan assembly (triangles) --------------------------------------------------
+// One CTA per tile of TN consecutive nodes, one thread per node (fan_assembly.cuh).
+//   stage  thread 0 arms an mbarrier and issues ONE bulk asynchronous copy (TMA engine,
+//          cp.async.bulk) of the tile's ring table -- the largest index stream, contiguous by
+//          construction -- while all threads stage the tile's own and halo vertices
+//          (coordinates, u1, v_nmk, a_nmk; 16-byte loads, SoA planes in shared memory);
+//   walk   every thread walks the fan of its node out of shared memory and stores the finished
+//          16-byte row entries straight to the CSR array, then its residual pair;
+//   tail   the inputs of the tile pf_dist CTAs ahead are pulled into L2.
+// There is one CTA-wide barrier (after staging); no per-cell records, no second phase.
+
+template <bool JAC, bool RES, int TN, int MINB>
+__global__ void __launch_bounds__(TN, MINB) asm_fan_kernel(
+    EngineDev E, int member, NewmarkCoef nc_arg, int is_static, JacMix mix, FanTablesDev T,
+    int rows_s, int pf_dist) {
+  extern __shared__ __align__(128) unsigned char fan_smem[];
+  uint2* s_ring = reinterpret_cast<uint2*>(fan_smem);
+  D2* s_xy = reinterpret_cast<D2*>(s_ring + (size_t)rows_s * TN);
+  D2* s_u = s_xy + T.max_verts;
+  D2* s_v = s_u + T.max_verts;
+  D2* s_a = s_v + T.max_verts;
+  __shared__ __align__(8) unsigned long long s_bar;
+  __shared__ FanCoef s_fc;
+  const int tid = threadIdx.x;
+  double* mb = E.members + (size_t)member * E.L.stride;
+  const Layout& L = E.L;
+  const MeshView& m = E.mesh;
+
+  const int4 d0 = __ldg(T.desc + 2 * blockIdx.x), d1 = __ldg(T.desc + 2 * blockIdx.x + 1);
+  const int i0 = d0.x, nT = d0.y & 0xffff, nH = (int)((unsigned)d0.y >> 16);
+  const int h0 = d0.z, ring0 = d0.w, rows = d1.x;
+  const int nV = nT + nH;
+  const uint2* ring_t = T.ring + ring0;
+  if (tid == 0) {
+    mbar_init(&s_bar, 1);
+    const unsigned bytes = (unsigned)min(rows, rows_s) * TN * (unsigned)sizeof(uint2);
+    mbar_expect_tx(&s_bar, bytes);
+    bulk_g2s(s_ring, ring_t, bytes, &s_bar);
+  }
+  const PropView pv = member_props<2>(E, mb);
+  if (tid == TN - 1) s_fc = fan_coef(lame_fac(pv.scal[SC_NU]), prop_damping(pv), mix);
+  const double* u1 = mb + L.off[VF_U1];
+  const double* u0 = is_static ? u1 : mb + L.off[VF_U0];
+  const double* v0 = mb + L.off[VF_V0];
+  const double* a0 = mb + L.off[VF_A0];
+
+  // ---- stage own + halo vertices: ids first, then every global load, then the stores --------
+  constexpr int KV = 3;
+  for (int base = 0; base < nV; base += KV * TN) {
+    int vt[KV];
+#pragma unroll
+    for (int k = 0; k < KV; ++k) {
+      const int t = base + k * TN + tid;
+      vt[k] = t < nT ? i0 + t : (t < nV ? __ldg(T.halo + h0 + t - nT) : -1);
+    }
+    D2 c2[KV];
+    NodeUVA s3[KV];
+#pragma unroll
+    for (int k = 0; k < KV; ++k) {
+      if (vt[k] >= 0) {
+        c2[k] = reinterpret_cast<const D2*>(m.xy)[vt[k]];
+        if (RES) s3[k] = gather_node_uva(nc_arg, is_static != 0, vt[k], u1, u0, v0, a0);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < KV; ++k) {
+      const int t = base + k * TN + tid;
+      if (vt[k] >= 0) {
+        s_xy[t] = c2[k];
+        if (RES) {
+          s_u[t] = s3[k].u;
+          s_v[t] = s3[k].v;
+          s_a[t] = s3[k].a;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  mbar_wait(&s_bar, 0);
+
+  // ---- walk ------------------------------------------------------------------------------------
+  if (tid < nT) {
+    const FanCoef fc = s_fc;
+    auto ring = [&](int r) {
+      const uint2 w = r < rows_s ? s_ring[r * TN + tid] : __ldg(ring_t + (size_t)r * TN + tid);
+      return FanEntry{w.x, w.y};
+    };
+    auto vtx_xy = [&](int s) { return s_xy[s]; };
+    auto vtx_uva = [&](int s, D2& u, D2& v, D2& a) {
+      u = s_u[s];
+      v = s_v[s];
+      a = s_a[s];
+    };
+    auto mat = [&](unsigned e, double& emod, double& eta, double& rho) {
+      emod = __ldg(pv.emod + e);
+      eta = __ldg(pv.eta + e);
+      rho = __ldg(pv.rho + e);
+    };
+    double res[2];
+    fan_walk_node<JAC, RES>(tid, ring, vtx_xy, vtx_uva, mat, fc, mb + L.off[VF_J], res);
+    if (RES) reinterpret_cast<D2*>(mb + L.off[VF_F])[i0 + tid] = D2{res[0], res[1]};
+  }
+
+  // ---- tail: pull the inputs of a later tile into L2 ---------------------------------------------
+  const int far = blockIdx.x + pf_dist;
+  if (pf_dist > 0 && far < (int)gridDim.x) {
+    const int4 f0 = __ldg(T.desc + 2 * far), f1 = __ldg(T.desc + 2 * far + 1);
+    const int f_i0 = f0.x, f_nT = f0.y & 0xffff, f_nH = (int)((unsigned)f0.y >> 16);
+    auto pull = [&](const void* p, int nbytes) {
+      const char* c = reinterpret_cast<const char*>(p);
+      for (int off = tid * 128; off < nbytes; off += TN * 128) prefetch_l2(c + off);
+    };
+    pull(T.ring + f0.w, f1.x * TN * (int)sizeof(uint2));
+    pull(m.xy + 2 * f_i0, 16 * f_nT);
+    if (RES) {
+      pull(u1 + 2 * f_i0, 16 * f_nT);
+      if (!is_static) {
+        pull(u0 + 2 * f_i0, 16 * f_nT);
+        pull(v0 + 2 * f_i0, 16 * f_nT);
+        pull(a0 + 2 * f_i0, 16 * f_nT);
+      }
+    }
+    pull(pv.emod + f1.y, 8 * f1.z);
+    pull(pv.eta + f1.y, 8 * f1.z);
+    pull(pv.rho + f1.y, 8 * f1.z);
+    for (int h = tid; h < f_nH; h += TN) {
+      const int v = __ldg(T.halo + f0.z + h);
+      prefetch_l2(m.xy + 2 * v);
+      if (RES) {
+        prefetch_l2(u1 + 2 * v);
+        if (!is_static) {
+          prefetch_l2(u0 + 2 * v);
+          prefetch_l2(v0 + 2 * v);
+          prefetch_l2(a0 + 2 * v);
+        }
+      }
+    }
+  }
+}
+
+template <int D, bool JAC, bool RES>
+__global__ void facet_bc_kernel(EngineDev E, int member, double dt, int is_static, JacMix mix,
+                                const int* __restrict__ touch_nodes, int n_touch) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_touch) return;
+  const int i = touch_nodes[t];
+  double* mb = E.members + (size_t)member * E.L.stride;
+  const Layout& L = E.L;
+  const PropView pv = member_props<D>(E, mb);
+  StateView sv;
+  sv.u1 = mb + L.off[VF_U1];
+  sv.u0 = is_static ? sv.u1 : mb + L.off[VF_U0];
+  sv.v0 = mb + L.off[VF_V0];
+  sv.a0 = mb + L.off[VF_A0];
+  sv.p1 = mb + L.off[VF_P1];
+  sv.dt = dt;
+  sv.is_static = is_static;
+  sv.mix = mix;
+  double* F = mb + L.off[VF_F];
+  double res[D];
+#pragma unroll
+  for (int c = 0; c < D; ++c) res[c] = RES ? F[D * i + c] : 0.0;
+  assemble_node_facets_bc<D, JAC, RES>(i, E.mesh, pv, sv,
+                                       mb + L.off[VF_J] + (size_t)D * D * E.mesh.brptr[i], res);
+  if (RES) {
+#pragma unroll
+    for (int c = 0; c < D; ++c) F[D * i + c] = res[c];
+  }
+}
+
+
+// partial[b][j] = sum over the block's chunk of V_j[i] w[i]; fixed-order reductions so the
+// result is bit-reproducible; a second kernel adds the partials in block order.
+
+// Thread-per-node gather writing the node's block row straight to the global CSR array (no
+// shared-memory slice).  Used for tetrahedra, where a block row is ~1 KB: staging it in shared
+// memory caps the resident threads at ~200 per SM, while here occupancy is bounded by
+// registers only.  Rows are private to their thread, so the accumulation is still
+// deterministic; the read-modify-write traffic stays in L1/L2.
+template <int D, bool JAC, bool RES>
+__global__ void __launch_bounds__(128, 3)
+asm_node_global_kernel(EngineDev E, int member, double dt, int is_static, JacMix mix) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= E.mesh.nn) return;
+  double* mb = E.members + (size_t)member * E.L.stride;
+  const Layout& L = E.L;
+  PropView pv = member_props<D>(E, mb);
+  StateView sv;
+  sv.u1 = mb + L.off[VF_U1];
+  sv.u0 = is_static ? sv.u1 : mb + L.off[VF_U0];
+  sv.v0 = mb + L.off[VF_V0];
+  sv.a0 = mb + L.off[VF_A0];
+  sv.p1 = mb + L.off[VF_P1];
+  sv.dt = dt;
+  sv.is_static = is_static;
+  sv.mix = mix;
+  double res[D];
+  assemble_node<D, JAC, RES>(i, E.mesh, pv, sv,
+                             JAC ? mb + L.off[VF_J] + (size_t)D * D * E.mesh.brptr[i] : nullptr, res);
+  if (RES) {
+    double* F = mb + L.off[VF_F];
+#pragma unroll
+    for (int c = 0; c < D; ++c) F[D * i + c] = res[c];
+  }
+}
+
+
+// d F_u / d p1 (transient.py:423-435): thread per pressure facet.  res_a += mw (1 + delta_ab)
+// p_b cof(F) N for facet vertices a, b (assemble_node_facets_bc), so the (a, b) block is
+// mw (1 + delta_ab) cof(F) N.  Dirichlet rows are not touched (the reference applies none).
+template <int D>
+__global__ void pressure_control_kernel(EngineDev E, int member, double* __restrict__ out) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= E.mesh.nfp) return;
+  const MeshView& m = E.mesh;
+  const double* mb = E.members + (size_t)member * E.L.stride;
+  const double* u1 = mb + E.L.off[VF_U1];
+  const int e = m.pf_cell[f], o = m.pf_opp[f];
+  int nd[D + 1];
+  double x[D + 1][D];
+  load_cell<D>(m, e, nd, x);
+  CellGeo<D> g;
+  p1_geometry(x, g);
+  double N[D], meas;
+  facet_geometry<D>(g, o, N, meas);
+  double U[D + 1][D], gu[D][D];
+  gather_vec<D>(u1, nd, U);
+  grad_u<D>(g, U, gu);
+  const double mw = meas / double(D * (D + 1));
+  double c[D];
+  cof_normal(gu, N, c);
+  double* dst = out + (size_t)f * D * D * D;
+  int ia = 0;
+  for (int a = 0; a <= D; ++a) {
+    if (a == o) continue;
+    int ib = 0;
+    for (int b = 0; b <= D; ++b) {
+      if (b == o) continue;
+      const double w = mw * (a == b ? 2.0 : 1.0);
+      for (int k = 0; k < D; ++k) dst[(ia * D + ib) * D + k] = w * c[k];
+      ++ib;
+    }
+    ++ia;
+  }
+}
+
+// Nodal Newmark residuals F_v = v1 - v_nmk(u1, u0, v0, a0), F_a = a1 - a_nmk(...)
+// (transient.py:374-377): streaming, 6 reads + 2 writes per DOF.
+__global__ void newmark_res_kernel(EngineDev E, int member, NewmarkCoef nc, double* fv,
+                                   double* fa) {
+  const double* mb = E.members + (size_t)member * E.L.stride;
+  const double* u1 = mb + E.L.off[VF_U1];
+  const double* v1 = mb + E.L.off[VF_V1];
+  const double* a1 = mb + E.L.off[VF_A1];
+  const double* u0 = mb + E.L.off[VF_U0];
+  const double* v0 = mb + E.L.off[VF_V0];
+  const double* a0 = mb + E.L.off[VF_A0];
+  const size_t n = (size_t)E.mesh.dim * E.mesh.nn;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const double u = u1[i], p0 = u0[i], pv = v0[i], pa = a0[i];
+    fv[i] = v1[i] - newmark_v(nc, u, p0, pv, pa);
+    fa[i] = a1[i] - newmark_a(nc, u, p0, pv, pa);
+  }
+}
+
+
+}  // namespace vf
+
+using namespace vf;
+
+namespace {
+
+
+// dynamic shared memory of asm_tile2_kernel: records, region A (CSR slice aliasing the nodal
+// staging: coordinates + u/v/a = 64 bytes per own or halo vertex), F, index slices
+size_t tile2_smem_bytes(const vf_problem_desc& d, bool direct = false) {
+  const size_t idx_words = (size_t)d.max_tile_pairs + 2 * ((size_t)d.tile_threads + 1);
+  const size_t region_a = direct ? (size_t)8 * d.max_tile_verts
+                                 : std::max((size_t)d.tile_max_values, (size_t)8 * d.max_tile_verts);
+  return sizeof(double) * ((size_t)d.max_tile_elems * kRec2D + region_a +
+                           2 * (size_t)d.tile_threads + ((idx_words + 3) / 4) * 2);
+}
+
+
+}  // namespace
+
+int vf::assembly_configure(vf_engine* e, const vf_problem_desc& d, bool two_phase) {
+  (void)e;
+  // opt in to large dynamic shared memory for the tile kernel
+  const int smem = d.tile_max_values * (int)sizeof(double);
+  if (d.dim == 2) {
+    VF_CUDA(cudaFuncSetAttribute(asm_tile_kernel<2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    VF_CUDA(cudaFuncSetAttribute(asm_tile_kernel<2, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  } else {
+    VF_CUDA(cudaFuncSetAttribute(asm_tile_kernel<3, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    VF_CUDA(cudaFuncSetAttribute(asm_tile_kernel<3, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  }
+  if (two_phase) {
+    const int smem2 = (int)tile2_smem_bytes(d);
+    if (smem2 > 227 * 1024) {
+      return fail("two-phase tile exceeds the 227 KB shared memory of an SM");
+    }
+#define VF_SMEM2(K) VF_CUDA(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2))
+#define VF_SMEM2_ALL(J_, R_, ROW_)                          \
+  VF_SMEM2((asm_tile2_kernel<J_, R_, ROW_, 128, 8>));       \
+  VF_SMEM2((asm_tile2_kernel<J_, R_, ROW_, 192, 5>));       \
+  VF_SMEM2((asm_tile2_kernel<J_, R_, ROW_, 256, 4>));       \
+  VF_SMEM2((asm_tile2_kernel<J_, R_, ROW_, 320, 3>))
+    VF_SMEM2_ALL(true, true, 0);
+    VF_SMEM2_ALL(true, true, 1);
+    VF_SMEM2_ALL(true, true, 2);
+    VF_SMEM2_ALL(true, false, 0);
+    VF_SMEM2_ALL(true, false, 1);
+    VF_SMEM2_ALL(true, false, 2);
+    VF_SMEM2_ALL(false, true, 1);
+#undef VF_SMEM2_ALL
+#undef VF_SMEM2
+  }
+  return 0;
+}
+
+extern "C" {
+
+int vf_set_fan_tables(vf_engine* e, int tile_nodes, int ntiles, const int32_t* desc_host,
+                      const uint32_t* ring_host, size_t n_ring, const int32_t* halo_host,
+                      size_t n_halo, int max_verts, int max_rows, void* stream) {
+  if (!e) return fail("null engine");
+  if (e->desc.dim != 2 || !e->fan_ok) return fail("fan tables need triangles with ordered fans");
+  if (tile_nodes != 64 && tile_nodes != 128 && tile_nodes != 256)
+    return fail("fan tile_nodes must be 64, 128 or 256");
+  if (ntiles <= 0 || !desc_host || !ring_host || !halo_host) return fail("missing fan tables");
+  if ((size_t)ntiles * tile_nodes < (size_t)e->desc.nn) return fail("fan tiles do not cover the mesh");
+  cudaStream_t st = as_stream(stream);
+  const size_t b_desc = align_up(sizeof(int32_t) * 8 * (size_t)ntiles, 256);
+  const size_t b_ring = align_up(sizeof(uint32_t) * 2 * n_ring, 256);
+  const size_t b_halo = align_up(sizeof(int32_t) * std::max<size_t>(n_halo, 1), 256);
+  if (e->fan_mem) {
+    cudaFree(e->fan_mem);
+    e->fan_mem = nullptr;
+    e->fan.ring = nullptr;
+  }
+  char* mem = nullptr;
+  VF_CUDA(cudaMalloc(&mem, b_desc + b_ring + b_halo));
+  e->fan_mem = mem;
+  VF_CUDA(cudaMemcpyAsync(mem, desc_host, sizeof(int32_t) * 8 * (size_t)ntiles,
+                          cudaMemcpyHostToDevice, st));
+  VF_CUDA(cudaMemcpyAsync(mem + b_desc, ring_host, sizeof(uint32_t) * 2 * n_ring,
+                          cudaMemcpyHostToDevice, st));
+  if (n_halo)
+    VF_CUDA(cudaMemcpyAsync(mem + b_desc + b_ring, halo_host, sizeof(int32_t) * n_halo,
+                            cudaMemcpyHostToDevice, st));
+  VF_CUDA(cudaStreamSynchronize(st));
+  e->fan.desc = reinterpret_cast<const int4*>(mem);
+  e->fan.ring = reinterpret_cast<const uint2*>(mem + b_desc);
+  e->fan.halo = reinterpret_cast<const int*>(mem + b_desc + b_ring);
+  e->fan.tile_nodes = tile_nodes;
+  e->fan.ntiles = ntiles;
+  e->fan.max_verts = max_verts;
+  e->fan.max_rows = max_rows;
+  return 0;
+}
+
+namespace {
+int assemble_impl(vf_engine* e, int member, int flags, double dt, int is_static, const JacMix& mix,
+                  void* stream);
+}
+
+int vf_assemble(vf_engine* e, int member, int flags, double dt, int is_static, void* stream) {
+  if (!e) return fail("null engine");
+  return assemble_impl(e, member, flags, dt, is_static,
+                       jac_mix_du1(newmark_coef(dt), is_static != 0), stream);
+}
+
+int vf_assemble_mix(vf_engine* e, int member, double dt, const double* coef4, int apply_bc,
+                    void* stream) {
+  if (!e) return fail("null engine");
+  if (!coef4) return fail("null coefficient array");
+  JacMix mix;
+  mix.k = coef4[0];
+  mix.c = coef4[1];
+  mix.m = coef4[2];
+  mix.p = coef4[3];
+  mix.bc = apply_bc ? 1 : 0;
+  return assemble_impl(e, member, 2, dt, 0, mix, stream);
+}
+
+namespace {
+// Node-centric fan kernel (triangles, ordered fans): the default 2D path once its tables are set.
+int launch_fan(vf_engine* e, int member, bool res, bool jac, double dt, int is_static,
+               const JacMix& mix, cudaStream_t st) {
+  const FanTablesDev& T = e->fan;
+  static const char* env_rows = getenv("VF_FAN_ROWS");
+  const int rows_cap = env_rows ? std::max(atoi(env_rows), 2) : 10;
+  const int rows_s = std::min(T.max_rows, rows_cap);
+  static const char* env_pf = getenv("VF_PF_DIST");
+  static const char* env_mb = getenv("VF_FAN_MINB");
+  const int minb_env = env_mb ? atoi(env_mb) : 0;
+  const NewmarkCoef nc = newmark_coef(dt);
+#define VF_FAN_GO(J_, R_, TN_, MB_)                                                               \
+  do {                                                                                            \
+    const size_t smem = sizeof(uint2) * (size_t)rows_s * TN_ +                                    \
+                        sizeof(D2) * (size_t)T.max_verts * ((R_) ? 4 : 1);                        \
+    if (smem > 227 * 1024) return fail("fan tile exceeds the 227 KB shared memory of an SM");     \
+    const int pf_dist = env_pf ? atoi(env_pf) : 148 * (MB_);                                      \
+    VF_CUDA(cudaFuncSetAttribute(asm_fan_kernel<J_, R_, TN_, MB_>,                                \
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
+    asm_fan_kernel<J_, R_, TN_, MB_><<<T.ntiles, TN_, smem, st>>>(e->dev, member, nc, is_static,  \
+                                                                   mix, T, rows_s, pf_dist);      \
+  } while (0)
+#define VF_FAN_BY_MODE(TN_, MB_)                                                                  \
+  do {                                                                                            \
+    if (jac && res) VF_FAN_GO(true, true, TN_, MB_);                                              \
+    else if (jac) VF_FAN_GO(true, false, TN_, MB_);                                               \
+    else VF_FAN_GO(false, true, TN_, MB_);                                                        \
+  } while (0)
+  if (T.tile_nodes == 64) VF_FAN_BY_MODE(64, 8);
+  else if (T.tile_nodes == 256) VF_FAN_BY_MODE(256, 2);
+  else if (minb_env == 3) VF_FAN_BY_MODE(128, 3);
+  else if (minb_env == 5) VF_FAN_BY_MODE(128, 5);
+  else VF_FAN_BY_MODE(128, 4);
+#undef VF_FAN_BY_MODE
+#undef VF_FAN_GO
+  e->launches += 1;
+  VF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_facet_bc(vf_engine* e, int member, bool res, bool jac, double dt, int is_static,
+                    const JacMix& mix, cudaStream_t st) {
+  if (e->n_touch <= 0) return 0;
+  const int fb = 128, fg = (e->n_touch + fb - 1) / fb;
+  if (jac && res)
+    facet_bc_kernel<2, true, true><<<fg, fb, 0, st>>>(e->dev, member, dt, is_static, mix, e->touch_dev, e->n_touch);
+  else if (jac)
+    facet_bc_kernel<2, true, false><<<fg, fb, 0, st>>>(e->dev, member, dt, is_static, mix, e->touch_dev, e->n_touch);
+  else
+    facet_bc_kernel<2, false, true><<<fg, fb, 0, st>>>(e->dev, member, dt, is_static, mix, e->touch_dev, e->n_touch);
+  e->launches += 1;
+  VF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int assemble_impl(vf_engine* e, int member, int flags, double dt, int is_static, const JacMix& mix,
+                  void* stream) {
+  if (member < 0 || member >= e->desc.n_members) return fail("member out of range");
+  const bool res = flags & 1, jac = flags & 2;
+  if (!res && !jac) return 0;
+  cudaStream_t st = as_stream(stream);
+  static const char* env_fan = getenv("VF_FAN");
+  if (e->fan.ring && !(env_fan && atoi(env_fan) == 0)) {
+    if (launch_fan(e, member, res, jac, dt, is_static, mix, st)) return 1;
+    return launch_facet_bc(e, member, res, jac, dt, is_static, mix, st);
+  }
+  const int grid = e->desc.ntiles, block = e->desc.tile_threads;
+  if (e->two_phase) {
+    const vf_problem_desc& d = e->desc;
+    const size_t smem2 = tile2_smem_bytes(d);
+#define VF_LAUNCH_ASM2(J_, R_, ROW_, MT_, MB_)                                                     \
+  asm_tile2_kernel<J_, R_, ROW_, MT_, MB_><<<grid, MT_, smem2, st>>>(                  \
+      e->dev, member, newmark_coef(dt), is_static, mix, e->tile_desc_dev, e->te_quad_dev,          \
+      e->pair_info_dev, e->tile_halo_dev, d.max_tile_elems, d.tile_max_values, d.max_tile_pairs,   \
+      d.tile_threads, d.max_tile_verts, pf_dist, dbg_skip)
+    const int dbg_skip = getenv("VF_DEBUG_SKIP") ? atoi(getenv("VF_DEBUG_SKIP")) : 0;
+    // L2 prefetch distance in tiles: one wave of resident CTAs (148 SMs x 3 CTAs; measured flat
+    // between one and two waves, worse below and far above: profiles/README.md)
+    const int pf_dist = getenv("VF_PF_DIST") ? atoi(getenv("VF_PF_DIST")) : 3 * 148;
+    int v_row = getenv("VF_TILE2_ROW") ? atoi(getenv("VF_TILE2_ROW")) : 2;
+    if (v_row == 2 && !e->fan_ok) v_row = 1;
+    // occupancy class by CTA size: small CTAs run many per SM so that their phases overlap
+    const int nt = d.tile2_threads;
+#define VF_ASM2_BY_SIZE(J_, R_, ROW_)                                                              \
+  do {                                                                                            \
+    if (nt <= 128) VF_LAUNCH_ASM2(J_, R_, ROW_, 128, 8);                                          \
+    else if (nt <= 192) VF_LAUNCH_ASM2(J_, R_, ROW_, 192, 5);                                     \
+    else if (nt <= 256) VF_LAUNCH_ASM2(J_, R_, ROW_, 256, 4);                                     \
+    else VF_LAUNCH_ASM2(J_, R_, ROW_, 320, 3);                                                    \
+  } while (0)
+#define VF_ASM2_BY_MODE(J_, R_)                                                                    \
+  do {                                                                                            \
+    if (v_row == 2) VF_ASM2_BY_SIZE(J_, R_, 2);                                                   \
+    else if (v_row == 1) VF_ASM2_BY_SIZE(J_, R_, 1);                                              \
+    else VF_ASM2_BY_SIZE(J_, R_, 0);                                                              \
+  } while (0)
+    // Default for the fan-ordered path: rows are stored straight to HBM from phase 2 (every
+    // 16-byte entry once; L2 merges the sectors), so no CSR slice is kept in shared memory and
+    // 4 CTAs of 256 threads fit per SM (measured 0.4015 -> 0.3751 ms with 80-node tiles;
+    // VF_TILE2_DIRECT=0 restores the staged write-out)
+    static const char* env_direct = getenv("VF_TILE2_DIRECT");
+    if (!(env_direct && atoi(env_direct) == 0) && jac && v_row == 2 && nt <= 320) {
+      const size_t smem_d = tile2_smem_bytes(d, true);
+#define VF_LAUNCH_ASM2D(R_, MT_, MB_)                                                              \
+  do {                                                                                            \
+    VF_CUDA(cudaFuncSetAttribute(asm_tile2_kernel<true, R_, 2, MT_, MB_, true>,                   \
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d));      \
+    asm_tile2_kernel<true, R_, 2, MT_, MB_, true><<<grid, MT_, smem_d, st>>>(                     \
+        e->dev, member, newmark_coef(dt), is_static, mix, e->tile_desc_dev, e->te_quad_dev,       \
+        e->pair_info_dev, e->tile_halo_dev, d.max_tile_elems, d.tile_max_values,                  \
+        d.max_tile_pairs, d.tile_threads, d.max_tile_verts, pf_dist, dbg_skip);                   \
+  } while (0)
+      if (nt <= 256) {
+        if (res) VF_LAUNCH_ASM2D(true, 256, 4); else VF_LAUNCH_ASM2D(false, 256, 4);
+      } else {
+        if (res) VF_LAUNCH_ASM2D(true, 320, 3); else VF_LAUNCH_ASM2D(false, 320, 3);
+      }
+#undef VF_LAUNCH_ASM2D
+    } else
+    if (jac && res) VF_ASM2_BY_MODE(true, true);
+    else if (jac) VF_ASM2_BY_MODE(true, false);
+    else VF_ASM2_BY_SIZE(false, true, 1);
+#undef VF_ASM2_BY_MODE
+#undef VF_ASM2_BY_SIZE
+#undef VF_LAUNCH_ASM2
+    e->launches += 1;
+    VF_CUDA(cudaGetLastError());
+    if (e->n_touch > 0) {
+      const int fb = 128, fg = (e->n_touch + fb - 1) / fb;
+      if (jac && res)
+        facet_bc_kernel<2, true, true><<<fg, fb, 0, st>>>(e->dev, member, dt, is_static, mix, e->touch_dev, e->n_touch);
+      else if (jac)
+        facet_bc_kernel<2, true, false><<<fg, fb, 0, st>>>(e->dev, member, dt, is_static, mix, e->touch_dev, e->n_touch);
+      else
+        facet_bc_kernel<2, false, true><<<fg, fb, 0, st>>>(e->dev, member, dt, is_static, mix, e->touch_dev, e->n_touch);
+      e->launches += 1;
+      VF_CUDA(cudaGetLastError());
+    }
+    return 0;
+  }
+  if (e->desc.dim == 3 && !(getenv("VF_TET_SMEM") && atoi(getenv("VF_TET_SMEM")))) {
+    const int nb = 128, ng = (e->desc.nn + nb - 1) / nb;
+    if (jac && res) asm_node_global_kernel<3, true, true><<<ng, nb, 0, st>>>(e->dev, member, dt, is_static, mix);
+    else if (jac) asm_node_global_kernel<3, true, false><<<ng, nb, 0, st>>>(e->dev, member, dt, is_static, mix);
+    else asm_node_global_kernel<3, false, true><<<ng, nb, 0, st>>>(e->dev, member, dt, is_static, mix);
+    e->launches += 1;
+    VF_CUDA(cudaGetLastError());
+    return 0;
+  }
+  const size_t smem = jac ? (size_t)e->desc.tile_max_values * sizeof(double) : 0;
+#define VF_LAUNCH_ASM(D)                                                                          \
+  if (jac && res)                                                                                 \
+    asm_tile_kernel<D, true, true><<<grid, block, smem, st>>>(e->dev, member, dt, is_static, mix, \
+                                                              e->tile_start_dev);                 \
+  else if (jac)                                                                                   \
+    asm_tile_kernel<D, true, false><<<grid, block, smem, st>>>(e->dev, member, dt, is_static, mix, \
+                                                               e->tile_start_dev);                \
+  else                                                                                            \
+    asm_tile_kernel<D, false, true><<<grid, block, 0, st>>>(e->dev, member, dt, is_static, mix, \
+                                                            e->tile_start_dev);
+  if (e->desc.dim == 2) {
+    VF_LAUNCH_ASM(2)
+  } else {
+    VF_LAUNCH_ASM(3)
+  }
+#undef VF_LAUNCH_ASM
+  e->launches += 1;
+  VF_CUDA(cudaGetLastError());
+  return 0;
+}
+}  // namespace
+
+int vf_pressure_control_blocks(vf_engine* e, int member, double* out_dev, int32_t* rows_host,
+                               int32_t* cols_host, void* stream) {
+  if (!e) return fail("null engine");
+  if (member < 0 || member >= e->desc.n_members) return fail("member out of range");
+  const int nfp = e->desc.nfp, d = e->desc.dim;
+  if (rows_host || cols_host) {
+    if (!rows_host || !cols_host) return fail("rows_host and cols_host go together");
+    if (e->pf_nodes.size() != (size_t)nfp * d) return fail("facet vertex table missing");
+    for (int f = 0; f < nfp; ++f)
+      for (int a = 0; a < d; ++a)
+        for (int b = 0; b < d; ++b) {
+          rows_host[((size_t)f * d + a) * d + b] = e->pf_nodes[(size_t)f * d + a];
+          cols_host[((size_t)f * d + a) * d + b] = e->pf_nodes[(size_t)f * d + b];
+        }
+  }
+  if (nfp == 0) return 0;
+  if (!out_dev) return fail("null output");
+  const int block = 128, grid = (nfp + block - 1) / block;
+  if (d == 2) pressure_control_kernel<2><<<grid, block, 0, as_stream(stream)>>>(e->dev, member, out_dev);
+  else pressure_control_kernel<3><<<grid, block, 0, as_stream(stream)>>>(e->dev, member, out_dev);
+  e->launches += 1;
+  VF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int vf_newmark_residual(vf_engine* e, int member, double dt, double* fv_dev, double* fa_dev,
+                        void* stream) {
+  if (!e) return fail("null engine");
+  if (member < 0 || member >= e->desc.n_members) return fail("member out of range");
+  if (!fv_dev || !fa_dev) return fail("null output");
+  if (!(dt > 0.0)) return fail("dt must be positive");
+  const size_t n = (size_t)e->desc.dim * e->desc.nn;
+  const int block = 256;
+  const int grid = (int)std::min<size_t>(148 * 8, (n + block - 1) / block);
+  newmark_res_kernel<<<grid, block, 0, as_stream(stream)>>>(e->dev, member, newmark_coef(dt),
+                                                             fv_dev, fa_dev);
+  e->launches += 1;
+  VF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+
+}  // extern "C"

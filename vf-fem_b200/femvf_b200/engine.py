@@ -172,6 +172,18 @@ class Engine:
                                       self._stream(), C.byref(handle)))
         self._h = handle
         self.nnz = int(self._lib.vf_nnz(self._h))
+        # node-centric fan kernel (triangles with ordered vertex fans): the default 2D assembly
+        self.fan_info = None
+        if d == 2 and tables.get('fan_ok', False) and os.environ.get('VF_FAN', '1') != '0':
+            fan = _tables.build_fan_tables(tables, int(os.environ.get('VF_FAN_NODES', '128')))
+            if fan is not None:
+                with torch.cuda.device(self.device):
+                    check(self._lib.vf_set_fan_tables(
+                        self._h, fan['tile_nodes'], fan['ntiles'], _ptr(fan['desc']),
+                        _ptr(fan['ring']), fan['ring'].shape[0], _ptr(fan['halo']),
+                        fan['n_halo'], fan['max_verts'], fan['max_rows'], self._stream()))
+                self.fan_info = {k: fan[k] for k in ('tile_nodes', 'ntiles', 'max_verts',
+                                                     'max_rows', 'n_halo')}
         self._views = {}
         self._pinned = {}
         self._pinned_up = {}

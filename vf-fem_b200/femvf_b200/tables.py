@@ -299,3 +299,126 @@ def build_tile_elem_tables(T: dict, tile_start: np.ndarray):
         'tile_halo': tile_halo if len(tile_halo) else np.zeros(1, np.int32),
         'n_tile_halo': int(len(tile_halo)), 'max_tile_verts': max_tile_verts,
     }
+
+
+def build_fan_tables(T: dict, tile_nodes: int):
+    """
+    Tables of the node-centric fan assembly kernel (``asm_fan_kernel``, triangles with
+    counter-clockwise vertex fans, ``T['fan_ok']``).
+
+    Every vertex n owns its block row of J and its residual entries.  Its adjacent cells are
+    walked counter-clockwise: cell j is (n, p_j, p_{j+1}), so walking the fan loads ONE new ring
+    vertex per cell and every off-diagonal block (n, p_j) is the sum of two consecutive cells.
+    Nodes are grouped in contiguous tiles of ``tile_nodes`` (the CTA size); a tile stages its own
+    vertices and the ring vertices outside its range (``halo``) in shared memory.
+
+    ring : uint32 (n_ring_words, 2), per tile a block of ``rows`` x ``tile_nodes`` 8-byte entries,
+        row-major (entry (r, t) of the tile belongs to its t-th node: consecutive threads read
+        consecutive words).  Row 0 is the node header
+            word0 = brptr[n]           word1 = deg | self_slot << 8 | ncell << 16 | closed << 24
+        rows 1 + j, j = 0..ncell are the ring vertices p_j
+            word0 = staged slot of p_j | CSR slot of p_j in n's block row << 16
+            word1 = id of cell j = (n, p_j, p_{j+1})   (0xffffffff for the last entry)
+        (a closed fan repeats p_0 as its last entry).
+    desc : int32 (ntiles, 8): i0, nT | nH << 16, halo0, ring0 (in entries), rows, cell_lo,
+        cell_cnt, 0 -- (cell_lo, cell_cnt) is the id window of the bulk of the tile's cells (L2
+        prefetch hint only).
+    halo : int32, ring vertices outside each tile's own range, ascending per tile.
+    Returns None when the packing limits do not hold.
+    """
+    if T['dim'] != 2 or not T.get('fan_ok', False):
+        return None
+    nn, ne = T['nn'], T['ne']
+    TN = int(tile_nodes)
+    cells = np.ascontiguousarray(T['cells'].T.astype(np.int64))
+    brptr = T['brptr'].astype(np.int64)
+    bcol = T['bcol'].astype(np.int64)
+    n2e_ptr = T['n2e_ptr'].astype(np.int64)
+    n2e = T['n2e'].astype(np.int64)
+    deg = np.diff(brptr)
+    ncell = np.diff(n2e_ptr)
+    if deg.max() >= 256 or ncell.max() >= 255 or np.any(ncell == 0):
+        return None
+    ntiles = -(-nn // TN)
+    node = np.repeat(np.arange(nn), ncell)
+    pe, pa = n2e >> 2, n2e & 3
+    vp = cells[pe, (pa + 1) % 3]            # p_j of every (node, cell) pair
+    vq = cells[pe, (pa + 2) % 3]            # p_{j+1}
+    first = n2e_ptr[:-1]
+    last = n2e_ptr[1:] - 1
+    closed = vq[last] == vp[first]
+    # ring entries: ncell + 1 per node
+    rptr = np.zeros(nn + 1, dtype=np.int64)
+    rptr[1:] = np.cumsum(ncell + 1)
+    nent = int(rptr[-1])
+    ent_node = np.repeat(np.arange(nn), ncell + 1)
+    ent_j = np.arange(nent) - rptr[ent_node]
+    is_last = ent_j == ncell[ent_node]
+    pair_of = n2e_ptr[ent_node] + np.minimum(ent_j, ncell[ent_node] - 1)
+    ent_v = np.where(is_last, vq[pair_of], vp[pair_of])
+    ent_cell = np.where(is_last, 0xffffffff, pe[pair_of])
+    # CSR slot of the ring vertex in the node's block row
+    gkey = np.repeat(np.arange(nn), deg) * nn + bcol
+    cslot = np.searchsorted(gkey, ent_node * nn + ent_v) - brptr[ent_node]
+    self_slot = np.searchsorted(gkey, np.arange(nn) * (nn + 1)) - brptr[:-1]
+    # halo vertices per tile and staged slots
+    tile_of = np.arange(nn) // TN
+    ent_tile = tile_of[ent_node]
+    halo_mask = tile_of[ent_v] != ent_tile
+    hkey = np.unique(ent_tile[halo_mask] * nn + ent_v[halo_mask])
+    htile, hvert = hkey // nn, hkey % nn
+    th_ptr = np.zeros(ntiles + 1, dtype=np.int64)
+    np.add.at(th_ptr, htile + 1, 1)
+    th_ptr = np.cumsum(th_ptr)
+    i0 = np.arange(ntiles, dtype=np.int64) * TN
+    nT = np.minimum(i0 + TN, nn) - i0
+    nH = np.diff(th_ptr)
+    if (nT + nH).max() >= 65536:
+        return None
+    vslot = np.where(halo_mask,
+                     np.searchsorted(hkey, ent_tile * nn + ent_v) - th_ptr[ent_tile] + nT[ent_tile],
+                     ent_v - i0[ent_tile])
+    # per-tile ring blocks
+    rows_node = ncell + 2                                  # header + ncell + 1 entries
+    rows = np.zeros(ntiles, dtype=np.int64)
+    np.maximum.at(rows, tile_of, rows_node)
+    ring0 = np.zeros(ntiles + 1, dtype=np.int64)
+    ring0[1:] = np.cumsum(rows * TN)
+    ring = np.zeros((int(ring0[-1]), 2), dtype=np.uint32)
+    ring[:, 1] = 0xffffffff
+    t_in = np.arange(nn) - i0[tile_of]
+    hdr = ring0[tile_of] + t_in
+    ring[hdr, 0] = brptr[:-1]
+    ring[hdr, 1] = deg | (self_slot << 8) | (ncell << 16) | (closed.astype(np.int64) << 24)
+    pos = ring0[ent_tile] + (1 + ent_j) * TN + t_in[ent_node]
+    ring[pos, 0] = vslot | (cslot << 16)
+    ring[pos, 1] = ent_cell
+    # id window of the bulk of each tile's cells (10%..90% quantiles): L2 prefetch hint
+    pt = tile_of[node]
+    order = np.lexsort((pe, pt))
+    pes = pe[order]
+    tp = np.zeros(ntiles + 1, dtype=np.int64)
+    np.add.at(tp, pt + 1, 1)
+    tp = np.cumsum(tp)
+    nb = np.diff(tp)
+    lo = pes[tp[:-1] + nb // 10]
+    hi = pes[tp[:-1] + np.maximum(nb - nb // 10 - 1, 0)]
+    cnt = np.minimum(hi - lo + 1, 4 * nb)
+    desc = np.zeros((ntiles, 8), dtype=np.int64)
+    desc[:, 0] = i0
+    desc[:, 1] = nT | (nH << 16)
+    desc[:, 2] = th_ptr[:-1]
+    desc[:, 3] = ring0[:-1]
+    desc[:, 4] = rows
+    desc[:, 5] = lo
+    desc[:, 6] = cnt
+    if ring0[-1] >= 2**31:
+        return None
+    return {
+        'tile_nodes': TN, 'ntiles': int(ntiles),
+        'desc': np.ascontiguousarray(desc.astype(np.uint32).view(np.int32)),
+        'ring': np.ascontiguousarray(ring),
+        'halo': hvert.astype(np.int32) if len(hvert) else np.zeros(1, np.int32),
+        'n_halo': int(len(hvert)), 'max_verts': int((nT + nH).max()),
+        'max_rows': int(rows.max()),
+    }
