@@ -105,6 +105,30 @@ def test_3d_interface_planes():
     assert model.control['psub'].size == 3
 
 
+def test_3d_fsi_map_gives_every_plane_its_own_channel():
+    """reference load.py:204-214: solid_dofs is interface_vertices.flat, fluid_dofs = arange of
+    the same length, so z-plane k maps to fluid DOFs k*ns .. (k+1)*ns - 1."""
+    zs = np.linspace(0, 1, 3)
+    model = build_fsi('cube332', zs=zs)
+    s = model.fluid.residual.mesh()
+    nz, ns = s.shape
+    fd, sd = model.fsimap.dofs_fluid, model.fsimap.dofs_solid
+    assert np.array_equal(np.sort(fd), np.arange(nz * ns))
+    coords = model.solid.residual.mesh().coordinates()
+    # every plane's solid vertices lie on that plane
+    for k in range(nz):
+        assert np.allclose(coords[sd[fd // ns == k], 2], zs[k])
+    # a displacement that differs per plane reaches each channel's area separately
+    area_solid = 2.0 * (1.05 - (coords[:, 1] + 0.01 * coords[:, 2]))
+    area = np.ones(nz * ns)
+    model.fsimap.map_solid_to_fluid(area_solid, area)
+    area = area.reshape(nz, ns)
+    for k in range(nz):
+        assert np.allclose(area[k], 2.0 * (1.05 - (coords[sd[k * ns:(k + 1) * ns], 1]
+                                                   + 0.01 * zs[k])))
+    assert not np.allclose(area[0], area[1])
+
+
 def test_integrate_argument_validation():
     model = build_fsi('square5')
     st = model.state0.copy(); ctl = model.control.copy(); prop = model.prop.copy()

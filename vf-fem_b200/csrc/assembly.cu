@@ -804,11 +804,11 @@ namespace {
 int launch_fan(vf_engine* e, int member, bool res, bool jac, double dt, int is_static,
                const JacMix& mix, cudaStream_t st) {
   const FanTablesDev& T = e->fan;
-  static const char* env_rows = getenv("VF_FAN_ROWS");
+  const char* env_rows = getenv("VF_FAN_ROWS");
   const int rows_cap = env_rows ? std::max(atoi(env_rows), 2) : 10;
   const int rows_s = std::min(T.max_rows, rows_cap);
-  static const char* env_pf = getenv("VF_PF_DIST");
-  static const char* env_mb = getenv("VF_FAN_MINB");
+  const char* env_pf = getenv("VF_PF_DIST");
+  const char* env_mb = getenv("VF_FAN_MINB");
   const int minb_env = env_mb ? atoi(env_mb) : 0;
   const NewmarkCoef nc = newmark_coef(dt);
 #define VF_FAN_GO(J_, R_, TN_, MB_)                                                               \
@@ -861,7 +861,7 @@ int assemble_impl(vf_engine* e, int member, int flags, double dt, int is_static,
   const bool res = flags & 1, jac = flags & 2;
   if (!res && !jac) return 0;
   cudaStream_t st = as_stream(stream);
-  static const char* env_fan = getenv("VF_FAN");
+  const char* env_fan = getenv("VF_FAN");
   if (e->fan.ring && !(env_fan && atoi(env_fan) == 0)) {
     if (launch_fan(e, member, res, jac, dt, is_static, mix, st)) return 1;
     return launch_facet_bc(e, member, res, jac, dt, is_static, mix, st);

@@ -102,11 +102,11 @@ def derive_1D_interface_from_facet_subdomain(mesh: Mesh, function_space, facet_f
     interface_coords, interface_vertices = derive_edge_mesh_from_facet_subdomain(
         mesh, facet_function, facet_values, zs
     )
+    # the reference indexes with ``interface_vertices.flat`` (load.py:204-214): solid_dofs is
+    # 1-D, so fluid_dofs = arange(solid_dofs.size) -- for nz z-planes of ns points, plane k owns
+    # the fluid DOFs k*ns .. (k+1)*ns - 1 of the (nz, ns) fluid state
     solid_dofs = np.asarray(interface_vertices, dtype=np.int64).reshape(-1)
-    shape = np.asarray(interface_vertices).shape
-    fluid_dofs = (
-        np.ones(shape[:-1] + (1,), dtype=int) * np.arange(shape[-1], dtype=int)
-    ).reshape(-1)
+    fluid_dofs = np.arange(solid_dofs.size, dtype=int)
     return interface_coords, solid_dofs, fluid_dofs
 
 
