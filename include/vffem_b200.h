@@ -149,15 +149,24 @@ int vf_assemble(vf_engine* e, int member, int flags, double dt, int is_static, v
 
 /* Tables of the node-centric fan assembly kernel (triangles whose vertex stars are single
  * counter-clockwise fans; femvf_b200/tables.py build_fan_tables).  Once set, vf_assemble /
- * vf_assemble_mix run asm_fan_kernel: one thread per vertex walks its fan and stores its two CSR
- * rows directly.  Still the same dfn.assemble call sites (models/assemblyutils.py:49-50).
- *   desc_host (ntiles, 8) int32: i0, nT | nH << 16, halo0, ring0, rows, cell_lo, cell_cnt, 0
- *   ring_host (n_ring, 2) uint32: per tile rows x tile_nodes entries (header row + ring rows)
- *   halo_host (n_halo) int32: ring vertices outside each tile's own node range
- * The tables are copied into a device allocation owned by the engine. */
+ * vf_assemble_mix run asm_fan_kernel: one thread per vertex walks its fan out of shared memory;
+ * the tile's ring table, cell properties and CSR slice move by bulk asynchronous copies.  Still
+ * the same dfn.assemble call sites (models/assemblyutils.py:49-50).
+ *   desc_host  (ntiles, 12) int32: i0, nT | nH << 16, halo0, ring0, rows, tcell0, padded cell
+ *              count, brptr[i0], #blocks of the tile, 0, 0, 0
+ *   ring_host  (n_ring) uint32: per tile rows x tile_nodes words (header row + ring rows)
+ *   halo_host  (n_halo) int32: ring vertices outside each tile's own node range
+ *   tcell_host (n_tcell) int32: cells touched by each tile, lists padded to even counts
+ * The tables are copied into a device allocation owned by the engine, which also holds a
+ * tile-ordered copy of emod / eta / rho per member (refreshed when vf_upload changes them or
+ * vf_props_changed is called). */
 int vf_set_fan_tables(vf_engine* e, int tile_nodes, int ntiles, const int32_t* desc_host,
                       const uint32_t* ring_host, size_t n_ring, const int32_t* halo_host,
-                      size_t n_halo, int max_verts, int max_rows, void* stream);
+                      size_t n_halo, const int32_t* tcell_host, size_t n_tcell, int max_verts,
+                      int max_rows, int max_cells, int max_blocks, void* stream);
+/* Tell the engine that VF_RHO / VF_ETA / VF_EMOD of `member` (-1: every member) were written
+ * directly in the arena (not through vf_upload). */
+int vf_props_changed(vf_engine* e, int member);
 
 /* The state0 sensitivities of FenicsModel.assem_dres_dstate0 (models/transient.py:408-421:
  * assemble_derivative(form, 'state/u0' | 'state/v0' | 'state/a0'), no bc.apply).  F_u depends on

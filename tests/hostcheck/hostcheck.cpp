@@ -114,7 +114,8 @@ extern "C" int hostcheck_assemble_tile2(
 
 // CPU emulation of asm_fan_kernel + facet_bc_kernel (node-centric fan assembly, triangles): the
 // same device function (fan_walk_node) driven by the product's fan tables, tile by tile, with
-// the staged vertex list (own vertices, then the tile's halo) rebuilt like the kernel does.
+// the staged vertex list (own vertices, then the tile's halo), the tile-ordered property
+// blocks and the tile's CSR slice rebuilt like the kernel does.
 extern "C" int hostcheck_assemble_fan(
     int nn, int ne, int nfp, const double* xyz, const int* cells, const int* brptr,
     const int* bcol, const int* n2e_ptr, const int* n2e, const int* n2f_ptr, const int* n2f,
@@ -123,7 +124,8 @@ extern "C" int hostcheck_assemble_fan(
     const double* nu_m, const double* th_m, int contact, int membrane, int damping,
     const double* u1, const double* u0, const double* v0, const double* a0, const double* p1,
     double dt, int is_static, int tile_nodes, int ntiles, const int* desc, const unsigned* ring,
-    const int* halo, int max_verts, int rows_s, double* J, double* F) {
+    const int* halo, const int* tcell, int max_verts, int max_rows, int max_cells,
+    int max_blocks, double* J, double* F) {
   vf::MeshView m{2, nn, ne, nfp, xyz, nullptr, cells, brptr, bcol, n2e_ptr, n2e,
                  n2f_ptr, n2f, pf_cell, pf_opp, bc};
   vf::PropView p{rho, eta, emod, scal, emod_m, nu_m, th_m, contact, membrane, damping};
@@ -134,39 +136,57 @@ extern "C" int hostcheck_assemble_fan(
   const int TN = tile_nodes;
   vf::D2* sxy = new vf::D2[max_verts];
   vf::NodeUVA* suva = new vf::NodeUVA[max_verts];
-  for (int t = 0; t < ntiles; ++t) {
-    const int* d = desc + 8 * t;
+  double* smat = new double[3 * (size_t)max_cells];
+  double* sJ = static_cast<double*>(aligned_alloc(16, sizeof(double) * 4 * (size_t)max_blocks));
+  int rc = 0;
+  for (int t = 0; t < ntiles && rc == 0; ++t) {
+    const int* d = desc + 12 * t;
     const int i0 = d[0], nT = d[1] & 0xffff, nH = (int)((unsigned)d[1] >> 16);
-    const int h0 = d[2], ring0 = d[3], rows = d[4];
-    if (nT + nH > max_verts) return 2;
+    const int h0 = d[2], ring0 = d[3], rows = d[4], tc0 = d[5], ncp = d[6], bbase = d[7];
+    const int nblk = d[8];
+    if (nT + nH > max_verts || rows > max_rows || ncp > max_cells || nblk > max_blocks ||
+        bbase != brptr[i0] || nblk != brptr[i0 + nT] - bbase) {
+      rc = 2;
+      break;
+    }
     for (int k = 0; k < nT + nH; ++k) {
       const int v = k < nT ? i0 + k : halo[h0 + k - nT];
       sxy[k] = vf::D2{xyz[v], xyz[nn + v]};
       suva[k] = vf::gather_node_uva(nc, is_static != 0, v, u1, s.u0, v0, a0);
     }
-    const unsigned* ring_t = ring + 2 * (size_t)ring0;
-    (void)rows_s;
+    for (int k = 0; k < ncp; ++k) {   // fan_pack_kernel + the bulk copy of the tile's block
+      const int e = tcell[tc0 + k];
+      smat[k] = emod[e];
+      smat[ncp + k] = eta[e];
+      smat[2 * ncp + k] = rho[e];
+    }
+    for (int k = 0; k < 4 * nblk; ++k) sJ[k] = std::nan("");
+    const unsigned* ring_t = ring + (size_t)ring0;
     for (int k = 0; k < nT; ++k) {
       auto ringf = [&](int r) {
         if (r >= rows) std::abort();
-        const unsigned* w = ring_t + 2 * ((size_t)r * TN + k);
-        return vf::FanEntry{w[0], w[1]};
+        return ring_t[(size_t)r * TN + k];
       };
       auto vxy = [&](int sl) { return sxy[sl]; };
       auto vuva = [&](int sl, vf::D2& u, vf::D2& v, vf::D2& a) {
         u = suva[sl].u; v = suva[sl].v; a = suva[sl].a;
       };
-      auto mat = [&](unsigned e, double& em, double& et, double& rh) {
-        em = emod[e]; et = eta[e]; rh = rho[e];
+      auto mat = [&](int c, double& em, double& et, double& rh) {
+        if (c >= ncp) std::abort();
+        em = smat[c]; et = smat[ncp + c]; rh = smat[2 * ncp + c];
       };
       double res[2];
-      vf::fan_walk_node<true, true>(k, ringf, vxy, vuva, mat, fc, J, res);
+      vf::fan_walk_node<true, true>(k, ringf, vxy, vuva, mat, fc, sJ, res);
       F[2 * (i0 + k)] = res[0];
       F[2 * (i0 + k) + 1] = res[1];
     }
+    for (int k = 0; k < 4 * nblk; ++k) J[4 * (size_t)bbase + k] = sJ[k];   // the bulk store
   }
   delete[] sxy;
   delete[] suva;
+  delete[] smat;
+  free(sJ);
+  if (rc) return rc;
   for (int i = 0; i < nn; ++i) {
     bool touch = n2f_ptr[i + 1] > n2f_ptr[i] || bc[2 * i] || bc[2 * i + 1];
     if (!touch) continue;

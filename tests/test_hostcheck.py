@@ -164,7 +164,8 @@ def test_fan_walk_algorithm_on_cpu(lib, mesh_name, tile_nodes, contact, membrane
         P(prop['emod_membrane']), P(prop['nu_membrane']), P(prop['th_membrane']),
         contact, membrane, damping, P(u1), P(u0), P(v0), P(a0), P(p1), ctypes.c_double(dt),
         is_static, FT['tile_nodes'], FT['ntiles'], P(FT['desc']), P(FT['ring']), P(FT['halo']),
-        FT['max_verts'], FT['max_rows'], P(J), P(F))
+        P(FT['tcell']), FT['max_verts'], FT['max_rows'], FT['max_cells'], FT['max_blocks'],
+        P(J), P(F))
     assert rc == 0
     assert not np.any(np.isnan(J)) and not np.any(np.isnan(F))
     assert rel_row_err(J, Jo) <= 1e-12

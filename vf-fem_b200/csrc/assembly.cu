@@ -413,23 +413,50 @@ __global__ void __launch_bounds__(MAXT, MINB) asm_tile2_kernel(
 
 
 // ---- node-centric fan assembly (triangles) --------------------------------------------------
-// One CTA per tile of TN consecutive nodes, one thread per node (fan_assembly.cuh).
-//   stage  thread 0 arms an mbarrier and issues ONE bulk asynchronous copy (TMA engine,
-//          cp.async.bulk) of the tile's ring table -- the largest index stream, contiguous by
-//          construction -- while all threads stage the tile's own and halo vertices
-//          (coordinates, u1, v_nmk, a_nmk; 16-byte loads, SoA planes in shared memory);
-//   walk   every thread walks the fan of its node out of shared memory and stores the finished
-//          16-byte row entries straight to the CSR array, then its residual pair;
+// One CTA per tile of TN consecutive nodes, one thread per node (fan_assembly.cuh).  Apart from
+// the gather of the nodal state, all global traffic of the kernel is bulk asynchronous copies
+// issued by one thread (TMA engine, cp.async.bulk + mbarrier), which do not occupy the LSU data
+// pipe -- the unit that bounded the round-1 kernel (79 % busy with shared-memory and scattered
+// 16-byte global wavefronts, profiles/README.md):
+//   stage  thread 0 arms an mbarrier and issues two bulk loads: the tile's ring table and the
+//          DG0 properties of the tile's cells (a tile-ordered copy kept by fan_pack_kernel);
+//          all threads stage the tile's own and halo vertices (coordinates, u1, v_nmk, a_nmk;
+//          16-byte loads, SoA planes in shared memory);
+//   walk   every thread walks the fan of its node reading shared memory only and puts the
+//          finished 16-byte row entries into the tile's slice of the CSR array in shared memory;
+//   store  ONE bulk store streams the slice (contiguous in the CSR array) to HBM; the residual
+//          pairs are stored coalesced;
 //   tail   the inputs of the tile pf_dist CTAs ahead are pulled into L2.
-// There is one CTA-wide barrier (after staging); no per-cell records, no second phase.
+// Two CTA-wide barriers (after staging, before the bulk store); no per-cell records.
+// Shared memory: [CSR slice][ring][properties][xy][u][v][a].
+
+// Tile-ordered copy of the DG0 properties: per tile a block [emod | eta | rho] over its (padded)
+// cell list, so that one bulk copy brings a tile's material into shared memory.
+__global__ void fan_pack_kernel(EngineDev E, int member, FanTablesDev T, double* mat) {
+  const int4 d1 = __ldg(T.desc + 3 * blockIdx.x + 1);
+  const int tc0 = d1.y, ncp = d1.z;
+  const double* mb = E.members + (size_t)member * E.L.stride;
+  const double* emod = mb + E.L.off[VF_EMOD];
+  const double* eta = mb + E.L.off[VF_ETA];
+  const double* rho = mb + E.L.off[VF_RHO];
+  double* dst = mat + (size_t)3 * tc0;
+  for (int k = threadIdx.x; k < ncp; k += blockDim.x) {
+    const int e = __ldg(T.tcell + tc0 + k);
+    dst[k] = emod[e];
+    dst[ncp + k] = eta[e];
+    dst[2 * ncp + k] = rho[e];
+  }
+}
 
 template <bool JAC, bool RES, int TN, int MINB>
 __global__ void __launch_bounds__(TN, MINB) asm_fan_kernel(
     EngineDev E, int member, NewmarkCoef nc_arg, int is_static, JacMix mix, FanTablesDev T,
-    int rows_s, int pf_dist) {
+    const double* __restrict__ mat_m, int pf_dist) {
   extern __shared__ __align__(128) unsigned char fan_smem[];
-  uint2* s_ring = reinterpret_cast<uint2*>(fan_smem);
-  D2* s_xy = reinterpret_cast<D2*>(s_ring + (size_t)rows_s * TN);
+  double* s_J = reinterpret_cast<double*>(fan_smem);
+  unsigned* s_ring = reinterpret_cast<unsigned*>(s_J + (JAC ? 4 * (size_t)T.max_blocks : 0));
+  double* s_mat = reinterpret_cast<double*>(s_ring + (size_t)T.max_rows * TN);
+  D2* s_xy = reinterpret_cast<D2*>(s_mat + 3 * (size_t)T.max_cells);
   D2* s_u = s_xy + T.max_verts;
   D2* s_v = s_u + T.max_verts;
   D2* s_a = s_v + T.max_verts;
@@ -440,16 +467,18 @@ __global__ void __launch_bounds__(TN, MINB) asm_fan_kernel(
   const Layout& L = E.L;
   const MeshView& m = E.mesh;
 
-  const int4 d0 = __ldg(T.desc + 2 * blockIdx.x), d1 = __ldg(T.desc + 2 * blockIdx.x + 1);
+  const int4* dsc = T.desc + 3 * blockIdx.x;
+  const int4 d0 = __ldg(dsc), d1 = __ldg(dsc + 1);
   const int i0 = d0.x, nT = d0.y & 0xffff, nH = (int)((unsigned)d0.y >> 16);
-  const int h0 = d0.z, ring0 = d0.w, rows = d1.x;
+  const int h0 = d0.z, ring0 = d0.w, rows = d1.x, tc0 = d1.y, ncp = d1.z, bbase = d1.w;
   const int nV = nT + nH;
-  const uint2* ring_t = T.ring + ring0;
   if (tid == 0) {
     mbar_init(&s_bar, 1);
-    const unsigned bytes = (unsigned)min(rows, rows_s) * TN * (unsigned)sizeof(uint2);
-    mbar_expect_tx(&s_bar, bytes);
-    bulk_g2s(s_ring, ring_t, bytes, &s_bar);
+    const unsigned b_ring = (unsigned)rows * TN * (unsigned)sizeof(unsigned);
+    const unsigned b_mat = (unsigned)ncp * 3u * (unsigned)sizeof(double);
+    mbar_expect_tx(&s_bar, b_ring + b_mat);
+    bulk_g2s(s_ring, T.ring + ring0, b_ring, &s_bar);
+    bulk_g2s(s_mat, mat_m + (size_t)3 * tc0, b_mat, &s_bar);
   }
   const PropView pv = member_props<2>(E, mb);
   if (tid == TN - 1) s_fc = fan_coef(lame_fac(pv.scal[SC_NU]), prop_damping(pv), mix);
@@ -492,39 +521,46 @@ __global__ void __launch_bounds__(TN, MINB) asm_fan_kernel(
   __syncthreads();
   mbar_wait(&s_bar, 0);
 
-  // ---- walk ------------------------------------------------------------------------------------
+  // ---- walk: shared memory only ------------------------------------------------------------------
   if (tid < nT) {
     const FanCoef fc = s_fc;
-    auto ring = [&](int r) {
-      const uint2 w = r < rows_s ? s_ring[r * TN + tid] : __ldg(ring_t + (size_t)r * TN + tid);
-      return FanEntry{w.x, w.y};
-    };
+    auto ring = [&](int r) { return s_ring[r * TN + tid]; };
     auto vtx_xy = [&](int s) { return s_xy[s]; };
     auto vtx_uva = [&](int s, D2& u, D2& v, D2& a) {
       u = s_u[s];
       v = s_v[s];
       a = s_a[s];
     };
-    auto mat = [&](unsigned e, double& emod, double& eta, double& rho) {
-      emod = __ldg(pv.emod + e);
-      eta = __ldg(pv.eta + e);
-      rho = __ldg(pv.rho + e);
+    auto mat = [&](int c, double& emod, double& eta, double& rho) {
+      emod = s_mat[c];
+      eta = s_mat[ncp + c];
+      rho = s_mat[2 * ncp + c];
     };
     double res[2];
-    fan_walk_node<JAC, RES>(tid, ring, vtx_xy, vtx_uva, mat, fc, mb + L.off[VF_J], res);
+    fan_walk_node<JAC, RES>(tid, ring, vtx_xy, vtx_uva, mat, fc, s_J, res);
     if (RES) reinterpret_cast<D2*>(mb + L.off[VF_F])[i0 + tid] = D2{res[0], res[1]};
+  }
+  if (JAC) {
+    // the slice written through the generic proxy must be visible to the bulk-copy engine
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      bulk_s2g(mb + L.off[VF_J] + 4 * (size_t)bbase, s_J, (unsigned)dsc[2].x * 32u);
+      bulk_commit();
+    }
   }
 
   // ---- tail: pull the inputs of a later tile into L2 ---------------------------------------------
   const int far = blockIdx.x + pf_dist;
   if (pf_dist > 0 && far < (int)gridDim.x) {
-    const int4 f0 = __ldg(T.desc + 2 * far), f1 = __ldg(T.desc + 2 * far + 1);
+    const int4 f0 = __ldg(T.desc + 3 * far), f1 = __ldg(T.desc + 3 * far + 1);
     const int f_i0 = f0.x, f_nT = f0.y & 0xffff, f_nH = (int)((unsigned)f0.y >> 16);
     auto pull = [&](const void* p, int nbytes) {
       const char* c = reinterpret_cast<const char*>(p);
       for (int off = tid * 128; off < nbytes; off += TN * 128) prefetch_l2(c + off);
     };
-    pull(T.ring + f0.w, f1.x * TN * (int)sizeof(uint2));
+    pull(T.ring + f0.w, f1.x * TN * (int)sizeof(unsigned));
+    pull(mat_m + (size_t)3 * f1.y, f1.z * 24);
     pull(m.xy + 2 * f_i0, 16 * f_nT);
     if (RES) {
       pull(u1 + 2 * f_i0, 16 * f_nT);
@@ -534,9 +570,6 @@ __global__ void __launch_bounds__(TN, MINB) asm_fan_kernel(
         pull(a0 + 2 * f_i0, 16 * f_nT);
       }
     }
-    pull(pv.emod + f1.y, 8 * f1.z);
-    pull(pv.eta + f1.y, 8 * f1.z);
-    pull(pv.rho + f1.y, 8 * f1.z);
     for (int h = tid; h < f_nH; h += TN) {
       const int v = __ldg(T.halo + f0.z + h);
       prefetch_l2(m.xy + 2 * v);
@@ -550,6 +583,8 @@ __global__ void __launch_bounds__(TN, MINB) asm_fan_kernel(
       }
     }
   }
+  // the CTA's shared memory must stay allocated until the bulk store has read it
+  if (JAC && tid == 0) bulk_wait_read();
 }
 
 template <int D, bool JAC, bool RES>
@@ -738,40 +773,62 @@ extern "C" {
 
 int vf_set_fan_tables(vf_engine* e, int tile_nodes, int ntiles, const int32_t* desc_host,
                       const uint32_t* ring_host, size_t n_ring, const int32_t* halo_host,
-                      size_t n_halo, int max_verts, int max_rows, void* stream) {
+                      size_t n_halo, const int32_t* tcell_host, size_t n_tcell, int max_verts,
+                      int max_rows, int max_cells, int max_blocks, void* stream) {
   if (!e) return fail("null engine");
   if (e->desc.dim != 2 || !e->fan_ok) return fail("fan tables need triangles with ordered fans");
-  if (tile_nodes != 64 && tile_nodes != 128 && tile_nodes != 256)
-    return fail("fan tile_nodes must be 64, 128 or 256");
-  if (ntiles <= 0 || !desc_host || !ring_host || !halo_host) return fail("missing fan tables");
+  if (tile_nodes != 64 && tile_nodes != 96 && tile_nodes != 128)
+    return fail("fan tile_nodes must be 64, 96 or 128");
+  if (ntiles <= 0 || !desc_host || !ring_host || !halo_host || !tcell_host || n_tcell == 0)
+    return fail("missing fan tables");
   if ((size_t)ntiles * tile_nodes < (size_t)e->desc.nn) return fail("fan tiles do not cover the mesh");
+  if (max_cells % 2) return fail("fan tile cell lists must be padded to an even count");
   cudaStream_t st = as_stream(stream);
-  const size_t b_desc = align_up(sizeof(int32_t) * 8 * (size_t)ntiles, 256);
-  const size_t b_ring = align_up(sizeof(uint32_t) * 2 * n_ring, 256);
+  const size_t b_desc = align_up(sizeof(int32_t) * 12 * (size_t)ntiles, 256);
+  const size_t b_ring = align_up(sizeof(uint32_t) * n_ring, 256);
   const size_t b_halo = align_up(sizeof(int32_t) * std::max<size_t>(n_halo, 1), 256);
+  const size_t b_tcell = align_up(sizeof(int32_t) * n_tcell, 256);
+  const size_t b_mat = sizeof(double) * 3 * n_tcell * (size_t)e->desc.n_members;
   if (e->fan_mem) {
     cudaFree(e->fan_mem);
     e->fan_mem = nullptr;
     e->fan.ring = nullptr;
   }
   char* mem = nullptr;
-  VF_CUDA(cudaMalloc(&mem, b_desc + b_ring + b_halo));
+  VF_CUDA(cudaMalloc(&mem, b_desc + b_ring + b_halo + b_tcell + b_mat));
   e->fan_mem = mem;
-  VF_CUDA(cudaMemcpyAsync(mem, desc_host, sizeof(int32_t) * 8 * (size_t)ntiles,
+  VF_CUDA(cudaMemcpyAsync(mem, desc_host, sizeof(int32_t) * 12 * (size_t)ntiles,
                           cudaMemcpyHostToDevice, st));
-  VF_CUDA(cudaMemcpyAsync(mem + b_desc, ring_host, sizeof(uint32_t) * 2 * n_ring,
+  VF_CUDA(cudaMemcpyAsync(mem + b_desc, ring_host, sizeof(uint32_t) * n_ring,
                           cudaMemcpyHostToDevice, st));
   if (n_halo)
     VF_CUDA(cudaMemcpyAsync(mem + b_desc + b_ring, halo_host, sizeof(int32_t) * n_halo,
                             cudaMemcpyHostToDevice, st));
+  VF_CUDA(cudaMemcpyAsync(mem + b_desc + b_ring + b_halo, tcell_host, sizeof(int32_t) * n_tcell,
+                          cudaMemcpyHostToDevice, st));
   VF_CUDA(cudaStreamSynchronize(st));
-  e->fan.desc = reinterpret_cast<const int4*>(mem);
-  e->fan.ring = reinterpret_cast<const uint2*>(mem + b_desc);
-  e->fan.halo = reinterpret_cast<const int*>(mem + b_desc + b_ring);
-  e->fan.tile_nodes = tile_nodes;
-  e->fan.ntiles = ntiles;
-  e->fan.max_verts = max_verts;
-  e->fan.max_rows = max_rows;
+  FanTablesDev& T = e->fan;
+  T.desc = reinterpret_cast<const int4*>(mem);
+  T.ring = reinterpret_cast<const unsigned*>(mem + b_desc);
+  T.halo = reinterpret_cast<const int*>(mem + b_desc + b_ring);
+  T.tcell = reinterpret_cast<const int*>(mem + b_desc + b_ring + b_halo);
+  T.mat = reinterpret_cast<double*>(mem + b_desc + b_ring + b_halo + b_tcell);
+  T.n_tcell = n_tcell;
+  T.tile_nodes = tile_nodes;
+  T.ntiles = ntiles;
+  T.max_verts = max_verts;
+  T.max_rows = max_rows;
+  T.max_cells = max_cells;
+  T.max_blocks = max_blocks;
+  e->fan_dirty.assign((size_t)e->desc.n_members, 1);
+  return 0;
+}
+
+int vf_props_changed(vf_engine* e, int member) {
+  if (!e) return fail("null engine");
+  if (member >= e->desc.n_members) return fail("member out of range");
+  if (member < 0) std::fill(e->fan_dirty.begin(), e->fan_dirty.end(), 1);
+  else if (!e->fan_dirty.empty()) e->fan_dirty[member] = 1;
   return 0;
 }
 
@@ -801,26 +858,35 @@ int vf_assemble_mix(vf_engine* e, int member, double dt, const double* coef4, in
 
 namespace {
 // Node-centric fan kernel (triangles, ordered fans): the default 2D path once its tables are set.
+size_t fan_smem_bytes(const FanTablesDev& T, bool jac, bool res) {
+  return (jac ? 32 * (size_t)T.max_blocks : 0) + sizeof(unsigned) * (size_t)T.max_rows * T.tile_nodes +
+         24 * (size_t)T.max_cells + sizeof(D2) * (size_t)T.max_verts * (res ? 4 : 1);
+}
+
 int launch_fan(vf_engine* e, int member, bool res, bool jac, double dt, int is_static,
                const JacMix& mix, cudaStream_t st) {
   const FanTablesDev& T = e->fan;
-  const char* env_rows = getenv("VF_FAN_ROWS");
-  const int rows_cap = env_rows ? std::max(atoi(env_rows), 2) : 10;
-  const int rows_s = std::min(T.max_rows, rows_cap);
+  double* mat_m = T.mat + (size_t)member * 3 * T.n_tcell;
+  if (e->fan_dirty[member]) {
+    // the tile-ordered copy of emod / eta / rho follows the member's properties
+    fan_pack_kernel<<<T.ntiles, 128, 0, st>>>(e->dev, member, T, mat_m);
+    e->fan_dirty[member] = 0;
+    e->launches += 1;
+    VF_CUDA(cudaGetLastError());
+  }
   const char* env_pf = getenv("VF_PF_DIST");
   const char* env_mb = getenv("VF_FAN_MINB");
   const int minb_env = env_mb ? atoi(env_mb) : 0;
   const NewmarkCoef nc = newmark_coef(dt);
+  const size_t smem = fan_smem_bytes(T, jac, res);
+  if (smem > 227 * 1024) return fail("fan tile exceeds the 227 KB shared memory of an SM");
 #define VF_FAN_GO(J_, R_, TN_, MB_)                                                               \
   do {                                                                                            \
-    const size_t smem = sizeof(uint2) * (size_t)rows_s * TN_ +                                    \
-                        sizeof(D2) * (size_t)T.max_verts * ((R_) ? 4 : 1);                        \
-    if (smem > 227 * 1024) return fail("fan tile exceeds the 227 KB shared memory of an SM");     \
     const int pf_dist = env_pf ? atoi(env_pf) : 148 * (MB_);                                      \
     VF_CUDA(cudaFuncSetAttribute(asm_fan_kernel<J_, R_, TN_, MB_>,                                \
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
     asm_fan_kernel<J_, R_, TN_, MB_><<<T.ntiles, TN_, smem, st>>>(e->dev, member, nc, is_static,  \
-                                                                   mix, T, rows_s, pf_dist);      \
+                                                                   mix, T, mat_m, pf_dist);       \
   } while (0)
 #define VF_FAN_BY_MODE(TN_, MB_)                                                                  \
   do {                                                                                            \
@@ -828,11 +894,10 @@ int launch_fan(vf_engine* e, int member, bool res, bool jac, double dt, int is_s
     else if (jac) VF_FAN_GO(true, false, TN_, MB_);                                               \
     else VF_FAN_GO(false, true, TN_, MB_);                                                        \
   } while (0)
-  if (T.tile_nodes == 64) VF_FAN_BY_MODE(64, 8);
-  else if (T.tile_nodes == 256) VF_FAN_BY_MODE(256, 2);
-  else if (minb_env == 3) VF_FAN_BY_MODE(128, 3);
-  else if (minb_env == 5) VF_FAN_BY_MODE(128, 5);
-  else VF_FAN_BY_MODE(128, 4);
+  if (T.tile_nodes == 64) VF_FAN_BY_MODE(64, 7);
+  else if (T.tile_nodes == 96) VF_FAN_BY_MODE(96, 5);
+  else if (minb_env == 4) VF_FAN_BY_MODE(128, 4);
+  else VF_FAN_BY_MODE(128, 3);
 #undef VF_FAN_BY_MODE
 #undef VF_FAN_GO
   e->launches += 1;

@@ -27,10 +27,13 @@ int fail(const std::string& msg);
   } while (0)
 
 struct FanTablesDev {
-  const int4* desc;    // (ntiles, 2) int4
-  const uint2* ring;
-  const int* halo;
-  int tile_nodes, ntiles, max_verts, max_rows;
+  const int4* desc;      // (ntiles, 3) int4
+  const unsigned* ring;  // header + ring words, per tile rows x tile_nodes
+  const int* halo;       // ring vertices outside each tile's node range
+  const int* tcell;      // cells touched by each tile (padded to even counts)
+  double* mat;           // per member: tile-ordered [emod | eta | rho] blocks (3 * n_tcell)
+  size_t n_tcell;
+  int tile_nodes, ntiles, max_verts, max_rows, max_cells, max_blocks;
 };
 
 }  // namespace vf
@@ -58,6 +61,7 @@ struct vf_engine {
   // node-centric fan assembly (vf_set_fan_tables): tables in their own device allocation
   vf::FanTablesDev fan;
   void* fan_mem;
+  std::vector<char> fan_dirty;  // per member: the tile-ordered property copy is stale
 };
 
 namespace vf {

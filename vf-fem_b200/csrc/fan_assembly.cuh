@@ -56,14 +56,17 @@ VF_HD FanCoef fan_coef(const LameFac& lf, const Damping& dp, const JacMix& mix) 
   return c;
 }
 
-// Header and ring entries of the fan tables (tables.build_fan_tables).
-struct FanEntry {
-  unsigned w0, w1;
-};
-VF_HD int fan_hdr_deg(unsigned w1) { return (int)(w1 & 0xffu); }
-VF_HD int fan_hdr_self(unsigned w1) { return (int)((w1 >> 8) & 0xffu); }
-VF_HD int fan_hdr_ncell(unsigned w1) { return (int)((w1 >> 16) & 0xffu); }
-VF_HD bool fan_hdr_closed(unsigned w1) { return ((w1 >> 24) & 1u) != 0; }
+// Header and ring words of the fan tables (tables.build_fan_tables).
+//   header: (brptr[n] - brptr[i0]) | deg << 12 | self_slot << 17 | ncell << 22 | closed << 27
+//   ring:   staged vertex slot | CSR slot << 10 | local cell << 15
+VF_HD int fan_hdr_b0(unsigned w) { return (int)(w & 0xfffu); }
+VF_HD int fan_hdr_deg(unsigned w) { return (int)((w >> 12) & 0x1fu); }
+VF_HD int fan_hdr_self(unsigned w) { return (int)((w >> 17) & 0x1fu); }
+VF_HD int fan_hdr_ncell(unsigned w) { return (int)((w >> 22) & 0x1fu); }
+VF_HD bool fan_hdr_closed(unsigned w) { return ((w >> 27) & 1u) != 0; }
+VF_HD int fan_ent_vslot(unsigned w) { return (int)(w & 0x3ffu); }
+VF_HD int fan_ent_cslot(unsigned w) { return (int)((w >> 10) & 0x1fu); }
+VF_HD int fan_ent_cell(unsigned w) { return (int)((w >> 15) & 0xfffu); }
 
 struct FanBlock {
   double b00, b01, b10, b11;
@@ -136,31 +139,32 @@ VF_HD void fan_cell(const FanRing& p, const FanRing& q, double emod, double eta,
   }
 }
 
-// ring(r)   -> FanEntry of row r of this node (0 = header, 1 + j = ring vertex j)
+// ring(r)   -> word of row r of this node (0 = header, 1 + j = ring vertex j)
 // vtx_xy(s) -> D2 coordinates of staged vertex s;  vtx_uva(s, u, v, a) -> nodal u1, v_nmk, a_nmk
-// mat(e, emod, eta, rho) -> DG0 properties of cell e
-// Jglob: the CSR value array (the node's block row starts at Jglob + 4 brptr[n]).
+// mat(c, emod, eta, rho) -> DG0 properties of the tile's local cell c
+// Jtile: where the tile's slice of the CSR value array goes (the node's block row starts
+// 4 (brptr[n] - brptr[i0]) doubles into it): shared memory in the kernel.
 // The loop over the cells is unrolled by two with the roles of the two ring-vertex register sets
 // swapped, so that "the new vertex becomes the previous one" costs no register moves.
 template <bool JAC, bool RES, class Ring, class VtxXY, class VtxUVA, class Mat>
 VF_HD void fan_walk_node(int nslot, const Ring& ring, const VtxXY& vtx_xy, const VtxUVA& vtx_uva,
-                         const Mat& mat, const FanCoef& fc, double* Jglob, double* res_out) {
-  const FanEntry hdr = ring(0);
-  const int deg = fan_hdr_deg(hdr.w1), self = fan_hdr_self(hdr.w1);
-  const int ncell = fan_hdr_ncell(hdr.w1);
-  const bool closed = fan_hdr_closed(hdr.w1);
-  D2* row0 = reinterpret_cast<D2*>(Jglob + 4 * (size_t)hdr.w0);
+                         const Mat& mat, const FanCoef& fc, double* Jtile, double* res_out) {
+  const unsigned hdr = ring(0);
+  const int deg = fan_hdr_deg(hdr), self = fan_hdr_self(hdr);
+  const int ncell = fan_hdr_ncell(hdr);
+  const bool closed = fan_hdr_closed(hdr);
+  D2* row0 = reinterpret_cast<D2*>(Jtile) + 2 * fan_hdr_b0(hdr);
   D2* row1 = row0 + deg;
 
   const D2 xn = vtx_xy(nslot);
   D2 un = D2{0.0, 0.0}, vn = D2{0.0, 0.0}, an = D2{0.0, 0.0};
   if (RES) vtx_uva(nslot, un, vn, an);
 
-  // loads ring entry `row` into rv and returns the id of the cell that FOLLOWS this vertex
-  auto load_ring = [&](int row, FanRing& rv) -> unsigned {
-    const FanEntry ent = ring(row);
-    const int vs = (int)(ent.w0 & 0xffffu);
-    rv.cs = (int)(ent.w0 >> 16);
+  // loads ring entry `row` into rv and returns the local cell that FOLLOWS this vertex
+  auto load_ring = [&](int row, FanRing& rv) -> int {
+    const unsigned ent = ring(row);
+    const int vs = fan_ent_vslot(ent);
+    rv.cs = fan_ent_cslot(ent);
     const D2 x = vtx_xy(vs);
     rv.ex = x.x - xn.x;
     rv.ey = x.y - xn.y;
@@ -171,7 +175,7 @@ VF_HD void fan_walk_node(int nslot, const Ring& ring, const VtxXY& vtx_xy, const
       rv.dvx = v.x - vn.x; rv.dvy = v.y - vn.y;
       rv.ax = a.x; rv.ay = a.y;
     }
-    return ent.w1;
+    return fan_ent_cell(ent);
   };
   auto store = [&](int slot, const FanBlock& a, const FanBlock& b) {
     row0[slot] = D2{a.b00 + b.b00, a.b01 + b.b01};
@@ -186,7 +190,7 @@ VF_HD void fan_walk_node(int nslot, const Ring& ring, const VtxXY& vtx_xy, const
   double emod, eta, rho;
 
   // cell 0 (peeled): its (n, p_0) block waits for the end of the fan
-  unsigned cell = load_ring(1, A);
+  int cell = load_ring(1, A);
   const int cs_first = A.cs;
   mat(cell, emod, eta, rho);
   cell = load_ring(2, B);

@@ -430,6 +430,7 @@ int vf_integrate_host(vf_engine* e, int nsteps, const double* dts_host, int ncon
   if (rc == 0) {
     pack_state_kernel<<<B, 256, 0, st>>>(e->dev, st_state, 1);
     e->launches += 1;
+    if (emod_host || eta_host) std::fill(e->fan_dirty.begin(), e->fan_dirty.end(), 1);
     if (emod_host) {
       pack_array_kernel<<<B, 256, 0, st>>>(e->dev, st_emod, VF_EMOD, (int)ne);
       e->launches += 1;

@@ -255,7 +255,7 @@ int vf_create(const vf_problem_desc* desc, void* arena_dev, size_t arena_bytes, 
   e->arena = A;
   e->arena_bytes = P.total;
   e->launches = 0;
-  e->fan = FanTablesDev{nullptr, nullptr, nullptr, 0, 0, 0, 0};
+  e->fan = FanTablesDev{};
   e->fan_mem = nullptr;
   e->brptr.assign(d.brptr_host, d.brptr_host + d.nn + 1);
   e->bcol.assign(d.bcol_host, d.bcol_host + nnzb);
@@ -354,6 +354,8 @@ int vf_upload(vf_engine* e, int array_id, int member, const double* src_host, si
   size_t off, cnt;
   if (vf_array_info(e, array_id, member, &off, &cnt)) return 1;
   if (count != cnt) return fail("vf_upload: size mismatch for array " + std::to_string(array_id));
+  if ((array_id == VF_RHO || array_id == VF_ETA || array_id == VF_EMOD) && !e->fan_dirty.empty())
+    e->fan_dirty[member] = 1;
   VF_CUDA(cudaMemcpyAsync(e->arena + off, src_host, sizeof(double) * cnt, cudaMemcpyHostToDevice,
                           as_stream(stream)));
   VF_CUDA(cudaStreamSynchronize(as_stream(stream)));

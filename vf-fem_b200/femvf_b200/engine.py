@@ -180,10 +180,12 @@ class Engine:
                 with torch.cuda.device(self.device):
                     check(self._lib.vf_set_fan_tables(
                         self._h, fan['tile_nodes'], fan['ntiles'], _ptr(fan['desc']),
-                        _ptr(fan['ring']), fan['ring'].shape[0], _ptr(fan['halo']),
-                        fan['n_halo'], fan['max_verts'], fan['max_rows'], self._stream()))
+                        _ptr(fan['ring']), fan['ring'].size, _ptr(fan['halo']), fan['n_halo'],
+                        _ptr(fan['tcell']), fan['tcell'].size, fan['max_verts'],
+                        fan['max_rows'], fan['max_cells'], fan['max_blocks'], self._stream()))
                 self.fan_info = {k: fan[k] for k in ('tile_nodes', 'ntiles', 'max_verts',
-                                                     'max_rows', 'n_halo')}
+                                                     'max_rows', 'max_cells', 'max_blocks',
+                                                     'n_halo')}
         self._views = {}
         self._pinned = {}
         self._pinned_up = {}
@@ -207,6 +209,8 @@ class Engine:
 
     def view(self, name: str, member: int = 0) -> torch.Tensor:
         """fp64 view into the arena of a named per-member array."""
+        if name in ('rho', 'eta', 'emod'):
+            self.props_changed(member)   # the caller may write through the view
         key = (name, member)
         if key not in self._views:
             off, cnt = C.c_size_t(), C.c_size_t()
@@ -215,8 +219,17 @@ class Engine:
             self._views[key] = self.arena[off.value:off.value + 8 * cnt.value].view(torch.float64)
         return self._views[key]
 
+    def props_changed(self, member: int = -1):
+        """DG0 properties (rho, eta, emod) were written in the arena directly: the tile-ordered
+        copy used by the fan assembly kernel is refreshed at the next assembly."""
+        h = getattr(self, '_h', None)
+        if h is not None:
+            check(self._lib.vf_props_changed(h, int(member)))
+
     def member_view(self, name: str) -> torch.Tensor:
         """(n_members, count) strided fp64 view of a named array across all members."""
+        if name in ('rho', 'eta', 'emod'):
+            self.props_changed(-1)
         v0 = self.view(name, 0)
         if self.n_members == 1:
             return v0.unsqueeze(0)

@@ -309,21 +309,23 @@ def build_fan_tables(T: dict, tile_nodes: int):
     Every vertex n owns its block row of J and its residual entries.  Its adjacent cells are
     walked counter-clockwise: cell j is (n, p_j, p_{j+1}), so walking the fan loads ONE new ring
     vertex per cell and every off-diagonal block (n, p_j) is the sum of two consecutive cells.
-    Nodes are grouped in contiguous tiles of ``tile_nodes`` (the CTA size); a tile stages its own
-    vertices and the ring vertices outside its range (``halo``) in shared memory.
+    Nodes are grouped in contiguous tiles of ``tile_nodes`` (the CTA size); a tile stages in
+    shared memory its own vertices, the ring vertices outside its range (``halo``), the DG0
+    properties of the cells it touches (``tcell``) and its slice of the CSR value array.
 
-    ring : uint32 (n_ring_words, 2), per tile a block of ``rows`` x ``tile_nodes`` 8-byte entries,
-        row-major (entry (r, t) of the tile belongs to its t-th node: consecutive threads read
-        consecutive words).  Row 0 is the node header
-            word0 = brptr[n]           word1 = deg | self_slot << 8 | ncell << 16 | closed << 24
+    ring : uint32, per tile a block of ``rows`` x ``tile_nodes`` words, row-major (word (r, t)
+        belongs to the tile's t-th node: consecutive threads read consecutive words).  Row 0 is
+        the node header
+            (brptr[n] - brptr[i0]) | deg << 12 | self_slot << 17 | ncell << 22 | closed << 27
         rows 1 + j, j = 0..ncell are the ring vertices p_j
-            word0 = staged slot of p_j | CSR slot of p_j in n's block row << 16
-            word1 = id of cell j = (n, p_j, p_{j+1})   (0xffffffff for the last entry)
-        (a closed fan repeats p_0 as its last entry).
-    desc : int32 (ntiles, 8): i0, nT | nH << 16, halo0, ring0 (in entries), rows, cell_lo,
-        cell_cnt, 0 -- (cell_lo, cell_cnt) is the id window of the bulk of the tile's cells (L2
-        prefetch hint only).
+            staged slot of p_j | CSR slot of p_j in n's block row << 10 | local cell << 15
+        where the local cell indexes the tile's ``tcell`` list and is that of cell
+        j = (n, p_j, p_{j+1}) (0xfff for the last entry; a closed fan repeats p_0 there).
+    tcell : int32, cells touched by each tile (ascending), every tile's list padded to an even
+        count with repeats of its last cell (16-byte granularity of the bulk copies).
     halo : int32, ring vertices outside each tile's own range, ascending per tile.
+    desc : int32 (ntiles, 12): i0, nT | nH << 16, halo0, ring0 (words), rows, tcell0,
+        padded cell count, brptr[i0], number of blocks of the tile, 0, 0, 0.
     Returns None when the packing limits do not hold.
     """
     if T['dim'] != 2 or not T.get('fan_ok', False):
@@ -337,7 +339,7 @@ def build_fan_tables(T: dict, tile_nodes: int):
     n2e = T['n2e'].astype(np.int64)
     deg = np.diff(brptr)
     ncell = np.diff(n2e_ptr)
-    if deg.max() >= 256 or ncell.max() >= 255 or np.any(ncell == 0):
+    if deg.max() >= 32 or ncell.max() >= 31 or np.any(ncell == 0):
         return None
     ntiles = -(-nn // TN)
     node = np.repeat(np.arange(nn), ncell)
@@ -347,6 +349,27 @@ def build_fan_tables(T: dict, tile_nodes: int):
     first = n2e_ptr[:-1]
     last = n2e_ptr[1:] - 1
     closed = vq[last] == vp[first]
+    tile_of = np.arange(nn) // TN
+    i0 = np.arange(ntiles, dtype=np.int64) * TN
+    nT = np.minimum(i0 + TN, nn) - i0
+    # cells touched by each tile, ascending; local index of every (node, cell) pair
+    pt = tile_of[node]
+    ckey = np.unique(pt * ne + pe)
+    ctile = ckey // ne
+    tc_cnt = np.zeros(ntiles, dtype=np.int64)
+    np.add.at(tc_cnt, ctile, 1)
+    tc_raw = np.zeros(ntiles + 1, dtype=np.int64)
+    tc_raw[1:] = np.cumsum(tc_cnt)
+    lcell_pair = np.searchsorted(ckey, pt * ne + pe) - tc_raw[pt]
+    ncp = tc_cnt + (tc_cnt & 1)             # padded to an even count
+    if ncp.max() >= 0xfff:
+        return None
+    tc_ptr = np.zeros(ntiles + 1, dtype=np.int64)
+    tc_ptr[1:] = np.cumsum(ncp)
+    tcell = np.empty(int(tc_ptr[-1]), dtype=np.int64)
+    tcell[tc_ptr[ctile] + (np.arange(len(ckey)) - tc_raw[ctile])] = ckey % ne
+    odd = np.nonzero(tc_cnt & 1)[0]
+    tcell[tc_ptr[odd] + tc_cnt[odd]] = tcell[tc_ptr[odd] + tc_cnt[odd] - 1]
     # ring entries: ncell + 1 per node
     rptr = np.zeros(nn + 1, dtype=np.int64)
     rptr[1:] = np.cumsum(ncell + 1)
@@ -356,13 +379,12 @@ def build_fan_tables(T: dict, tile_nodes: int):
     is_last = ent_j == ncell[ent_node]
     pair_of = n2e_ptr[ent_node] + np.minimum(ent_j, ncell[ent_node] - 1)
     ent_v = np.where(is_last, vq[pair_of], vp[pair_of])
-    ent_cell = np.where(is_last, 0xffffffff, pe[pair_of])
+    ent_cell = np.where(is_last, 0xfff, lcell_pair[pair_of])
     # CSR slot of the ring vertex in the node's block row
     gkey = np.repeat(np.arange(nn), deg) * nn + bcol
     cslot = np.searchsorted(gkey, ent_node * nn + ent_v) - brptr[ent_node]
     self_slot = np.searchsorted(gkey, np.arange(nn) * (nn + 1)) - brptr[:-1]
     # halo vertices per tile and staged slots
-    tile_of = np.arange(nn) // TN
     ent_tile = tile_of[ent_node]
     halo_mask = tile_of[ent_v] != ent_tile
     hkey = np.unique(ent_tile[halo_mask] * nn + ent_v[halo_mask])
@@ -370,55 +392,48 @@ def build_fan_tables(T: dict, tile_nodes: int):
     th_ptr = np.zeros(ntiles + 1, dtype=np.int64)
     np.add.at(th_ptr, htile + 1, 1)
     th_ptr = np.cumsum(th_ptr)
-    i0 = np.arange(ntiles, dtype=np.int64) * TN
-    nT = np.minimum(i0 + TN, nn) - i0
     nH = np.diff(th_ptr)
-    if (nT + nH).max() >= 65536:
+    if (nT + nH).max() >= 1024:
         return None
     vslot = np.where(halo_mask,
                      np.searchsorted(hkey, ent_tile * nn + ent_v) - th_ptr[ent_tile] + nT[ent_tile],
                      ent_v - i0[ent_tile])
+    bbase = brptr[i0]
+    nblk = brptr[np.minimum(i0 + TN, nn)] - bbase
+    rel_b0 = brptr[:-1] - bbase[tile_of]
+    if rel_b0.max() >= 4096:
+        return None
     # per-tile ring blocks
     rows_node = ncell + 2                                  # header + ncell + 1 entries
     rows = np.zeros(ntiles, dtype=np.int64)
     np.maximum.at(rows, tile_of, rows_node)
     ring0 = np.zeros(ntiles + 1, dtype=np.int64)
     ring0[1:] = np.cumsum(rows * TN)
-    ring = np.zeros((int(ring0[-1]), 2), dtype=np.uint32)
-    ring[:, 1] = 0xffffffff
+    if ring0[-1] >= 2**31:
+        return None
+    ring = np.full(int(ring0[-1]), 0xfff << 15, dtype=np.uint32)
     t_in = np.arange(nn) - i0[tile_of]
     hdr = ring0[tile_of] + t_in
-    ring[hdr, 0] = brptr[:-1]
-    ring[hdr, 1] = deg | (self_slot << 8) | (ncell << 16) | (closed.astype(np.int64) << 24)
+    ring[hdr] = (rel_b0 | (deg << 12) | (self_slot << 17) | (ncell << 22)
+                 | (closed.astype(np.int64) << 27))
     pos = ring0[ent_tile] + (1 + ent_j) * TN + t_in[ent_node]
-    ring[pos, 0] = vslot | (cslot << 16)
-    ring[pos, 1] = ent_cell
-    # id window of the bulk of each tile's cells (10%..90% quantiles): L2 prefetch hint
-    pt = tile_of[node]
-    order = np.lexsort((pe, pt))
-    pes = pe[order]
-    tp = np.zeros(ntiles + 1, dtype=np.int64)
-    np.add.at(tp, pt + 1, 1)
-    tp = np.cumsum(tp)
-    nb = np.diff(tp)
-    lo = pes[tp[:-1] + nb // 10]
-    hi = pes[tp[:-1] + np.maximum(nb - nb // 10 - 1, 0)]
-    cnt = np.minimum(hi - lo + 1, 4 * nb)
-    desc = np.zeros((ntiles, 8), dtype=np.int64)
+    ring[pos] = vslot | (cslot << 10) | (ent_cell << 15)
+    desc = np.zeros((ntiles, 12), dtype=np.int64)
     desc[:, 0] = i0
     desc[:, 1] = nT | (nH << 16)
     desc[:, 2] = th_ptr[:-1]
     desc[:, 3] = ring0[:-1]
     desc[:, 4] = rows
-    desc[:, 5] = lo
-    desc[:, 6] = cnt
-    if ring0[-1] >= 2**31:
-        return None
+    desc[:, 5] = tc_ptr[:-1]
+    desc[:, 6] = ncp
+    desc[:, 7] = bbase
+    desc[:, 8] = nblk
     return {
         'tile_nodes': TN, 'ntiles': int(ntiles),
         'desc': np.ascontiguousarray(desc.astype(np.uint32).view(np.int32)),
         'ring': np.ascontiguousarray(ring),
+        'tcell': np.ascontiguousarray(tcell.astype(np.int32)),
         'halo': hvert.astype(np.int32) if len(hvert) else np.zeros(1, np.int32),
         'n_halo': int(len(hvert)), 'max_verts': int((nT + nH).max()),
-        'max_rows': int(rows.max()),
+        'max_rows': int(rows.max()), 'max_cells': int(ncp.max()), 'max_blocks': int(nblk.max()),
     }
