@@ -13,12 +13,11 @@ from femvf_b200.engine import Engine
 levels = int(sys.argv[1]) if len(sys.argv) > 1 else 7
 model = bench.build_big_model(levels, 0)
 T = model.assembly_tables
-TUNABLES = ('VF_FAN', 'VF_FAN_NODES', 'VF_FAN_MINB', 'VF_PF_DIST')
-configs = [dict(VF_FAN='0')]
-configs += [dict(VF_FAN_NODES='128', VF_FAN_MINB=mb) for mb in ('3', '4')]
-configs += [dict(VF_FAN_NODES=tn) for tn in ('96', '64')]
-configs += [dict(VF_FAN_NODES=tn, VF_PF_DIST='0') for tn in ('128', '96', '64')]
-configs += [dict(VF_FAN_NODES='96', VF_PF_DIST=pf) for pf in ('370', '1480')]
+TUNABLES = ('VF_FAN', 'VF_FAN_NODES', 'VF_FAN_MINB', 'VF_PF_DIST', 'VF_FAN_PIPE', 'VF_PIPE_GROUPS',
+            'VF_PIPE_POOL_KB', 'VF_PIPE_PF', 'VF_PIPE_GRID')
+configs = [dict(VF_FAN='0'), dict(VF_FAN_PIPE='0'), dict()]
+configs += [dict(VF_PIPE_PF=pf) for pf in ('0', '1', '4')]
+configs += [dict(VF_PIPE_GROUPS='2'), dict(VF_PIPE_POOL_KB='100'), dict(VF_PIPE_POOL_KB='70')]
 ref = None
 for cfg in configs:
     for k in TUNABLES:

@@ -587,6 +587,408 @@ __global__ void __launch_bounds__(TN, MINB) asm_fan_kernel(
   if (JAC && tid == 0) bulk_wait_read();
 }
 
+// ---- the same fan walk as a persistent, warp-specialised pipeline ---------------------------
+// One CTA per SM, alive for the whole launch; tile k of CTA b is tile b + k * gridDim.x.
+// Warpgroup 0 (keeps 56 registers per thread, the rest goes to the consumers: setmaxnreg):
+//   warps 0-2   producer team.  Warp 0 owns a circular byte pool in shared memory: for every tile
+//               it carves a stage of exactly the tile's size out of it (waiting, oldest first, for
+//               consumed stages to be released: mbarrier `empty`).  The team then brings the
+//               tile's inputs in WITHOUT touching registers: bulk asynchronous copies (TMA engine,
+//               complete_tx on the stage's `full` mbarrier) for everything contiguous -- ring
+//               table, tile-ordered cell properties, the own-vertex ranges of xy, u1, u0, v0, a0
+//               -- and 16-byte cp.async gathers for the halo vertices
+//               (cp.async.mbarrier.arrive.noinc ties them to the same mbarrier).  While those are
+//               in flight it turns the raw nodal state of the PREVIOUS tile's stage into
+//               (u1, v_nmk, a_nmk) in place and arrives on that stage's `ready` mbarrier.
+//   warp 3      pulls the inputs of the tiles pf_dist rounds ahead into L2.
+// Warpgroups 1 .. NG (152 registers per thread when NG = 3): consumer groups, one thread per node
+// of a 128-node tile; group g takes tiles k = g, g + NG, ...  Every consumer WARP is on its own:
+// it waits on `ready`, walks the fans of its 32 nodes out of shared memory into its private slice
+// buffer, hands the slice (contiguous in the CSR array) to one bulk store and arrives on `empty`.
+// Consumers never wait on global memory and never on each other.
+// Stage: [ring | cell properties | xy | u1 | u0 | v0 -> v_nmk | a0 -> a_nmk], sized per tile.
+constexpr int kPipeSlots = 8;  // tiles in flight per CTA (barrier slots)
+constexpr int kRecSlots = 8;   // ring of producer records ...
+constexpr int kRecAhead = 7;   // ... fetched this many tiles ahead of their use (DRAM latency)
+
+template <bool JAC, bool RES, int NG>
+__global__ void __launch_bounds__(128 + 128 * NG, 1) asm_fan_pipe_kernel(
+    EngineDev E, int member, NewmarkCoef nc_arg, int is_static, JacMix mix, FanTablesDev T,
+    const double* __restrict__ mat_m, int wj_bytes, int pool_bytes, int pf_dist, int dbg) {
+  constexpr int TN = 128;
+  extern __shared__ __align__(128) unsigned char pipe_smem[];
+  __shared__ __align__(8) unsigned long long s_full[kPipeSlots], s_ready[kPipeSlots],
+      s_empty[kPipeSlots], s_rec[kRecSlots];
+  __shared__ int s_off[kPipeSlots];
+  __shared__ int4 s_desc[kPipeSlots][3];  // the tile's descriptor, for the consumers
+  __shared__ FanCoef s_fc;
+  unsigned char* const s_recbuf = pipe_smem + (JAC ? (size_t)4 * NG * wj_bytes : 0);
+  unsigned char* const pool = s_recbuf + (size_t)kRecSlots * T.prec_stride;
+  double* mb = E.members + (size_t)member * E.L.stride;
+  const Layout& L = E.L;
+  const MeshView& m = E.mesh;
+  const int ntiles = T.ntiles;
+  const double* u1 = mb + L.off[VF_U1];
+  const double* u0 = mb + L.off[VF_U0];
+  const double* v0 = mb + L.off[VF_V0];
+  const double* a0 = mb + L.off[VF_A0];
+  const bool dyn = RES && !is_static;
+  constexpr int kPlanes = RES ? 5 : 1;
+  // producer team: warps 0-2 (warp 3 converts) or, team4, all of warpgroup 0 (consumers convert)
+  const bool team4 = (dbg & 256) != 0;
+  const int kTeam = team4 ? 128 : 96;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kPipeSlots; ++s) {
+      mbar_init_only(&s_full[s], 3 + kTeam);   // 3 expect_tx arrivals + one cp.async arrival per team thread
+      mbar_init_only(&s_ready[s], 32);         // every converter thread
+      mbar_init_only(&s_empty[s], 4);   // lane 0 of each consumer warp of the group
+    }
+    for (int s = 0; s < kRecSlots; ++s) mbar_init_only(&s_rec[s], 1);
+    mbar_init_fence();
+    const PropView pv = member_props<2>(E, mb);
+    s_fc = fan_coef(lame_fac(pv.scal[SC_NU]), prop_damping(pv), mix);
+  }
+  __syncthreads();
+
+  if (threadIdx.x < 128) {
+    if (NG == 3) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    if (threadIdx.x >= kTeam) {
+      // ============================ converter: warp 3 ==============================================
+      if (!RES) return;
+      const int ct = (int)threadIdx.x - kTeam;
+      for (int k = 0; k < my_tiles; ++k) {
+        const int i = k & (kPipeSlots - 1);
+        mbar_wait(&s_full[i], (unsigned)(k / kPipeSlots) & 1u);
+        const int4 d0 = s_desc[i][0], d1 = s_desc[i][1];
+        const int nV = (d0.y & 0xffff) + (int)((unsigned)d0.y >> 16);
+        D2* s_u = reinterpret_cast<D2*>(pool + s_off[i] + d1.x * TN * (int)sizeof(unsigned) + d1.z * 24) + nV;
+        D2* s_u0 = s_u + nV;
+        D2* s_v = s_u0 + nV;
+        D2* s_a = s_v + nV;
+        if (is_static) {
+          for (int t = ct; t < nV; t += 32) {
+            s_v[t] = D2{0.0, 0.0};
+            s_a[t] = D2{0.0, 0.0};
+          }
+        } else {
+          // two vertices per pass: independent chains hide the fp64 latency of a lone warp
+          for (int t = ct; t < nV; t += 64) {
+            const int t2 = t + 32 < nV ? t + 32 : t;
+            const D2 a_u = s_u[t], a_u0 = s_u0[t], a_v = s_v[t], a_a = s_a[t];
+            const D2 b_u = s_u[t2], b_u0 = s_u0[t2], b_v = s_v[t2], b_a = s_a[t2];
+            const NodeUVA ra = node_uva(nc_arg, false, a_u, a_u0, a_v, a_a);
+            const NodeUVA rb = node_uva(nc_arg, false, b_u, b_u0, b_v, b_a);
+            s_v[t] = ra.v;
+            s_a[t] = ra.a;
+            if (t2 != t) {
+              s_v[t2] = rb.v;
+              s_a[t2] = rb.a;
+            }
+          }
+        }
+        mbar_arrive(&s_ready[i]);
+      }
+      return;
+    }
+    // ================= producer team: warps 0-2 -- 96 threads in lockstep per tile ================
+    const int tt = threadIdx.x, lane = tt & 31, role = tt >> 5;
+    const int rstride = T.prec_stride;  // bytes
+    // producer records (descriptor + halo vertex ids of a tile) arrive by bulk copies kRecAhead
+    // tiles ahead of their use: no index load is ever on the critical path of the team
+    auto fetch_record = [&](int k) {
+      if (tt == 0 && k < my_tiles) {
+        const size_t tile = (size_t)blockIdx.x + (size_t)k * gridDim.x;
+        mbar_expect_tx(&s_rec[k & (kRecSlots - 1)], (unsigned)rstride);
+        bulk_g2s(s_recbuf + (size_t)(k & (kRecSlots - 1)) * rstride, T.prec + tile * rstride,
+                 (unsigned)rstride, &s_rec[k & (kRecSlots - 1)]);
+      }
+    };
+    for (int k = 0; k < kRecAhead; ++k) fetch_record(k);
+    int head = 0, tail_off = 0, tail = 0, inflight = 0;  // allocator state (warp 0 only)
+    bool wrapped = false;
+    for (int k = 0; k < my_tiles; ++k) {
+      const int i = k & (kPipeSlots - 1);
+      mbar_wait(&s_rec[k & (kRecSlots - 1)], (unsigned)(k / kRecSlots) & 1u);
+      const int* rec = reinterpret_cast<const int*>(s_recbuf + (size_t)(k & (kRecSlots - 1)) * rstride);
+      const int4 d0 = reinterpret_cast<const int4*>(rec)[0], d1 = reinterpret_cast<const int4*>(rec)[1];
+      const int i0 = d0.x, nT = d0.y & 0xffff, nH = (int)((unsigned)d0.y >> 16);
+      const int ring0 = d0.w, rows = d1.x, tc0 = d1.y, ncp = d1.z;
+      const int nV = nT + nH;
+      const int n_ring = rows * TN * (int)sizeof(unsigned), n_mat = ncp * 24, n_vec = nV * 16;
+      if (role == 0) {
+        // ---- carve the stage out of the circular pool; stages are released oldest first ----------
+        const int sz = (n_ring + n_mat + kPlanes * n_vec + 127) & ~127;
+        int off;
+        for (;;) {
+          if (inflight == 0) {
+            off = 0;
+            wrapped = false;
+            break;
+          }
+          if (inflight < kPipeSlots) {
+            if (!wrapped) {
+              if (head + sz <= pool_bytes) {
+                off = head;
+                break;
+              }
+              if (sz <= tail_off) {
+                off = 0;
+                wrapped = true;
+                break;
+              }
+            } else if (head + sz <= tail_off) {
+              off = head;
+              break;
+            }
+          }
+          mbar_wait(&s_empty[tail & (kPipeSlots - 1)], (unsigned)(tail / kPipeSlots) & 1u);
+          ++tail;
+          --inflight;
+          if (inflight) {
+            const int t_new = s_off[tail & (kPipeSlots - 1)];
+            if (t_new < tail_off) wrapped = false;  // the oldest stage is past the wrap point too
+            tail_off = t_new;
+          }
+        }
+        if (inflight == 0) tail_off = off;
+        head = off + sz;
+        ++inflight;
+        if (lane == 0) {
+          // published to the consumers by this thread's arrive.expect_tx (release) on `full`
+          s_off[i] = off;
+          s_desc[i][0] = d0;
+          s_desc[i][1] = d1;
+          s_desc[i][2] = reinterpret_cast<const int4*>(rec)[2];
+        }
+      }
+      named_barrier(1, kTeam);
+      // the record slot of tile k - 1 is free now (every thread is past its reads)
+      fetch_record(k - 1 + kRecSlots);
+      unsigned char* st = pool + s_off[i];
+      D2* s_xy = reinterpret_cast<D2*>(st + n_ring + n_mat);
+      D2* s_u1 = s_xy + nV;
+      D2* s_u0 = s_u1 + nV;
+      D2* s_v0 = s_u0 + nV;
+      D2* s_a0 = s_v0 + nV;
+      if (!(dbg & 128)) {
+        // contiguous inputs as coalesced 16-byte cp.async (LSU path, 512 bytes per warp
+        // instruction): measured, the bulk-copy engine moves ~16 B/clk per SM in both directions
+        // together, and the CSR slices going out already keep it busy (profiles/README.md)
+        auto copy16 = [&](void* dst, const void* src, int nbytes) {
+          for (int o = tt * 16; o < nbytes; o += kTeam * 16)
+            cp_async16(reinterpret_cast<unsigned char*>(dst) + o,
+                       reinterpret_cast<const unsigned char*>(src) + o);
+        };
+        const int n_own = nT * 16;
+        copy16(st, T.ring + ring0, n_ring);
+        copy16(st + n_ring, mat_m + (size_t)3 * tc0, n_mat);
+        copy16(s_xy, m.xy + 2 * (size_t)i0, n_own);
+        if (RES) {
+          copy16(s_u1, u1 + 2 * (size_t)i0, n_own);
+          if (dyn) {
+            copy16(s_u0, u0 + 2 * (size_t)i0, n_own);
+            copy16(s_v0, v0 + 2 * (size_t)i0, n_own);
+            copy16(s_a0, a0 + 2 * (size_t)i0, n_own);
+          }
+        }
+        if (lane == 0 && role < 3) mbar_arrive(&s_full[i]);  // stands in for the expect_tx arrival
+      } else
+      if (lane == 0 && role < 3 && !(dbg & 6)) {
+        // VF_PIPE_DBG 128: the seven bulk copies of the tile (bulk-copy engine), spread over the warps
+        const unsigned n_own = (unsigned)nT * 16u;
+        if (role == 0) {
+          mbar_expect_tx(&s_full[i], (unsigned)(n_ring + n_mat));
+          bulk_g2s(st, T.ring + ring0, (unsigned)n_ring, &s_full[i]);
+          bulk_g2s(st + n_ring, mat_m + (size_t)3 * tc0, (unsigned)n_mat, &s_full[i]);
+        } else if (role == 1) {
+          mbar_expect_tx(&s_full[i], n_own * (RES ? (dyn ? 3u : 2u) : 1u));
+          bulk_g2s(s_xy, m.xy + 2 * (size_t)i0, n_own, &s_full[i]);
+          if (RES) bulk_g2s(s_u1, u1 + 2 * (size_t)i0, n_own, &s_full[i]);
+          if (dyn) bulk_g2s(s_u0, u0 + 2 * (size_t)i0, n_own, &s_full[i]);
+        } else if (role == 2) {
+          mbar_expect_tx(&s_full[i], dyn ? 2u * n_own : 0u);
+          if (dyn) {
+            bulk_g2s(s_v0, v0 + 2 * (size_t)i0, n_own, &s_full[i]);
+            bulk_g2s(s_a0, a0 + 2 * (size_t)i0, n_own, &s_full[i]);
+          }
+        }
+      } else if (lane == 0 && role < 3) {
+        mbar_expect_tx(&s_full[i], 0u);  // VF_PIPE_DBG 2 / 4 (measurement aid): no bulk copies
+      }
+      __syncwarp();
+      // one halo vertex per thread: 16-byte asynchronous gathers
+      for (int h = tt; h < nH && !(dbg & 1); h += kTeam) {
+        const size_t v = (size_t)rec[16 + h];
+        cp_async16(s_xy + nT + h, m.xy + 2 * v);
+        if (RES) {
+          cp_async16(s_u1 + nT + h, u1 + 2 * v);
+          if (dyn) {
+            cp_async16(s_u0 + nT + h, u0 + 2 * v);
+            cp_async16(s_v0 + nT + h, v0 + 2 * v);
+            cp_async16(s_a0 + nT + h, a0 + 2 * v);
+          }
+        }
+      }
+      cp_async_mbar_arrive_noinc(&s_full[i]);
+      // pull the inputs of the tile pf_dist rounds ahead into L2 (its record is already here)
+      if (pf_dist > 0 && k + pf_dist < my_tiles) {
+        const int kf = k + pf_dist;
+        const bool pf_halo = !(dbg & 32);  // VF_PIPE_DBG 32: no prefetch of the halo vertex lines
+        mbar_wait(&s_rec[kf & (kRecSlots - 1)], (unsigned)(kf / kRecSlots) & 1u);
+        const int* fr = reinterpret_cast<const int*>(s_recbuf + (size_t)(kf & (kRecSlots - 1)) * rstride);
+        const int4 f0 = reinterpret_cast<const int4*>(fr)[0], f1 = reinterpret_cast<const int4*>(fr)[1];
+        const int f_i0 = f0.x, f_nT = f0.y & 0xffff, f_nH = (int)((unsigned)f0.y >> 16);
+        if (lane == 0) {
+          // contiguous inputs: one bulk prefetch each, split like the copies
+          const unsigned f_own = (unsigned)f_nT * 16u;
+          if (role == 0) {
+            bulk_prefetch_l2(T.ring + f0.w, (unsigned)f1.x * TN * (unsigned)sizeof(unsigned));
+            bulk_prefetch_l2(mat_m + (size_t)3 * f1.y, (unsigned)f1.z * 24u);
+          } else if (role == 1) {
+            bulk_prefetch_l2(m.xy + 2 * (size_t)f_i0, f_own);
+            if (RES) bulk_prefetch_l2(u1 + 2 * (size_t)f_i0, f_own);
+            if (dyn) bulk_prefetch_l2(u0 + 2 * (size_t)f_i0, f_own);
+          } else if (role == 2 && dyn) {
+            bulk_prefetch_l2(v0 + 2 * (size_t)f_i0, f_own);
+            bulk_prefetch_l2(a0 + 2 * (size_t)f_i0, f_own);
+          }
+        }
+        __syncwarp();
+        if (pf_halo)
+        for (int h = tt; h < f_nH; h += kTeam) {
+          const size_t v = (size_t)fr[16 + h];
+          prefetch_l2(m.xy + 2 * v);
+          if (RES) {
+            prefetch_l2(u1 + 2 * v);
+            if (dyn) {
+              prefetch_l2(u0 + 2 * v);
+              prefetch_l2(v0 + 2 * v);
+              prefetch_l2(a0 + 2 * v);
+            }
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  // ================================== consumer warps ===============================================
+  if (NG == 3) asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+  const int g = ((int)threadIdx.x - 128) / TN;
+  const int tid = ((int)threadIdx.x - 128) % TN;
+  const int lane = tid & 31, w0 = tid & ~31;
+  double* s_Jw = reinterpret_cast<double*>(pipe_smem + (size_t)(4 * g + (tid >> 5)) * wj_bytes);
+#ifdef VF_PIPE_PROF
+  long long ck_wait = 0, ck_jwait = 0, ck_walk = 0, ck_t0 = clock64();
+#endif
+  for (int k = g;; k += NG) {
+    const long long tile_ll = (long long)blockIdx.x + (long long)k * gridDim.x;
+    if (tile_ll >= ntiles) break;
+    const int i = k & (kPipeSlots - 1);
+    const unsigned ph = (unsigned)(k / kPipeSlots) & 1u;
+#ifdef VF_PIPE_PROF
+    const long long c0 = clock64();
+#endif
+    mbar_wait(RES && !team4 ? &s_ready[i] : &s_full[i], ph);
+#ifdef VF_PIPE_PROF
+    const long long c1 = clock64();
+    ck_wait += c1 - c0;
+#endif
+    const int4 d0 = s_desc[i][0], d1 = s_desc[i][1];
+    const int i0 = d0.x, nT = d0.y & 0xffff, nH = (int)((unsigned)d0.y >> 16);
+    const int ncp = d1.z, bbase = d1.w;
+    const int nV = nT + nH;
+    const int nblk = JAC ? s_desc[i][2].x : 0;
+    const unsigned char* st = pool + s_off[i];
+    const unsigned* s_ring = reinterpret_cast<const unsigned*>(st);
+    const double* s_mat = reinterpret_cast<const double*>(st + d1.x * TN * (int)sizeof(unsigned));
+    const D2* s_xy = reinterpret_cast<const D2*>(s_mat + 3 * ncp);
+    const D2* s_u = s_xy + nV;
+    D2* s_v = const_cast<D2*>(s_u) + 2 * nV;
+    D2* s_a = s_v + nV;
+    if (RES && team4) {
+      // raw nodal state -> (u1, v_nmk, a_nmk), once per staged vertex, in place, by the group
+      const D2* s_u0 = s_u + nV;
+      for (int t = tid; t < nV; t += TN) {
+        if (is_static) {
+          s_v[t] = D2{0.0, 0.0};
+          s_a[t] = D2{0.0, 0.0};
+        } else {
+          const NodeUVA r = node_uva(nc_arg, false, s_u[t], s_u0[t], s_v[t], s_a[t]);
+          s_v[t] = r.v;
+          s_a[t] = r.a;
+        }
+      }
+      named_barrier(2 + g, TN);
+    }
+    // this warp's slice of the tile's CSR values: blocks [b_lo, b_hi) relative to the tile
+    int b_lo = 0, b_hi = 0;
+    if (JAC && w0 < nT) {
+      b_lo = fan_hdr_b0(s_ring[w0]);
+      b_hi = w0 + 32 < nT ? fan_hdr_b0(s_ring[w0 + 32]) : nblk;
+      // the slice buffer is free once the bulk store of the previous tile has read it
+      if (lane == 0 && !(dbg & 64)) bulk_wait_read();
+      __syncwarp();
+    }
+#ifdef VF_PIPE_PROF
+    const long long c2 = clock64();
+    ck_jwait += c2 - c1;
+#endif
+    if (tid < nT && !(dbg & 8)) {
+      const FanCoef& fc = s_fc;
+      auto ring = [&](int r) { return s_ring[r * TN + tid]; };
+      auto vtx_xy = [&](int v) { return s_xy[v]; };
+      auto vtx_uva = [&](int v, D2& pu, D2& pv, D2& pa) {
+        pu = s_u[v];
+        pv = s_v[v];
+        pa = s_a[v];
+      };
+      auto mat = [&](int c, double& emod, double& eta, double& rho) {
+        emod = s_mat[c];
+        eta = s_mat[ncp + c];
+        rho = s_mat[2 * ncp + c];
+      };
+      double res[2];
+      fan_walk_node<JAC, RES>(tid, ring, vtx_xy, vtx_uva, mat, fc, s_Jw - 4 * (ptrdiff_t)b_lo, res);
+      if (RES) reinterpret_cast<D2*>(mb + L.off[VF_F])[i0 + tid] = D2{res[0], res[1]};
+    }
+    // generic-proxy writes (slice, converted state) are read / overwritten by the bulk-copy engine
+    fence_proxy_async_smem();
+    __syncwarp();
+#ifdef VF_PIPE_PROF
+    ck_walk += clock64() - c2;
+#endif
+    if (JAC && (dbg & 64) && b_hi > b_lo) {
+      // VF_PIPE_DBG 64: the warp streams its slice out itself (coalesced 16-byte stores)
+      const double2* src = reinterpret_cast<const double2*>(s_Jw);
+      double2* dst = reinterpret_cast<double2*>(mb + L.off[VF_J] + 4 * ((size_t)bbase + b_lo));
+      const int n2 = 2 * (b_hi - b_lo);
+      for (int o = lane; o < n2; o += 32) __stcs(dst + o, src[o]);
+      __syncwarp();
+    }
+    if (lane == 0) {
+      if (JAC && b_hi > b_lo && !(dbg & (16 | 64))) {
+        bulk_s2g(mb + L.off[VF_J] + 4 * ((size_t)bbase + b_lo), s_Jw, (unsigned)(b_hi - b_lo) * 32u);
+        bulk_commit();
+      }
+      mbar_arrive(&s_empty[i]);
+    }
+  }
+  // shared memory must stay allocated until the last bulk store has read it
+  if (JAC && lane == 0) bulk_wait_read();
+#ifdef VF_PIPE_PROF
+  if (lane == 0) {
+    double* info = mb + L.off[VF_INFO];
+    atomicAdd(info + 12, (double)(clock64() - ck_t0));  // consumer warp: loop total
+    atomicAdd(info + 13, (double)ck_wait);              //   waiting for a ready stage
+    atomicAdd(info + 14, (double)ck_jwait);             //   waiting for the slice buffer
+    atomicAdd(info + 15, (double)ck_walk);              //   walking
+  }
+#endif
+}
+
 template <int D, bool JAC, bool RES>
 __global__ void facet_bc_kernel(EngineDev E, int member, double dt, int is_static, JacMix mix,
                                 const int* __restrict__ touch_nodes, int n_touch) {
@@ -789,13 +1191,29 @@ int vf_set_fan_tables(vf_engine* e, int tile_nodes, int ntiles, const int32_t* d
   const size_t b_halo = align_up(sizeof(int32_t) * std::max<size_t>(n_halo, 1), 256);
   const size_t b_tcell = align_up(sizeof(int32_t) * n_tcell, 256);
   const size_t b_mat = sizeof(double) * 3 * n_tcell * (size_t)e->desc.n_members;
+  // producer records of the pipelined kernel: [descriptor (12 int32) | 4 pad | halo vertex ids],
+  // one fixed stride per tile, so that one bulk copy brings a tile's control data on chip
+  int max_nh = 0;
+  for (int t = 0; t < ntiles; ++t)
+    max_nh = std::max(max_nh, (int)((uint32_t)desc_host[12 * (size_t)t + 1] >> 16));
+  const int prec_stride = 64 + 4 * ((max_nh + 3) / 4 * 4);
+  std::vector<int32_t> prec((size_t)ntiles * (prec_stride / 4), 0);
+  for (int t = 0; t < ntiles; ++t) {
+    int32_t* r = prec.data() + (size_t)t * (prec_stride / 4);
+    const int32_t* d = desc_host + 12 * (size_t)t;
+    std::copy(d, d + 12, r);
+    const int nh = (int)((uint32_t)d[1] >> 16);
+    if ((size_t)d[2] + nh > std::max<size_t>(n_halo, 1)) return fail("fan halo list out of range");
+    std::copy(halo_host + d[2], halo_host + d[2] + nh, r + 16);
+  }
+  const size_t b_prec = align_up(prec.size() * sizeof(int32_t), 256);
   if (e->fan_mem) {
     cudaFree(e->fan_mem);
     e->fan_mem = nullptr;
     e->fan.ring = nullptr;
   }
   char* mem = nullptr;
-  VF_CUDA(cudaMalloc(&mem, b_desc + b_ring + b_halo + b_tcell + b_mat));
+  VF_CUDA(cudaMalloc(&mem, b_desc + b_ring + b_halo + b_tcell + b_prec + b_mat));
   e->fan_mem = mem;
   VF_CUDA(cudaMemcpyAsync(mem, desc_host, sizeof(int32_t) * 12 * (size_t)ntiles,
                           cudaMemcpyHostToDevice, st));
@@ -806,13 +1224,17 @@ int vf_set_fan_tables(vf_engine* e, int tile_nodes, int ntiles, const int32_t* d
                             cudaMemcpyHostToDevice, st));
   VF_CUDA(cudaMemcpyAsync(mem + b_desc + b_ring + b_halo, tcell_host, sizeof(int32_t) * n_tcell,
                           cudaMemcpyHostToDevice, st));
+  VF_CUDA(cudaMemcpyAsync(mem + b_desc + b_ring + b_halo + b_tcell, prec.data(),
+                          prec.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   VF_CUDA(cudaStreamSynchronize(st));
   FanTablesDev& T = e->fan;
   T.desc = reinterpret_cast<const int4*>(mem);
   T.ring = reinterpret_cast<const unsigned*>(mem + b_desc);
   T.halo = reinterpret_cast<const int*>(mem + b_desc + b_ring);
   T.tcell = reinterpret_cast<const int*>(mem + b_desc + b_ring + b_halo);
-  T.mat = reinterpret_cast<double*>(mem + b_desc + b_ring + b_halo + b_tcell);
+  T.prec = reinterpret_cast<const unsigned char*>(mem + b_desc + b_ring + b_halo + b_tcell);
+  T.prec_stride = prec_stride;
+  T.mat = reinterpret_cast<double*>(mem + b_desc + b_ring + b_halo + b_tcell + b_prec);
   T.n_tcell = n_tcell;
   T.tile_nodes = tile_nodes;
   T.ntiles = ntiles;
@@ -821,6 +1243,13 @@ int vf_set_fan_tables(vf_engine* e, int tile_nodes, int ntiles, const int32_t* d
   T.max_cells = max_cells;
   T.max_blocks = max_blocks;
   e->fan_dirty.assign((size_t)e->desc.n_members, 1);
+  // largest number of CSR blocks owned by 32 consecutive nodes (a consumer warp of the pipeline)
+  e->fan_max_wblocks = 0;
+  if (e->brptr.size() == (size_t)e->desc.nn + 1) {
+    const int nn = e->desc.nn;
+    for (int n = 0; n < nn; n += 32)
+      e->fan_max_wblocks = std::max(e->fan_max_wblocks, e->brptr[std::min(n + 32, nn)] - e->brptr[n]);
+  }
   return 0;
 }
 
@@ -905,6 +1334,80 @@ int launch_fan(vf_engine* e, int member, bool res, bool jac, double dt, int is_s
   return 0;
 }
 
+// Persistent producer / consumer pipeline (asm_fan_pipe_kernel): the default when the tile is
+// 128 nodes and the slice buffers of the consumer warps leave a pool of at least two of the
+// largest stages in the 227 KB of an SM.
+size_t fan_pipe_stage_bytes(const FanTablesDev& T, bool res) {
+  return sizeof(unsigned) * (size_t)T.max_rows * 128 + 24 * (size_t)T.max_cells +
+         sizeof(D2) * (size_t)T.max_verts * (res ? 5 : 1) + 128;
+}
+
+// returns 0 when launched, -1 when the configuration does not fit (caller falls back), 1 on error
+int launch_fan_pipe(vf_engine* e, int member, bool res, bool jac, double dt, int is_static,
+                    const JacMix& mix, cudaStream_t st) {
+  const FanTablesDev& T = e->fan;
+  if (T.tile_nodes != 128 || e->fan_max_wblocks <= 0) return -1;
+  const char* env_ng = getenv("VF_PIPE_GROUPS");
+  const char* env_pool = getenv("VF_PIPE_POOL_KB");
+  const char* env_pf = getenv("VF_PIPE_PF");
+  const char* env_grid = getenv("VF_PIPE_GRID");
+  const size_t b_stage = fan_pipe_stage_bytes(T, res);
+  const size_t wj = jac ? align_up(32 * (size_t)e->fan_max_wblocks, 128) : 0;
+  // static shared memory of the kernel (barriers, FanCoef) and its ring of producer records
+  const size_t cap = 227 * 1024 - 1024 - (size_t)kRecSlots * T.prec_stride;
+  int ng = env_ng ? atoi(env_ng) : 3;
+  if (ng != 2 && ng != 3) ng = 3;
+  // three of the largest stages: with fewer, the circular pool could have room for the next tile
+  // only where the previous, not yet converted one sits (the producer team would wait forever)
+  while (ng > 2 && 4 * ng * wj + 3 * b_stage > cap) --ng;
+  if (4 * ng * wj + 3 * b_stage > cap) return -1;
+  size_t pool = cap - 4 * ng * wj;
+  if (env_pool) pool = std::min(pool, std::max(3 * b_stage, (size_t)atoi(env_pool) * 1024));
+  pool &= ~(size_t)127;
+  const size_t smem = 4 * ng * wj + (size_t)kRecSlots * T.prec_stride + pool;
+  int dev = 0, n_sm = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  int grid = env_grid ? atoi(env_grid) : n_sm;
+  grid = std::max(1, std::min(grid, T.ntiles));
+  const int pf_dist = env_pf ? atoi(env_pf) : 1;
+  // VF_PIPE_DBG: variants kept for A/B timing (profiles/README.md) and measurement aids.
+  //   32 also prefetch the halo vertex lines, 64 consumer warps store their slices themselves,
+  //   128 contiguous inputs by cp.async instead of the bulk-copy engine, 256 three producer warps
+  //   + one converter warp (default: four producer warps, consumer groups convert);
+  //   results are WRONG with 1 (no halo gathers), 2 / 4 (no bulk copies), 8 (no walk),
+  //   16 (no slice store).  The kernel's own bits 32, 128, 256 have the opposite sense.
+  const int dbg = (getenv("VF_PIPE_DBG") ? atoi(getenv("VF_PIPE_DBG")) : 0) ^ (32 | 128 | 256);
+  double* mat_m = T.mat + (size_t)member * 3 * T.n_tcell;
+  if (e->fan_dirty[member]) {
+    fan_pack_kernel<<<T.ntiles, 128, 0, st>>>(e->dev, member, T, mat_m);
+    e->fan_dirty[member] = 0;
+    e->launches += 1;
+    VF_CUDA(cudaGetLastError());
+  }
+  const NewmarkCoef nc = newmark_coef(dt);
+#define VF_PIPE_GO(J_, R_, NG_)                                                                   \
+  do {                                                                                            \
+    VF_CUDA(cudaFuncSetAttribute(asm_fan_pipe_kernel<J_, R_, NG_>,                                \
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
+    asm_fan_pipe_kernel<J_, R_, NG_><<<grid, 128 + 128 * NG_, smem, st>>>(                        \
+        e->dev, member, nc, is_static, mix, T, mat_m, (int)wj, (int)pool, pf_dist, dbg);               \
+  } while (0)
+#define VF_PIPE_BY_MODE(NG_)                                                                      \
+  do {                                                                                            \
+    if (jac && res) VF_PIPE_GO(true, true, NG_);                                                  \
+    else if (jac) VF_PIPE_GO(true, false, NG_);                                                   \
+    else VF_PIPE_GO(false, true, NG_);                                                            \
+  } while (0)
+  if (ng == 2) VF_PIPE_BY_MODE(2);
+  else VF_PIPE_BY_MODE(3);
+#undef VF_PIPE_BY_MODE
+#undef VF_PIPE_GO
+  e->launches += 1;
+  VF_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int launch_facet_bc(vf_engine* e, int member, bool res, bool jac, double dt, int is_static,
                     const JacMix& mix, cudaStream_t st) {
   if (e->n_touch <= 0) return 0;
@@ -928,7 +1431,12 @@ int assemble_impl(vf_engine* e, int member, int flags, double dt, int is_static,
   cudaStream_t st = as_stream(stream);
   const char* env_fan = getenv("VF_FAN");
   if (e->fan.ring && !(env_fan && atoi(env_fan) == 0)) {
-    if (launch_fan(e, member, res, jac, dt, is_static, mix, st)) return 1;
+    const char* env_pipe = getenv("VF_FAN_PIPE");
+    int rc = -1;
+    if (!(env_pipe && atoi(env_pipe) == 0))
+      rc = launch_fan_pipe(e, member, res, jac, dt, is_static, mix, st);
+    if (rc > 0) return 1;
+    if (rc < 0 && launch_fan(e, member, res, jac, dt, is_static, mix, st)) return 1;
     return launch_facet_bc(e, member, res, jac, dt, is_static, mix, st);
   }
   const int grid = e->desc.ntiles, block = e->desc.tile_threads;

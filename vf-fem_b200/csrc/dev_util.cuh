@@ -22,6 +22,11 @@ __device__ __forceinline__ int4 ldg_nc_v4(const int4* p) {
                : "l"(p));
   return r;
 }
+__device__ __forceinline__ int ldg_nc_s32(const int* p) {
+  int r;
+  asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(r) : "l"(p));
+  return r;
+}
 __device__ __forceinline__ void prefetch_l2(const void* p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
@@ -74,6 +79,35 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 // waits until the committed bulk stores have finished READING their shared-memory source
 __device__ __forceinline__ void bulk_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+// ---- producer / consumer pipeline helpers (asm_fan_pipe_kernel) ------------------------------
+__device__ __forceinline__ void mbar_init_only(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_init_fence() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// the mbarrier receives one (pre-counted) arrival when every cp.async issued so far by this
+// thread has landed in shared memory
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(unsigned long long* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// barrier among `count` threads of the CTA (a multiple of 32), hardware barrier `id` (1..15)
+__device__ __forceinline__ void named_barrier(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+// one instruction asks the bulk-copy engine to bring a contiguous range (multiple of 16 bytes,
+// 16-byte aligned) into L2
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gmem_src, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
 }  // namespace vf

@@ -32,6 +32,8 @@ struct FanTablesDev {
   const int* halo;       // ring vertices outside each tile's node range
   const int* tcell;      // cells touched by each tile (padded to even counts)
   double* mat;           // per member: tile-ordered [emod | eta | rho] blocks (3 * n_tcell)
+  const unsigned char* prec;  // per tile: [descriptor | pad | halo vertex ids], prec_stride bytes
+  int prec_stride;
   size_t n_tcell;
   int tile_nodes, ntiles, max_verts, max_rows, max_cells, max_blocks;
 };
@@ -62,6 +64,7 @@ struct vf_engine {
   vf::FanTablesDev fan;
   void* fan_mem;
   std::vector<char> fan_dirty;  // per member: the tile-ordered property copy is stale
+  int fan_max_wblocks;          // most CSR blocks owned by 32 consecutive nodes
 };
 
 namespace vf {

@@ -257,6 +257,7 @@ int vf_create(const vf_problem_desc* desc, void* arena_dev, size_t arena_bytes, 
   e->launches = 0;
   e->fan = FanTablesDev{};
   e->fan_mem = nullptr;
+  e->fan_max_wblocks = 0;
   e->brptr.assign(d.brptr_host, d.brptr_host + d.nn + 1);
   e->bcol.assign(d.bcol_host, d.bcol_host + nnzb);
   e->pf_nodes.resize((size_t)d.nfp * d.dim);
