@@ -233,16 +233,13 @@ def _reference_worker(levels, steps, barrier, queue):
     queue.put((prob.N, prob.ne, time.perf_counter() - t0))
 
 
-def run_reference(args, rank, world):
-    """Reference arm: the reference's FEniCS/PETSc path cannot be installed (SURVEY.md F2), so
-    the CPU restatement (oracle) is timed for the same metric on ALL host cores: one process
-    per core (the numpy/scipy oracle is single-threaded), each assembling the bounded sample,
-    started together; value = total DOF assembled / slowest process time."""
-    if rank != 0:
-        return
+def reference_rate(steps, procs=None):
+    """The CPU restatement (oracle) on ALL host cores: one process per core (the numpy/scipy
+    oracle is single-threaded), each assembling the bounded sample, started together.
+    Returns (DOF/s = total DOF assembled / slowest process time, seconds of the slowest process,
+    processes, description)."""
     import multiprocessing as mp
-    steps = min(max(args.steps, 1), 10)
-    procs = int(os.environ.get('VF_REF_PROCS', '0')) or min(os.cpu_count() or 1, 64)
+    procs = procs or int(os.environ.get('VF_REF_PROCS', '0')) or min(os.cpu_count() or 1, 64)
     ctx = mp.get_context('fork')
     barrier = ctx.Barrier(procs)
     queue = ctx.Queue()
@@ -260,6 +257,16 @@ def run_reference(args, rank, world):
             f"{4 ** (REFINE_LEVELS - SAMPLE_LEVELS)} of the workload) per process, {steps} "
             f"residual+Jacobian assemblies each, {procs} processes started together, "
             "numpy/scipy oracle (CPU restatement of the FEniCS path)")
+    return value, slowest, procs, desc
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the reference's FEniCS/PETSc path cannot be installed (SURVEY.md F2), so
+    the CPU restatement (oracle) is timed for the same metric on all host cores."""
+    if rank != 0:
+        return
+    steps = min(max(args.steps, 1), 10)
+    value, slowest, procs, desc = reference_rate(steps)
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT,
         'n_gpus': args.gpus, 'steps': steps, 'warmup': 1,
@@ -283,22 +290,24 @@ def workload_config():
     }
 
 
-def run_partition(args, rank, world, local_rank):
+def run_partition(args, rank, world, local_rank, standalone=True, tets=None):
     """BASELINE configs[4]: extruded M5 tetrahedral mesh partitioned over the ranks; local
     (communication-free) assembly and a fixed number of GMRES iterations with NCCL halo
-    exchange.  Extra measurement (own JSON line), not the driver's default workload."""
+    exchange.  ``--workload partition`` prints it as its own JSON line; the default workload
+    carries it (on a smaller mesh, --partition-tets) as the ``partition`` object of its line."""
     import torch
     import torch.distributed as dist
     from femvf_b200 import meshgen
     from femvf_b200.distributed import DistributedSolid
     from femvf_b200.residuals import solid as slr
+    tets = args.tets if tets is None else tets
     torch.cuda.set_device(local_rank)
-    if world > 1:
+    if world > 1 and standalone:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     t0 = time.perf_counter()
     mt2 = meshgen.m5_cb_refined(BASE_H, args.levels2d, renumber=False)
-    nz = max(int(round(args.tets / (3.0 * mt2[0].num_cells()))), 1)
+    nz = max(int(round(tets / (3.0 * mt2[0].num_cells()))), 1)
     mt3 = meshgen.renumber_for_locality(meshgen.extrude_to_tets(mt2, 1.5, nz))
     res = slr.KelvinVoigt(*mt3)
     ds = DistributedSolid(res, rank, world, restart=30)
@@ -345,10 +354,40 @@ def run_partition(args, rank, world, local_rank):
         'gmres': {'iterations': iters, 'ms_total': float(t[1]),
                   'iterations_per_s': iters / (float(t[1]) * 1e-3),
                   'operator_applications': ds.gmres.spmv_count,
+                  'halo_exchanges_per_iteration': 1 if world > 1 else 0,
+                  'allreduces_per_iteration': 2 if world > 1 else 0,
                   'note': 'host-launched, device-resident Arnoldi data (one device->host read per 8 '
                           'iterations); CGS2, restart 30, left block-Jacobi'},
         'setup_s': setup_s, 'gpu_launches': int(eng.launch_count),
     }
+    if world > 1:
+        # the check of tests/test_gpu_partition.py::test_two_gpu_distributed_solve_matches_lu,
+        # moved into the multi-GPU run itself (the GPU test box has one GPU): block-Jacobi GMRES
+        # is partition-independent, so the iterate after `iters` iterations across `world` ranks
+        # must equal the single-rank iterate to round-off
+        pieces = [None] * world
+        dist.all_gather_object(pieces, (ds.part.n0, x.cpu().numpy()))
+        if rank == 0:
+            ds1 = DistributedSolid(res, 0, 1, restart=30)
+            ds1.upload_global(prop, state, p1, scal)
+            ds1.assemble(dt)
+            b1 = ds1.owned('F').clone()
+            x1 = torch.empty_like(b1)
+            ds1.solve(b1, x1, rtol=0.0, atol=0.0, maxiter=iters)
+            x_all = np.concatenate([p[1] for p in sorted(pieces, key=lambda p: p[0])])
+            x1 = x1.cpu().numpy()
+            diff = float(np.linalg.norm(x_all - x1) / np.linalg.norm(x1))
+            line['check'] = {'what': f'{world}-rank iterate after {iters} GMRES iterations vs the '
+                                     'single-rank iterate (NCCL halo exchange + all-reduces)',
+                             'rel_diff': diff, 'ok': bool(diff <= 1e-8)}
+            del ds1
+        dist.barrier()
+    del ds
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    if not standalone:
+        return line
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -368,6 +407,8 @@ def main():
     ap.add_argument('--tets', type=float, default=5.0e6)
     ap.add_argument('--levels2d', type=int, default=3)
     ap.add_argument('--gmres-iters', type=int, default=60)
+    ap.add_argument('--partition-tets', type=float, default=1.0e6,
+                    help='size of the mesh-partition run carried by the default line (0: skip)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
 
@@ -440,12 +481,13 @@ def main():
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': dict(workload_config(), nn=nn, ne=ne, dof=N, nnz=nnz,
                        parallelism=f'{world} independent mesh shards, no collective'),
-        'roofline': {'kernel': 'asm_tile2_kernel<true,true,2,256,4,direct> (+ facet_bc_kernel on boundary nodes)', 'bound': 'hbm',
+        'roofline': {'kernel': 'asm_fan_pipe_kernel<true,true,3> (+ facet_bc_kernel on boundary nodes)',
+                     'bound': 'hbm',
                      'achieved': asm_gbs, 'peak': peak, 'unit': 'GB/s', 'frac': asm_gbs / peak,
                      # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel on
                      # this workload, from the ncu --set full capture summarised in
-                     # profiles/r1_ncu_full_asm2_final.csv (not re-measured in this run)
-                     'traffic': 855256832 if args.levels == REFINE_LEVELS else None,
+                     # profiles/r2_ncu_full_asm_fan_pipe.csv (not re-measured in this run)
+                     'traffic': 794902272 if args.levels == REFINE_LEVELS else None,
                      'algorithmic_bytes': B_asm, 'peak_source': peak_src},
         'spmv': {'kernel': 'spmv_kernel<2,4>', 'bound': 'hbm', 'achieved': spmv_gbs,
                  'peak': peak, 'unit': 'GB/s', 'frac': spmv_gbs / peak,
@@ -465,7 +507,10 @@ def main():
         def e2e_step():
             model.set_fin_state(s1)
             r = model.assem_res()
+            # dF_u/du1 stays on the device (femvf_b200.devmat.DeviceCSR): a Newton loop hands it
+            # straight back to solve_dres_dstate1; nothing but its handle crosses PCIe
             J = model.assem_dres_dstate1().sub['u', 'state/u1']
+            assert J.on_device
             return r, J
         e2e_step()
         torch.cuda.synchronize()
@@ -480,10 +525,12 @@ def main():
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         line['e2e'] = {'value': N * world * e2e_steps / float(te.item()), 'unit': UNIT,
-                       'h2d_bytes_per_step': 8 * 3 * N, 'd2h_bytes_per_step': 8 * (3 * N + nnz),
+                       'h2d_bytes_per_step': 8 * 3 * N, 'd2h_bytes_per_step': 8 * 3 * N,
                        'api': 'FenicsModel.set_fin_state + assem_res + assem_dres_dstate1 '
-                              '(host BlockVector in, host scipy CSR out; trust_setters=True: '
-                              'only the state changed through the setter is re-uploaded)'}
+                              '(host BlockVector in; host F_u, F_v, F_a out; dF_u/du1 returned '
+                              'as a device-resident DeviceCSR, downloaded only if the caller '
+                              'reads its values; trust_setters=True: only the state changed '
+                              'through the setter is re-uploaded)'}
 
     # release the big model now (engine arena, page-locked staging buffers): left to the
     # cyclic garbage collector it would be freed at a random point inside a later timed loop
@@ -512,53 +559,84 @@ def main():
                                        '99 steps dt=1e-4, forward.integrate(write=False)',
                            'steps_per_s': fwd}
 
-        # ensemble: 1024 members per GPU, randomised emod / eta fields (SURVEY.md 8d cfg 4)
-        from femvf_b200.ensemble import EnsembleRunner
-        B = 1024
-        runner = EnsembleRunner(fm, B)
-        emod = np.empty((B, runner.ne)); eta = np.empty((B, runner.ne))
-        for b in range(B):
-            g = np.random.default_rng([4, rank * B + b])
-            emod[b] = 5e4 * np.exp(0.3 * g.standard_normal(runner.ne))
-            eta[b] = 3.0 * np.exp(0.3 * g.standard_normal(runner.ne))
-        ini = np.zeros((B, runner.state_size))
+        # ensemble (SURVEY.md 8d cfg 4): 1024 members IN TOTAL, randomised emod / eta fields,
+        # sharded contiguously over the ranks (strong scaling, no data-path collective); the
+        # weak-scaled variant (1024 members per GPU) is reported beside it
+        from femvf_b200.ensemble import EnsembleRunner, shard_members
         dts = np.full(99, 1e-4)
         ctl = np.array([[[8e3], [0.0]]])
-        runner.set_common_prop(prop)
-        runner.run_host(dts, ctl, ini, emod, eta)  # warm-up
-        if barrier:
-            barrier()
-        dt_hs = []
-        for _ in range(3):          # median of three: a single host-timed run is noisy
-            t0 = time.perf_counter()
-            fin, series = runner.run_host(dts, ctl, ini, emod, eta)
-            dt_hs.append(time.perf_counter() - t0)
-        dt_h = sorted(dt_hs)[1]
-        # device-resident timing of the same work
-        ms_devs = []
-        for _ in range(3):
-            runner.upload_members(ini, emod, eta)   # every repetition starts from the same state
-            ms_devs.append(time_events(lambda: runner.run_device(dts, ctl), 1, 0, barrier))
-        ms_dev = sorted(ms_devs)[1]
-        tt = torch.tensor([ms_dev, dt_h * 1e3], dtype=torch.float64, device='cuda')
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        line['ensemble'] = {
-            'workload': f'BASELINE configs[3]: {B} members per GPU x 99 steps, emod/eta '
-                        'log-normal per cell, seed = member id',
-            'member_steps_per_s': B * world * 99 / (float(tt[0]) * 1e-3),
-            'e2e_member_steps_per_s': B * world * 99 / (float(tt[1]) * 1e-3),
-            'h2d_bytes': int(ini.nbytes + emod.nbytes + eta.nbytes),
-            'd2h_bytes': int(fin.nbytes + series.nbytes),
-            'max_newton_iters': float(series[:, :, 0].max()),
-            'e2e_run_seconds': [round(x, 4) for x in dt_hs],
-            'scaling': 'weak',
-        }
 
-    # ---- CPU baseline (rank 0, N = 1 only): the oracle on a bounded sample ---------------------
+        def run_ensemble(first, count):
+            runner = EnsembleRunner(fm, count)
+            emod = np.empty((count, runner.ne)); eta = np.empty((count, runner.ne))
+            for b in range(count):
+                g = np.random.default_rng([4, first + b])
+                emod[b] = 5e4 * np.exp(0.3 * g.standard_normal(runner.ne))
+                eta[b] = 3.0 * np.exp(0.3 * g.standard_normal(runner.ne))
+            ini = np.zeros((count, runner.state_size))
+            runner.set_common_prop(prop)
+            runner.run_host(dts, ctl, ini, emod, eta)  # warm-up
+            if barrier:
+                barrier()
+            dt_hs = []
+            for _ in range(3):          # median of three: a single host-timed run is noisy
+                t0 = time.perf_counter()
+                fin, series = runner.run_host(dts, ctl, ini, emod, eta)
+                dt_hs.append(time.perf_counter() - t0)
+            # device-resident timing of the same work
+            ms_devs = []
+            for _ in range(3):
+                runner.upload_members(ini, emod, eta)   # every repetition starts from the same state
+                ms_devs.append(time_events(lambda: runner.run_device(dts, ctl), 1, 0, barrier))
+            tt = torch.tensor([sorted(ms_devs)[1], sorted(dt_hs)[1] * 1e3], dtype=torch.float64,
+                              device='cuda')
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            out = {'ms_device': float(tt[0]), 'ms_host_buffers': float(tt[1]),
+                   'h2d_bytes': int(ini.nbytes + emod.nbytes + eta.nbytes),
+                   'd2h_bytes': int(fin.nbytes + series.nbytes),
+                   'max_newton_iters': float(series[:, :, 0].max()),
+                   'e2e_run_seconds': [round(x, 4) for x in dt_hs]}
+            del runner
+            return out
+        B = 1024
+        lo, hi = shard_members(B, rank, world)
+        strong = run_ensemble(lo, hi - lo)
+        line['ensemble'] = {
+            'workload': f'BASELINE configs[3]: {B} members in total x 99 steps, emod/eta '
+                        f'log-normal per cell, seed = member id; {hi - lo} members on rank 0',
+            'scaling': 'strong',
+            'member_steps_per_s': B * 99 / (strong['ms_device'] * 1e-3),
+            'e2e_member_steps_per_s': B * 99 / (strong['ms_host_buffers'] * 1e-3),
+            'h2d_bytes': strong['h2d_bytes'], 'd2h_bytes': strong['d2h_bytes'],
+            'max_newton_iters': strong['max_newton_iters'],
+            'e2e_run_seconds': strong['e2e_run_seconds'],
+        }
+        if world > 1:
+            weak = run_ensemble(rank * B, B)
+            line['ensemble']['weak'] = {
+                'workload': f'{B} members PER GPU',
+                'member_steps_per_s': B * world * 99 / (weak['ms_device'] * 1e-3),
+                'e2e_member_steps_per_s': B * world * 99 / (weak['ms_host_buffers'] * 1e-3)}
+
+    # ---- mesh partition (BASELINE configs[4]) on the same ranks: owner-computes assembly and a
+    # fixed number of GMRES iterations with halo exchange + all-reduces over NCCL -----------------
+    if args.partition_tets > 0 and not args.skip_extras:
+        try:
+            line['partition'] = run_partition(args, rank, world, local_rank, standalone=False,
+                                              tets=args.partition_tets)
+            line['config']['parallelism'] = (
+                f'assembly: {world} mesh shards, no collective; ensemble: members sharded over '
+                f'{world} ranks, no collective; partition: {world} vertex-range partitions, NCCL '
+                'halo exchange + all-reduce per GMRES iteration')
+        except Exception as ex:  # keep the primary line if the extra fails
+            line['partition'] = {'error': repr(ex)}
+
+    # ---- CPU baseline (rank 0, N = 1 only): the oracle on a bounded sample, all host cores
+    # (the same measurement as the reference arm, --impl reference) -------------------------------
     if rank == 0 and world == 1:
-        cpu_val, desc, _ = cpu_assembly_sample(SAMPLE_LEVELS, 5)
-        line['cpu_baseline'] = {'value': cpu_val, 'unit': UNIT, 'cores': 1, 'kind': 'port',
+        cpu_val, _, procs, desc = reference_rate(5)
+        line['cpu_baseline'] = {'value': cpu_val, 'unit': UNIT, 'cores': procs, 'kind': 'port',
                                 'sample': desc}
         if not args.skip_extras:
             from oracle import model as om

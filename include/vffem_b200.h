@@ -213,6 +213,21 @@ int vf_axpby(vf_engine* e, double alpha, const double* x_dev, double beta, doubl
 int vf_glottal_width_series(vf_engine* e, int member, int nt, const double* u_hist_dev, size_t ldu,
                             double* out_dev, void* stream);
 
+/* Multicolour block ILU(0) of J_uu on node rows [node0, node1): the cuSPARSE-free stand-in for
+ * the reference's sparse LU (dfn.solve(A, x, b, 'petsc'), models/transient.py:487, static.py:140)
+ * as preconditioner of the grid-wide GMRES on meshes that do not fit one CTA.
+ *   rows_host      (node1 - node0) int32: the nodes of the range grouped by colour
+ *   color_ptr_host (ncolors + 1) int32: offsets of the colour classes in rows_host
+ *   color_host     (nn) int32: colour of every local node, -1 outside the range; no two nodes of
+ *                  one colour may share a cell (femvf_b200/tables.py color_node_graph)
+ * vf_ilu_factor copies the member's current J and factorises it in place (ncolors launches);
+ * vf_ilu_apply computes z = U^-1 L^-1 r on the DOFs of the range (2 ncolors - 1 launches; r and z
+ * are full local vectors and may alias). */
+int vf_ilu_setup(vf_engine* e, int node0, int node1, int ncolors, const int32_t* rows_host,
+                 const int32_t* color_ptr_host, const int32_t* color_host, void* stream);
+int vf_ilu_factor(vf_engine* e, int member, void* stream);
+int vf_ilu_apply(vf_engine* e, const double* r_dev, double* z_dev, void* stream);
+
 /* y = x / sqrt(s), s = *s2_dev - sum_{i<nsub} sub_dev[i]^2, all read on the device; s is also
  * stored to *s_out_dev when non-null (must not alias s2_dev).  Krylov-vector normalisation
  * with the squared norm left on the device by vf_multidot (KSPGMRES's VecNormalize without the

@@ -144,6 +144,32 @@ def test_assembly_parity_many_tiles(torch_cuda, monkeypatch, tile_nodes):
     assert info['nodes_per_tile'] == int(tile_nodes)
 
 
+@pytest.mark.parametrize('grid,groups,pool_kb', [('5', '3', '0'), ('3', '2', '0'), ('7', '3', '104'),
+                                                  ('1', '3', '0')])
+def test_assembly_parity_pipeline(torch_cuda, monkeypatch, grid, groups, pool_kb):
+    """Entry-wise parity of the persistent producer / consumer pipeline (asm_fan_pipe_kernel) when
+    every CTA walks many tiles: 62 tiles of 128 nodes (M5_CB refined 3x) on 1-7 CTAs, two and
+    three consumer groups, and a small stage pool that wraps around every few tiles."""
+    from femvf_b200 import meshgen
+    from femvf_b200.models import transient
+    from femvf_b200.residuals import solid as slr
+    monkeypatch.setenv('VF_PIPE_GRID', grid)
+    monkeypatch.setenv('VF_PIPE_GROUPS', groups)
+    if pool_kb != '0':
+        monkeypatch.setenv('VF_PIPE_POOL_KB', pool_kb)
+    mt = meshgen.m5_cb_refined(0.05, 3)
+    model = transient.FenicsModel(slr.KelvinVoigt(*mt))
+    model = _assemble_and_compare(model, np.random.default_rng(int(grid)))
+    assert model.engine.fan_info is not None and model.engine.fan_info['ntiles'] >= 60
+    # Jacobian-only and residual-only launches of the same pipeline
+    eng = model.engine
+    J = eng.view('J').clone(); F = eng.view('F').clone()
+    eng.view('J').zero_(); eng.assemble(0, res=False, jac=True, dt=model.dt)
+    assert torch_cuda.equal(J, eng.view('J'))
+    eng.view('F').zero_(); eng.assemble(0, res=True, jac=False, dt=model.dt)
+    assert torch_cuda.equal(F, eng.view('F'))
+
+
 def test_assembly_parity_degenerate_meshes(torch_cuda):
     """Smallest inputs: two triangles; a mesh with no Dirichlet and no pressure facets."""
     from femvf_b200 import mesh as M

@@ -43,8 +43,10 @@ def oracle_run(model, state0, control, prop, times, fluid_kind='area_ratio'):
     return hist, infos
 
 
-@pytest.mark.parametrize('mesh_name', ['m5', 'square5'])
-def test_integrate_matches_oracle(mesh_name, tmp_path):
+# ('m5', 100) is BASELINE config 1 in full: times = 1e-4 arange(100), 99 steps
+# (benchmarks/setup.py:34-49)
+@pytest.mark.parametrize('mesh_name,ntimes', [('m5', 30), ('square5', 30), ('m5', 100)])
+def test_integrate_matches_oracle(mesh_name, ntimes, tmp_path):
     import torch
     assert torch.cuda.is_available()
     from femvf_b200 import forward, statefile as sf
@@ -52,7 +54,7 @@ def test_integrate_matches_oracle(mesh_name, tmp_path):
     state0, control, prop = benchmark_setup(model)
     if mesh_name == 'square5':
         prop['ymid'][:] = 1.05
-    times = 1e-4 * np.arange(30)
+    times = 1e-4 * np.arange(ntimes)
     path = str(tmp_path / 'out.h5')
     with sf.StateFile(model, path, mode='w') as f:
         fin_state, info = forward.integrate(model, f, state0, [control], prop, times)
@@ -67,8 +69,10 @@ def test_integrate_matches_oracle(mesh_name, tmp_path):
                 # Newton tolerance (abs 1e-8) bounds them no tighter than this
                 tol = {'v': 1e-5, 'a': 1e-2}.get(key, TRAJ_TOL)
                 assert np.max(np.abs(st[key] - ref)) <= tol * scale, (n, key)
-    # glottal flow series
-    q_ref = np.array([h[3][0] for h in hist])
+        # glottal flow at EVERY step
+        q_ref = np.array([h[3][0] for h in hist])
+        q = np.array([f.get_state(n)['q'][0] for n in range(len(times))])
+        assert np.max(np.abs(q - q_ref)) <= TRAJ_TOL * np.max(np.abs(q_ref))
     assert abs(fin_state['q'][0] - q_ref[-1]) <= TRAJ_TOL * abs(q_ref[-1])
     assert info['num_iter'] >= 1
 

@@ -66,3 +66,62 @@ def test_bitwise_reproducible_and_rigid_motion(big):
     eng.assemble(0, res=False, jac=True, dt=dt)
     diag_scale = torch.max(torch.abs(eng.view('J'))).item() * 0.01
     assert torch.max(torch.abs(F)).item() <= 1e-9 * diag_scale
+
+
+def test_benchmark_mesh_entrywise_vs_oracle():
+    """The benchmarked configuration itself (bench.py: M5_CB refined 7x, 4.01 M P1 triangles,
+    4.02 M DOF, 5.6e7 non-zeros): F_u and every entry of J_uu against the oracle, <= 1e-12
+    relative (row scale), CSR pattern bit-exact.  The oracle needs about a minute and ~15 GB of
+    host memory at this size."""
+    import gc
+    import bench
+    from helpers import oracle_problem, rel_row_err
+    from oracle import model as om
+    model = bench.build_big_model(bench.REFINE_LEVELS, seed=0)
+    eng = model.engine
+    model._push_all()
+    eng.assemble(0, res=True, jac=True, dt=model.dt)
+    F = eng.view('F').cpu().numpy()
+    vals = eng.view('J').cpu().numpy()
+    indptr, indices = eng.csr_pattern()
+    prob = oracle_problem(model.residual)
+    prop = {k: np.array(v) for k, v in model.prop.items()}
+    prop['nu'] = float(prop['nu'][0])
+    s0, s1 = model.state0, model.state1
+    so = om.SolidOracle(prob)
+    p1 = np.asarray(model.control['p'])
+    F_ref = so.res(np.asarray(s1['u']), (np.asarray(s0['u']), np.asarray(s0['v']),
+                                         np.asarray(s0['a'])), model.dt, prop, p1)
+    assert np.max(np.abs(F - F_ref)) <= 1e-12 * np.max(np.abs(F_ref))
+    del F_ref
+    gc.collect()
+    J_ref = so.jac(np.asarray(s1['u']), model.dt, prop, p1)
+    assert J_ref.nnz == eng.nnz == vals.size
+    assert np.array_equal(indptr, J_ref.indptr)
+    assert np.array_equal(indices, J_ref.indices)
+    assert rel_row_err(vals, J_ref) <= 1e-12
+
+
+def test_benchmark_mesh_grid_solve_manufactured():
+    """ILU(0)-GMRES on the 4.02 M-DOF benchmark matrix: x* random, b = J x* by the device SpMV
+    (itself pinned entry-wise above), solve, compare with x*.  (A sparse LU of this matrix needs
+    more than an hour of CPU: the LU comparison is done at 63 k DOF in test_gpu_gridsolve.py.)"""
+    import torch
+    import bench
+    from femvf_b200.gridsolve import GridSolver
+    model = bench.build_big_model(bench.REFINE_LEVELS, seed=0)
+    eng = model.engine
+    model._push_all()
+    eng.assemble(0, res=False, jac=True, dt=model.dt)
+    gs = GridSolver(eng)
+    g = torch.Generator(device='cuda'); g.manual_seed(0)
+    xs = torch.randn(eng.N, dtype=torch.float64, device='cuda', generator=g)
+    b = torch.empty_like(xs)
+    eng.spmv(xs, b)
+    x = torch.empty_like(xs)
+    # at h = 4e-4 cm the stiffness dominates the Newmark mass term: ~900 ILU(0)-GMRES(40)
+    # iterations per 1e-10 of residual reduction (block-Jacobi: > 3000), 1.6 ms each
+    # (profiles/README.md); 1e-13 is needed for 1e-9 in x
+    info = gs.linear_solve(b, x, rtol=1e-13, maxiter=6000)
+    err = (torch.linalg.vector_norm(x - xs) / torch.linalg.vector_norm(xs)).item()
+    assert err <= 1e-9, (err, info)

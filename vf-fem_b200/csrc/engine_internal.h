@@ -38,6 +38,18 @@ struct FanTablesDev {
   int tile_nodes, ntiles, max_verts, max_rows, max_cells, max_blocks;
 };
 
+// multicolour block ILU(0) (ilu.cu): factor storage and colouring tables, one device allocation
+struct IluState {
+  char* mem = nullptr;
+  double* LU = nullptr;    // pattern and layout of J
+  double* Dinv = nullptr;  // inverses of the diagonal blocks of U
+  int* color = nullptr;    // per node: colour, -1 outside the solved range
+  int* rows = nullptr;     // nodes of the solved range grouped by colour
+  int node0 = 0, node1 = 0, ncolors = 0;
+  std::vector<int32_t> color_ptr;
+};
+void ilu_release(struct ::vf_engine* e);
+
 }  // namespace vf
 
 struct vf_engine {
@@ -65,6 +77,8 @@ struct vf_engine {
   void* fan_mem;
   std::vector<char> fan_dirty;  // per member: the tile-ordered property copy is stale
   int fan_max_wblocks;          // most CSR blocks owned by 32 consecutive nodes
+  bool pool_user;               // this engine holds a reference on the raised mempool threshold
+  vf::IluState ilu;
 };
 
 namespace vf {

@@ -9,6 +9,8 @@
 
 #include "engine_internal.h"
 
+#include <mutex>
+
 namespace vf {
 
 static thread_local std::string g_err;
@@ -28,6 +30,12 @@ static_assert(VF_ARRAY_COUNT == 26, "vf_array_id changed: update _cabi.ARRAY_IDS
 
 
 namespace {
+
+// engines that raised the release threshold of a device's default memory pool (vf_create), and
+// the value to put back when the last of them is destroyed
+std::mutex g_pool_mutex;
+int g_pool_users = 0, g_pool_dev = -1;
+unsigned long long g_pool_prev = 0;
 
 struct ArenaPlan {
   // byte offsets of the shared tables
@@ -187,14 +195,28 @@ int vf_create(const vf_problem_desc* desc, void* arena_dev, size_t arena_bytes, 
   const int n_n2e = d.n2e_ptr_host[d.nn];
   const int n_n2f = d.n2f_ptr_host[d.nn];
 
+  bool pool_user = false;
   {
-    // vf_integrate_host stages through cudaMallocAsync: keep freed blocks in the device's default
-    // pool instead of returning them to the driver at every synchronisation point
+    // vf_integrate_host stages through cudaMallocAsync: let the device's default pool keep up to
+    // 1 GiB of freed blocks instead of returning them to the driver at every synchronisation
+    // point.  The previous threshold is restored by vf_destroy.
     int dev = 0;
     cudaMemPool_t pool;
     if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-      unsigned long long keep = ~0ull;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      unsigned long long prev = 0, keep = 1ull << 30;
+      std::lock_guard<std::mutex> lock(g_pool_mutex);
+      if (g_pool_users > 0 && g_pool_dev == dev) {
+        ++g_pool_users;
+        pool_user = true;
+      } else if (g_pool_users == 0 &&
+                 cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &prev) == cudaSuccess &&
+                 prev < keep &&
+                 cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep) == cudaSuccess) {
+        g_pool_prev = prev;
+        g_pool_dev = dev;
+        g_pool_users = 1;
+        pool_user = true;
+      }
     }
     (void)cudaGetLastError();
   }
@@ -258,6 +280,7 @@ int vf_create(const vf_problem_desc* desc, void* arena_dev, size_t arena_bytes, 
   e->fan = FanTablesDev{};
   e->fan_mem = nullptr;
   e->fan_max_wblocks = 0;
+  e->pool_user = pool_user;
   e->brptr.assign(d.brptr_host, d.brptr_host + d.nn + 1);
   e->bcol.assign(d.bcol_host, d.bcol_host + nnzb);
   e->pf_nodes.resize((size_t)d.nfp * d.dim);
@@ -334,7 +357,18 @@ int vf_create(const vf_problem_desc* desc, void* arena_dev, size_t arena_bytes, 
 }
 
 void vf_destroy(vf_engine* e) {
-  if (e && e->fan_mem) cudaFree(e->fan_mem);
+  if (!e) return;
+  if (e->fan_mem) cudaFree(e->fan_mem);
+  ilu_release(e);
+  if (e->pool_user) {
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    if (--g_pool_users == 0) {
+      cudaMemPool_t pool;
+      if (cudaDeviceGetDefaultMemPool(&pool, g_pool_dev) == cudaSuccess)
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &g_pool_prev);
+      (void)cudaGetLastError();
+    }
+  }
   delete e;
 }
 

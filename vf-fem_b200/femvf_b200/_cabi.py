@@ -73,7 +73,7 @@ EXPORTED_SYMBOLS = [
     'vf_block_jacobi_apply', 'vf_multidot', 'vf_multi_axpy', 'vf_axpby',
     'vf_newmark_residual', 'vf_scale_rsqrt', 'vf_glottal_width_series',
     'vf_assemble_mix', 'vf_pressure_control_blocks', 'vf_set_fan_tables',
-    'vf_props_changed',
+    'vf_props_changed', 'vf_ilu_setup', 'vf_ilu_factor', 'vf_ilu_apply',
 ]
 
 _lib = None
@@ -141,6 +141,10 @@ def load_library() -> C.CDLL:
                                       C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
                                       C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.vf_props_changed.argtypes = [C.c_void_p, C.c_int]
+    lib.vf_ilu_setup.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_void_p]
+    lib.vf_ilu_factor.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    lib.vf_ilu_apply.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.vf_launch_count.argtypes = [C.c_void_p]
     lib.vf_launch_count.restype = C.c_int64
     _lib = lib

@@ -152,7 +152,7 @@ class GridGMRES:
     """
 
     def __init__(self, engine, n_own_nodes: int, halo: Optional[HaloPlan] = None,
-                 restart: int = 30, group=None):
+                 restart: int = 30, group=None, precond: str = 'jacobi'):
         self.e = engine
         self.d = engine.dim
         self.n_own = n_own_nodes
@@ -178,6 +178,29 @@ class GridGMRES:
             if want is None else want == '1'
         self._graphs = {}
         self.spmv_count = 0
+        # left preconditioner of the owned diagonal block: 'jacobi' (d x d node blocks) or
+        # 'ilu0' (multicolour block ILU(0), csrc/ilu.cu; block-Jacobi across ranks)
+        if precond not in ('jacobi', 'ilu0'):
+            raise ValueError(f"unknown preconditioner '{precond}'")
+        self.precond = precond
+        if precond == 'ilu0':
+            engine.ilu_setup(0, n_own_nodes)
+            self.tl = torch.zeros(self.nloc, dtype=f64, device=dev)
+
+    def _prec_setup(self):
+        if self.precond == 'ilu0':
+            self.e.ilu_factor(0)
+        else:
+            self.e.block_jacobi_setup(0, self.n_own)
+
+    def _prec(self, r_own: torch.Tensor, z_own: torch.Tensor):
+        """z = M^-1 r on the owned DOFs."""
+        if self.precond == 'ilu0':
+            self.tl[:self.nown].copy_(r_own)
+            self.e.ilu_apply(self.tl, self.tl)
+            z_own.copy_(self.tl[:self.nown])
+        else:
+            self.e.block_jacobi_apply(r_own, z_own, 0, self.n_own)
 
     def _allreduce(self, t: torch.Tensor):
         if self.distributed:
@@ -189,7 +212,7 @@ class GridGMRES:
         if self.distributed:
             self.halo.exchange(self.xl)
         self.e.spmv_rows(self.xl, self.t, 0, self.n_own)
-        self.e.block_jacobi_apply(self.t, out_own, 0, self.n_own)
+        self._prec(self.t, out_own)
         self.spmv_count += 1
 
     def dots(self, nvec: int, w: torch.Tensor) -> torch.Tensor:
@@ -255,10 +278,10 @@ class GridGMRES:
         test convergence.  Iterations computed past the converged one are discarded.
         """
         e, m, n = self.e, self.m, self.nown
-        e.block_jacobi_setup(0, self.n_own)
+        self._prec_setup()
         x_own.zero_()
         w, V = self.w, self.V
-        e.block_jacobi_apply(b_own, w, 0, self.n_own)
+        self._prec(b_own, w)
         bnorm = self.norm(w)
         info = {'iterations': 0, 'bnorm': bnorm, 'residual': bnorm, 'restarts': 0}
         if bnorm == 0.0:
@@ -272,8 +295,8 @@ class GridGMRES:
         while True:
             if not first:
                 self.apply(x_own, w)                    # w = Dinv J x
-                e.block_jacobi_apply(b_own, self.t, 0, self.n_own)
-                e.axpby(1.0, self.t, -1.0, w, n)        # w = Dinv b - Dinv J x
+                self._prec(b_own, self.t)
+                e.axpby(1.0, self.t, -1.0, w, n)        # w = M^-1 b - M^-1 J x
                 beta = self.norm(w)
                 info['restarts'] += 1
                 if beta <= tol:

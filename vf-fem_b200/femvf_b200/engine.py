@@ -347,6 +347,24 @@ class Engine:
         check(self._lib.vf_block_jacobi_apply(self._h, member, r.data_ptr(), z.data_ptr(),
                                               int(node0), int(node1), self._stream()))
 
+    def ilu_setup(self, node0: int = 0, node1: Optional[int] = None) -> int:
+        """Colour the node graph of rows [node0, node1) and allocate the block ILU(0) storage;
+        returns the number of colours."""
+        node1 = self.nn if node1 is None else node1
+        color, rows, cptr = _tables.color_node_graph(self.tables['brptr'], self.tables['bcol'],
+                                                     node0, node1)
+        check(self._lib.vf_ilu_setup(self._h, node0, node1, len(cptr) - 1, _ptr(rows), _ptr(cptr),
+                                     _ptr(color), self._stream()))
+        self.ilu_colors = len(cptr) - 1
+        return self.ilu_colors
+
+    def ilu_factor(self, member: int = 0):
+        check(self._lib.vf_ilu_factor(self._h, member, self._stream()))
+
+    def ilu_apply(self, r: torch.Tensor, z: torch.Tensor):
+        """z = U^-1 L^-1 r on the DOFs of the factorised node range (full local vectors)."""
+        check(self._lib.vf_ilu_apply(self._h, r.data_ptr(), z.data_ptr(), self._stream()))
+
     def multidot(self, V: torch.Tensor, nvec: int, w: torch.Tensor, n: int, out: torch.Tensor,
                  scratch: torch.Tensor):
         check(self._lib.vf_multidot(self._h, V.data_ptr(), V.stride(0), int(nvec), w.data_ptr(),

@@ -98,7 +98,9 @@ def integrate_steps(
     step_info = {}
     times = np.asarray(times, dtype=float)
 
-    if isinstance(model, ExplicitFSIModel):
+    # the in-kernel time loop runs one CTA per simulation: meshes that do not fit one CTA take the
+    # per-step path below, whose solid solve is the whole-GPU Newton (gridsolve.py)
+    if isinstance(model, ExplicitFSIModel) and model.solid._grid_solver() is None:
         return _integrate_steps_device(model, f, state0, controls, times, idx_meas,
                                        newton_solver_prm, write)
 
@@ -132,7 +134,8 @@ def _integrate_steps_device(model: ExplicitFSIModel, f, state0, controls, times,
         n1 = min(n0 + nchunk, nsteps)
         # control index min(n, len-1) per step (forward.py:170), relative to this chunk
         chunk_controls = [controls[min(n, len(controls) - 1)] for n in range(n0, n1)]
-        states, infos = model.device_integrate(dts_all[n0:n1], chunk_controls, newton_solver_prm)
+        states, infos = model.device_integrate(dts_all[n0:n1], chunk_controls, newton_solver_prm,
+                                               store_states=bool(write))
         for k in range(n1 - n0):
             n = n0 + k
             info = {'num_iter': int(infos[k + 1, 0]), 'abs_err': float(infos[k + 1, 1]),

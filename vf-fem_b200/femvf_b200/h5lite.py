@@ -19,11 +19,18 @@ class Dataset:
     def __init__(self, name, shape, dtype, data=None, maxshape=None, chunks=None):
         self.name = name
         self.dtype = np.dtype(dtype)
-        self._data = np.zeros(shape, dtype=self.dtype)
+        # storage grows geometrically along axis 0 (StateFile appends one row per step);
+        # _n is the logical length, _buf the allocated block
+        self._buf = np.zeros(shape, dtype=self.dtype)
+        self._n = self._buf.shape[0] if self._buf.ndim else 0
         if data is not None:
-            self._data[...] = data
+            self._buf[...] = data
         self.maxshape = maxshape
         self.chunks = chunks
+
+    @property
+    def _data(self):
+        return self._buf[:self._n] if self._buf.ndim else self._buf
 
     @property
     def shape(self):
@@ -40,10 +47,22 @@ class Dataset:
             new_shape = list(self._data.shape)
             new_shape[axis] = size
             new_shape = tuple(new_shape)
+        if self._buf.ndim and new_shape[1:] == self._buf.shape[1:]:
+            n_new = new_shape[0]
+            if n_new > self._buf.shape[0]:
+                cap = max(n_new, 2 * self._buf.shape[0], 16)
+                buf = np.zeros((cap,) + new_shape[1:], dtype=self.dtype)
+                buf[:self._n] = self._buf[:self._n]
+                self._buf = buf
+            elif n_new < self._n:
+                self._buf[n_new:self._n] = 0
+            self._n = n_new
+            return
         new = np.zeros(new_shape, dtype=self.dtype)
         sl = tuple(slice(0, min(a, b)) for a, b in zip(self._data.shape, new_shape))
         new[sl] = self._data[sl]
-        self._data = new
+        self._buf = new
+        self._n = new.shape[0] if new.ndim else 0
 
     def __getitem__(self, key):
         return self._data[key]

@@ -296,9 +296,43 @@ class FenicsModel(BaseTransientModel):
             self._pattern = self.engine.csr_pattern()
         return self._pattern
 
-    def _assem_jac_uu(self, is_static: bool = False) -> sp.csr_matrix:
+    # --- the engine has ONE J array: value semantics for the matrices handed out -------------
+    lazy_jacobian = True   # assem_dres_dstate1 returns dF_u/du1 as a device-resident DeviceCSR
+
+    def _live_jacobian(self):
+        ref = getattr(self, '_live_jac_ref', None)
+        return ref() if ref is not None else None
+
+    def _retire_live_jacobian(self):
+        """Before anything overwrites the engine's J: a DeviceCSR that is still referenced and
+        still on the device keeps its values in a private device tensor (copy-on-write)."""
+        live = self._live_jacobian()
+        if live is not None:
+            live._detach()
+        self._live_jac_ref = None
+
+    def _grid_solver(self):
+        """The whole-GPU solver for meshes that do not fit one CTA (None for small meshes, and
+        for engines shared by an ensemble)."""
+        from .. import gridsolve
+        e = self.engine
+        if e.N < gridsolve.grid_threshold() or e.n_members != 1 or self._member != 0:
+            return None
+        gs = getattr(self, '_grid', None)
+        if gs is None or gs.e is not e:
+            gs = self._grid = gridsolve.GridSolver(e)
+        return gs
+
+    def _assem_jac_uu(self, is_static: bool = False):
         self._push_all()
+        self._retire_live_jacobian()
         self.engine.assemble(self._member, res=False, jac=True, dt=self.dt, is_static=is_static)
+        if self.lazy_jacobian:
+            import weakref
+            from ..devmat import DeviceCSR
+            A = DeviceCSR(self, self._member, pinned=self.trust_setters)
+            self._live_jac_ref = weakref.ref(A)
+            return A
         vals = self.engine.download('J', self._member, pinned=self.trust_setters)
         rowptr, colidx = self.csr_pattern()
         N = self.state0['u'].size
@@ -334,6 +368,7 @@ class FenicsModel(BaseTransientModel):
         N = self.state0['u'].size
         dt = self.dt
         self._push_all()
+        self._retire_live_jacobian()
         rowptr, colidx = self.csr_pattern()
         eye = sp.identity(N, format='csr')
         cv_c = {'u': newmark.newmark_v_du0(dt), 'v': newmark.newmark_v_dv0(dt),
@@ -374,7 +409,17 @@ class FenicsModel(BaseTransientModel):
             options = DEFAULT_NEWTON_SOLVER_PRM
         self.set_fin_state(state1)
         self._push_all()
+        self._retire_live_jacobian()
         e, m = self.engine, self._member
+        grid = self._grid_solver()
+        if grid is not None:
+            # a mesh that does not fit one CTA: whole-GPU assembly + ILU(0)-GMRES (gridsolve.py)
+            ginfo = grid.solve_state1(self.dt, dict(options))
+            x = state1.copy()
+            x['u'][:] = e.download('u1', m)
+            x['v'][:] = e.download('v1', m)
+            x['a'][:] = e.download('a1', m)
+            return x, ginfo
         e.solve_state1(self.dt, m, 1, options)
         x = state1.copy()
         x['u'][:] = e.download('u1', m)
@@ -389,11 +434,26 @@ class FenicsModel(BaseTransientModel):
     def solve_dres_dstate1(self, dres_dstate1, x, b):
         """``transient.py:470-491``: one J_uu solve on the device + nodal v/a rows."""
         import torch
+        from ..devmat import DeviceCSR
         e, m = self.engine, self._member
         bu, bv_, ba = b.sub_blocks
+        # the solve runs on the engine's resident J: make sure it holds the values of the
+        # matrix that was passed in (it does, without any copy, when the matrix came from the
+        # latest assem_dres_dstate1 call)
+        A = dres_dstate1.sub['u', 'state/u1']
+        if not (isinstance(A, DeviceCSR) and A._is_live()):
+            self._retire_live_jacobian()
+            if isinstance(A, DeviceCSR) and A.on_device:
+                e.view('J', m).copy_(A._values_tensor())
+            else:
+                e.upload('J', np.ascontiguousarray(A.tocsr().data), m)
         b_t = torch.as_tensor(np.ascontiguousarray(bu), device=e.device)
         x_t = torch.empty_like(b_t)
-        e.linear_solve(b_t, x_t, m)
+        grid = self._grid_solver()
+        if grid is not None:
+            grid.linear_solve(b_t, x_t)
+        else:
+            e.linear_solve(b_t, x_t, m)
         xu = x_t.cpu().numpy()
         x['u'][:] = xu
         x['v'][:] = bv_ - dres_dstate1.sub['v', 'state/u1'] @ xu
@@ -667,12 +727,13 @@ class ExplicitFSIModel(BaseTransientFSIModel):
         for name, vec in zip(names, self.state0.vecs):
             e.upload(name, vec, 0)
 
-    def device_integrate(self, dts, controls, options=None):
+    def device_integrate(self, dts, controls, options=None, store_states: bool = True):
         """
         Run ``len(dts)`` explicit-coupling steps on the device from the uploaded state0.
 
         controls : list of control BlockVectors (psub, psup)
-        Returns (states, infos): host arrays (nsteps+1, state_size) and (nsteps+1, 4).
+        Returns (states, infos): host arrays (nsteps+1, state_size) and (nsteps+1, 4); with
+        ``store_states=False`` states is (1, state_size): the final state only.
         """
         n_fluid = self.engine.n_fluid
         # (steps usually share one control object: expand each distinct object once)
@@ -682,8 +743,16 @@ class ExplicitFSIModel(BaseTransientFSIModel):
                 rows[id(c)] = np.array([np.broadcast_to(c['psub'], (n_fluid,)),
                                         np.broadcast_to(c['psup'], (n_fluid,))])
         ctl = np.array([rows[id(c)] for c in controls])
-        hs, hi = self.engine.integrate(dts, ctl, options, store_states=True, store_info=True)
-        return hs[0].cpu().numpy(), hi[0].cpu().numpy()
+        self.solid._retire_live_jacobian()
+        hs, hi = self.engine.integrate(dts, ctl, options, store_states=store_states,
+                                       store_info=True)
+        if store_states:
+            return hs[0].cpu().numpy(), hi[0].cpu().numpy()
+        # no history asked for: only the final state (resident in state0 after the last swap)
+        # comes back, as a one-row "history"
+        eng = self.engine
+        fin = np.concatenate([eng.download(k) for k in ('u0', 'v0', 'a0', 'q0', 'p0')])
+        return fin[None, :], hi[0].cpu().numpy()
 
     def state_from_row(self, row: np.ndarray) -> BlockVector:
         state = self.state0.copy()

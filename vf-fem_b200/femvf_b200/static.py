@@ -42,7 +42,14 @@ def static_solid_configuration(model: transient.FenicsModel, control: bv.BlockVe
     model.set_fin_state(guess)
 
     model._push_all()
+    model._retire_live_jacobian()
     e, m = model.engine, model._member
+    grid = model._grid_solver()
+    if grid is not None:
+        from .solverconst import DEFAULT_NEWTON_SOLVER_PRM
+        ginfo = grid.solve_state1(1.0, dict(options or DEFAULT_NEWTON_SOLVER_PRM), is_static=True)
+        state_n['u'][:] = e.download('u1', m)
+        return state_n, {k: ginfo[k] for k in ('num_iter', 'abs_err', 'rel_err')}
     e.solve_state1(1.0, m, 1, options, is_static=True)
     state_n['u'][:] = e.download('u1', m)
     raw = e.download('info', m)
