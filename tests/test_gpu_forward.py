@@ -312,3 +312,81 @@ def test_dense_inverse_preconditioner_opt_in(monkeypatch):
     assert np.max(np.abs(u1 - u0)) <= 1e-8 * np.max(np.abs(u0))
     assert abs(q1 - q0) <= 1e-8 * abs(q0)
     assert it1 < it0          # fewer Krylov iterations with the inverse
+
+
+def test_coupled_model_linearisation_matches_finite_differences():
+    """ExplicitFSIModel.assem_dres_dstate1 / assem_dres_dstate0 / solve_dres_dstate1
+    (transient.py:873-896, 922-937) against central differences of assem_res."""
+    from femvf_b200 import forward
+    model = build_fsi('m5')
+    state0, control, prop = benchmark_setup(model)
+    model.set_prop(prop)
+    model.set_control(control)
+    model.dt = 1e-4
+    # a state on the trajectory (non-trivial area, flow and pressure)
+    fin, _ = forward.integrate(model, None, state0, [control], prop, 1e-4 * np.arange(12),
+                               write=False)
+    st0 = fin.copy()
+    st1, _ = forward.integrate_step(model, st0, control, prop, 1e-4)
+    rng = np.random.default_rng(0)
+    st1['u'][:] += 1e-6 * rng.standard_normal(st1['u'].size)   # off the solution: F != 0
+    model.set_ini_state(st0)
+    model.set_fin_state(st1)
+    d1 = model.assem_dres_dstate1()
+    d0 = model.assem_dres_dstate0()
+    keys = ('u', 'v', 'a', 'q', 'p')
+
+    def res_at(s0, s1):
+        model.set_ini_state(s0)
+        model.set_fin_state(s1)
+        r = model.assem_res()
+        return {k: np.array(r[k]) for k in keys}
+
+    def column(dres, ckey, j, suffix):
+        return {k: np.asarray(dres.sub[k, f'state/{ckey}{suffix}'].tocsr()[:, [j]].todense()).ravel()
+                for k in keys}
+    ndim = 2
+    fsi_y = np.asarray(model.fsimap.dofs_solid) * ndim + 1
+    # state1: displacement of FSI surface nodes (moves the area -> q and p), an interior DOF,
+    # and the fluid state itself
+    for ckey, j, h in [('u', int(fsi_y[len(fsi_y) // 2]), 1e-7), ('u', int(fsi_y[3]), 1e-7),
+                       ('u', 5, 1e-7), ('v', 7, 1e-4), ('a', 9, 1e-1), ('q', 0, 1e-3),
+                       ('p', 4, 1e-2)]:
+        sp_, sm = st1.copy(), st1.copy()
+        sp_[ckey][j] += h; sm[ckey][j] -= h
+        rp, rm = res_at(st0, sp_), res_at(st0, sm)
+        col = column(d1, ckey, j, '1')
+        for k in keys:
+            fd = (rp[k] - rm[k]) / (2 * h)
+            scale = max(np.abs(col[k]).max(), np.abs(fd).max(), 1e-30)
+            assert np.max(np.abs(fd - col[k])) <= 2e-5 * scale + 1e-9, (ckey, j, k)
+    # state0: u0, v0, a0 through the Newmark relations, p0 through the pressure map
+    for ckey, j, h in [('u', 11, 1e-7), ('v', 12, 1e-4), ('a', 13, 1e-1), ('p', 10, 1e-2),
+                       ('q', 0, 1e-3)]:
+        sp_, sm = st0.copy(), st0.copy()
+        sp_[ckey][j] += h; sm[ckey][j] -= h
+        rp, rm = res_at(sp_, st1), res_at(sm, st1)
+        col = column(d0, ckey, j, '0')
+        # as in the reference (transient.py:408-421) no Dirichlet condition is applied to the
+        # state0 blocks, while assem_res zeroes F_u on the fixed DOFs: compare the free rows
+        col['u'][model.solid.residual.fixed_dofs()] = 0.0
+        for k in keys:
+            fd = (rp[k] - rm[k]) / (2 * h)
+            scale = max(np.abs(col[k]).max(), np.abs(fd).max(), 1e-30)
+            assert np.max(np.abs(fd - col[k])) <= 2e-5 * scale + 1e-9, (ckey, j, k)
+    # linear solve: x = (dF/dstate1)^-1 b, checked by multiplying back block by block
+    model.set_ini_state(st0)
+    model.set_fin_state(st1)
+    d1 = model.assem_dres_dstate1()
+    b = model.state1.copy()
+    for k in keys:
+        b[k][:] = rng.standard_normal(b[k].size)
+    x = model.solve_dres_dstate1(b, d1)
+    for k in keys:
+        acc = np.zeros(b[k].size)
+        for c in keys:
+            acc += d1.sub[k, f'state/{c}1'] @ np.asarray(x[c])
+        err = float(np.max(np.abs(acc - b[k])))
+        # the device GMRES stops on the left-preconditioned residual (1e-13): the true residual of
+        # the u rows is ~1e-8 of |b|
+        assert err <= 1e-7 * max(float(np.abs(b[k]).max()), 1.0), (k, err)

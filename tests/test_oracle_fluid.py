@@ -3,6 +3,7 @@
 import os
 
 import numpy as np
+import pytest
 
 from oracle import fluid as ofl
 
@@ -80,3 +81,32 @@ def test_golden_forward_fixture():
     for key in ('u_last', 'q', 'p_last'):
         scale = np.max(np.abs(z[key]))
         assert np.max(np.abs(case[key] - z[key])) <= 1e-9 * scale, key
+
+
+@pytest.mark.parametrize('kind', ['area_ratio', 'fixed'])
+def test_bernoulli_linearisation_matches_finite_differences(kind):
+    """femvf_b200.equations.bernoulli_lin (closed-form d(q, p)/d(area) used by the coupled-model
+    Jacobians) against central differences of the oracle's Bernoulli functions."""
+    from femvf_b200.equations import bernoulli_lin
+    from femvf_b200.residuals.fluid import FLUID_AREA_RATIO_SEP, FLUID_FIXED_SEP
+    rng = np.random.default_rng(2)
+    s = np.linspace(0, 1, 21)
+    area = 0.2 + 0.1 * np.cos(2 * np.pi * s) ** 2 + 0.02 * rng.uniform(size=s.size)
+    area[3] = 0.05            # one entry below the lower bound (clipped: zero derivative)
+    psub, psup, rho, r_sep, lb, idx = 800.0, 10.0, 1.2e-3, 1.2, 0.08, 12
+
+    def qp(a):
+        if kind == 'area_ratio':
+            q, p = ofl.bernoulli_area_ratio_sep(s, a, psub, psup, rho, r_sep, lb)
+        else:
+            q, p = ofl.bernoulli_fixed_sep(s, a, psub, psup, rho, idx)
+        return float(np.ravel(q)[0]), np.ravel(p)
+    k = FLUID_AREA_RATIO_SEP if kind == 'area_ratio' else FLUID_FIXED_SEP
+    dq, dP = bernoulli_lin.dqp_darea(k, s, area, psub, psup, rho, r_sep, lb, idx)
+    h = 1e-7
+    for j in range(s.size):
+        ap, am = area.copy(), area.copy()
+        ap[j] += h; am[j] -= h
+        (qp_, pp), (qm, pm) = qp(ap), qp(am)
+        assert abs((qp_ - qm) / (2 * h) - dq[j]) <= 1e-6 * max(abs(dq).max(), 1e-30)
+        assert np.max(np.abs((pp - pm) / (2 * h) - dP[:, j])) <= 1e-5 * np.abs(dP).max()

@@ -704,6 +704,87 @@ class ExplicitFSIModel(BaseTransientFSIModel):
         res_fl = self.fluid.assem_res()
         return bv.concatenate((res_sl, res_fl))
 
+    # --- linearisation (transient.py:873-896, 922-937).  The reference marks these methods
+    # incomplete: they call fluid methods that do not exist (JaxModel.assem_dres_dstate0,
+    # solve_dqp1_du1_solid) and build dstate1 from the solid's dstate0.  What follows is the
+    # linearisation of the residual this class actually assembles:
+    #   F_solid(uva1; uva0, p_solid = map(p0)),   F_fluid = (q1, p1) - Bernoulli(area(u1)).
+    def _fluid_dqp_darea(self):
+        """d(q, p)/d(area) of every fluid channel at the current fluid control, stacked as
+        (n_fluid x ns_total) and (ns_total x ns_total) CSR blocks."""
+        from ..equations import bernoulli_lin
+        fl, r = self.fluid, self.fluid.residual
+        s = np.atleast_2d(r.mesh())
+        n_fluid, ns = s.shape
+        area = np.asarray(fl.control['area']).reshape(n_fluid, ns)
+        get = lambda key, dflt: np.broadcast_to(fl.prop[key], (n_fluid,)) if key in fl.prop \
+            else np.full(n_fluid, dflt)
+        rho, r_sep, lb = get('rho_air', 1.0), get('r_sep', 1.0), get('area_lb', 0.0)
+        psub = np.broadcast_to(fl.control['psub'], (n_fluid,))
+        psup = np.broadcast_to(fl.control['psup'], (n_fluid,))
+        dq = sp.lil_matrix((n_fluid, n_fluid * ns))
+        dps = []
+        for k in range(n_fluid):
+            dqk, dpk = bernoulli_lin.dqp_darea(r.kind, s[k], area[k], psub[k], psup[k], rho[k],
+                                               r_sep[k], lb[k], r.idx_sep)
+            dq[k, k * ns:(k + 1) * ns] = dqk
+            dps.append(sp.csr_matrix(dpk))
+        return dq.tocsr(), sp.block_diag(dps, format='csr')
+
+    def assem_dres_dstate1(self):
+        """Block Jacobian over (u, v, a, q, p) x (u1, v1, a1, q1, p1)."""
+        sl = self.solid.assem_dres_dstate1()
+        N = self.solid.state0['u'].size
+        nq, npf = self.fluid.state0['q'].size, self.fluid.state0['p'].size
+        dq_da, dp_da = self._fluid_dqp_darea()
+        dfq_du = -(dq_da @ self._dflarea_dslu)        # F_q = q1 - q(area(u1))
+        dfp_du = -(dp_da @ self._dflarea_dslu)
+        Z = lambda m, n: sp.csr_matrix((m, n))
+        rows = []
+        for i in range(3):
+            rows.append([sl.mats[3 * i + j] for j in range(3)] + [Z(N, nq), Z(N, npf)])
+        rows.append([dfq_du, Z(nq, N), Z(nq, N), sp.identity(nq, format='csr'), Z(nq, npf)])
+        rows.append([dfp_du, Z(npf, N), Z(npf, N), Z(npf, nq), sp.identity(npf, format='csr')])
+        keys0 = tuple(self.state1.keys())
+        return BlockMatrix([m for row in rows for m in row], (5, 5),
+                           (keys0, tuple(f'state/{k}1' for k in keys0)))
+
+    def assem_dres_dstate0(self):
+        """Block Jacobian over (u, v, a, q, p) x (u0, v0, a0, q0, p0): the solid depends on p0
+        through the pressure map (explicit coupling); the fluid residual does not depend on
+        state0."""
+        sl = self.solid.assem_dres_dstate0()
+        dsl_dp = self.solid.assem_dres_dcontrol()
+        N = self.solid.state0['u'].size
+        nq, npf = self.fluid.state0['q'].size, self.fluid.state0['p'].size
+        Z = lambda m, n: sp.csr_matrix((m, n))
+        rows = []
+        for i in range(3):
+            rows.append([sl.mats[3 * i + j] for j in range(3)] +
+                        [Z(N, nq), (dsl_dp.mats[i] @ self._dslp_dflp).tocsr()])
+        rows.append([Z(nq, N)] * 3 + [Z(nq, nq), Z(nq, npf)])
+        rows.append([Z(npf, N)] * 3 + [Z(npf, nq), Z(npf, npf)])
+        keys0 = tuple(self.state1.keys())
+        return BlockMatrix([m for row in rows for m in row], (5, 5),
+                           (keys0, tuple(f'state/{k}0' for k in keys0)))
+
+    def solve_dres_dstate1(self, b, dres_dstate1=None):
+        """Solve dF/dstate1 x = b (``transient.py:922-937``): the solid block on the device, then
+        the fluid rows by substitution (their diagonal blocks are identities)."""
+        if dres_dstate1 is None:
+            dres_dstate1 = self.assem_dres_dstate1()
+        x = self.state0.copy()
+        sl_labels = (self.solid.FORM_KEYS, self.solid.STATE1_KEYS)
+        dsl = BlockMatrix(dres_dstate1.mats[0:3] + dres_dstate1.mats[5:8] + dres_dstate1.mats[10:13],
+                          (3, 3), sl_labels)
+        xs = self.solid.solve_dres_dstate1(dsl, self.solid.state0.copy(), b[:3])
+        for key in ('u', 'v', 'a'):
+            x[key][:] = xs[key]
+        xu = np.asarray(xs['u'])
+        x['q'][:] = b['q'] - dres_dstate1.sub['q', 'state/u1'] @ xu
+        x['p'][:] = b['p'] - dres_dstate1.sub['p', 'state/u1'] @ xu
+        return x
+
     def solve_state1(self, ini_state, options=None):
         """``transient.py:899-920``: solid Newton solve, area update, fluid solve."""
         self.set_fin_state(ini_state)
