@@ -619,6 +619,38 @@ def main():
                 'member_steps_per_s': B * world * 99 / (weak['ms_device'] * 1e-3),
                 'e2e_member_steps_per_s': B * world * 99 / (weak['ms_host_buffers'] * 1e-3)}
 
+    # ---- configs[2] as written: ~1 M P2 triangles (the reference itself is P1 only; P2 is the
+    # extension BASELINE.json names).  First P2 kernel: node-gather, not yet tiled / pipelined ----
+    if not args.skip_extras and args.levels >= REFINE_LEVELS and rank == 0:
+        try:
+            from femvf_b200 import meshgen
+            from femvf_b200.p2 import P2Assembler
+            mt = meshgen.m5_cb_refined(BASE_H, REFINE_LEVELS - 1)
+            mesh2 = mt[0]
+            asm = P2Assembler(mesh2.coordinates(), mesh2.cells())
+            g = torch.Generator(device='cuda'); g.manual_seed(0)
+            rnd = lambda n, lo, hi: lo + (hi - lo) * torch.rand(n, dtype=torch.float64,
+                                                                device='cuda', generator=g)
+            Np, nnp, nep = asm.N, asm.nn, asm.ne
+            vec = [rnd(Np, -1e-3, 1e-3), rnd(Np, -1e-3, 1e-3), rnd(Np, -1e-2, 1e-2),
+                   rnd(Np, -1e2, 1e2), rnd(nnp, 0.0, 8e3), rnd(nep, 2.5e4, 1e5), rnd(nep, 1, 5),
+                   torch.ones(nep, dtype=torch.float64, device='cuda')]
+            fn = lambda: asm.assemble(*vec, 0.45, 1e-4)
+            ms_p2 = time_events(fn, 20, 3) / 20
+            B_p2 = 8 * asm.nnz + 8 * Np + 32 * Np + 16 * nnp + (4 * 6 + 24) * nep + 8 * nnp
+            line['p2'] = {
+                'workload': f'BASELINE configs[2]: residual+Jacobian assembly, {nep} P2 triangles '
+                            f'(M5_CB refined {REFINE_LEVELS - 1}x), {Np} DOF, {asm.nnz} non-zeros',
+                'kernel': 'p2_assemble_kernel (node gather, closed-form reference tensors)',
+                'ms_per_step': ms_p2, 'value': Np / (ms_p2 * 1e-3), 'unit': UNIT,
+                'roofline': {'bound': 'hbm', 'algorithmic_bytes': B_p2,
+                             'achieved': B_p2 / (ms_p2 * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
+                             'frac': B_p2 / (ms_p2 * 1e-3) / 1e9 / peak}}
+            del asm, vec
+            torch.cuda.empty_cache()
+        except Exception as ex:
+            line['p2'] = {'error': repr(ex)}
+
     # ---- mesh partition (BASELINE configs[4]) on the same ranks: owner-computes assembly and a
     # fixed number of GMRES iterations with halo exchange + all-reduces over NCCL -----------------
     if args.partition_tets > 0 and not args.skip_extras:

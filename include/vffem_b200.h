@@ -213,6 +213,35 @@ int vf_axpby(vf_engine* e, double alpha, const double* x_dev, double beta, doubl
 int vf_glottal_width_series(vf_engine* e, int member, int nt, const double* u_hist_dev, size_t ldu,
                             double* out_dev, void* stream);
 
+/* P2 (6-node) triangle residual + Jacobian assembly: the P2 extension named by BASELINE.json
+ * (north_star subsystem 1, configs[2]); the reference itself is P1 only (equations/form.py:521-524).
+ * Same call sites as vf_assemble (models/assemblyutils.py:49-50, models/transient.py:363-406) on a
+ * P2 function space: F_u = M a_nmk + C v_nmk + K u1 + follower pressure, J = ca M + cv C + K + K_p,
+ * Dirichlet rows applied.  Self-contained object; every vector is a caller-owned device array.
+ *   coords_host (nn, 2) incl. mid-edge nodes; cells6_host (ne, 6), local order v0 v1 v2 e(12) e(02) e(01)
+ *   brptr/bcol: node graph (block CSR pattern, columns ascending, <= 31 blocks per row)
+ *   n2e_ptr/n2e: per node its (cell * 8 + local node) pairs; n2e_slots: per pair the CSR slots of
+ *                the cell's six nodes in that node's row, 5 bits each
+ *   n2f_ptr/n2f: per node its pressure edges (edge * 4 + position 0/1/2 = va/vb/mid);
+ *                n2f_pair: index of the (node, parent cell) pair in n2e
+ *   pf_cell (nfp), pf_loc (nfp, 3) local nodes (va, vb, mid) in the parent cell,
+ *   pf_geo (nfp, 3) = outward unit normal, edge length; fixed_host (nn) Dirichlet flags
+ * J_dev receives vf_p2_nnz doubles in scalar CSR order of the node-major interleaved DOFs. */
+typedef struct vf_p2 vf_p2;
+int vf_p2_create(int nn, int ne, const double* coords_host, const int32_t* cells6_host,
+                 const int32_t* brptr_host, const int32_t* bcol_host, const int32_t* n2e_ptr_host,
+                 const int32_t* n2e_host, const uint32_t* n2e_slots_host,
+                 const int32_t* n2f_ptr_host, const int32_t* n2f_host,
+                 const int32_t* n2f_pair_host, int nfp, const int32_t* pf_cell_host,
+                 const int32_t* pf_loc_host, const double* pf_geo_host, const uint8_t* fixed_host,
+                 void* stream, vf_p2** out);
+void vf_p2_destroy(vf_p2* p);
+long long vf_p2_nnz(const vf_p2* p);
+int vf_p2_assemble(vf_p2* p, int flags, double dt, double nu, const double* emod_dev,
+                   const double* eta_dev, const double* rho_dev, const double* u1_dev,
+                   const double* u0_dev, const double* v0_dev, const double* a0_dev,
+                   const double* p1_dev, double* F_dev, double* J_dev, void* stream);
+
 /* Multicolour block ILU(0) of J_uu on node rows [node0, node1): the cuSPARSE-free stand-in for
  * the reference's sparse LU (dfn.solve(A, x, b, 'petsc'), models/transient.py:487, static.py:140)
  * as preconditioner of the grid-wide GMRES on meshes that do not fit one CTA.

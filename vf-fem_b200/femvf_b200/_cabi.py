@@ -74,6 +74,7 @@ EXPORTED_SYMBOLS = [
     'vf_newmark_residual', 'vf_scale_rsqrt', 'vf_glottal_width_series',
     'vf_assemble_mix', 'vf_pressure_control_blocks', 'vf_set_fan_tables',
     'vf_props_changed', 'vf_ilu_setup', 'vf_ilu_factor', 'vf_ilu_apply',
+    'vf_p2_create', 'vf_p2_destroy', 'vf_p2_nnz', 'vf_p2_assemble',
 ]
 
 _lib = None
@@ -145,6 +146,14 @@ def load_library() -> C.CDLL:
                                  C.c_void_p, C.c_void_p]
     lib.vf_ilu_factor.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     lib.vf_ilu_apply.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.vf_p2_create.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 10 + [C.c_int] + \
+        [C.c_void_p] * 6
+    lib.vf_p2_destroy.argtypes = [C.c_void_p]
+    lib.vf_p2_destroy.restype = None
+    lib.vf_p2_nnz.argtypes = [C.c_void_p]
+    lib.vf_p2_nnz.restype = C.c_longlong
+    lib.vf_p2_assemble.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double] + \
+        [C.c_void_p] * 11
     lib.vf_launch_count.argtypes = [C.c_void_p]
     lib.vf_launch_count.restype = C.c_int64
     _lib = lib
