@@ -7,53 +7,6 @@
 
 namespace vf {
 
-template <int D, bool JAC, bool RES>
-__global__ void asm_tile_kernel(EngineDev E, int member, double dt, int is_static, JacMix mix,
-                                const int* __restrict__ tile_start) {
-  extern __shared__ double tile[];
-  double* mb = E.members + (size_t)member * E.L.stride;
-  const Layout& L = E.L;
-  const int i0 = tile_start[blockIdx.x], i1 = tile_start[blockIdx.x + 1];
-  const size_t base = (size_t)D * D * E.mesh.brptr[i0];
-  const int nvals = int((size_t)D * D * E.mesh.brptr[i1] - base);
-  const int i = i0 + threadIdx.x;
-  if (i < i1) {
-    PropView pv = member_props<D>(E, mb);
-    StateView sv;
-    sv.u1 = mb + L.off[VF_U1];
-    sv.u0 = is_static ? sv.u1 : mb + L.off[VF_U0];
-    sv.v0 = mb + L.off[VF_V0];
-    sv.a0 = mb + L.off[VF_A0];
-    sv.p1 = mb + L.off[VF_P1];
-    sv.dt = dt;
-    sv.is_static = is_static;
-  sv.mix = mix;
-    sv.mix = mix;
-    double res[D];
-    double* rowblk = JAC ? tile + ((size_t)D * D * E.mesh.brptr[i] - base) : nullptr;
-    assemble_node<D, JAC, RES>(i, E.mesh, pv, sv, rowblk, res);
-    if (RES) {
-      double* F = mb + L.off[VF_F];
-#pragma unroll
-      for (int c = 0; c < D; ++c) F[D * i + c] = res[c];
-    }
-  }
-  if (JAC) {
-    __syncthreads();
-    double* Jg = mb + L.off[VF_J] + base;
-    if (D == 2) {
-      // base and nvals are multiples of 4 doubles: 16-byte vector stores, fully coalesced
-      double2* dst = reinterpret_cast<double2*>(Jg);
-      const double2* src = reinterpret_cast<const double2*>(tile);
-      for (int t = threadIdx.x; t < nvals / 2; t += blockDim.x) dst[t] = src[t];
-    } else {
-      for (int t = threadIdx.x; t < nvals; t += blockDim.x) Jg[t] = tile[t];
-    }
-  }
-}
-
-
-
 // Two-phase, element-centric tile assembly (triangles).  Replaces the thread-per-node gather
 // for 2D: every cell touching the tile is processed ONCE per CTA.
 //   phase 0  one 32-byte tile descriptor, then all index data of the tile (vertex quads,
@@ -333,50 +286,6 @@ __global__ void __launch_bounds__(MAXT, MINB) asm_tile2_kernel(
         if (RES) racc += rec[9 + 2 * a + comp];
       }
       if (RES) tileF[r] = racc;
-    }
-  } else {
-    // one thread per node (both scalar rows of its block row)
-    for (int n = threadIdx.x; n < nT; n += kThreads) {
-      const int b0 = s_brptr[n], deg = s_brptr[n + 1] - b0;
-      double* row0 = tileJ + D * D * (b0 - bbase);
-      double* row1 = row0 + D * deg;
-      if (JAC) {
-        const D2 z = D2{0.0, 0.0};
-        for (int t = 0; t < D * deg; ++t) reinterpret_cast<D2*>(row0)[t] = z;
-      }
-      double r0 = 0.0, r1 = 0.0;
-      const int qe = s_n2e[n + 1] - pr0;
-      for (int q = s_n2e[n] - pr0; q < qe; ++q) {
-        const unsigned info = s_pair[q];
-        const double* rec = recs + (size_t)(info & 0xfffu) * kRec2D;
-        const int a = (info >> 12) & 3;
-        if (JAC) {
-#pragma unroll
-          for (int sft = 0; sft < 3; ++sft) {
-            const int slot = (info >> (14 + 6 * sft)) & 63;  // slots are (self, next, prev)
-            const int c = (a + sft) % 3;
-            double b[2][2];
-            tri_block(rec, a, c, b);
-            D2* p0 = reinterpret_cast<D2*>(row0 + D * slot);
-            D2* p1 = reinterpret_cast<D2*>(row1 + D * slot);
-            D2 c0 = *p0, c1 = *p1;
-            c0.x += b[0][0];
-            c0.y += b[0][1];
-            c1.x += b[1][0];
-            c1.y += b[1][1];
-            *p0 = c0;
-            *p1 = c1;
-          }
-        }
-        if (RES) {
-          r0 += rec[9 + 2 * a];
-          r1 += rec[10 + 2 * a];
-        }
-      }
-      if (RES) {
-        tileF[D * n] = r0;
-        tileF[D * n + 1] = r1;
-      }
     }
   }
   __syncthreads();
@@ -1138,15 +1047,6 @@ size_t tile2_smem_bytes(const vf_problem_desc& d, bool direct = false) {
 
 int vf::assembly_configure(vf_engine* e, const vf_problem_desc& d, bool two_phase) {
   (void)e;
-  // opt in to large dynamic shared memory for the tile kernel
-  const int smem = d.tile_max_values * (int)sizeof(double);
-  if (d.dim == 2) {
-    VF_CUDA(cudaFuncSetAttribute(asm_tile_kernel<2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    VF_CUDA(cudaFuncSetAttribute(asm_tile_kernel<2, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  } else {
-    VF_CUDA(cudaFuncSetAttribute(asm_tile_kernel<3, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    VF_CUDA(cudaFuncSetAttribute(asm_tile_kernel<3, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  }
   if (two_phase) {
     const int smem2 = (int)tile2_smem_bytes(d);
     if (smem2 > 227 * 1024) {
@@ -1158,12 +1058,8 @@ int vf::assembly_configure(vf_engine* e, const vf_problem_desc& d, bool two_phas
   VF_SMEM2((asm_tile2_kernel<J_, R_, ROW_, 192, 5>));       \
   VF_SMEM2((asm_tile2_kernel<J_, R_, ROW_, 256, 4>));       \
   VF_SMEM2((asm_tile2_kernel<J_, R_, ROW_, 320, 3>))
-    VF_SMEM2_ALL(true, true, 0);
     VF_SMEM2_ALL(true, true, 1);
-    VF_SMEM2_ALL(true, true, 2);
-    VF_SMEM2_ALL(true, false, 0);
     VF_SMEM2_ALL(true, false, 1);
-    VF_SMEM2_ALL(true, false, 2);
     VF_SMEM2_ALL(false, true, 1);
 #undef VF_SMEM2_ALL
 #undef VF_SMEM2
@@ -1439,7 +1335,7 @@ int assemble_impl(vf_engine* e, int member, int flags, double dt, int is_static,
     if (rc < 0 && launch_fan(e, member, res, jac, dt, is_static, mix, st)) return 1;
     return launch_facet_bc(e, member, res, jac, dt, is_static, mix, st);
   }
-  const int grid = e->desc.ntiles, block = e->desc.tile_threads;
+  const int grid = e->desc.ntiles;
   if (e->two_phase) {
     const vf_problem_desc& d = e->desc;
     const size_t smem2 = tile2_smem_bytes(d);
@@ -1452,9 +1348,10 @@ int assemble_impl(vf_engine* e, int member, int flags, double dt, int is_static,
     // L2 prefetch distance in tiles: one wave of resident CTAs (148 SMs x 3 CTAs; measured flat
     // between one and two waves, worse below and far above: profiles/README.md)
     const int pf_dist = getenv("VF_PF_DIST") ? atoi(getenv("VF_PF_DIST")) : 3 * 148;
-    int v_row = getenv("VF_TILE2_ROW") ? atoi(getenv("VF_TILE2_ROW")) : 2;
-    if (v_row == 2 && !e->fan_ok) v_row = 1;
-    // occupancy class by CTA size: small CTAs run many per SM so that their phases overlap
+    // fan-ordered meshes: one thread per scalar row completes every off-diagonal block in
+    // registers and stores it straight to HBM (ROW 2, direct: 4 CTAs of 256 threads per SM);
+    // meshes whose vertex fans cannot be ordered, and residual-only launches, accumulate the row
+    // slice in shared memory by read-modify-write (ROW 1)
     const int nt = d.tile2_threads;
 #define VF_ASM2_BY_SIZE(J_, R_, ROW_)                                                              \
   do {                                                                                            \
@@ -1463,18 +1360,7 @@ int assemble_impl(vf_engine* e, int member, int flags, double dt, int is_static,
     else if (nt <= 256) VF_LAUNCH_ASM2(J_, R_, ROW_, 256, 4);                                     \
     else VF_LAUNCH_ASM2(J_, R_, ROW_, 320, 3);                                                    \
   } while (0)
-#define VF_ASM2_BY_MODE(J_, R_)                                                                    \
-  do {                                                                                            \
-    if (v_row == 2) VF_ASM2_BY_SIZE(J_, R_, 2);                                                   \
-    else if (v_row == 1) VF_ASM2_BY_SIZE(J_, R_, 1);                                              \
-    else VF_ASM2_BY_SIZE(J_, R_, 0);                                                              \
-  } while (0)
-    // Default for the fan-ordered path: rows are stored straight to HBM from phase 2 (every
-    // 16-byte entry once; L2 merges the sectors), so no CSR slice is kept in shared memory and
-    // 4 CTAs of 256 threads fit per SM (measured 0.4015 -> 0.3751 ms with 80-node tiles;
-    // VF_TILE2_DIRECT=0 restores the staged write-out)
-    static const char* env_direct = getenv("VF_TILE2_DIRECT");
-    if (!(env_direct && atoi(env_direct) == 0) && jac && v_row == 2 && nt <= 320) {
+    if (jac && e->fan_ok && nt <= 320) {
       const size_t smem_d = tile2_smem_bytes(d, true);
 #define VF_LAUNCH_ASM2D(R_, MT_, MB_)                                                              \
   do {                                                                                            \
@@ -1491,57 +1377,32 @@ int assemble_impl(vf_engine* e, int member, int flags, double dt, int is_static,
         if (res) VF_LAUNCH_ASM2D(true, 320, 3); else VF_LAUNCH_ASM2D(false, 320, 3);
       }
 #undef VF_LAUNCH_ASM2D
-    } else
-    if (jac && res) VF_ASM2_BY_MODE(true, true);
-    else if (jac) VF_ASM2_BY_MODE(true, false);
+    } else if (jac && res) VF_ASM2_BY_SIZE(true, true, 1);
+    else if (jac) VF_ASM2_BY_SIZE(true, false, 1);
     else VF_ASM2_BY_SIZE(false, true, 1);
-#undef VF_ASM2_BY_MODE
 #undef VF_ASM2_BY_SIZE
 #undef VF_LAUNCH_ASM2
     e->launches += 1;
     VF_CUDA(cudaGetLastError());
-    if (e->n_touch > 0) {
-      const int fb = 128, fg = (e->n_touch + fb - 1) / fb;
-      if (jac && res)
-        facet_bc_kernel<2, true, true><<<fg, fb, 0, st>>>(e->dev, member, dt, is_static, mix, e->touch_dev, e->n_touch);
-      else if (jac)
-        facet_bc_kernel<2, true, false><<<fg, fb, 0, st>>>(e->dev, member, dt, is_static, mix, e->touch_dev, e->n_touch);
-      else
-        facet_bc_kernel<2, false, true><<<fg, fb, 0, st>>>(e->dev, member, dt, is_static, mix, e->touch_dev, e->n_touch);
-      e->launches += 1;
-      VF_CUDA(cudaGetLastError());
-    }
-    return 0;
+    return launch_facet_bc(e, member, res, jac, dt, is_static, mix, st);
   }
-  if (e->desc.dim == 3 && !(getenv("VF_TET_SMEM") && atoi(getenv("VF_TET_SMEM")))) {
+  // tetrahedra, and triangle meshes whose tiles do not fit the two-phase kernel: thread-per-node
+  // gather writing the block rows straight to the CSR array
+  {
     const int nb = 128, ng = (e->desc.nn + nb - 1) / nb;
-    if (jac && res) asm_node_global_kernel<3, true, true><<<ng, nb, 0, st>>>(e->dev, member, dt, is_static, mix);
-    else if (jac) asm_node_global_kernel<3, true, false><<<ng, nb, 0, st>>>(e->dev, member, dt, is_static, mix);
-    else asm_node_global_kernel<3, false, true><<<ng, nb, 0, st>>>(e->dev, member, dt, is_static, mix);
+#define VF_LAUNCH_NODE(D)                                                                         \
+  do {                                                                                            \
+    if (jac && res) asm_node_global_kernel<D, true, true><<<ng, nb, 0, st>>>(e->dev, member, dt, is_static, mix); \
+    else if (jac) asm_node_global_kernel<D, true, false><<<ng, nb, 0, st>>>(e->dev, member, dt, is_static, mix); \
+    else asm_node_global_kernel<D, false, true><<<ng, nb, 0, st>>>(e->dev, member, dt, is_static, mix); \
+  } while (0)
+    if (e->desc.dim == 3) VF_LAUNCH_NODE(3);
+    else VF_LAUNCH_NODE(2);
+#undef VF_LAUNCH_NODE
     e->launches += 1;
     VF_CUDA(cudaGetLastError());
     return 0;
   }
-  const size_t smem = jac ? (size_t)e->desc.tile_max_values * sizeof(double) : 0;
-#define VF_LAUNCH_ASM(D)                                                                          \
-  if (jac && res)                                                                                 \
-    asm_tile_kernel<D, true, true><<<grid, block, smem, st>>>(e->dev, member, dt, is_static, mix, \
-                                                              e->tile_start_dev);                 \
-  else if (jac)                                                                                   \
-    asm_tile_kernel<D, true, false><<<grid, block, smem, st>>>(e->dev, member, dt, is_static, mix, \
-                                                               e->tile_start_dev);                \
-  else                                                                                            \
-    asm_tile_kernel<D, false, true><<<grid, block, 0, st>>>(e->dev, member, dt, is_static, mix, \
-                                                            e->tile_start_dev);
-  if (e->desc.dim == 2) {
-    VF_LAUNCH_ASM(2)
-  } else {
-    VF_LAUNCH_ASM(3)
-  }
-#undef VF_LAUNCH_ASM
-  e->launches += 1;
-  VF_CUDA(cudaGetLastError());
-  return 0;
 }
 }  // namespace
 
