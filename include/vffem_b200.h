@@ -226,6 +226,7 @@ int vf_glottal_width_series(vf_engine* e, int member, int nt, const double* u_hi
  *                n2f_pair: index of the (node, parent cell) pair in n2e
  *   pf_cell (nfp), pf_loc (nfp, 3) local nodes (va, vb, mid) in the parent cell,
  *   pf_geo (nfp, 3) = outward unit normal, edge length; fixed_host (nn) Dirichlet flags
+ *   order_host (nn): thread -> node map, the n_class0 vertex nodes first, then the mid-edge nodes
  * J_dev receives vf_p2_nnz doubles in scalar CSR order of the node-major interleaved DOFs. */
 typedef struct vf_p2 vf_p2;
 int vf_p2_create(int nn, int ne, const double* coords_host, const int32_t* cells6_host,
@@ -234,7 +235,7 @@ int vf_p2_create(int nn, int ne, const double* coords_host, const int32_t* cells
                  const int32_t* n2f_ptr_host, const int32_t* n2f_host,
                  const int32_t* n2f_pair_host, int nfp, const int32_t* pf_cell_host,
                  const int32_t* pf_loc_host, const double* pf_geo_host, const uint8_t* fixed_host,
-                 void* stream, vf_p2** out);
+                 const int32_t* order_host, int n_class0, void* stream, vf_p2** out);
 void vf_p2_destroy(vf_p2* p);
 long long vf_p2_nnz(const vf_p2* p);
 int vf_p2_assemble(vf_p2* p, int flags, double dt, double nu, const double* emod_dev,

@@ -52,6 +52,9 @@ struct vf_p2 {
   int* pf_loc;       // (nfp, 3) local nodes of the edge in the parent cell (va, vb, mid)
   double* pf_geo;    // (nfp, 3): outward unit normal, length
   unsigned char* fixed;  // nn
+  int* order;        // thread -> node: vertex nodes first, then mid-edge nodes (uniform warps)
+  int n_class0;      // number of vertex nodes in `order`
+  int max_deg0, max_deg1;  // longest block row of each class
 };
 
 namespace {
@@ -90,7 +93,8 @@ __device__ __forceinline__ void p2_shape_edge(double t, int la, int lb, double (
   D[5][1] = 4 * L[0];
 }
 
-__global__ void __launch_bounds__(64) p2_assemble_kernel(vf_p2 P, P2Args A) {
+__global__ void __launch_bounds__(64) p2_assemble_kernel(vf_p2 P, P2Args A, int first, int count,
+                                                         int max_deg) {
   extern __shared__ double s_rows[];
   // the reference tensors are indexed by the thread's local node: shared memory, not the
   // (warp-uniform) constant cache
@@ -98,9 +102,10 @@ __global__ void __launch_bounds__(64) p2_assemble_kernel(vf_p2 P, P2Args A) {
   for (int t = threadIdx.x; t < 324; t += blockDim.x) (&sW[0][0][0][0])[t] = (&kP2W[0][0][0][0])[t];
   for (int t = threadIdx.x; t < 36; t += blockDim.x) (&sM[0][0])[t] = (&kP2M[0][0])[t];
   __syncthreads();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P.nn) return;
-  const int stride = 4 * P.max_deg + 2;  // +2: 16-byte aligned rows on different banks
+  const int tix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tix >= count) return;
+  const int i = P.order[first + tix];
+  const int stride = 4 * max_deg + 2;  // +2: 16-byte aligned rows on different banks
   double* row = s_rows + (size_t)threadIdx.x * stride;
   const int b0 = P.brptr[i], deg = P.brptr[i + 1] - b0;
   // row layout in shared memory: block s = (r00, r01, r10, r11)
@@ -285,10 +290,11 @@ int vf_p2_create(int nn, int ne, const double* coords_host, const int32_t* cells
                  const int32_t* n2f_ptr_host, const int32_t* n2f_host,
                  const int32_t* n2f_pair_host, int nfp, const int32_t* pf_cell_host,
                  const int32_t* pf_loc_host, const double* pf_geo_host, const uint8_t* fixed_host,
-                 void* stream, vf_p2** out) {
+                 const int32_t* order_host, int n_class0, void* stream, vf_p2** out) {
   if (!out) return vf::fail("vf_p2_create: null output");
   if (nn <= 0 || ne <= 0 || !coords_host || !cells6_host || !brptr_host || !bcol_host ||
-      !n2e_ptr_host || !n2e_host || !n2e_slots_host || !n2f_ptr_host || !fixed_host)
+      !n2e_ptr_host || !n2e_host || !n2e_slots_host || !n2f_ptr_host || !fixed_host ||
+      !order_host || n_class0 < 0 || n_class0 > nn)
     return vf::fail("vf_p2_create: missing tables");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
@@ -307,6 +313,17 @@ int vf_p2_create(int nn, int ne, const double* coords_host, const int32_t* cells
     return vf::fail("vf_p2_create: a node couples to more than 31 nodes");
   }
   P->max_deg = max_deg;
+  P->n_class0 = n_class0;
+  P->max_deg0 = P->max_deg1 = 1;
+  for (int t = 0; t < nn; ++t) {
+    const int i = order_host[t];
+    if (i < 0 || i >= nn) {
+      delete P;
+      return vf::fail("vf_p2_create: order is not a permutation of the nodes");
+    }
+    int& md = t < n_class0 ? P->max_deg0 : P->max_deg1;
+    md = std::max(md, brptr_host[i + 1] - brptr_host[i]);
+  }
   struct Item {
     void** dst;
     const void* src;
@@ -327,6 +344,7 @@ int vf_p2_create(int nn, int ne, const double* coords_host, const int32_t* cells
       {(void**)&P->pf_loc, pf_loc_host, sizeof(int) * 3 * (size_t)std::max(nfp, 1)},
       {(void**)&P->pf_geo, pf_geo_host, sizeof(double) * 3 * (size_t)std::max(nfp, 1)},
       {(void**)&P->fixed, fixed_host, (size_t)nn},
+      {(void**)&P->order, order_host, sizeof(int) * (size_t)nn},
   };
   size_t total = 0;
   for (auto& it : items) total += align256(it.bytes);
@@ -375,14 +393,23 @@ int vf_p2_assemble(vf_p2* P, int flags, double dt, double nu, const double* emod
   A.emod = emod_dev; A.eta = eta_dev; A.rho = rho_dev;
   A.u1 = u1_dev; A.u0 = u0_dev; A.v0 = v0_dev; A.a0 = a0_dev; A.p1 = p1_dev;
   A.F = F_dev; A.J = J_dev; A.nu = nu; A.dt = dt;
-  const int block = 64, grid = (P->nn + block - 1) / block;
-  const size_t smem = sizeof(double) * (size_t)block * (4 * P->max_deg + 2);
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(p2_assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     attr_set = true;
   }
-  p2_assemble_kernel<<<grid, block, smem, reinterpret_cast<cudaStream_t>(stream)>>>(*P, A);
+  // one launch per node class (vertex nodes: ~19 blocks per row, 6 cells; mid-edge nodes: 9 blocks,
+  // 2 cells): uniform trip counts inside a warp, shared-memory rows sized per class
+  const int block = 64;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int first[2] = {0, P->n_class0}, count[2] = {P->n_class0, P->nn - P->n_class0};
+  const int mdeg[2] = {P->max_deg0, P->max_deg1};
+  for (int c = 0; c < 2; ++c) {
+    if (count[c] <= 0) continue;
+    const size_t smem = sizeof(double) * (size_t)block * (4 * mdeg[c] + 2);
+    p2_assemble_kernel<<<(count[c] + block - 1) / block, block, smem, st>>>(*P, A, first[c],
+                                                                             count[c], mdeg[c]);
+  }
   if (cudaGetLastError() != cudaSuccess) return vf::fail("vf_p2_assemble: launch failed");
   return 0;
 }

@@ -147,7 +147,7 @@ def load_library() -> C.CDLL:
     lib.vf_ilu_factor.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     lib.vf_ilu_apply.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.vf_p2_create.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 10 + [C.c_int] + \
-        [C.c_void_p] * 6
+        [C.c_void_p] * 5 + [C.c_int, C.c_void_p, C.c_void_p]
     lib.vf_p2_destroy.argtypes = [C.c_void_p]
     lib.vf_p2_destroy.restype = None
     lib.vf_p2_nnz.argtypes = [C.c_void_p]

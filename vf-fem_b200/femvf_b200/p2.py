@@ -144,19 +144,21 @@ class P2Assembler:
             fixed[enode[idx]] = 1
         self.fixed_nodes = np.nonzero(fixed)[0]
         self.brptr, self.bcol = brptr, bcol
+        # thread -> node map: vertex nodes, then mid-edge nodes (each class in node order)
+        node_order = np.concatenate([np.sort(vid), np.sort(enode)])
         i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
         keep = [np.ascontiguousarray(c6), i32(cells6), i32(brptr), i32(bcol), i32(n2e_ptr),
                 i32(n2e), np.ascontiguousarray(slots.astype(np.uint32)), i32(n2f_ptr), i32(n2f),
                 i32(n2f_pair), i32(pc), i32(pf_loc), np.ascontiguousarray(pf_geo),
-                np.ascontiguousarray(fixed)]
+                np.ascontiguousarray(fixed), i32(node_order)]
         handle = C.c_void_p()
         with torch.cuda.device(self.device):
             stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
             check(self._lib.vf_p2_create(
                 nn, ne, _ptr(keep[0]), _ptr(keep[1]), _ptr(keep[2]), _ptr(keep[3]), _ptr(keep[4]),
                 _ptr(keep[5]), _ptr(keep[6]), _ptr(keep[7]), _ptr(keep[8]), _ptr(keep[9]), nfp,
-                _ptr(keep[10]), _ptr(keep[11]), _ptr(keep[12]), _ptr(keep[13]), stream,
-                C.byref(handle)))
+                _ptr(keep[10]), _ptr(keep[11]), _ptr(keep[12]), _ptr(keep[13]), _ptr(keep[14]),
+                self.nv, stream, C.byref(handle)))
         self._h = handle
         self.nnz = int(self._lib.vf_p2_nnz(self._h))
         f64 = dict(dtype=torch.float64, device=self.device)
