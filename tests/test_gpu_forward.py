@@ -390,3 +390,37 @@ def test_coupled_model_linearisation_matches_finite_differences():
         # the device GMRES stops on the left-preconditioned residual (1e-13): the true residual of
         # the u rows is ~1e-8 of |b|
         assert err <= 1e-7 * max(float(np.abs(b[k]).max()), 1.0), (k, err)
+
+
+def test_ensemble_statefiles_match_single_runs(tmp_path):
+    """EnsembleRunner.run_to_statefiles: every member's StateFile equals the file written by
+    forward.integrate for that member's properties (the reference's output layout, statefile.py)."""
+    from femvf_b200 import forward, statefile as sf
+    from femvf_b200.ensemble import EnsembleRunner
+    model = build_fsi('m5')
+    state0, control, prop = benchmark_setup(model)
+    times = 1e-4 * np.arange(13)
+    B = 3
+    runner = EnsembleRunner(model, B)
+    rng = np.random.default_rng(1)
+    emod = 5e4 * np.exp(0.3 * rng.standard_normal((B, runner.ne)))
+    eta = 3.0 * np.exp(0.3 * rng.standard_normal((B, runner.ne)))
+    ini = np.zeros((B, runner.state_size))
+    names = [str(tmp_path / f'member{b}.h5') for b in range(B)]
+    infos = runner.run_to_statefiles(names, times, [control], prop, ini, emod, eta, nchunk=5)
+    assert infos.shape == (B, len(times), 4)
+    single = build_fsi('m5')
+    for b in range(B):
+        p = prop.copy(); p['emod'][:] = emod[b]; p['eta'][:] = eta[b]
+        ref_name = str(tmp_path / f'ref{b}.h5')
+        with sf.StateFile(single, ref_name, mode='w') as f:
+            forward.integrate(single, f, state0, [control], p, times)
+        with sf.StateFile(single, ref_name, mode='r') as fr, \
+                sf.StateFile(single, names[b], mode='r') as fe:
+            assert fe.size == fr.size == len(times)
+            for n in (0, 1, 6, len(times) - 1):
+                a, r = fe.get_state(n), fr.get_state(n)
+                for key in ('u', 'q', 'p'):
+                    scale = max(np.max(np.abs(r[key])), 1e-300)
+                    assert np.max(np.abs(a[key] - r[key])) <= 1e-12 * scale, (b, n, key)
+            assert np.allclose(fe.get_prop()['emod'], emod[b])

@@ -553,7 +553,8 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) asm_fan_pipe_kernel(
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kPipeSlots; ++s) {
-      mbar_init_only(&s_full[s], 3 + kTeam);   // 3 expect_tx arrivals + one cp.async arrival per team thread
+      mbar_init_only(&s_full[s], kTeam / 32 + kTeam);  // one expect_tx arrival per team warp + one
+                                                       // cp.async arrival per team thread
       mbar_init_only(&s_ready[s], 32);         // every converter thread
       mbar_init_only(&s_empty[s], 4);   // lane 0 of each consumer warp of the group
     }
@@ -706,29 +707,38 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) asm_fan_pipe_kernel(
             copy16(s_a0, a0 + 2 * (size_t)i0, n_own);
           }
         }
-        if (lane == 0 && role < 3) mbar_arrive(&s_full[i]);  // stands in for the expect_tx arrival
+        if (lane == 0) mbar_arrive(&s_full[i]);  // stands in for the expect_tx arrival
       } else
-      if (lane == 0 && role < 3 && !(dbg & 6)) {
-        // VF_PIPE_DBG 128: the seven bulk copies of the tile (bulk-copy engine), spread over the warps
+      if (lane == 0 && !(dbg & 6)) {
+        // VF_PIPE_DBG 128: the seven bulk copies of the tile (bulk-copy engine).  Issuing one
+        // costs the issuing lane ~150-200 cycles, so they are spread over the team's warps
+        // (four warps: at most three each, counting the record fetch of warp 0)
         const unsigned n_own = (unsigned)nT * 16u;
+        const bool st8 = RES && !own_lsu;       // own-vertex state by bulk copies
+        const bool dy8 = st8 && dyn;
         if (role == 0) {
           mbar_expect_tx(&s_full[i], (unsigned)(n_ring + n_mat));
           bulk_g2s(st, T.ring + ring0, (unsigned)n_ring, &s_full[i]);
           bulk_g2s(st + n_ring, mat_m + (size_t)3 * tc0, (unsigned)n_mat, &s_full[i]);
         } else if (role == 1) {
-          const bool st8 = RES && !own_lsu;
-          mbar_expect_tx(&s_full[i], n_own * (st8 ? (dyn ? 3u : 2u) : 1u));
+          const bool with_u0 = dy8 && !team4;
+          mbar_expect_tx(&s_full[i], n_own * (1u + (st8 ? 1u : 0u) + (with_u0 ? 1u : 0u)));
           bulk_g2s(s_xy, m.xy + 2 * (size_t)i0, n_own, &s_full[i]);
           if (st8) bulk_g2s(s_u1, u1 + 2 * (size_t)i0, n_own, &s_full[i]);
-          if (st8 && dyn) bulk_g2s(s_u0, u0 + 2 * (size_t)i0, n_own, &s_full[i]);
+          if (with_u0) bulk_g2s(s_u0, u0 + 2 * (size_t)i0, n_own, &s_full[i]);
         } else if (role == 2) {
-          mbar_expect_tx(&s_full[i], dyn && !own_lsu ? 2u * n_own : 0u);
-          if (dyn && !own_lsu) {
+          // four warps: u0, v0 here and a0 on warp 3; three warps: v0, a0 here
+          mbar_expect_tx(&s_full[i], dy8 ? 2u * n_own : 0u);
+          if (dy8) {
+            if (team4) bulk_g2s(s_u0, u0 + 2 * (size_t)i0, n_own, &s_full[i]);
             bulk_g2s(s_v0, v0 + 2 * (size_t)i0, n_own, &s_full[i]);
-            bulk_g2s(s_a0, a0 + 2 * (size_t)i0, n_own, &s_full[i]);
+            if (!team4) bulk_g2s(s_a0, a0 + 2 * (size_t)i0, n_own, &s_full[i]);
           }
+        } else {
+          mbar_expect_tx(&s_full[i], dy8 ? n_own : 0u);
+          if (dy8) bulk_g2s(s_a0, a0 + 2 * (size_t)i0, n_own, &s_full[i]);
         }
-      } else if (lane == 0 && role < 3) {
+      } else if (lane == 0) {
         mbar_expect_tx(&s_full[i], 0u);  // VF_PIPE_DBG 2 / 4 (measurement aid): no bulk copies
       }
       __syncwarp();
@@ -759,14 +769,18 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) asm_fan_pipe_kernel(
           const unsigned f_own = (unsigned)f_nT * 16u;
           if (role == 0) {
             bulk_prefetch_l2(T.ring + f0.w, (unsigned)f1.x * TN * (unsigned)sizeof(unsigned));
-            bulk_prefetch_l2(mat_m + (size_t)3 * f1.y, (unsigned)f1.z * 24u);
+            if (!team4) bulk_prefetch_l2(mat_m + (size_t)3 * f1.y, (unsigned)f1.z * 24u);
           } else if (role == 1) {
             bulk_prefetch_l2(m.xy + 2 * (size_t)f_i0, f_own);
             if (RES) bulk_prefetch_l2(u1 + 2 * (size_t)f_i0, f_own);
-            if (dyn) bulk_prefetch_l2(u0 + 2 * (size_t)f_i0, f_own);
-          } else if (role == 2 && dyn) {
-            bulk_prefetch_l2(v0 + 2 * (size_t)f_i0, f_own);
-            bulk_prefetch_l2(a0 + 2 * (size_t)f_i0, f_own);
+            if (dyn && !team4) bulk_prefetch_l2(u0 + 2 * (size_t)f_i0, f_own);
+          } else if (role == 2) {
+            if (dyn && team4) bulk_prefetch_l2(u0 + 2 * (size_t)f_i0, f_own);
+            if (dyn) bulk_prefetch_l2(v0 + 2 * (size_t)f_i0, f_own);
+            if (dyn && !team4) bulk_prefetch_l2(a0 + 2 * (size_t)f_i0, f_own);
+          } else {
+            bulk_prefetch_l2(mat_m + (size_t)3 * f1.y, (unsigned)f1.z * 24u);
+            if (dyn) bulk_prefetch_l2(a0 + 2 * (size_t)f_i0, f_own);
           }
         }
         __syncwarp();

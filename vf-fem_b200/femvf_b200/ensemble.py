@@ -85,3 +85,74 @@ class EnsembleRunner:
                                           None if emod is None else np.ascontiguousarray(emod),
                                           None if eta is None else np.ascontiguousarray(eta),
                                           options)
+
+    def run_to_statefiles(self, fnames, times, controls, prop, ini_state, emod=None, eta=None,
+                          options=None, nchunk: int = 100):
+        """
+        One ``StateFile`` per member (the drop-in output layout of ``forward.integrate``,
+        ``/root/reference/src/femvf/statefile.py:163-339``): the ensemble advances on the device in
+        chunks of ``nchunk`` steps; after every chunk the state history of ALL members comes back
+        in one device->host copy and is appended to the members' files.
+
+        fnames : one path per member;  times : (nt,) shared time grid
+        controls : list of control BlockVectors (control n is used for step n, the last one
+        for the remaining steps, as in ``forward.py:169-171``);  prop : the common properties
+        (per-member ``emod`` / ``eta`` fields overwrite the common ones)
+        Returns the (n_members, nt, 4) info series (num_iter, abs_err, rel_err, min area).
+        """
+        from . import statefile as sf
+        if len(fnames) != self.n_members:
+            raise ValueError("one file name per member")
+        times = np.asarray(times, dtype=float)
+        nsteps = len(times) - 1
+        m, e = self.model, self.engine
+        self.set_common_prop(prop)
+        self.upload_members(np.ascontiguousarray(ini_state), emod, eta)
+        n_fluid = e.n_fluid
+        ctl_rows = np.array([[np.broadcast_to(c['psub'], (n_fluid,)),
+                              np.broadcast_to(c['psup'], (n_fluid,))] for c in controls])
+        files = []
+        try:
+            for b, fname in enumerate(fnames):
+                mprop = prop.copy()
+                if emod is not None:
+                    mprop['emod'][:] = emod[b]
+                if eta is not None:
+                    mprop['eta'][:] = eta[b]
+                m.set_prop(mprop)
+                f = sf.StateFile(m, fname, mode='w', NCHUNK=nchunk)
+                f.init_layout()                          # forward.py:84-89
+                st = m.state0.copy()
+                st[:] = ini_state[b]
+                f.append_state(st)
+                f.append_control(controls[0])
+                f.append_time(times[0])
+                f.append_solver_info({'num_iter': 0, 'abs_err': 0, 'rel_err': 0})
+                f.append_prop(mprop)
+                files.append(f)
+            m.set_prop(prop)
+            infos = np.zeros((self.n_members, nsteps + 1, 4))
+            n0 = 0
+            while n0 < nsteps:
+                n1 = min(n0 + nchunk, nsteps)
+                idx = [min(n, len(controls) - 1) for n in range(n0, n1)]
+                hs, hi = self.run_device(np.diff(times)[n0:n1], ctl_rows[idx], options,
+                                         store_states=True)
+                hs, hi = hs.cpu().numpy(), hi.cpu().numpy()
+                infos[:, n0 + 1:n1 + 1] = hi[:, 1:]
+                for b, f in enumerate(files):
+                    for k in range(n1 - n0):
+                        st = m.state0.copy()
+                        st[:] = hs[b, k + 1]
+                        f.append_state(st)
+                        f.append_control(controls[idx[k]])
+                        f.append_time(times[n0 + k + 1])
+                        f.append_solver_info({'num_iter': int(hi[b, k + 1, 0]),
+                                              'abs_err': float(hi[b, k + 1, 1]),
+                                              'rel_err': float(hi[b, k + 1, 2])})
+                n0 = n1
+        finally:
+            for f in files:
+                f.close()
+        return infos
+
