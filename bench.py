@@ -619,6 +619,49 @@ def main():
                 'member_steps_per_s': B * world * 99 / (weak['ms_device'] * 1e-3),
                 'e2e_member_steps_per_s': B * world * 99 / (weak['ms_host_buffers'] * 1e-3)}
 
+    # ---- forward.integrate on a REFINED mesh: the coupled model on a solid that does not fit one
+    # CTA takes the per-step path (whole-GPU Newton: pipelined assembly + ILU(0)-GMRES) ------------
+    if not args.skip_extras and rank == 0:
+        try:
+            from femvf_b200 import forward, meshgen
+            from femvf_b200.load import load_fsi_model
+            from femvf_b200.residuals import solid as slr, fluid as flr
+            lv = 4
+            fr = load_fsi_model(meshgen.m5_cb_refined(BASE_H, lv), slr.KelvinVoigt,
+                                flr.BernoulliAreaRatioSep,
+                                {'dirichlet_bcs': {'state/u1': [(np.zeros(2), 'facet', 'fixed')]}}, {})
+            st0, ctl_r, prop_r = config1_args(fr)
+            nst = 10
+            tms = 1e-4 * np.arange(nst + 1)
+            forward.integrate(fr, None, st0, [ctl_r], prop_r, tms[:3], write=False)   # warm-up
+            gs = fr.solid._grid_solver()
+            it0 = gs.gmres.spmv_count
+            l0 = fr.engine.launch_count
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            forward.integrate(fr, None, st0, [ctl_r], prop_r, tms, write=False)
+            torch.cuda.synchronize()
+            dt_r = time.perf_counter() - t0
+            e_r = fr.engine
+            ops = gs.gmres.spmv_count - it0
+            # bytes of the dominant kernels: one SpMV + one ILU(0) application (~1.3 SpMV) per
+            # operator application, the Krylov basis read twice (CGS2); assemblies are a few per step
+            B_op = 2.3 * spmv_bytes(e_r.nnz, e_r.N) + 8 * e_r.N * (gs.gmres.m + 4)
+            line['forward_refined'] = {
+                'workload': f'M5_CB refined {lv}x coupled to the Bernoulli fluid: {e_r.ne} P1 '
+                            f'triangles, {e_r.N} DOF, {nst} steps dt=1e-4, forward.integrate '
+                            '(per-step API, whole-GPU Newton with ILU(0)-GMRES(40))',
+                'steps_per_s': nst / dt_r, 'ms_per_step': 1e3 * dt_r / nst,
+                'operator_applications_per_step': ops / nst,
+                'gpu_launches_per_step': (e_r.launch_count - l0) / nst,
+                'roofline': {'bound': 'hbm', 'achieved': ops * B_op / dt_r / 1e9, 'peak': peak,
+                             'unit': 'GB/s', 'frac': ops * B_op / dt_r / 1e9 / peak,
+                             'bytes_model': '2.3 B_spmv + 8 N (m + 4) per operator application'}}
+            del fr, gs
+            torch.cuda.empty_cache()
+        except Exception as ex:
+            line['forward_refined'] = {'error': repr(ex)}
+
     # ---- configs[2] as written: ~1 M P2 triangles (the reference itself is P1 only; P2 is the
     # extension BASELINE.json names).  First P2 kernel: node-gather, not yet tiled / pipelined ----
     if not args.skip_extras and args.levels >= REFINE_LEVELS and rank == 0:

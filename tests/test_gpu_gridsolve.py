@@ -160,3 +160,38 @@ def test_grid_static_contact_solve(monkeypatch):
                                                     np.zeros(prob.nn))
     assert info['num_iter'] == info_ref['num_iter']
     assert np.max(np.abs(state['u'] - u_ref)) <= 1e-7 * np.max(np.abs(u_ref))
+
+
+def test_forward_integrate_on_the_grid_path(monkeypatch):
+    """forward.integrate of the coupled model on a mesh routed to the whole-GPU solver (per-step
+    API: grid Newton for the solid, fluid kernel, FSI maps) reproduces the in-kernel time loop."""
+    from femvf_b200 import forward, meshgen
+    from femvf_b200.load import load_fsi_model
+    from femvf_b200.residuals import solid as slr, fluid as flr
+
+    def build():
+        mt = meshgen.m5_cb_refined(0.05, 1)
+        return load_fsi_model(mt, slr.KelvinVoigt, flr.BernoulliAreaRatioSep,
+                              {'dirichlet_bcs': {'state/u1': [(np.zeros(2), 'facet', 'fixed')]}}, {})
+
+    def setup(model):
+        state0 = model.state0.copy(); state0[:] = 0
+        control = model.control.copy(); control[:] = 0; control['psub'][:] = 8e3
+        prop = model.prop.copy()
+        ymax = model.solid.residual.mesh().coordinates()[:, 1].max()
+        prop['emod'][:] = 5e4; prop['rho'][:] = 1; prop['eta'][:] = 3; prop['nu'][:] = 0.45
+        prop['ycontact'][:] = ymax + 0.05; prop['kcontact'][:] = 1e8; prop['ymid'][:] = 1.0
+        return state0, control, prop
+    times = 1e-4 * np.arange(9)
+    ref = build()
+    s0, c, p = setup(ref)
+    fin_ref, _ = forward.integrate(ref, None, s0, [c], p, times, write=False)
+    monkeypatch.setenv('VF_GRID_MIN_DOF', '500')
+    model = build()
+    assert model.solid._grid_solver() is not None
+    s0, c, p = setup(model)
+    fin, info = forward.integrate(model, None, s0, [c], p, times, write=False)
+    for key in ('u', 'q', 'p'):
+        scale = max(np.max(np.abs(fin_ref[key])), 1e-300)
+        assert np.max(np.abs(fin[key] - fin_ref[key])) <= 1e-8 * scale, key
+    assert info['num_iter'] >= 1
