@@ -967,6 +967,93 @@ __global__ void facet_bc_kernel(EngineDev E, int member, double dt, int is_stati
 }
 
 
+// The same terms from the boundary-node records (engine_internal.h FacetRec2D): triangles with
+// follower pressure and Dirichlet rows only.  facet_bc_kernel walks brptr -> n2f -> pf_cell ->
+// cells -> coordinates before it can touch the state: six dependent loads from tables that the
+// 0.8 GB stream of the assembly has just evicted (19 us for 10 k nodes).  Here one record load is
+// followed by all nodal loads at once, then the row blocks.
+template <bool JAC, bool RES>
+__global__ void facet_bc_fast_kernel(EngineDev E, int member, JacMix mix,
+                                     const FacetRec2D* __restrict__ recs, int n_touch) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_touch) return;
+  const FacetRec2D r = recs[t];
+  double* mb = E.members + (size_t)member * E.L.stride;
+  const double* u1 = mb + E.L.off[VF_U1];
+  const double* p1 = mb + E.L.off[VF_P1];
+  double* F = mb + E.L.off[VF_F];
+  double* rowblk = mb + E.L.off[VF_J] + (size_t)4 * r.b0;
+  const int ld = 2 * r.deg;
+  // every nodal value of both facets first
+  D2 U[2][3];
+  double P[2][3];
+#pragma unroll
+  for (int k = 0; k < 2; ++k)
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      const bool on = k < r.nfac;
+      U[k][b] = on ? reinterpret_cast<const D2*>(u1)[r.f[k].nd[b]] : D2{0.0, 0.0};
+      P[k][b] = on ? p1[r.f[k].nd[b]] : 0.0;
+    }
+  // launched with programmatic stream serialisation: everything above (record, nodal values:
+  // inputs of the assembly) may run while the assembly kernel drains; its outputs (F, J) are
+  // touched only after this point
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  double res[2] = {0.0, 0.0};
+  if (RES) {
+    const D2 f2 = reinterpret_cast<const D2*>(F)[r.node];
+    res[0] = f2.x;
+    res[1] = f2.y;
+  }
+  for (int k = 0; k < r.nfac; ++k) {
+    const FacetRec2D::Facet& q = r.f[k];
+    if (q.a == q.o) continue;
+    double gu[2][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        double sacc = 0.0;
+#pragma unroll
+        for (int b = 0; b < 3; ++b) sacc += (i == 0 ? U[k][b].x : U[k][b].y) * q.G[b][j];
+        gu[i][j] = sacc;
+      }
+    const double mw = q.meas / 6.0;  // facet mass weight: mw (1 + delta_ab)
+    double pw = 0.0;
+#pragma unroll
+    for (int b = 0; b < 3; ++b)
+      if (b != q.o) pw += (q.a == b ? 2.0 : 1.0) * P[k][b];
+    pw *= mw;
+    const double N[2] = {q.N[0], q.N[1]};
+    if (RES) {
+      double c[2];
+      cof_normal(gu, N, c);
+      res[0] += pw * c[0];
+      res[1] += pw * c[1];
+    }
+    if (JAC) {
+#pragma unroll
+      for (int b = 0; b < 3; ++b) {
+        double dc[2][2];
+        dcof_normal(gu, N, q.G[b], dc);
+        add_block<2>(rowblk, ld, q.slot[b], dc, pw * mix.p);
+      }
+    }
+  }
+  // Dirichlet rows: zero row, unit diagonal, zero residual (App. A.4)
+#pragma unroll
+  for (int a = 0; a < 2; ++a) {
+    if (r.bc & (1 << a)) {
+      if (JAC && mix.bc) {
+        for (int c = 0; c < ld; ++c) rowblk[a * ld + c] = 0.0;
+        rowblk[a * ld + r.self * 2 + a] = 1.0;
+      }
+      if (RES) res[a] = 0.0;
+    }
+  }
+  if (RES) reinterpret_cast<D2*>(F)[r.node] = D2{res[0], res[1]};
+}
+
 // partial[b][j] = sum over the block's chunk of V_j[i] w[i]; fixed-order reductions so the
 // result is bit-reproducible; a second kernel adds the partials in block order.
 
@@ -1346,6 +1433,33 @@ int launch_fan_pipe(vf_engine* e, int member, bool res, bool jac, double dt, int
 int launch_facet_bc(vf_engine* e, int member, bool res, bool jac, double dt, int is_static,
                     const JacMix& mix, cudaStream_t st) {
   if (e->n_touch <= 0) return 0;
+  static const char* env_fast = getenv("VF_FACET_FAST");
+  if (e->facet_rec_dev && !(env_fast && atoi(env_fast) == 0)) {
+    const int fb = 64, fg = (e->n_touch + fb - 1) / fb;
+    // programmatic dependent launch: the kernel may start while the assembly kernel before it
+    // in the stream is still draining (it synchronises on that grid itself, griddepcontrol.wait)
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(fg);
+    cfg.blockDim = dim3(fb);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const FacetRec2D* recs = e->facet_rec_dev;
+    const int n_touch = e->n_touch;
+    if (jac && res)
+      VF_CUDA(cudaLaunchKernelEx(&cfg, facet_bc_fast_kernel<true, true>, e->dev, member, mix, recs, n_touch));
+    else if (jac)
+      VF_CUDA(cudaLaunchKernelEx(&cfg, facet_bc_fast_kernel<true, false>, e->dev, member, mix, recs, n_touch));
+    else
+      VF_CUDA(cudaLaunchKernelEx(&cfg, facet_bc_fast_kernel<false, true>, e->dev, member, mix, recs, n_touch));
+    e->launches += 1;
+    VF_CUDA(cudaGetLastError());
+    return 0;
+  }
   const int fb = 128, fg = (e->n_touch + fb - 1) / fb;
   if (jac && res)
     facet_bc_kernel<2, true, true><<<fg, fb, 0, st>>>(e->dev, member, dt, is_static, mix, e->touch_dev, e->n_touch);

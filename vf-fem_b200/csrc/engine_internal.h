@@ -38,6 +38,21 @@ struct FanTablesDev {
   int tile_nodes, ntiles, max_verts, max_rows, max_cells, max_blocks;
 };
 
+// Boundary-node record of facet_bc_fast_kernel (triangles, follower pressure + Dirichlet only):
+// everything the node's exterior-facet terms need that does not depend on the state, so that the
+// kernel's dependent-load chain is record -> nodal values / row blocks -> stores.
+struct FacetRec2D {
+  int node, b0, deg, self;   // node id, first block of its row, blocks in the row, own slot
+  int bc, nfac, pad0, pad1;  // bc: bit c set = component c is fixed
+  struct Facet {
+    int nd[3];               // nodes of the parent cell
+    int slot[3];             // their CSR slots in this node's block row
+    int a, o;                // local index of the node / of the vertex opposite the facet
+    double N[2], meas;       // outward unit normal, facet length
+    double G[3][2];          // P1 gradients of the parent cell
+  } f[2];
+};
+
 // multicolour block ILU(0) (ilu.cu): factor storage and colouring tables, one device allocation
 struct IluState {
   char* mem = nullptr;
@@ -66,6 +81,7 @@ struct vf_engine {
   int* tile_halo_dev;
   int* touch_dev;
   int n_touch;
+  vf::FacetRec2D* facet_rec_dev;  // one per touched node, or null (generic facet_bc_kernel)
   bool two_phase;
   bool fan_ok;
   std::vector<int32_t> brptr, bcol;

@@ -305,6 +305,57 @@ int vf_create(const vf_problem_desc* desc, void* arena_dev, size_t arena_bytes, 
   e->fan_ok = d.fan_ok != 0;
   e->touch_dev = reinterpret_cast<int*>(A + P.touch);
   e->n_touch = (int)touch.size();
+  // boundary-node records (triangles without contact / membrane terms, at most two pressure
+  // facets per node): state-independent facet data gathered once on the host
+  e->facet_rec_dev = nullptr;
+  if (d.dim == 2 && !d.contact && !d.membrane && !touch.empty()) {
+    std::vector<FacetRec2D> recs(touch.size());
+    bool ok = true;
+    for (size_t t = 0; t < touch.size() && ok; ++t) {
+      const int i = touch[t];
+      FacetRec2D& r = recs[t];
+      memset(&r, 0, sizeof(r));
+      r.node = i;
+      r.b0 = d.brptr_host[i];
+      r.deg = d.brptr_host[i + 1] - r.b0;
+      const int* bcol_i = d.bcol_host + r.b0;
+      r.self = find_slot(bcol_i, r.deg, i);
+      r.bc = (d.bc_host[2 * i] ? 1 : 0) | (d.bc_host[2 * i + 1] ? 2 : 0);
+      r.nfac = d.n2f_ptr_host[i + 1] - d.n2f_ptr_host[i];
+      if (r.nfac > 2) {
+        ok = false;
+        break;
+      }
+      for (int k = 0; k < r.nfac; ++k) {
+        const int ref = d.n2f_host[d.n2f_ptr_host[i] + k];
+        const int f = ref >> 2;
+        FacetRec2D::Facet& q = r.f[k];
+        q.a = ref & 3;
+        q.o = d.pf_opp_host[f];
+        const int cell = d.pf_cell_host[f];
+        double x[3][2];
+        for (int b = 0; b < 3; ++b) {
+          q.nd[b] = d.cells_host[(size_t)b * d.ne + cell];
+          x[b][0] = d.xyz_host[q.nd[b]];
+          x[b][1] = d.xyz_host[(size_t)d.nn + q.nd[b]];
+          q.slot[b] = find_slot(bcol_i, r.deg, q.nd[b]);
+        }
+        CellGeo<2> g;
+        p1_geometry(x, g);
+        facet_geometry<2>(g, q.o, q.N, q.meas);
+        for (int b = 0; b < 3; ++b) {
+          q.G[b][0] = g.G[b][0];
+          q.G[b][1] = g.G[b][1];
+        }
+      }
+    }
+    if (ok) {
+      VF_CUDA(cudaMalloc(&e->facet_rec_dev, sizeof(FacetRec2D) * recs.size()));
+      VF_CUDA(cudaMemcpyAsync(e->facet_rec_dev, recs.data(), sizeof(FacetRec2D) * recs.size(),
+                              cudaMemcpyHostToDevice, st));
+      VF_CUDA(cudaStreamSynchronize(st));
+    }
+  }
   e->te_ptr_dev = reinterpret_cast<int*>(A + P.te_ptr);
   e->te_elem_dev = reinterpret_cast<int*>(A + P.te_elem);
   e->pair_info_dev = reinterpret_cast<unsigned*>(A + P.pair_info);
@@ -359,6 +410,7 @@ int vf_create(const vf_problem_desc* desc, void* arena_dev, size_t arena_bytes, 
 void vf_destroy(vf_engine* e) {
   if (!e) return;
   if (e->fan_mem) cudaFree(e->fan_mem);
+  if (e->facet_rec_dev) cudaFree(e->facet_rec_dev);
   ilu_release(e);
   if (e->pool_user) {
     std::lock_guard<std::mutex> lock(g_pool_mutex);
