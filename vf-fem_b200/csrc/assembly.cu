@@ -520,7 +520,7 @@ constexpr int kPipeSlots = 8;  // tiles in flight per CTA (barrier slots)
 constexpr int kRecSlots = 8;   // ring of producer records ...
 constexpr int kRecAhead = 7;   // ... fetched this many tiles ahead of their use (DRAM latency)
 
-template <bool JAC, bool RES, int NG>
+template <bool JAC, bool RES, int NG, bool RAY>
 __global__ void __launch_bounds__(128 + 128 * NG, 1) asm_fan_pipe_kernel(
     EngineDev E, int member, NewmarkCoef nc_arg, int is_static, JacMix mix, FanTablesDev T,
     const double* __restrict__ mat_m, int wj_bytes, int pool_bytes, int pf_dist, int dbg) {
@@ -898,7 +898,8 @@ __global__ void __launch_bounds__(128 + 128 * NG, 1) asm_fan_pipe_kernel(
         rho = s_mat[2 * ncp + c];
       };
       double res[2];
-      fan_walk_node<JAC, RES>(tid, ring, vtx_xy, vtx_uva, mat, fc, s_Jw - 4 * (ptrdiff_t)b_lo, res);
+      fan_walk_node<JAC, RES, RAY>(tid, ring, vtx_xy, vtx_uva, mat, fc, s_Jw - 4 * (ptrdiff_t)b_lo,
+                                   res);
       if (RES) reinterpret_cast<D2*>(mb + L.off[VF_F])[i0 + tid] = D2{res[0], res[1]};
     }
     // generic-proxy writes (slice, converted state) are read / overwritten by the bulk-copy engine
@@ -1408,21 +1409,26 @@ int launch_fan_pipe(vf_engine* e, int member, bool res, bool jac, double dt, int
     VF_CUDA(cudaGetLastError());
   }
   const NewmarkCoef nc = newmark_coef(dt);
-#define VF_PIPE_GO(J_, R_, NG_)                                                                   \
+#define VF_PIPE_GO(J_, R_, NG_, RAY_)                                                             \
   do {                                                                                            \
-    VF_CUDA(cudaFuncSetAttribute(asm_fan_pipe_kernel<J_, R_, NG_>,                                \
+    VF_CUDA(cudaFuncSetAttribute(asm_fan_pipe_kernel<J_, R_, NG_, RAY_>,                          \
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
-    asm_fan_pipe_kernel<J_, R_, NG_><<<grid, 128 + 128 * NG_, smem, st>>>(                        \
-        e->dev, member, nc, is_static, mix, T, mat_m, (int)wj, (int)pool, pf_dist, dbg);               \
+    asm_fan_pipe_kernel<J_, R_, NG_, RAY_><<<grid, 128 + 128 * NG_, smem, st>>>(                  \
+        e->dev, member, nc, is_static, mix, T, mat_m, (int)wj, (int)pool, pf_dist, dbg);          \
   } while (0)
-#define VF_PIPE_BY_MODE(NG_)                                                                      \
+#define VF_PIPE_BY_MODE(NG_, RAY_)                                                                \
   do {                                                                                            \
-    if (jac && res) VF_PIPE_GO(true, true, NG_);                                                  \
-    else if (jac) VF_PIPE_GO(true, false, NG_);                                                   \
-    else VF_PIPE_GO(false, true, NG_);                                                            \
+    if (jac && res) VF_PIPE_GO(true, true, NG_, RAY_);                                            \
+    else if (jac) VF_PIPE_GO(true, false, NG_, RAY_);                                             \
+    else VF_PIPE_GO(false, true, NG_, RAY_);                                                      \
   } while (0)
-  if (ng == 2) VF_PIPE_BY_MODE(2);
-  else VF_PIPE_BY_MODE(3);
+  // the Rayleigh-only terms of the residual are compiled out for the Kelvin-Voigt model
+  const bool ray = e->desc.damping != 0;
+  if (ng == 2) {
+    if (ray) VF_PIPE_BY_MODE(2, true); else VF_PIPE_BY_MODE(2, false);
+  } else {
+    if (ray) VF_PIPE_BY_MODE(3, true); else VF_PIPE_BY_MODE(3, false);
+  }
 #undef VF_PIPE_BY_MODE
 #undef VF_PIPE_GO
   e->launches += 1;
