@@ -97,12 +97,14 @@ struct FanRing {
 };
 
 struct FanAcc {
-  double d00, d01, d11;  // diagonal block (symmetric)
+  double d00, d01, d11;  // diagonal block (symmetric), without ...
+  double ds;             // ... its isotropic part, added to d00 and d11 at the end
   double r0, r1;         // residual
 };
 
-// One cell (n, p, q) of the fan: adds its share of the diagonal block and of the residual and
-// returns its blocks (n, p) and (n, q).
+// One cell (n, p, q) of the fan: adds its share of the diagonal block and of the residual, ADDS its
+// block (n, p) to P (which arrives holding the previous cell's share of that block) and returns
+// its block (n, q) in Q.
 // RAY = false drops the terms that exist only with Rayleigh damping (the stiffness-proportional
 // viscous stress and the mass-proportional damping force): for the Kelvin-Voigt model their
 // coefficients are zero, so the results are the same and ~10 of 128 operations are saved.
@@ -121,15 +123,16 @@ VF_HD void fan_cell(const FanRing& p, const FanRing& q, double emod, double eta,
     const double mb = rho * det * fc.jmass;
     const double anx = L * gnx, any = L * gny, bnx = M * gnx, bny = M * gny;
     // block (n, c)[i][k] = an_i gc_k + gc_i bn_k + delta_ik (bn . gc + mb (1 + delta_nc))
-    const double dgn = bnx * gnx + bny * gny + 2.0 * mb;
-    acc.d00 += anx * gnx + (gnx * bnx + dgn);
-    acc.d01 += anx * gny + gnx * bny;
-    acc.d11 += any * gny + (gny * bny + dgn);
+    // the isotropic part of the diagonal block is summed on its own and added once per node
+    acc.ds += bnx * gnx + bny * gny + 2.0 * mb;
+    acc.d00 = anx * gnx + (gnx * bnx + acc.d00);
+    acc.d01 = anx * gny + (gnx * bny + acc.d01);
+    acc.d11 = any * gny + (gny * bny + acc.d11);
     const double dgp = bnx * gpx + bny * gpy + mb;
-    P.b00 = anx * gpx + (gpx * bnx + dgp);
-    P.b01 = anx * gpy + gpx * bny;
-    P.b10 = any * gpx + gpy * bnx;
-    P.b11 = any * gpy + (gpy * bny + dgp);
+    P.b00 = anx * gpx + (gpx * bnx + (dgp + P.b00));
+    P.b01 = anx * gpy + (gpx * bny + P.b01);
+    P.b10 = any * gpx + (gpy * bnx + P.b10);
+    P.b11 = any * gpy + (gpy * bny + (dgp + P.b11));
     const double dgq = bnx * gqx + bny * gqy + mb;
     Q.b00 = anx * gqx + (gqx * bnx + dgq);
     Q.b01 = anx * gqy + gqx * bny;
@@ -137,17 +140,19 @@ VF_HD void fan_cell(const FanRing& p, const FanRing& q, double emod, double eta,
     Q.b11 = any * gqy + (gqy * bny + dgq);
   }
   if (RES) {
-    // H = dU_p (x) g_p + dU_q (x) g_q  (det * grad), for u1 and v_nmk
-    const double hu00 = p.dux * gpx + q.dux * gqx, hu01 = p.dux * gpy + q.dux * gqy;
-    const double hu10 = p.duy * gpx + q.duy * gqx, hu11 = p.duy * gpy + q.duy * gqy;
-    const double hv00 = p.dvx * gpx + q.dvx * gqx, hv01 = p.dvx * gpy + q.dvx * gqy;
-    const double hv10 = p.dvy * gpx + q.dvy * gqx, hv11 = p.dvy * gpy + q.dvy * gqy;
+    // det * (mu grad u + vmu grad v) = dW_p (x) g_p + dW_q (x) g_q with dW = mu dU + vmu dV, and
+    // det * div u for the isotropic part
     const double mu = emod * fc.rm, lam = emod * fc.rl;
     const double vmu = RAY ? emod * fc.rvm_e + eta * fc.rvm_eta : eta * fc.rvm_eta;
-    const double iso = RAY ? lam * (hu00 + hu11) + (emod * fc.rvl) * (hv00 + hv11)
-                           : lam * (hu00 + hu11);
-    const double t00 = mu * hu00 + vmu * hv00, t11 = mu * hu11 + vmu * hv11;
-    const double s01 = mu * (hu01 + hu10) + vmu * (hv01 + hv10);
+    const double wpx = mu * p.dux + vmu * p.dvx, wpy = mu * p.duy + vmu * p.dvy;
+    const double wqx = mu * q.dux + vmu * q.dvx, wqy = mu * q.duy + vmu * q.dvy;
+    const double t00 = wpx * gpx + wqx * gqx, t01 = wpx * gpy + wqx * gqy;
+    const double t10 = wpy * gpx + wqy * gqx, t11 = wpy * gpy + wqy * gqy;
+    const double divu = (p.dux * gpx + q.dux * gqx) + (p.duy * gpy + q.duy * gqy);
+    const double iso = RAY ? lam * divu + (emod * fc.rvl) *
+                                 ((p.dvx * gpx + q.dvx * gqx) + (p.dvy * gpy + q.dvy * gqy))
+                           : lam * divu;
+    const double s01 = t01 + t10;
     const double s00 = (t00 + t00) + iso, s11 = (t11 + t11) + iso;
     const double md = rho * det;
     const double ma = md * fc.rmass;
@@ -203,17 +208,17 @@ VF_HD void fan_walk_node(int nslot, const Ring& ring, const VtxXY& vtx_xy, const
     }
     return fan_ent_cell(ent);
   };
-  auto store = [&](int slot, const FanBlock& a, const FanBlock& b) {
-    row0[slot] = D2{a.b00 + b.b00, a.b01 + b.b01};
-    row1[slot] = D2{a.b10 + b.b10, a.b11 + b.b11};
-  };
-
   FanRing A, B;
   A.dux = A.duy = A.dvx = A.dvy = A.ax = A.ay = 0.0;
   B = A;
-  FanAcc acc = {0.0, 0.0, 0.0, 0.0, 0.0};
-  FanBlock first, cA, cB, P;
+  FanAcc acc = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  const FanBlock zero = {0.0, 0.0, 0.0, 0.0};
+  FanBlock first = zero, cA, cB;
   double emod, eta, rho;
+  auto put = [&](int slot, const FanBlock& b) {
+    row0[slot] = D2{b.b00, b.b01};
+    row1[slot] = D2{b.b10, b.b11};
+  };
 
   // cell 0 (peeled): its (n, p_0) block waits for the end of the fan
   int cell = load_ring(1, A);
@@ -223,35 +228,35 @@ VF_HD void fan_walk_node(int nslot, const Ring& ring, const VtxXY& vtx_xy, const
   fan_cell<JAC, RES, RAY>(A, B, emod, eta, rho, fc, vn, an, acc, first, cB);
   int j = 1;
   for (; j + 1 < ncell; j += 2) {
+    // cB holds cell j-1's share of block (n, B): cell j adds its own and the block is complete
     mat(cell, emod, eta, rho);
     cell = load_ring(2 + j, A);
-    fan_cell<JAC, RES, RAY>(B, A, emod, eta, rho, fc, vn, an, acc, P, cA);
-    if (JAC) store(B.cs, cB, P);
+    fan_cell<JAC, RES, RAY>(B, A, emod, eta, rho, fc, vn, an, acc, cB, cA);
+    if (JAC) put(B.cs, cB);
     mat(cell, emod, eta, rho);
     cell = load_ring(3 + j, B);
-    fan_cell<JAC, RES, RAY>(A, B, emod, eta, rho, fc, vn, an, acc, P, cB);
-    if (JAC) store(A.cs, cA, P);
+    fan_cell<JAC, RES, RAY>(A, B, emod, eta, rho, fc, vn, an, acc, cA, cB);
+    if (JAC) put(A.cs, cA);
   }
   int cs_last = B.cs;
   if (j < ncell) {  // odd remainder
     mat(cell, emod, eta, rho);
     load_ring(2 + j, A);
-    fan_cell<JAC, RES, RAY>(B, A, emod, eta, rho, fc, vn, an, acc, P, cA);
-    if (JAC) store(B.cs, cB, P);
+    fan_cell<JAC, RES, RAY>(B, A, emod, eta, rho, fc, vn, an, acc, cB, cA);
+    if (JAC) put(B.cs, cB);
     cB = cA;
     cs_last = A.cs;
   }
   if (JAC) {
     if (closed) {  // the last cell meets the first: cs_last == cs_first
-      store(cs_first, first, cB);
+      row0[cs_first] = D2{first.b00 + cB.b00, first.b01 + cB.b01};
+      row1[cs_first] = D2{first.b10 + cB.b10, first.b11 + cB.b11};
     } else {
-      row0[cs_first] = D2{first.b00, first.b01};
-      row1[cs_first] = D2{first.b10, first.b11};
-      row0[cs_last] = D2{cB.b00, cB.b01};
-      row1[cs_last] = D2{cB.b10, cB.b11};
+      put(cs_first, first);
+      put(cs_last, cB);
     }
-    row0[self] = D2{acc.d00, acc.d01};
-    row1[self] = D2{acc.d01, acc.d11};
+    row0[self] = D2{acc.d00 + acc.ds, acc.d01};
+    row1[self] = D2{acc.d01, acc.d11 + acc.ds};
   }
   if (RES) {
     res_out[0] = acc.r0;
