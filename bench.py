@@ -487,7 +487,7 @@ def main():
                      # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel on
                      # this workload, from the ncu --set full capture summarised in
                      # profiles/r2_ncu_full_asm_fan_pipe.csv (not re-measured in this run)
-                     'traffic': 794902272 if args.levels == REFINE_LEVELS else None,
+                     'traffic': 792462080 if args.levels == REFINE_LEVELS else None,
                      'algorithmic_bytes': B_asm, 'peak_source': peak_src},
         'spmv': {'kernel': 'spmv_kernel<2,4>', 'bound': 'hbm', 'achieved': spmv_gbs,
                  'peak': peak, 'unit': 'GB/s', 'frac': spmv_gbs / peak,
