@@ -481,7 +481,7 @@ def main():
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': dict(workload_config(), nn=nn, ne=ne, dof=N, nnz=nnz,
                        parallelism=f'{world} independent mesh shards, no collective'),
-        'roofline': {'kernel': 'asm_fan_pipe_kernel<true,true,3> (+ facet_bc_kernel on boundary nodes)',
+        'roofline': {'kernel': 'asm_fan_pipe_kernel<true,true,3,false> (+ facet_bc_fast_kernel on boundary nodes)',
                      'bound': 'hbm',
                      'achieved': asm_gbs, 'peak': peak, 'unit': 'GB/s', 'frac': asm_gbs / peak,
                      # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel on
