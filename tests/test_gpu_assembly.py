@@ -134,6 +134,7 @@ def test_assembly_parity_many_tiles(torch_cuda, monkeypatch, tile_nodes):
     from femvf_b200 import meshgen
     from femvf_b200.models import transient
     from femvf_b200.residuals import solid as slr
+    monkeypatch.setenv('VF_FAN', '0')              # the round-1 tile kernel (fallback path)
     monkeypatch.setenv('VF_TILE_NODES', tile_nodes)
     monkeypatch.setenv('VF_PF_DIST', '7')          # a far tile that exists on a small grid
     mt = meshgen.m5_cb_refined(0.05, 3)
@@ -168,6 +169,22 @@ def test_assembly_parity_pipeline(torch_cuda, monkeypatch, grid, groups, pool_kb
     assert torch_cuda.equal(J, eng.view('J'))
     eng.view('F').zero_(); eng.assemble(0, res=True, jac=False, dt=model.dt)
     assert torch_cuda.equal(F, eng.view('F'))
+
+
+@pytest.mark.parametrize('fan_nodes', ['64', '96', '128'])
+def test_assembly_parity_fan_kernel_per_tile(torch_cuda, monkeypatch, fan_nodes):
+    """The non-persistent fan kernel (asm_fan_kernel, one CTA per tile): the fallback when the
+    pipeline's shared-memory plan does not fit, and the only path for 64- / 96-node tiles."""
+    from femvf_b200 import meshgen
+    from femvf_b200.models import transient
+    from femvf_b200.residuals import solid as slr
+    monkeypatch.setenv('VF_FAN_PIPE', '0')
+    monkeypatch.setenv('VF_FAN_NODES', fan_nodes)
+    monkeypatch.setenv('VF_PF_DIST', '5')
+    mt = meshgen.m5_cb_refined(0.05, 3)
+    model = transient.FenicsModel(slr.KelvinVoigt(*mt))
+    model = _assemble_and_compare(model, np.random.default_rng(int(fan_nodes)))
+    assert model.engine.fan_info['tile_nodes'] == int(fan_nodes)
 
 
 def test_assembly_parity_degenerate_meshes(torch_cuda):
