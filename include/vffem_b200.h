@@ -213,6 +213,17 @@ int vf_axpby(vf_engine* e, double alpha, const double* x_dev, double beta, doubl
 int vf_glottal_width_series(vf_engine* e, int member, int nt, const double* u_hist_dev, size_t ldu,
                             double* out_dev, void* stream);
 
+/* Banded LU of J_uu (no pivoting) in a bandwidth-reducing ordering: the direct stand-in for the
+ * reference's sparse LU (dfn.solve(A, x, b, 'petsc'), models/transient.py:487, static.py:140) on
+ * meshes of up to a few 1e4 DOF that do not fit the one-CTA solver.
+ *   perm_host (dim * nn) int32: band index of every scalar DOF (a permutation; reverse
+ *   Cuthill-McKee of the node graph in femvf_b200/gridsolve.py); half_bandwidth = max |perm[i] -
+ *   perm[j]| over the non-zeros.  vf_band_factor scatters the member's current J into the band
+ *   and factorises it in place; vf_band_solve computes x = J^-1 b (device vectors, may alias). */
+int vf_band_setup(vf_engine* e, const int32_t* perm_host, int half_bandwidth, void* stream);
+int vf_band_factor(vf_engine* e, int member, void* stream);
+int vf_band_solve(vf_engine* e, const double* b_dev, double* x_dev, void* stream);
+
 /* P2 (6-node) triangle residual + Jacobian assembly: the P2 extension named by BASELINE.json
  * (north_star subsystem 1, configs[2]); the reference itself is P1 only (equations/form.py:521-524).
  * Same call sites as vf_assemble (models/assemblyutils.py:49-50, models/transient.py:363-406) on a

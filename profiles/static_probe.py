@@ -7,8 +7,10 @@ import numpy as np, torch
 from femvf_b200 import meshgen, static
 from femvf_b200.models import transient
 from femvf_b200.residuals import solid as slr
-for levels, min_dof in ((1, 10**9), (1, 500), (2, 10**9), (2, 500), (3, 500)):
-    os.environ['VF_GRID_MIN_DOF'] = str(min_dof)
+for levels, min_dof, direct in ((1, 10**9, '1'), (1, 500, '1'), (2, 500, '0'), (2, 500, '1'),
+                                (3, 500, '0'), (3, 500, '1')):
+    os.environ['VF_GRID_MIN_DOF_STATIC'] = str(min_dof)
+    os.environ['VF_GRID_DIRECT'] = direct
     model = transient.NodalContactModel(slr.KelvinVoigt(*meshgen.m5_cb_refined(0.05, levels)))
     ymax = model.residual.mesh().coordinates()[:, 1].max()
     prop = model.prop.copy()
@@ -19,8 +21,8 @@ for levels, min_dof in ((1, 10**9), (1, 500), (2, 10**9), (2, 500), (3, 500)):
     torch.cuda.synchronize(); t0 = time.perf_counter()
     state, info = static.static_solid_configuration(model, control, prop)
     torch.cuda.synchronize(); dt = time.perf_counter() - t0
-    gs = model._grid_solver()
+    gs = model._grid_solver(static=True)
     print(json.dumps({'levels': levels, 'dof': int(state['u'].size),
-                      'path': 'whole GPU (ILU(0)-GMRES)' if gs is not None else 'one CTA',
+                      'path': ('banded LU' if gs.direct else 'whole GPU ILU(0)-GMRES') if gs is not None else 'one CTA',
                       'newton_iterations': info['num_iter'], 'ms': round(1e3 * dt, 2),
                       'abs_err': info['abs_err']}), flush=True)

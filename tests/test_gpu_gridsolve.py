@@ -195,3 +195,30 @@ def test_forward_integrate_on_the_grid_path(monkeypatch):
         scale = max(np.max(np.abs(fin_ref[key])), 1e-300)
         assert np.max(np.abs(fin[key] - fin_ref[key])) <= 1e-8 * scale, key
     assert info['num_iter'] >= 1
+
+
+def test_banded_lu_matches_sparse_lu():
+    """csrc/band.cu: banded LU in reverse Cuthill-McKee ordering + one refinement step against
+    splu of the oracle matrix, transient and static (stiffness + contact penalty) matrices."""
+    import torch
+    from femvf_b200 import meshgen
+    from femvf_b200.gridsolve import GridSolver
+    rng = np.random.default_rng(13)
+    model, prob, prop, (u1, u0, v0, a0), p1 = _setup_model(meshgen.m5_cb_refined(0.05, 2), rng,
+                                                           contact=True)
+    eng = model.engine
+    model._push_all()
+    gs = GridSolver(eng)
+    assert gs.direct and gs.half_bandwidth < prob.N // 4
+    for is_static in (False, True):
+        eng.assemble(0, res=False, jac=True, dt=model.dt, is_static=is_static)
+        vals = eng.download('J')
+        rowptr, colidx = eng.csr_pattern()
+        J = sp.csr_matrix((vals, colidx, rowptr), shape=(prob.N, prob.N))
+        b = rng.standard_normal(prob.N)
+        bt = torch.as_tensor(b, device='cuda')
+        xt = torch.empty_like(bt)
+        info = gs.linear_solve(bt, xt)
+        x_ref = spla.splu(J.tocsc()).solve(b)
+        err = np.linalg.norm(xt.cpu().numpy() - x_ref) / np.linalg.norm(x_ref)
+        assert err <= 1e-10, (is_static, err, info)

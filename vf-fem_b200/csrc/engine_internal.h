@@ -65,6 +65,16 @@ struct IluState {
 };
 void ilu_release(struct ::vf_engine* e);
 
+// banded LU (band.cu): row-major band storage in a bandwidth-reducing ordering
+struct BandState {
+  char* mem = nullptr;
+  double* AB = nullptr;  // N x (2 b + 1)
+  int* perm = nullptr;   // band index of scalar DOF i
+  double* x = nullptr;   // work vector in the band ordering
+  int b = 0, N = 0;
+};
+void band_release(struct ::vf_engine* e);
+
 }  // namespace vf
 
 struct vf_engine {
@@ -95,6 +105,7 @@ struct vf_engine {
   int fan_max_wblocks;          // most CSR blocks owned by 32 consecutive nodes
   bool pool_user;               // this engine holds a reference on the raised mempool threshold
   vf::IluState ilu;
+  vf::BandState band;
 };
 
 namespace vf {

@@ -412,6 +412,7 @@ void vf_destroy(vf_engine* e) {
   if (e->fan_mem) cudaFree(e->fan_mem);
   if (e->facet_rec_dev) cudaFree(e->facet_rec_dev);
   ilu_release(e);
+  band_release(e);
   if (e->pool_user) {
     std::lock_guard<std::mutex> lock(g_pool_mutex);
     if (--g_pool_users == 0) {

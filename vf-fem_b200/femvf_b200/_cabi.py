@@ -75,6 +75,7 @@ EXPORTED_SYMBOLS = [
     'vf_assemble_mix', 'vf_pressure_control_blocks', 'vf_set_fan_tables',
     'vf_props_changed', 'vf_ilu_setup', 'vf_ilu_factor', 'vf_ilu_apply',
     'vf_p2_create', 'vf_p2_destroy', 'vf_p2_nnz', 'vf_p2_assemble',
+    'vf_band_setup', 'vf_band_factor', 'vf_band_solve',
 ]
 
 _lib = None
@@ -148,6 +149,9 @@ def load_library() -> C.CDLL:
     lib.vf_ilu_apply.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.vf_p2_create.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 10 + [C.c_int] + \
         [C.c_void_p] * 5 + [C.c_int, C.c_void_p, C.c_void_p]
+    lib.vf_band_setup.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib.vf_band_factor.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    lib.vf_band_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.vf_p2_destroy.argtypes = [C.c_void_p]
     lib.vf_p2_destroy.restype = None
     lib.vf_p2_nnz.argtypes = [C.c_void_p]

@@ -347,6 +347,31 @@ class Engine:
         check(self._lib.vf_block_jacobi_apply(self._h, member, r.data_ptr(), z.data_ptr(),
                                               int(node0), int(node1), self._stream()))
 
+    def band_setup(self):
+        """Reverse Cuthill-McKee ordering of the node graph and the band storage of the banded LU
+        (``csrc/band.cu``); returns the half bandwidth in scalar DOFs."""
+        import scipy.sparse as sp
+        from scipy.sparse.csgraph import reverse_cuthill_mckee
+        brptr, bcol = self.tables['brptr'], self.tables['bcol']
+        nn, d = self.nn, self.dim
+        g = sp.csr_matrix((np.ones(len(bcol), dtype=np.int8), bcol, brptr), shape=(nn, nn))
+        order = reverse_cuthill_mckee(g, symmetric_mode=True)        # new position -> old node
+        pos = np.empty(nn, dtype=np.int64)
+        pos[order] = np.arange(nn)
+        row = np.repeat(np.arange(nn), np.diff(brptr))
+        hb_nodes = int(np.max(np.abs(pos[row] - pos[bcol])))
+        hb = d * hb_nodes + d - 1
+        perm = (d * pos[:, None] + np.arange(d)[None, :]).ravel().astype(np.int32)
+        check(self._lib.vf_band_setup(self._h, _ptr(perm), hb, self._stream()))
+        self.band_half_bandwidth = hb
+        return hb
+
+    def band_factor(self, member: int = 0):
+        check(self._lib.vf_band_factor(self._h, member, self._stream()))
+
+    def band_solve(self, b: torch.Tensor, x: torch.Tensor):
+        check(self._lib.vf_band_solve(self._h, b.data_ptr(), x.data_ptr(), self._stream()))
+
     def ilu_setup(self, node0: int = 0, node1: Optional[int] = None) -> int:
         """Colour the node graph of rows [node0, node1) and allocate the block ILU(0) storage;
         returns the number of colours."""

@@ -25,8 +25,21 @@ from .distributed import GridGMRES
 from .equations import newmark
 
 
-def grid_threshold() -> int:
-    """Smallest number of solid DOFs solved by the grid-wide path (``VF_GRID_MIN_DOF``)."""
+def band_limit() -> int:
+    """Largest number of solid DOFs solved DIRECTLY by the banded LU (``VF_BAND_MAX_DOF``); above
+    it the whole-GPU GMRES with the ILU(0) preconditioner takes over."""
+    return int(os.environ.get('VF_BAND_MAX_DOF', '20000'))
+
+
+def grid_threshold(static: bool = False) -> int:
+    """Smallest number of solid DOFs solved by the grid-wide path.  Transient steps
+    (``VF_GRID_MIN_DOF``, 20000): below it the in-kernel time loop of one CTA wins (no host round
+    trip per step, well-conditioned matrices).  Static solves (``VF_GRID_MIN_DOF_STATIC``, 1025):
+    the one-CTA solver has a dense inverse up to 1024 DOF and only block-Jacobi GMRES above, which
+    needs thousands of iterations on the stiffness matrix with a contact penalty."""
+    if static:
+        return int(os.environ.get('VF_GRID_MIN_DOF_STATIC',
+                                  os.environ.get('VF_GRID_MIN_DOF', '1025')))
     return int(os.environ.get('VF_GRID_MIN_DOF', '20000'))
 
 
@@ -38,14 +51,35 @@ class GridSolver:
             raise ValueError("the grid-wide solver works on member 0 of an engine")
         self.e = engine
         precond = precond or os.environ.get('VF_GRID_PRECOND', 'ilu0')
-        self.gmres = GridGMRES(engine, engine.nn, None, restart, precond=precond)
+        # mid-size meshes: banded LU in reverse Cuthill-McKee ordering (csrc/band.cu), one step of
+        # iterative refinement; larger ones: restarted GMRES
+        self.direct = precond != 'jacobi' and engine.N <= band_limit() and \
+            os.environ.get('VF_GRID_DIRECT', '1') != '0'
+        if self.direct:
+            self.half_bandwidth = engine.band_setup()
+            self.gmres = None
+            self.res = torch.zeros(engine.N, dtype=torch.float64, device=engine.device)
+        else:
+            self.gmres = GridGMRES(engine, engine.nn, None, restart, precond=precond)
         self.dx = torch.zeros(engine.N, dtype=torch.float64, device=engine.device)
         self.rhs = torch.zeros_like(self.dx)
 
     # --- J x = b with the engine's resident J ------------------------------------------------
     def linear_solve(self, b: torch.Tensor, x: torch.Tensor, rtol: float = 1e-12,
                      atol: float = 0.0, maxiter: int = 4000):
-        return self.gmres.solve(b, x, rtol=rtol, atol=atol, maxiter=maxiter)
+        if not self.direct:
+            return self.gmres.solve(b, x, rtol=rtol, atol=atol, maxiter=maxiter)
+        e = self.e
+        e.band_factor(0)
+        e.band_solve(b, x)
+        # one step of iterative refinement with the matrix itself (no pivoting in the factor)
+        e.spmv(x, self.res, 0)
+        torch.sub(b, self.res, out=self.res)
+        resid0 = float(torch.linalg.vector_norm(self.res).item())
+        e.band_solve(self.res, self.res)
+        x.add_(self.res)
+        return {'iterations': 1, 'restarts': 0, 'residual': resid0,
+                'bnorm': float(torch.linalg.vector_norm(b).item()), 'direct': True}
 
     # --- Newton loop (oracle/model.py SolidOracle.solve_state1 semantics) -----------------------
     def solve_state1(self, dt: float, options: dict, is_static: bool = False):

@@ -311,12 +311,12 @@ class FenicsModel(BaseTransientModel):
             live._detach()
         self._live_jac_ref = None
 
-    def _grid_solver(self):
+    def _grid_solver(self, static: bool = False):
         """The whole-GPU solver for meshes that do not fit one CTA (None for small meshes, and
         for engines shared by an ensemble)."""
         from .. import gridsolve
         e = self.engine
-        if e.N < gridsolve.grid_threshold() or e.n_members != 1 or self._member != 0:
+        if e.N < gridsolve.grid_threshold(static) or e.n_members != 1 or self._member != 0:
             return None
         gs = getattr(self, '_grid', None)
         if gs is None or gs.e is not e:

@@ -44,7 +44,7 @@ def static_solid_configuration(model: transient.FenicsModel, control: bv.BlockVe
     model._push_all()
     model._retire_live_jacobian()
     e, m = model.engine, model._member
-    grid = model._grid_solver()
+    grid = model._grid_solver(static=True)
     if grid is not None:
         from .solverconst import DEFAULT_NEWTON_SOLVER_PRM
         ginfo = grid.solve_state1(1.0, dict(options or DEFAULT_NEWTON_SOLVER_PRM), is_static=True)
