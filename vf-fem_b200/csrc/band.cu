@@ -9,8 +9,8 @@
 // is the sum of a positive definite stiffness / mass part, the follower-pressure block and
 // identity rows, for which the elimination is stable; the caller adds one step of iterative
 // refinement with the device SpMV.
-// One CTA of 1024 threads walks the N pivots; every step updates a (b x b) window that lives in
-// L2.  Cost N b^2 multiply-adds: 4 118 DOF / b = 150: ~4 ms; 16 074 DOF / b = 300: ~60 ms.
+// One CTA of 1024 threads walks the pivots in panels of 16 (band_lu_kernel).  Cost N b^2
+// multiply-adds: 4 118 DOF (b = 101) 0.04 G, 16 074 DOF (b = 197) 0.6 G.
 #include "engine_internal.h"
 
 namespace vf {
@@ -41,64 +41,162 @@ __global__ void band_fill_kernel(MeshView m, int d, const double* __restrict__ J
     }
 }
 
+// Blocked right-looking factorisation, kNB pivots per pass, one CTA of 1024 threads:
+//   A  the panel -- the kNB pivot rows (full band width) and the kNB pivot columns below them --
+//      is loaded into shared memory and factorised there (sequential over the pivots, parallel
+//      over rows / columns);
+//   B  multipliers and finished U rows go back to the band;
+//   C  the trailing (b x b) window gets its rank-kNB update: every element is read and written
+//      ONCE per pass with up to kNB multiply-adds from shared memory.  (Updating it pivot by pivot
+//      costs one L2 round trip per element and pivot: 8000 cycles per pivot at b = 100.)
+constexpr int kNB = 16;
+
 __global__ void __launch_bounds__(1024, 1) band_lu_kernel(double* __restrict__ AB, int N, int b) {
   extern __shared__ double s_band[];
-  double* sl = s_band;          // multipliers of the current column
-  double* su = s_band + b + 1;  // row k of U right of the diagonal
   const int W = 2 * b + 1;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  for (int k = 0; k < N - 1; ++k) {
-    const int nr = min(b, N - 1 - k);
-    const double inv = 1.0 / AB[(size_t)k * W + b];
-    for (int i = threadIdx.x + 1; i <= nr; i += blockDim.x) {
-      const size_t at = (size_t)(k + i) * W + (b - i);
-      const double l = AB[at] * inv;
-      AB[at] = l;
-      sl[i] = l;
-      su[i] = AB[(size_t)k * W + b + i];
+  const int LW = b + kNB;                 // rows of the column panel / columns of the row panel
+  double* Up = s_band;                    // Up[p][c]: row k0 + p, column k0 + c   (kNB x LW)
+  double* Lp = s_band + (size_t)kNB * LW; // Lp[r][p]: row k0 + kNB + r, column k0 + p   (b x kNB)
+  const int tid = threadIdx.x, nt = blockDim.x;
+  auto at = [&](int r, int c) -> double& { return AB[(size_t)r * W + (c - r + b)]; };
+  for (int k0 = 0; k0 < N; k0 += kNB) {
+    const int np = min(kNB, N - k0);              // pivots of this pass
+    const int nc = min(LW, N - k0);               // columns k0 .. k0 + nc - 1 touched by the pass
+    const int nr = min(b, N - k0 - np);           // rows below the pivot rows touched by the pass
+    // ---- A: load the panel (entries outside the band are zero)
+    for (int t = tid; t < np * LW; t += nt) {
+      const int p = t / LW, c = t % LW;
+      Up[p * LW + c] = (c < nc && c - p <= b && p - c <= b) ? at(k0 + p, k0 + c) : 0.0;
+    }
+    for (int t = tid; t < nr * kNB; t += nt) {
+      const int r = t / kNB, p = t % kNB;
+      const int row = k0 + np + r, col = k0 + p;
+      Lp[r * kNB + p] = (p < np && row - col <= b) ? at(row, col) : 0.0;
     }
     __syncthreads();
-    for (int i = ty + 1; i <= nr; i += 32) {
-      const double l = sl[i];
-      if (l != 0.0) {
-        double* row = AB + (size_t)(k + i) * W + (b - i);
-        for (int j = tx + 1; j <= nr; j += 32) row[j] -= l * su[j];
+    for (int p = 0; p < np; ++p) {
+      const double inv = 1.0 / Up[p * LW + p];
+      // multipliers of column p: pivot rows below p (kept in Up's lower triangle) and Lp rows
+      for (int t = tid; t < (np - 1 - p) + nr; t += nt) {
+        if (t < np - 1 - p) Up[(p + 1 + t) * LW + p] *= inv;
+        else Lp[(t - (np - 1 - p)) * kNB + p] *= inv;
       }
+      __syncthreads();
+      // eliminate: pivot rows q > p over their whole width, Lp rows over the panel columns > p
+      const int wq = nc - (p + 1);
+      for (int t = tid; t < (np - 1 - p) * wq; t += nt) {
+        const int q = p + 1 + t / wq, c = p + 1 + t % wq;
+        Up[q * LW + c] -= Up[q * LW + p] * Up[p * LW + c];
+      }
+      const int wl = np - 1 - p;
+      for (int t = tid; t < nr * wl; t += nt) {
+        const int r = t / wl, c = p + 1 + t % wl;
+        Lp[r * kNB + c] -= Lp[r * kNB + p] * Up[p * LW + c];
+      }
+      __syncthreads();
+    }
+    // ---- B: write the panel back
+    for (int t = tid; t < np * LW; t += nt) {
+      const int p = t / LW, c = t % LW;
+      if (c < nc && c - p <= b && p - c <= b) at(k0 + p, k0 + c) = Up[p * LW + c];
+    }
+    for (int t = tid; t < nr * kNB; t += nt) {
+      const int r = t / kNB, p = t % kNB;
+      const int row = k0 + np + r, col = k0 + p;
+      if (p < np && row - col <= b) at(row, col) = Lp[r * kNB + p];
+    }
+    // ---- C: rank-np update of the trailing window (rows and columns k0 + np .. k0 + np + nr - 1)
+    for (int t = tid; t < nr * nr; t += nt) {
+      const int r = t / nr, c = t % nr;
+      if (r - c > b || c - r > b) continue;
+      double acc = 0.0;
+#pragma unroll 4
+      for (int p = 0; p < np; ++p) acc += Lp[r * kNB + p] * Up[p * LW + np + c];
+      at(k0 + np + r, k0 + np + c) -= acc;
     }
     __syncthreads();
   }
 }
 
-// x := U^-1 L^-1 x in the band ordering (one CTA).  SMEM: the vector lives in shared memory for
-// the N sequential steps (a few hundred cycles each from global memory, ~100 from shared).
+// x := U^-1 L^-1 x in the band ordering (one CTA), blocked like the factorisation: the kNB x kNB
+// triangular block of a panel is solved by one warp (lane q owns row q, the finished unknown is
+// broadcast by shuffle), then every other row of the band gets its rank-kNB update from kNB
+// CONTIGUOUS entries of its row -- N / kNB barrier pairs instead of N.
+// SMEM: the vector lives in shared memory during the sweeps.
 template <bool SMEM>
 __global__ void __launch_bounds__(1024, 1) band_solve_kernel(const double* __restrict__ AB,
                                                             double* __restrict__ xg, int N, int b) {
   extern __shared__ double s_x[];
   const int W = 2 * b + 1;
   double* x = SMEM ? s_x : xg;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+  auto at = [&](int r, int c) -> double { return AB[(size_t)r * W + (c - r + b)]; };
   if (SMEM) {
-    for (int i = threadIdx.x; i < N; i += blockDim.x) s_x[i] = xg[i];
+    for (int i = tid; i < N; i += nt) s_x[i] = xg[i];
     __syncthreads();
   }
-  for (int k = 0; k < N - 1; ++k) {
-    const int nr = min(b, N - 1 - k);
-    const double xk = x[k];
-    for (int i = threadIdx.x + 1; i <= nr; i += blockDim.x)
-      x[k + i] -= AB[(size_t)(k + i) * W + (b - i)] * xk;
+  // ---- forward: L y = x, unit lower triangular
+  for (int k0 = 0; k0 < N; k0 += kNB) {
+    const int np = min(kNB, N - k0);
+    if (tid < 32) {
+      // the lane's row of the triangular block first (independent loads: one round trip)
+      double lrow[kNB];
+#pragma unroll
+      for (int p = 0; p < kNB; ++p) lrow[p] = (p < lane && lane < np) ? at(k0 + lane, k0 + p) : 0.0;
+      double xv = lane < np ? x[k0 + lane] : 0.0;
+#pragma unroll
+      for (int p = 0; p < kNB; ++p) {
+        const double xp = __shfl_sync(0xffffffffu, xv, p);
+        xv -= lrow[p] * xp;
+      }
+      if (lane < np) x[k0 + lane] = xv;
+    }
+    __syncthreads();
+    const int nr = min(b, N - k0 - np);
+    for (int r = tid; r < nr; r += nt) {
+      const int row = k0 + np + r;
+      double acc = 0.0;
+      for (int p = 0; p < np; ++p)
+        if (row - (k0 + p) <= b) acc += at(row, k0 + p) * x[k0 + p];
+      x[row] -= acc;
+    }
     __syncthreads();
   }
-  for (int k = N - 1; k >= 0; --k) {
-    const double xk = x[k] / AB[(size_t)k * W + b];   // every thread: same value, no broadcast
-    const int nr = min(b, k);
-    for (int i = threadIdx.x + 1; i <= nr; i += blockDim.x)
-      x[k - i] -= AB[(size_t)(k - i) * W + (b + i)] * xk;
+  // ---- backward: U z = y
+  const int last = ((N - 1) / kNB) * kNB;
+  for (int k0 = last; k0 >= 0; k0 -= kNB) {
+    const int np = min(kNB, N - k0);
+    if (tid < 32) {
+      double urow[kNB];
+#pragma unroll
+      for (int p = 0; p < kNB; ++p)
+        urow[p] = (p >= lane && p < np && lane < np) ? at(k0 + lane, k0 + p) : 0.0;
+      double dinv = 1.0;
+#pragma unroll
+      for (int p = 0; p < kNB; ++p)
+        if (p == lane && lane < np) dinv = 1.0 / urow[p];
+      double xv = lane < np ? x[k0 + lane] : 0.0;
+#pragma unroll
+      for (int p = kNB - 1; p >= 0; --p) {
+        if (lane == p) xv *= dinv;
+        const double xp = __shfl_sync(0xffffffffu, xv, p);
+        if (lane < p) xv -= urow[p] * xp;
+      }
+      if (lane < np) x[k0 + lane] = xv;
+    }
     __syncthreads();
-    if (threadIdx.x == 0) x[k] = xk;
+    const int nr = min(b, k0);
+    for (int r = tid; r < nr; r += nt) {
+      const int row = k0 - 1 - r;
+      double acc = 0.0;
+      for (int p = 0; p < np; ++p)
+        if ((k0 + p) - row <= b) acc += at(row, k0 + p) * x[k0 + p];
+      x[row] -= acc;
+    }
+    __syncthreads();
   }
   if (SMEM) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < N; i += blockDim.x) xg[i] = s_x[i];
+    for (int i = tid; i < N; i += nt) xg[i] = s_x[i];
   }
 }
 
@@ -160,7 +258,7 @@ int vf_band_factor(vf_engine* e, int member, void* stream) {
   const int block = 256;
   band_fill_kernel<<<(unsigned)((nblk + block - 1) / block), block, 0, st>>>(
       e->dev.mesh, e->desc.dim, member_array(e, VF_J, member), S.perm, S.AB, S.b);
-  const size_t smem = sizeof(double) * 2 * ((size_t)S.b + 1);
+  const size_t smem = sizeof(double) * ((size_t)kNB * (S.b + kNB) + (size_t)S.b * kNB);
   if (smem > 200 * 1024) return fail("vf_band_factor: bandwidth too large for the factor kernel");
   VF_CUDA(cudaFuncSetAttribute(band_lu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   band_lu_kernel<<<1, 1024, smem, st>>>(S.AB, S.N, S.b);
