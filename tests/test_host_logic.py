@@ -252,3 +252,33 @@ def test_grid_gmres_host_logic_with_stub_engine():
     g = GridGMRES(StubEngine(A), n // 2, None, restart=10)
     info = g.solve(torch.as_tensor(b), torch.zeros(n, dtype=torch.float64), rtol=0.0, maxiter=25)
     assert info['iterations'] == 25 and g.spmv_count == 27
+
+
+def test_node_colouring_and_band_ordering_tables():
+    """Host tables of the whole-GPU solvers: the multicolour ordering of csrc/ilu.cu (no two
+    adjacent nodes share a colour, classes cover the range) and the reverse Cuthill-McKee band
+    ordering handed to csrc/band.cu (a permutation whose bandwidth bounds every non-zero)."""
+    import scipy.sparse as sp
+    from scipy.sparse.csgraph import reverse_cuthill_mckee
+    from femvf_b200 import meshgen, tables
+    mesh = meshgen.m5_cb_refined(0.05, 2)[0]
+    T = tables.build_tables(mesh.coordinates(), mesh.cells(), [], [], [])
+    nn, brptr, bcol = T['nn'], T['brptr'].astype(np.int64), T['bcol']
+    row = np.repeat(np.arange(nn), np.diff(brptr))
+    for node0, node1 in ((0, nn), (100, nn - 57)):
+        color, rows, cptr = tables.color_node_graph(T['brptr'], T['bcol'], node0, node1)
+        inside = (row >= node0) & (row < node1) & (bcol >= node0) & (bcol < node1) & (row != bcol)
+        assert not np.any(color[row[inside]] == color[bcol[inside]])
+        assert np.all(color[:node0] == -1) and np.all(color[node1:] == -1)
+        assert np.array_equal(np.sort(rows), np.arange(node0, node1))
+        assert cptr[0] == 0 and cptr[-1] == node1 - node0 and len(cptr) - 1 <= 12
+        for c in range(len(cptr) - 1):
+            assert np.all(color[rows[cptr[c]:cptr[c + 1]]] == c)
+    # band ordering as built by Engine.band_setup
+    g = sp.csr_matrix((np.ones(len(bcol), dtype=np.int8), bcol, T['brptr']), shape=(nn, nn))
+    order = reverse_cuthill_mckee(g, symmetric_mode=True)
+    pos = np.empty(nn, dtype=np.int64)
+    pos[order] = np.arange(nn)
+    hb = int(np.max(np.abs(pos[row] - pos[bcol])))
+    assert np.array_equal(np.sort(pos), np.arange(nn))
+    assert hb < nn // 10          # RCM finds the thin direction of the M5_CB outline
