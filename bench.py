@@ -325,6 +325,19 @@ def run_partition(args, rank, world, local_rank, standalone=True, tets=None):
     barrier = dist.barrier if world > 1 else None
     dt = 1e-4
     ms_asm = time_events(lambda: ds.assemble(dt), args.steps, args.warmup, barrier)
+    # the two thread-per-node kernels side by side (VF_NODE_WARP selects)
+    asm_by_kernel = {}
+    try:
+        for setting, name in (('00', 'asm_node_global_kernel, generic gathers (round 1)'),
+                              ('11', 'asm_node_warp_kernel + gather tables (default)')):
+            os.environ['VF_NODE_WARP'], os.environ['VF_TET_TABLES'] = setting[0], setting[1]
+            asm_by_kernel[name] = time_events(lambda: ds.assemble(dt), 10, 2, barrier) / 10
+    except Exception as ex:
+        asm_by_kernel = {'error': repr(ex)}
+    finally:
+        os.environ.pop('VF_NODE_WARP', None)
+        os.environ.pop('VF_TET_TABLES', None)
+    ds.assemble(dt)
     b = ds.owned('F').clone()
     x = torch.empty_like(b)
     iters = args.gmres_iters
@@ -359,6 +372,7 @@ def run_partition(args, rank, world, local_rank, standalone=True, tets=None):
                   'note': 'host-launched, device-resident Arnoldi data (one device->host read per 8 '
                           'iterations); CGS2, restart 30, left block-Jacobi'},
         'setup_s': setup_s, 'gpu_launches': int(eng.launch_count),
+        'assembly_ms_per_step_by_kernel': asm_by_kernel,
     }
     if world > 1:
         # the check of tests/test_gpu_partition.py::test_two_gpu_distributed_solve_matches_lu,
@@ -684,11 +698,24 @@ def main():
             line['p2'] = {
                 'workload': f'BASELINE configs[2]: residual+Jacobian assembly, {nep} P2 triangles '
                             f'(M5_CB refined {REFINE_LEVELS - 1}x), {Np} DOF, {asm.nnz} non-zeros',
-                'kernel': 'p2_assemble_kernel (node gather, closed-form reference tensors)',
+                'kernel': 'p2_assemble_warp_kernel (node gather, closed-form reference tensors, '
+                          'structural zeros skipped, coalesced row write-out)',
                 'ms_per_step': ms_p2, 'value': Np / (ms_p2 * 1e-3), 'unit': UNIT,
                 'roofline': {'bound': 'hbm', 'algorithmic_bytes': B_p2,
                              'achieved': B_p2 / (ms_p2 * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
                              'frac': B_p2 / (ms_p2 * 1e-3) / 1e9 / peak}}
+            # both versions of the kernel side by side (VF_P2_WARP selects)
+            try:
+                both = {}
+                for setting, name in (('0', 'p2_assemble_kernel'),
+                                      ('1', 'p2_assemble_warp_kernel (default)')):
+                    os.environ['VF_P2_WARP'] = setting
+                    both[name] = time_events(fn, 10, 2) / 10
+                line['p2']['ms_per_step_by_kernel'] = both
+            except Exception as ex:
+                line['p2']['ms_per_step_by_kernel'] = {'error': repr(ex)}
+            finally:
+                os.environ.pop('VF_P2_WARP', None)
             del asm, vec
             torch.cuda.empty_cache()
         except Exception as ex:

@@ -197,3 +197,116 @@ extern "C" int hostcheck_assemble_fan(
   }
   return 0;
 }
+
+// CPU run of the second P2 triangle kernel (p2_assemble_warp_kernel, csrc/p2.cu): the same
+// per-node function (vf::p2_node_row) in a loop over the class-sorted thread -> node map, with
+// the kernel's staging (64 rows at an odd stride, then 4 * deg consecutive doubles copied to the
+// CSR array per row).
+#define __device__
+#define __constant__
+#include "../../vf-fem_b200/csrc/p2_tables.h"
+#undef __device__
+#undef __constant__
+#include "../../vf-fem_b200/csrc/p2_node.cuh"
+
+extern "C" int hostcheck_p2_assemble(
+    int nn, const double* xy, const int* cells6, const int* brptr, const int* bcol,
+    const int* n2e_ptr, const int* n2e, const unsigned* n2e_slots, const int* n2f_ptr,
+    const int* n2f, const int* n2f_pair, const int* pf_cell, const int* pf_loc,
+    const double* pf_geo, const unsigned char* fixed, const int* order, int n_class0,
+    const double* emod, const double* eta, const double* rho, double nu, const double* u1,
+    const double* u0, const double* v0, const double* a0, const double* p1, double dt, int flags,
+    double* J, double* F) {
+  vf::P2View V{xy, cells6, brptr, bcol, n2e_ptr, n2e, n2e_slots, n2f_ptr, n2f, n2f_pair,
+               pf_cell, pf_loc, pf_geo, fixed};
+  vf::P2Args A;
+  A.emod = emod; A.eta = eta; A.rho = rho; A.u1 = u1; A.u0 = u0; A.v0 = v0; A.a0 = a0; A.p1 = p1;
+  A.F = F; A.J = J; A.nu = nu; A.dt = dt;
+  A.res = flags & 1;
+  A.jac = (flags & 2) != 0;
+  double* uva = nullptr;
+  if (flags & 4) {  // the pre-pass of version 2: packed (u1, v_nmk, a_nmk) per node
+    uva = static_cast<double*>(aligned_alloc(16, sizeof(double) * 6 * (size_t)nn));
+    for (int n = 0; n < nn; ++n) vf::p2_pack_state(A, vf::newmark_coef(dt), n, uva);
+    A.uva = uva;
+  }
+  const int first[2] = {0, n_class0}, count[2] = {n_class0, nn - n_class0};
+  for (int c = 0; c < 2; ++c) {
+    int max_deg = 1;
+    for (int t = 0; t < count[c]; ++t) {
+      const int i = order[first[c] + t];
+      max_deg = std::max(max_deg, brptr[i + 1] - brptr[i]);
+    }
+    const int stride = (4 * max_deg) | 1, block = 64;
+    double* s_rows = static_cast<double*>(aligned_alloc(16, sizeof(double) * ((size_t)block * stride + 2)));
+    for (int blk = 0; blk * block < count[c]; ++blk) {
+      int b0[64], deg[64];
+      for (int tid = 0; tid < block; ++tid) {
+        const int tix = blk * block + tid;
+        b0[tid] = deg[tid] = 0;
+        if (tix >= count[c]) continue;
+        const int i = order[first[c] + tix];
+        b0[tid] = brptr[i];
+        deg[tid] = brptr[i + 1] - brptr[i];
+        double r0, r1;
+        if (c == 0) vf::p2_node_row<0>(V, A, &vf::kP2W[0][0][0][0], &vf::kP2M[0][0], i, s_rows + (size_t)tid * stride, r0, r1);
+        else vf::p2_node_row<1>(V, A, &vf::kP2W[0][0][0][0], &vf::kP2M[0][0], i, s_rows + (size_t)tid * stride, r0, r1);
+        if (A.res) {
+          F[2 * i] = r0;
+          F[2 * i + 1] = r1;
+        }
+      }
+      if (A.jac)
+        for (int tid = 0; tid < block; ++tid) {
+          const int lane0 = tid & ~31;  // rows of a warp are written by that warp, lane by lane
+          (void)lane0;
+          const double* rs = s_rows + (size_t)tid * stride;
+          double* out = J + (size_t)4 * b0[tid];
+          for (int j = 0; j < 4 * deg[tid]; ++j) out[j] = rs[j];
+        }
+    }
+    free(s_rows);
+  }
+  free(uva);
+  return 0;
+}
+
+// CPU run of the table-driven tetrahedral node assembly (vf::assemble_node_tet via
+// assemble_node_auto) with the gather tables of csrc/tet_tables.h built like the engine does.
+#include "../../vf-fem_b200/csrc/tet_tables.h"
+
+extern "C" int hostcheck_assemble_tet_tables(
+    int nn, int ne, int nfp, const double* xyz, const int* cells, const int* brptr,
+    const int* bcol, const int* n2e_ptr, const int* n2e, const int* n2f_ptr, const int* n2f,
+    const int* pf_cell, const int* pf_opp, const unsigned char* bc, const double* rho,
+    const double* eta, const double* emod, const double* scal, const double* emod_m,
+    const double* nu_m, const double* th_m, int contact, int membrane, int damping,
+    const double* u1, const double* u0, const double* v0, const double* a0, const double* p1,
+    double dt, double* J, double* F) {
+  std::vector<int32_t> cells4;
+  std::vector<double> xyz4;
+  std::vector<uint32_t> slots;
+  if (!vf::build_tet_gather_tables(nn, ne, xyz, cells, brptr, bcol, n2e_ptr, n2e, cells4, xyz4,
+                                   slots))
+    return 2;
+  // 32-byte aligned copies, as on the device
+  int* c4 = static_cast<int*>(aligned_alloc(32, (cells4.size() * sizeof(int) + 31) / 32 * 32));
+  double* x4 = static_cast<double*>(aligned_alloc(32, xyz4.size() * sizeof(double)));
+  std::copy(cells4.begin(), cells4.end(), c4);
+  std::copy(xyz4.begin(), xyz4.end(), x4);
+  vf::MeshView m{3, nn, ne, nfp, xyz, nullptr, cells, brptr, bcol, n2e_ptr, n2e,
+                 n2f_ptr, n2f, pf_cell, pf_opp, bc};
+  m.cells4 = c4;
+  m.xyz4 = x4;
+  m.n2e_slots = slots.data();
+  vf::PropView p{rho, eta, emod, scal, emod_m, nu_m, th_m, contact, membrane, damping};
+  vf::StateView s{u1, u0, v0, a0, p1, dt, 0, vf::jac_mix_du1(vf::newmark_coef(dt), false)};
+  for (int i = 0; i < nn; ++i) {
+    double res[3];
+    vf::assemble_node_auto<3, true, true>(i, m, p, s, J + 9 * (size_t)brptr[i], res);
+    for (int c = 0; c < 3; ++c) F[3 * i + c] = res[c];
+  }
+  free(c4);
+  free(x4);
+  return 0;
+}

@@ -282,3 +282,57 @@ def test_node_colouring_and_band_ordering_tables():
     hb = int(np.max(np.abs(pos[row] - pos[bcol])))
     assert np.array_equal(np.sort(pos), np.arange(nn))
     assert hb < nn // 10          # RCM finds the thin direction of the M5_CB outline
+
+
+def test_kelvin_voigt_w_shape_moves_the_mesh():
+    """``KelvinVoigtWShape`` (reference ``residuals/solid.py:192-215``): 'umesh' is the last
+    property and ``set_prop`` displaces the mesh coordinates by it
+    (``models/transient.py:347-360``); the device tables follow and the engine is rebuilt."""
+    mt = mesh_tuples()['m5']()
+    model = transient.FenicsModel(slr.KelvinVoigtWShape(*mt))
+    assert model.prop.keys() == ['rho', 'emod', 'nu', 'eta', 'ycontact', 'ncontact', 'kcontact',
+                                 'umesh']
+    mesh = model.residual.mesh()
+    ref = mesh.coordinates().copy()
+    nn = ref.shape[0]
+    assert model.prop['umesh'].size == 2 * nn and not np.any(model.prop['umesh'])
+    tables0 = model.assembly_tables
+    model._engine = sentinel = object()       # stands for a live engine (no device here)
+    prop = model.prop.copy()
+    prop['emod'][:] = 5e4
+    model.set_prop(prop)                      # umesh still zero: geometry and engine are kept
+    assert model._engine is sentinel and model.assembly_tables is tables0
+    rng = np.random.default_rng(0)
+    du = 1e-3 * rng.standard_normal((nn, 2))
+    prop['umesh'][:] = du.ravel()
+    model.set_prop(prop)
+    assert np.array_equal(mesh.coordinates(), ref + du)
+    assert np.array_equal(model.XREF, (ref + du).ravel())
+    assert model._engine is None              # next device call builds an engine on the new mesh
+    assert np.array_equal(model.assembly_tables['xyz'], (ref + du).T)
+    assert all(model._dirty.values())
+    # the pattern and the pressure / Dirichlet tables are topological: unchanged
+    for key in ('brptr', 'bcol', 'bc', 'pf_cell'):
+        assert np.array_equal(model.assembly_tables[key], tables0[key])
+    prop['umesh'][:] = 0.0
+    model.set_prop(prop)
+    assert np.array_equal(mesh.coordinates(), ref)
+
+
+def test_shape_change_drops_the_shared_fsi_engine():
+    mt = mesh_tuples()['m5']()
+    model = load.load_fsi_model(
+        mt, slr.KelvinVoigtWShape, flr.BernoulliAreaRatioSep,
+        {'dirichlet_bcs': {'state/u1': [(np.zeros(2), 'facet', 'fixed')]}}, {})
+    assert model.prop.keys()[:8] == ['rho', 'emod', 'nu', 'eta', 'ycontact', 'ncontact',
+                                     'kcontact', 'umesh']
+    model._engine = model.solid._engine = model.fluid._engine = object()
+    prop = model.prop.copy()
+    prop['umesh'][:] = 1e-3
+    model.set_prop(prop)
+    assert model._engine is None and model.solid._engine is None and model.fluid._engine is None
+    # an engine shared by an ensemble cannot follow a shape change
+    model.solid._engine_attached = True
+    prop['umesh'][:] = 2e-3
+    with pytest.raises(NotImplementedError):
+        model.set_prop(prop)

@@ -24,7 +24,10 @@ def lib():
     srcs = [os.path.join(hc, 'hostcheck.cpp'),
             os.path.join(HERE, '..', 'vf-fem_b200', 'csrc', 'elem.cuh'),
             os.path.join(HERE, '..', 'vf-fem_b200', 'csrc', 'node_assembly.cuh'),
-            os.path.join(HERE, '..', 'vf-fem_b200', 'csrc', 'fan_assembly.cuh')]
+            os.path.join(HERE, '..', 'vf-fem_b200', 'csrc', 'fan_assembly.cuh'),
+            os.path.join(HERE, '..', 'vf-fem_b200', 'csrc', 'p2_node.cuh'),
+            os.path.join(HERE, '..', 'vf-fem_b200', 'csrc', 'tet_tables.h'),
+            os.path.join(HERE, '..', 'vf-fem_b200', 'csrc', 'p2_tables.h')]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.run(['g++', '-O2', '-shared', '-fPIC', '-o', so, srcs[0]], check=True)
     return ctypes.CDLL(so)
@@ -72,6 +75,20 @@ def test_device_element_math_on_cpu(lib, mesh_name, contact, membrane, damping):
     assert rc == 0
     assert rel_row_err(J, Jo) <= 1e-12
     assert np.max(np.abs(F - Fo)) <= 1e-12 * np.max(np.abs(Fo))
+    if d == 3:
+        # table-driven form (csrc/tet_tables.h + assemble_node_tet): same cells, same order, same
+        # arithmetic -> the same bits
+        J2 = np.full(len(T['colidx']), np.nan)
+        F2 = np.full(N, np.nan)
+        rc = lib.hostcheck_assemble_tet_tables(
+            nn, ne, T['nfp'], P(T['xyz']), P(T['cells']), P(T['brptr']), P(T['bcol']),
+            P(T['n2e_ptr']), P(T['n2e']), P(T['n2f_ptr']), P(T['n2f']), P(T['pf_cell']),
+            P(T['pf_opp']), P(T['bc']), P(prop['rho']), P(prop['eta']), P(prop['emod']), P(scal),
+            P(prop['emod_membrane']), P(prop['nu_membrane']), P(prop['th_membrane']),
+            contact, membrane, damping, P(u1), P(u0), P(v0), P(a0), P(p1), ctypes.c_double(dt),
+            P(J2), P(F2))
+        assert rc == 0
+        assert np.array_equal(J2, J) and np.array_equal(F2, F)
 
 
 @pytest.mark.parametrize('mesh_name,nodes_per_tile', [('square5', 7), ('m5', 16), ('m5', 96)])
@@ -170,3 +187,72 @@ def test_fan_walk_algorithm_on_cpu(lib, mesh_name, tile_nodes, contact, membrane
     assert not np.any(np.isnan(J)) and not np.any(np.isnan(F))
     assert rel_row_err(J, Jo) <= 1e-12
     assert np.max(np.abs(F - Fo)) <= 1e-12 * np.max(np.abs(Fo))
+
+
+@pytest.mark.parametrize('mesh_name,interleave', [('square5', False), ('square5', True),
+                                                  ('m5', True)])
+@pytest.mark.parametrize('flags', [3, 2, 1, 7, 5])   # +4: packed nodal state of the pre-pass
+def test_p2_second_kernel_arithmetic_on_cpu(lib, mesh_name, interleave, flags):
+    """vf::p2_node_row (the per-node code of p2_assemble_warp_kernel: structural zeros of the
+    reference tensor skipped, rows in CSR layout) in a CPU loop with the product's P2 tables,
+    against the quadrature oracle."""
+    from femvf_b200.p2 import build_p2_tables
+    from oracle import fem_p2
+    import scipy.sparse as sp
+    res = slr.KelvinVoigt(*mesh_tuples()[mesh_name]())
+    mesh = res.mesh()
+    coords, cells = mesh.coordinates(), mesh.cells()
+    p1prob = oracle_problem(res)
+    # Dirichlet edges: boundary edges between two fixed vertices of the P1 problem
+    fv = np.unique(p1prob.fixed_dofs // 2)
+    e = np.sort(np.concatenate([cells[:, [1, 2]], cells[:, [0, 2]], cells[:, [0, 1]]]), axis=1)
+    key, cnt = np.unique(e[:, 0] * len(coords) + e[:, 1], return_counts=True)
+    be = np.stack([key // len(coords), key % len(coords)], axis=1)[cnt == 1]
+    fe = be[np.isin(be[:, 0], fv) & np.isin(be[:, 1], fv)]
+    T = build_p2_tables(coords, cells, p1prob.pfacets, p1prob.pfacet_cells, fe, interleave)
+    keep = T['keep']
+    prob0 = fem_p2.SolidProblemP2(coords, cells, p1prob.pfacets, p1prob.pfacet_cells, [])
+    fixed_old = prob0.closure_nodes(fe)
+    prob = fem_p2.SolidProblemP2(coords, cells, p1prob.pfacets, p1prob.pfacet_cells, fixed_old)
+    new_of_old = np.concatenate([T['vertex_ids'], T['edge_node']])
+    rng = np.random.default_rng(7)
+    N, nn, ne = prob.N, prob.nn, prob.ne
+    prop = dict(rho=rng.uniform(0.9, 1.1, ne), eta=rng.uniform(1, 5, ne),
+                emod=rng.uniform(2.5e4, 1e5, ne), nu=0.45)
+    u1, u0 = rng.uniform(-1e-2, 1e-2, N), rng.uniform(-1e-2, 1e-2, N)
+    v0, a0 = rng.uniform(-1, 1, N), rng.uniform(-1e3, 1e3, N)
+    p1 = rng.uniform(0, 8e3, nn)
+    dt = 1e-4
+    F_ref = fem_p2.assemble_res_u(prob, u1, u0, v0, a0, dt, prop, p1)
+    J_ref = fem_p2.assemble_jac_uu(prob, u1, dt, prop, p1)
+    dof_new_of_old = (2 * new_of_old[:, None] + np.arange(2)[None, :]).ravel()
+    old_of_new = np.argsort(dof_new_of_old)
+    F_ref_n = F_ref[old_of_new]
+    J_ref_n = J_ref[old_of_new][:, old_of_new].tocsr()
+    J_ref_n.sort_indices()
+
+    def nodal(v, width):
+        out = np.empty_like(v)
+        out.reshape(-1, width)[new_of_old] = v.reshape(-1, width)
+        return out
+    indptr, indices = tables.scalar_csr_from_graph(T['brptr'].astype(np.int32),
+                                                   T['bcol'].astype(np.int32), 2)
+    assert np.array_equal(indptr, J_ref_n.indptr) and np.array_equal(indices, J_ref_n.indices)
+    J = np.full(len(indices), np.nan)
+    F = np.full(N, np.nan)
+    U1, U0, V0, A0, P1 = nodal(u1, 2), nodal(u0, 2), nodal(v0, 2), nodal(a0, 2), nodal(p1, 1)
+    rc = lib.hostcheck_p2_assemble(
+        nn, P(keep[0]), P(keep[1]), P(keep[2]), P(keep[3]), P(keep[4]), P(keep[5]), P(keep[6]),
+        P(keep[7]), P(keep[8]), P(keep[9]), P(keep[10]), P(keep[11]), P(keep[12]), P(keep[13]),
+        P(keep[14]), T['nv'], P(prop['emod']), P(prop['eta']), P(prop['rho']),
+        ctypes.c_double(0.45), P(U1), P(U0), P(V0), P(A0), P(P1), ctypes.c_double(dt), flags,
+        P(J), P(F))
+    assert rc == 0
+    if flags & 2:
+        assert rel_row_err(J, J_ref_n) <= 1e-12
+    else:
+        assert np.all(np.isnan(J))
+    if flags & 1:
+        assert np.max(np.abs(F - F_ref_n)) <= 1e-12 * np.max(np.abs(F_ref_n))
+    else:
+        assert np.all(np.isnan(F))

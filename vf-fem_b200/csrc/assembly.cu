@@ -2,6 +2,7 @@
 // vf_assemble_mix, vf_set_fan_tables, vf_pressure_control_blocks, vf_newmark_residual).
 // See DESIGN.md section 5 for the roofline of each kernel.
 #include "engine_internal.h"
+#include "tet_tables.h"
 #include "dev_util.cuh"
 #include "fan_assembly.cuh"
 
@@ -1081,13 +1082,59 @@ asm_node_global_kernel(EngineDev E, int member, double dt, int is_static, JacMix
   sv.is_static = is_static;
   sv.mix = mix;
   double res[D];
-  assemble_node<D, JAC, RES>(i, E.mesh, pv, sv,
-                             JAC ? mb + L.off[VF_J] + (size_t)D * D * E.mesh.brptr[i] : nullptr, res);
+  assemble_node_auto<D, JAC, RES>(
+      i, E.mesh, pv, sv, JAC ? mb + L.off[VF_J] + (size_t)D * D * E.mesh.brptr[i] : nullptr, res);
   if (RES) {
     double* F = mb + L.off[VF_F];
 #pragma unroll
     for (int c = 0; c < D; ++c) F[D * i + c] = res[c];
   }
+}
+
+
+// The same thread-per-node gather with the block rows of one warp's 32 consecutive nodes
+// accumulated in shared memory, packed exactly like the CSR array (rows of consecutive nodes are
+// contiguous there), and streamed out by ONE coalesced copy.  The ~800 read-modify-writes a
+// tetrahedral node makes on its row (24 cells x 4 blocks x 9 entries) then stay in shared memory
+// instead of going through to L2 one partial sector at a time, which is what bounds
+// asm_node_global_kernel.  One warp per CTA (no block barrier; the CTA's shared memory is the
+// largest group of 32 rows, e->node_warp_blocks), several CTAs per SM.  Same visiting order per
+// entry as the global variant, so the two produce identical bits.
+template <int D, bool RES>
+__global__ void __launch_bounds__(32)
+asm_node_warp_kernel(EngineDev E, int member, double dt, int is_static, JacMix mix) {
+  extern __shared__ double s_rows[];
+  const int nn = E.mesh.nn;
+  const int i0 = blockIdx.x * 32;
+  const int i = i0 + threadIdx.x;
+  const int bfirst = E.mesh.brptr[i0];
+  const int blast = E.mesh.brptr[min(i0 + 32, nn)];
+  double* mb = E.members + (size_t)member * E.L.stride;
+  const Layout& L = E.L;
+  if (i < nn) {
+    PropView pv = member_props<D>(E, mb);
+    StateView sv;
+    sv.u1 = mb + L.off[VF_U1];
+    sv.u0 = is_static ? sv.u1 : mb + L.off[VF_U0];
+    sv.v0 = mb + L.off[VF_V0];
+    sv.a0 = mb + L.off[VF_A0];
+    sv.p1 = mb + L.off[VF_P1];
+    sv.dt = dt;
+    sv.is_static = is_static;
+    sv.mix = mix;
+    double res[D];
+    assemble_node_auto<D, true, RES>(i, E.mesh, pv, sv,
+                                     s_rows + (size_t)D * D * (E.mesh.brptr[i] - bfirst), res);
+    if (RES) {
+      double* F = mb + L.off[VF_F];
+#pragma unroll
+      for (int c = 0; c < D; ++c) F[D * i + c] = res[c];
+    }
+  }
+  __syncwarp();
+  double* __restrict__ out = mb + L.off[VF_J] + (size_t)D * D * bfirst;
+  const int total = D * D * (blast - bfirst);
+  for (int t = threadIdx.x; t < total; t += 32) out[t] = s_rows[t];
 }
 
 
@@ -1172,7 +1219,47 @@ size_t tile2_smem_bytes(const vf_problem_desc& d, bool direct = false) {
 }  // namespace
 
 int vf::assembly_configure(vf_engine* e, const vf_problem_desc& d, bool two_phase) {
-  (void)e;
+  // tetrahedra: gather-friendly copies of the mesh tables + precomputed CSR slots (tet_tables.h)
+  if (d.dim == 3 && d.nn > 0 && d.ne > 0) {
+    std::vector<int32_t> cells4;
+    std::vector<double> xyz4;
+    std::vector<uint32_t> slots;
+    if (build_tet_gather_tables(d.nn, d.ne, d.xyz_host, d.cells_host, e->brptr.data(),
+                                e->bcol.data(), d.n2e_ptr_host, d.n2e_host, cells4, xyz4, slots)) {
+      const size_t b_xyz = align_up(xyz4.size() * sizeof(double), 256);
+      const size_t b_cells = align_up(cells4.size() * sizeof(int32_t), 256);
+      const size_t b_slots = align_up(std::max<size_t>(slots.size(), 1) * sizeof(uint32_t), 256);
+      char* mem = nullptr;
+      VF_CUDA(cudaMalloc(&mem, b_xyz + b_cells + b_slots));
+      e->node_mem = mem;
+      VF_CUDA(cudaMemcpy(mem, xyz4.data(), xyz4.size() * sizeof(double), cudaMemcpyHostToDevice));
+      VF_CUDA(cudaMemcpy(mem + b_xyz, cells4.data(), cells4.size() * sizeof(int32_t),
+                         cudaMemcpyHostToDevice));
+      VF_CUDA(cudaMemcpy(mem + b_xyz + b_cells, slots.data(), slots.size() * sizeof(uint32_t),
+                         cudaMemcpyHostToDevice));
+      e->dev.mesh.xyz4 = reinterpret_cast<const double*>(mem);
+      e->dev.mesh.cells4 = reinterpret_cast<const int*>(mem + b_xyz);
+      e->dev.mesh.n2e_slots = reinterpret_cast<const unsigned*>(mem + b_xyz + b_cells);
+    }
+  }
+  // asm_node_warp_kernel: most CSR blocks owned by 32 consecutive nodes = its shared memory
+  e->node_warp_blocks = 0;
+  for (int n = 0; n < d.nn; n += 32)
+    e->node_warp_blocks =
+        std::max(e->node_warp_blocks, e->brptr[std::min(n + 32, d.nn)] - e->brptr[n]);
+  {
+    const size_t smem = sizeof(double) * d.dim * d.dim * (size_t)e->node_warp_blocks;
+    if (smem <= (size_t)kNodeWarpMaxSmem) {
+      const int sm = (int)smem;
+      if (d.dim == 3) {
+        VF_CUDA(cudaFuncSetAttribute(asm_node_warp_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+        VF_CUDA(cudaFuncSetAttribute(asm_node_warp_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+      } else {
+        VF_CUDA(cudaFuncSetAttribute(asm_node_warp_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+        VF_CUDA(cudaFuncSetAttribute(asm_node_warp_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+      }
+    }
+  }
   if (two_phase) {
     const int smem2 = (int)tile2_smem_bytes(d);
     if (smem2 > 227 * 1024) {
@@ -1547,13 +1634,40 @@ int assemble_impl(vf_engine* e, int member, int flags, double dt, int is_static,
   }
   // tetrahedra, and triangle meshes whose tiles do not fit the two-phase kernel: thread-per-node
   // gather writing the block rows straight to the CSR array
+  // VF_TET_TABLES=0: generic gathers even when the tetrahedral gather tables exist (A/B, tests)
+  EngineDev dev = e->dev;
+  {
+    const char* env_tt = getenv("VF_TET_TABLES");
+    if (env_tt ? atoi(env_tt) == 0 : !kTetTablesDefault) dev.mesh.n2e_slots = nullptr;
+  }
+  // Jacobian launches: rows of 32 consecutive nodes accumulated in shared memory and written by one
+  // coalesced copy (VF_NODE_WARP=0: the global read-modify-write variant below)
+  {
+    const char* env_nw = getenv("VF_NODE_WARP");  // read per call: tests switch it
+    const size_t smem =
+        sizeof(double) * e->desc.dim * e->desc.dim * (size_t)e->node_warp_blocks;
+    const bool want = env_nw ? atoi(env_nw) != 0 : kNodeWarpDefault;
+    if (jac && want && e->node_warp_blocks > 0 && smem <= (size_t)kNodeWarpMaxSmem) {
+      const int ng = (e->desc.nn + 31) / 32;
+      if (e->desc.dim == 3) {
+        if (res) asm_node_warp_kernel<3, true><<<ng, 32, smem, st>>>(dev, member, dt, is_static, mix);
+        else asm_node_warp_kernel<3, false><<<ng, 32, smem, st>>>(dev, member, dt, is_static, mix);
+      } else {
+        if (res) asm_node_warp_kernel<2, true><<<ng, 32, smem, st>>>(dev, member, dt, is_static, mix);
+        else asm_node_warp_kernel<2, false><<<ng, 32, smem, st>>>(dev, member, dt, is_static, mix);
+      }
+      e->launches += 1;
+      VF_CUDA(cudaGetLastError());
+      return 0;
+    }
+  }
   {
     const int nb = 128, ng = (e->desc.nn + nb - 1) / nb;
 #define VF_LAUNCH_NODE(D)                                                                         \
   do {                                                                                            \
-    if (jac && res) asm_node_global_kernel<D, true, true><<<ng, nb, 0, st>>>(e->dev, member, dt, is_static, mix); \
-    else if (jac) asm_node_global_kernel<D, true, false><<<ng, nb, 0, st>>>(e->dev, member, dt, is_static, mix); \
-    else asm_node_global_kernel<D, false, true><<<ng, nb, 0, st>>>(e->dev, member, dt, is_static, mix); \
+    if (jac && res) asm_node_global_kernel<D, true, true><<<ng, nb, 0, st>>>(dev, member, dt, is_static, mix); \
+    else if (jac) asm_node_global_kernel<D, true, false><<<ng, nb, 0, st>>>(dev, member, dt, is_static, mix); \
+    else asm_node_global_kernel<D, false, true><<<ng, nb, 0, st>>>(dev, member, dt, is_static, mix); \
   } while (0)
     if (e->desc.dim == 3) VF_LAUNCH_NODE(3);
     else VF_LAUNCH_NODE(2);

@@ -103,6 +103,8 @@ struct vf_engine {
   void* fan_mem;
   std::vector<char> fan_dirty;  // per member: the tile-ordered property copy is stale
   int fan_max_wblocks;          // most CSR blocks owned by 32 consecutive nodes
+  void* node_mem = nullptr;     // tetrahedral gather tables (tet_tables.h), own allocation
+  int node_warp_blocks = 0;     // same count over ALL nodes (asm_node_warp_kernel's shared memory)
   bool pool_user;               // this engine holds a reference on the raised mempool threshold
   vf::IluState ilu;
   vf::BandState band;

@@ -9,6 +9,14 @@ namespace vf {
 
 constexpr int kMaxRestart = 128;
 constexpr int kMaxDenseN = 1024;  // dense inverse preconditioner: largest system
+// asm_node_warp_kernel (assembly.cu): largest shared-memory row group it is launched with, and
+// whether Jacobian launches of the thread-per-node path use it by default (VF_NODE_WARP overrides)
+constexpr int kNodeWarpMaxSmem = 160 * 1024;
+// Measured on B200, 0.99 M tetrahedra, residual + Jacobian (profiles/r2_variants_ab.json): global
+// rows 1.98 ms, shared-memory rows 1.90, global rows + gather tables 1.59, both 0.758 ms.
+constexpr bool kNodeWarpDefault = true;
+// table-driven gathers of the tetrahedral node kernels (tet_tables.h; VF_TET_TABLES overrides)
+constexpr bool kTetTablesDefault = true;
 constexpr int kDenseNb = 8;       // ... and the pivot block of its Gauss-Jordan
 // leading dimension of the fp32 inverse: rows padded to 128 bytes for aligned float4 loads
 __host__ __device__ __forceinline__ int dense_ldp(int N) { return (N + 31) & ~31; }

@@ -45,6 +45,21 @@ struct MeshView {
   const int* pf_cell;   // pressure facet -> parent cell
   const int* pf_opp;    // pressure facet -> local vertex of the parent cell opposite to it
   const unsigned char* bc;  // per-DOF Dirichlet flag
+  // tetrahedra only, optional (tet_tables.h; null: generic gathers): one record per cell / node
+  // and the precomputed CSR slots of every (node, cell) pair
+  const int* cells4 = nullptr;           // (ne, 4), 16-byte aligned
+  const double* xyz4 = nullptr;          // (nn, 4): x, y, z, 0, 32-byte aligned
+  const unsigned* n2e_slots = nullptr;   // per n2e entry: byte c = slot of local node c
+};
+
+struct
+#if defined(__CUDACC__)
+    __align__(16)
+#else
+    alignas(16)
+#endif
+        I4 {
+  int x, y, z, w;
 };
 
 struct PropView {
@@ -266,6 +281,82 @@ VF_HD void assemble_node(int i, const MeshView& m, const PropView& p, const Stat
   }
 
   assemble_node_facets_bc<D, JAC, RES>(i, m, p, s, rowblk, res);
+}
+
+// assemble_node<3> reading the gather tables of tet_tables.h: the same cells in the same order with
+// the same arithmetic (identical bits), but 1 + 4 record loads per cell instead of 4 + 12 scattered
+// ones, and the CSR slots from the pair's packed word instead of four scans of the column list.
+template <bool JAC, bool RES>
+VF_HD void assemble_node_tet(int i, const MeshView& m, const PropView& p, const StateView& s,
+                             double* rowblk, double (&res)[3]) {
+  constexpr int D = 3;
+  const int b0 = m.brptr[i];
+  const int deg = m.brptr[i + 1] - b0;
+  const int ld = D * deg;
+  if (JAC)
+    for (int t = 0; t < D * ld; ++t) rowblk[t] = 0.0;
+  if (RES)
+    for (int c = 0; c < D; ++c) res[c] = 0.0;
+
+  const LameFac lf = lame_fac(p.scal[SC_NU]);
+  const Damping dp = prop_damping(p);
+  const NewmarkCoef nc = newmark_coef(s.dt);
+  const I4* cells4 = reinterpret_cast<const I4*>(m.cells4);
+
+  for (int t = m.n2e_ptr[i]; t < m.n2e_ptr[i + 1]; ++t) {
+    const int ref = m.n2e[t];
+    const int e = ref >> 2, a = ref & 3;
+    const unsigned slots = m.n2e_slots[t];
+    const I4 c4 = cells4[e];
+    const int nd[D + 1] = {c4.x, c4.y, c4.z, c4.w};
+    double x[D + 1][D];
+    for (int b = 0; b <= D; ++b) {
+      const D2* q = reinterpret_cast<const D2*>(m.xyz4 + 4 * (size_t)nd[b]);
+      const D2 q0 = q[0], q1 = q[1];
+      x[b][0] = q0.x;
+      x[b][1] = q0.y;
+      x[b][2] = q1.x;
+    }
+    CellGeo<D> g;
+    p1_geometry(x, g);
+    const CellCoef cf = cell_coef<D>(p.emod[e], lf, p.eta[e], p.rho[e], g.vol, dp);
+    if (JAC) {
+      for (int c = 0; c <= D; ++c) {
+        double blk[D][D];
+        cell_block<D>(g, cf, s.mix, a, c, blk);
+        add_block<D>(rowblk, ld, (int)((slots >> (8 * c)) & 255u), blk, 1.0);
+      }
+    }
+    if (RES) {
+      double U[D + 1][D], V[D + 1][D], A[D + 1][D];
+      for (int b = 0; b <= D; ++b)
+        for (int c = 0; c < D; ++c) {
+          const int dof = D * nd[b] + c;
+          const double u1 = s.u1[dof], u0 = s.u0[dof], v0 = s.v0[dof], a0 = s.a0[dof];
+          U[b][c] = u1;
+          V[b][c] = s.is_static ? 0.0 : newmark_v(nc, u1, u0, v0, a0);
+          A[b][c] = s.is_static ? 0.0 : newmark_a(nc, u1, u0, v0, a0);
+        }
+      double r[D];
+      cell_residual<D>(g, cf, a, U, V, A, r);
+      for (int c = 0; c < D; ++c) res[c] += r[c];
+    }
+  }
+
+  assemble_node_facets_bc<D, JAC, RES>(i, m, p, s, rowblk, res);
+}
+
+// assemble_node, or its table-driven form when the mesh view carries the tetrahedral gather tables
+template <int D, bool JAC, bool RES>
+VF_HD void assemble_node_auto(int i, const MeshView& m, const PropView& p, const StateView& s,
+                              double* rowblk, double (&res)[D]) {
+  if constexpr (D == 3) {
+    if (m.n2e_slots) {
+      assemble_node_tet<JAC, RES>(i, m, p, s, rowblk, res);
+      return;
+    }
+  }
+  assemble_node<D, JAC, RES>(i, m, p, s, rowblk, res);
 }
 
 }  // namespace vf

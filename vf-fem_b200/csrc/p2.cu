@@ -22,12 +22,14 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
 #include "../../include/vffem_b200.h"
 #include "elem.cuh"
 #include "p2_tables.h"
+#include "p2_node.cuh"
 
 namespace vf {
 int fail(const std::string& msg);
@@ -53,6 +55,7 @@ struct vf_p2 {
   double* pf_geo;    // (nfp, 3): outward unit normal, length
   unsigned char* fixed;  // nn
   int* order;        // thread -> node: vertex nodes first, then mid-edge nodes (uniform warps)
+  double* uva;       // (nn, 6) packed nodal (u1, v_nmk, a_nmk) of the current assembly (version 2)
   int n_class0;      // number of vertex nodes in `order`
   int max_deg0, max_deg1;  // longest block row of each class
 };
@@ -61,37 +64,9 @@ namespace {
 
 using namespace vf;
 
-struct P2Args {
-  const double *emod, *eta, *rho, *u1, *u0, *v0, *a0, *p1;
-  double* F;
-  double* J;
-  double nu, dt;
-  int jac, res;
-};
-
-__device__ __forceinline__ void p2_shape_edge(double t, int la, int lb, double (&N)[6],
-                                              double (&D)[6][3]) {
-  double L[3] = {0.0, 0.0, 0.0};
-  L[la] = 1.0 - t;
-  L[lb] = t;
-  N[0] = L[0] * (2 * L[0] - 1);
-  N[1] = L[1] * (2 * L[1] - 1);
-  N[2] = L[2] * (2 * L[2] - 1);
-  N[3] = 4 * L[1] * L[2];
-  N[4] = 4 * L[0] * L[2];
-  N[5] = 4 * L[0] * L[1];
-  for (int a = 0; a < 6; ++a)
-    for (int k = 0; k < 3; ++k) D[a][k] = 0.0;
-  D[0][0] = 4 * L[0] - 1;
-  D[1][1] = 4 * L[1] - 1;
-  D[2][2] = 4 * L[2] - 1;
-  D[3][1] = 4 * L[2];
-  D[3][2] = 4 * L[1];
-  D[4][0] = 4 * L[2];
-  D[4][2] = 4 * L[0];
-  D[5][0] = 4 * L[1];
-  D[5][1] = 4 * L[0];
-}
+// vf_p2_assemble runs version 2 of the kernel by default (measured on B200, 1.0 M P2 triangles:
+// 1.24 -> 1.02 ms, identical bits; profiles/r2_variants_ab.json).  VF_P2_WARP=0 selects version 1.
+constexpr bool kP2WarpDefault = true;
 
 __global__ void __launch_bounds__(64) p2_assemble_kernel(vf_p2 P, P2Args A, int first, int count,
                                                          int max_deg) {
@@ -278,6 +253,62 @@ __global__ void __launch_bounds__(64) p2_assemble_kernel(vf_p2 P, P2Args A, int 
   }
 }
 
+// Second version of the kernel above; same node-owner scheme, same summation order per entry
+// (so the two agree to the last bits), three changes for the memory system:
+//   * the private row is kept in the layout of the CSR array ([row 0: deg x (c0, c1)][row 1: ...])
+//     at an ODD stride in doubles (rows of the 32 lanes start on different banks), and a warp
+//     writes its 32 rows out one after another with all lanes on consecutive doubles: coalesced
+//     256-byte stores instead of 32 partial sectors per store instruction;
+//   * dphi_a/dL_k is non-zero only for k = a (vertex node a) or the two vertices of the edge
+//     (mid-edge node a), so W_abkl has 1 / 2 / 4 structural non-zeros per (a, b) instead of 9:
+//     the class of the launch (CLS 0: vertex nodes, 1: mid-edge nodes) fixes the count and only
+//     those terms are summed, in the same (k, l) order;
+//   * nodal pairs (x, y) are fetched by 16-byte loads.
+__global__ void p2_pack_state_kernel(P2Args A, int nn, double* __restrict__ uva) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n < nn) p2_pack_state(A, newmark_coef(A.dt), n, uva);
+}
+
+template <int CLS>
+__global__ void __launch_bounds__(64) p2_assemble_warp_kernel(vf_p2 P, P2Args A, int first,
+                                                              int count, int max_deg) {
+  extern __shared__ double s_rows[];
+  __shared__ double sW[6][6][3][3], sM[6][6];
+  for (int t = threadIdx.x; t < 324; t += blockDim.x) (&sW[0][0][0][0])[t] = (&kP2W[0][0][0][0])[t];
+  for (int t = threadIdx.x; t < 36; t += blockDim.x) (&sM[0][0])[t] = (&kP2M[0][0])[t];
+  __syncthreads();
+  const int tix = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = tix < count;
+  const int lane = threadIdx.x & 31;
+  const int stride = (4 * max_deg) | 1;
+  double* row = s_rows + (size_t)threadIdx.x * stride;
+  int b0 = 0, deg = 0;
+  if (active) {
+    const int i = P.order[first + tix];
+    b0 = P.brptr[i];
+    deg = P.brptr[i + 1] - b0;
+    P2View V;
+    V.xy = P.xy; V.cells = P.cells; V.brptr = P.brptr; V.bcol = P.bcol;
+    V.n2e_ptr = P.n2e_ptr; V.n2e = P.n2e; V.n2e_slots = P.n2e_slots;
+    V.n2f_ptr = P.n2f_ptr; V.n2f = P.n2f; V.n2f_pair = P.n2f_pair;
+    V.pf_cell = P.pf_cell; V.pf_loc = P.pf_loc; V.pf_geo = P.pf_geo; V.fixed = P.fixed;
+    double r0, r1;
+    p2_node_row<CLS>(V, A, &sW[0][0][0][0], &sM[0][0], i, row, r0, r1);
+    if (A.res) reinterpret_cast<P2Pair*>(A.F)[i] = P2Pair{r0, r1};
+  }
+  if (A.jac) {
+    __syncwarp();
+    const double* wrow = s_rows + (size_t)(threadIdx.x - lane) * stride;
+    for (int src = 0; src < 32; ++src) {
+      const int n4 = 4 * __shfl_sync(0xffffffffu, deg, src);
+      const int bs = __shfl_sync(0xffffffffu, b0, src);
+      double* __restrict__ out = A.J + (size_t)4 * bs;
+      const double* rs = wrow + (size_t)src * stride;
+      for (int j = lane; j < n4; j += 32) out[j] = rs[j];
+    }
+  }
+}
+
 size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
 }  // namespace
@@ -345,6 +376,7 @@ int vf_p2_create(int nn, int ne, const double* coords_host, const int32_t* cells
       {(void**)&P->pf_geo, pf_geo_host, sizeof(double) * 3 * (size_t)std::max(nfp, 1)},
       {(void**)&P->fixed, fixed_host, (size_t)nn},
       {(void**)&P->order, order_host, sizeof(int) * (size_t)nn},
+      {(void**)&P->uva, nullptr, sizeof(double) * 6 * (size_t)nn},  // work space, not uploaded
   };
   size_t total = 0;
   for (auto& it : items) total += align256(it.bytes);
@@ -396,19 +428,44 @@ int vf_p2_assemble(vf_p2* P, int flags, double dt, double nu, const double* emod
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(p2_assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(p2_assemble_warp_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(p2_assemble_warp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     attr_set = true;
   }
+  // version 2 (coalesced row write-out, structural zeros of W skipped): VF_P2_WARP=0/1 overrides
+  // the default; it needs 16-byte aligned nodal vectors (double2 loads), else version 1 runs
+  const char* env_warp = getenv("VF_P2_WARP");  // read per call: tests switch it
+  const bool want_warp = env_warp ? atoi(env_warp) != 0 : kP2WarpDefault;
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  const bool warp_ok = want_warp && al16(u1_dev) && al16(u0_dev) && al16(v0_dev) && al16(a0_dev) &&
+                       (!A.res || al16(F_dev));
   // one launch per node class (vertex nodes: ~19 blocks per row, 6 cells; mid-edge nodes: 9 blocks,
   // 2 cells): uniform trip counts inside a warp, shared-memory rows sized per class
   const int block = 64;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (warp_ok && A.res) {
+    // optional pre-pass (VF_P2_PACK=1): (u1, v_nmk, a_nmk) per node, packed for the residual
+    // gathers of version 2.  Measured neutral (1.020 ms with and without: the kernel is not bound
+    // by those gathers), so it is off by default
+    const char* env_pack = getenv("VF_P2_PACK");
+    if (env_pack && atoi(env_pack) != 0) {
+      p2_pack_state_kernel<<<(P->nn + 255) / 256, 256, 0, st>>>(A, P->nn, P->uva);
+      A.uva = P->uva;
+    }
+  }
   const int first[2] = {0, P->n_class0}, count[2] = {P->n_class0, P->nn - P->n_class0};
   const int mdeg[2] = {P->max_deg0, P->max_deg1};
   for (int c = 0; c < 2; ++c) {
     if (count[c] <= 0) continue;
+    const int grid = (count[c] + block - 1) / block;
+    if (warp_ok) {
+      const size_t smem = sizeof(double) * (size_t)block * ((4 * mdeg[c]) | 1);
+      if (c == 0) p2_assemble_warp_kernel<0><<<grid, block, smem, st>>>(*P, A, first[c], count[c], mdeg[c]);
+      else p2_assemble_warp_kernel<1><<<grid, block, smem, st>>>(*P, A, first[c], count[c], mdeg[c]);
+      continue;
+    }
     const size_t smem = sizeof(double) * (size_t)block * (4 * mdeg[c] + 2);
-    p2_assemble_kernel<<<(count[c] + block - 1) / block, block, smem, st>>>(*P, A, first[c],
-                                                                             count[c], mdeg[c]);
+    p2_assemble_kernel<<<grid, block, smem, st>>>(*P, A, first[c], count[c], mdeg[c]);
   }
   if (cudaGetLastError() != cudaSuccess) return vf::fail("vf_p2_assemble: launch failed");
   return 0;

@@ -400,6 +400,7 @@ int vf_create(const vf_problem_desc* desc, void* arena_dev, size_t arena_bytes, 
   e->member_threads = (P.N <= 2048) ? 256 : 512;
 
   if (assembly_configure(e, d, two_phase)) {
+    if (e->node_mem) cudaFree(e->node_mem);
     delete e;
     return 1;
   }
@@ -410,6 +411,7 @@ int vf_create(const vf_problem_desc* desc, void* arena_dev, size_t arena_bytes, 
 void vf_destroy(vf_engine* e) {
   if (!e) return;
   if (e->fan_mem) cudaFree(e->fan_mem);
+  if (e->node_mem) cudaFree(e->node_mem);
   if (e->facet_rec_dev) cudaFree(e->facet_rec_dev);
   ilu_release(e);
   band_release(e);

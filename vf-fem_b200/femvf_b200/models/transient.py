@@ -152,11 +152,13 @@ class FenicsModel(BaseTransientModel):
         self.prop = properties_bvec_from_forms(form)
         assert self.state0['u'].size == N
 
-        fids, pf_cell, pf_opp = residual.pressure_facets()
-        self._tables = _tables.build_tables(mesh.coordinates(), mesh.cells(), pf_cell, pf_opp,
-                                            residual.fixed_dofs())
+        # reference configuration of the mesh: 'prop/umesh' displaces it (transient.py:347-360)
+        self._ref_coords = mesh.coordinates().copy()
+        self._build_tables()
         self._engine: Optional[Engine] = None
         self._engine_provider = None
+        self._engine_attached = False
+        self._geometry_listeners = []   # called after the mesh coordinates changed
         self._member = 0
         # Host -> device synchronisation policy.  The reference mutates host vectors freely, so
         # by default every device call re-uploads state, control and properties.  With
@@ -184,7 +186,37 @@ class FenicsModel(BaseTransientModel):
 
     def _attach_engine(self, engine: Engine, member: int = 0):
         self._engine = engine
+        self._engine_attached = True
         self._member = member
+
+    def _build_tables(self):
+        residual = self._residual
+        mesh = residual.mesh()
+        fids, pf_cell, pf_opp = residual.pressure_facets()
+        self._tables = _tables.build_tables(mesh.coordinates(), mesh.cells(), pf_cell, pf_opp,
+                                            residual.fixed_dofs())
+
+    def _apply_mesh_displacement(self):
+        """``transient.py:347-360``: mesh coordinates = reference coordinates + umesh (the DOFs of
+        this package are vertex-major interleaved, so VERT_TO_VDOF is the identity).  The device
+        tables hold the geometry, so a changed shape drops the engine; the next device call
+        builds a new one and uploads state, control and properties again."""
+        mesh = self._residual.mesh()
+        new = self._ref_coords + np.asarray(
+            self._residual.form['prop/umesh'].vector()).reshape(self._ref_coords.shape)
+        if np.array_equal(new, mesh.coordinates()):
+            return
+        if self._engine_attached:
+            raise NotImplementedError(
+                "'umesh' cannot move the mesh of an engine shared by an ensemble")
+        mesh.coordinates()[:] = new
+        self._build_tables()
+        self._retire_live_jacobian()
+        self._engine = None
+        self._grid = None
+        self.mark_dirty()
+        for notify in self._geometry_listeners:
+            notify()
 
     @property
     def assembly_tables(self) -> dict:
@@ -231,6 +263,8 @@ class FenicsModel(BaseTransientModel):
                 if np.size(value) > 1 else np.ravel(value)[0]
         if prop is not self.prop:
             self.prop[:] = prop
+        if 'prop/umesh' in self.residual.form:
+            self._apply_mesh_displacement()
 
     # --- host -> device ----------------------------------------------------------------
     def _scalar_block(self, ymid: float = 0.0) -> np.ndarray:
@@ -610,6 +644,15 @@ class BaseTransientFSIModel(BaseTransientModel):
         solid._engine, fluid._engine = None, None
         solid._engine_provider = lambda: self.engine
         fluid._engine_provider = lambda: self.engine
+        solid._geometry_listeners.append(self._drop_engine)
+
+    def _drop_engine(self):
+        """The solid's mesh moved ('prop/umesh'): the shared engine holds the old geometry."""
+        self._engine = None
+        self.solid._engine = None
+        self.fluid._engine = None
+        if hasattr(self.fluid, 'mark_dirty'):
+            self.fluid.mark_dirty()
 
     @property
     def engine(self) -> Engine:

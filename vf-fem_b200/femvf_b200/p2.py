@@ -61,6 +61,89 @@ def p2_nodes(coords: np.ndarray, cells: np.ndarray, interleave: bool = True):
     return coords6, cells6, vertex_ids, edges, edge_node
 
 
+def build_p2_tables(coords, cells, pfacets=None, pfacet_cells=None, fixed_edges=None,
+                    interleave: bool = True) -> dict:
+    """Host tables of the P2 kernels (arguments as for ``P2Assembler``): mid-edge nodes, node
+    graph, (node, cell) pairs with the CSR slots of the cell's six nodes, pressure-edge records,
+    Dirichlet flags and the class-sorted thread -> node map.  ``keep`` is the argument list of
+    ``vf_p2_create`` in order."""
+    coords = np.asarray(coords, dtype=np.float64)
+    cells = np.asarray(cells, dtype=np.int64)
+    nv = coords.shape[0]
+    c6, cells6, vid, edges, enode = p2_nodes(coords, cells, interleave)
+    nn, ne = c6.shape[0], cells6.shape[0]
+    brptr, bcol = _tables.node_graph(nn, cells6)
+    brptr = brptr.astype(np.int64); bcol = bcol.astype(np.int64)
+    deg = np.diff(brptr)
+    if deg.max() > 31:
+        raise ValueError("a P2 node couples to more than 31 nodes")
+    # (node, cell) pairs grouped by node
+    pair_node = cells6.ravel()
+    pair_ref = (np.repeat(np.arange(ne), 6) * 8 + np.tile(np.arange(6), ne))
+    order = np.argsort(pair_node, kind='stable')
+    n2e = pair_ref[order]
+    n2e_ptr = np.zeros(nn + 1, dtype=np.int64)
+    np.add.at(n2e_ptr, pair_node + 1, 1)
+    n2e_ptr = np.cumsum(n2e_ptr)
+    # CSR slots of the six nodes of every pair's cell in the pair's node row
+    pn = pair_node[order]
+    gkey = np.repeat(np.arange(nn), deg) * nn + bcol
+    slots = np.zeros(len(n2e), dtype=np.uint64)
+    for b in range(6):
+        nb = cells6[n2e >> 3, b]
+        s = np.searchsorted(gkey, pn * nn + nb) - brptr[pn]
+        slots |= s.astype(np.uint64) << np.uint64(5 * b)
+    # pressure edges
+    nfp = 0 if pfacets is None else len(pfacets)
+    if nfp:
+        pf = np.asarray(pfacets, dtype=np.int64).reshape(-1, 2)
+        pc = np.asarray(pfacet_cells, dtype=np.int64)
+        tri = cells[pc]
+        loc = np.argmax(tri[:, None, :] == pf[:, :, None], axis=2)          # (nfp, 2)
+        mid = _MID_OF[loc[:, 0], loc[:, 1]]
+        pf_loc = np.concatenate([loc, mid[:, None]], axis=1)
+        opp = tri[np.arange(nfp), 3 - loc[:, 0] - loc[:, 1]]
+        t = coords[pf[:, 1]] - coords[pf[:, 0]]
+        length = np.linalg.norm(t, axis=1)
+        nrm = np.stack([t[:, 1], -t[:, 0]], axis=1) / length[:, None]
+        sgn = np.sign(((coords[pf[:, 0]] - coords[opp]) * nrm).sum(axis=1))
+        pf_geo = np.concatenate([nrm * sgn[:, None], length[:, None]], axis=1)
+        fnodes = cells6[pc[:, None], pf_loc]                                 # (nfp, 3) P2 ids
+        f_node = fnodes.ravel()
+        f_ref = np.repeat(np.arange(nfp), 3) * 4 + np.tile(np.arange(3), nfp)
+        f_cell = np.repeat(pc, 3)
+        fo = np.argsort(f_node, kind='stable')
+        n2f = f_ref[fo]
+        n2f_ptr = np.zeros(nn + 1, dtype=np.int64)
+        np.add.at(n2f_ptr, f_node + 1, 1)
+        n2f_ptr = np.cumsum(n2f_ptr)
+        # index of the (node, parent cell) pair in n2e
+        pair_key = pn * ne + (n2e >> 3)                                      # sorted by node
+        n2f_pair = np.searchsorted(pair_key, f_node[fo] * ne + f_cell[fo])
+    else:
+        pc = np.zeros(0, np.int64); pf_loc = np.zeros((0, 3), np.int64)
+        pf_geo = np.zeros((0, 3)); n2f = np.zeros(0, np.int64)
+        n2f_ptr = np.zeros(nn + 1, np.int64); n2f_pair = np.zeros(0, np.int64)
+    # Dirichlet nodes: closure of the fixed edges
+    fixed = np.zeros(nn, dtype=np.uint8)
+    if fixed_edges is not None and len(fixed_edges):
+        fe = np.sort(np.asarray(fixed_edges, dtype=np.int64).reshape(-1, 2), axis=1)
+        ekey = edges[:, 0] * nv + edges[:, 1]
+        idx = np.searchsorted(ekey, fe[:, 0] * nv + fe[:, 1])
+        fixed[vid[fe.ravel()]] = 1
+        fixed[enode[idx]] = 1
+    # thread -> node map: vertex nodes, then mid-edge nodes (each class in node order)
+    node_order = np.concatenate([np.sort(vid), np.sort(enode)])
+    i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+    keep = [np.ascontiguousarray(c6), i32(cells6), i32(brptr), i32(bcol), i32(n2e_ptr),
+            i32(n2e), np.ascontiguousarray(slots.astype(np.uint32)), i32(n2f_ptr), i32(n2f),
+            i32(n2f_pair), i32(pc), i32(pf_loc), np.ascontiguousarray(pf_geo),
+            np.ascontiguousarray(fixed), i32(node_order)]
+    return dict(coords6=c6, cells6=cells6, vertex_ids=vid, edges=edges, edge_node=enode, nn=nn,
+                ne=ne, nv=nv, nfp=nfp, brptr=brptr, bcol=bcol,
+                fixed_nodes=np.nonzero(fixed)[0], keep=keep)
+
+
 class P2Assembler:
     def __init__(self, coords, cells, pfacets=None, pfacet_cells=None, fixed_edges=None,
                  device=None, interleave: bool = True):
@@ -77,80 +160,14 @@ class P2Assembler:
         coords = np.asarray(coords, dtype=np.float64)
         cells = np.asarray(cells, dtype=np.int64)
         self.nv = coords.shape[0]
-        c6, cells6, vid, edges, enode = p2_nodes(coords, cells, interleave)
-        self.coords6, self.cells6 = c6, cells6
-        self.vertex_ids, self.edges, self.edge_node = vid, edges, enode
-        nn, ne = c6.shape[0], cells6.shape[0]
+        T = build_p2_tables(coords, cells, pfacets, pfacet_cells, fixed_edges, interleave)
+        self.coords6, self.cells6 = T['coords6'], T['cells6']
+        self.vertex_ids, self.edges, self.edge_node = T['vertex_ids'], T['edges'], T['edge_node']
+        nn, ne, nfp = T['nn'], T['ne'], T['nfp']
         self.nn, self.ne, self.N = nn, ne, 2 * nn
-        brptr, bcol = _tables.node_graph(nn, cells6)
-        brptr = brptr.astype(np.int64); bcol = bcol.astype(np.int64)
-        deg = np.diff(brptr)
-        if deg.max() > 31:
-            raise ValueError("a P2 node couples to more than 31 nodes")
-        # (node, cell) pairs grouped by node
-        pair_node = cells6.ravel()
-        pair_ref = (np.repeat(np.arange(ne), 6) * 8 + np.tile(np.arange(6), ne))
-        order = np.argsort(pair_node, kind='stable')
-        n2e = pair_ref[order]
-        n2e_ptr = np.zeros(nn + 1, dtype=np.int64)
-        np.add.at(n2e_ptr, pair_node + 1, 1)
-        n2e_ptr = np.cumsum(n2e_ptr)
-        # CSR slots of the six nodes of every pair's cell in the pair's node row
-        pn = pair_node[order]
-        gkey = np.repeat(np.arange(nn), deg) * nn + bcol
-        slots = np.zeros(len(n2e), dtype=np.uint64)
-        for b in range(6):
-            nb = cells6[n2e >> 3, b]
-            s = np.searchsorted(gkey, pn * nn + nb) - brptr[pn]
-            slots |= s.astype(np.uint64) << np.uint64(5 * b)
-        # pressure edges
-        nfp = 0 if pfacets is None else len(pfacets)
-        if nfp:
-            pf = np.asarray(pfacets, dtype=np.int64).reshape(-1, 2)
-            pc = np.asarray(pfacet_cells, dtype=np.int64)
-            tri = cells[pc]
-            loc = np.argmax(tri[:, None, :] == pf[:, :, None], axis=2)          # (nfp, 2)
-            mid = _MID_OF[loc[:, 0], loc[:, 1]]
-            pf_loc = np.concatenate([loc, mid[:, None]], axis=1)
-            opp = tri[np.arange(nfp), 3 - loc[:, 0] - loc[:, 1]]
-            t = coords[pf[:, 1]] - coords[pf[:, 0]]
-            length = np.linalg.norm(t, axis=1)
-            nrm = np.stack([t[:, 1], -t[:, 0]], axis=1) / length[:, None]
-            sgn = np.sign(((coords[pf[:, 0]] - coords[opp]) * nrm).sum(axis=1))
-            pf_geo = np.concatenate([nrm * sgn[:, None], length[:, None]], axis=1)
-            fnodes = cells6[pc[:, None], pf_loc]                                 # (nfp, 3) P2 ids
-            f_node = fnodes.ravel()
-            f_ref = np.repeat(np.arange(nfp), 3) * 4 + np.tile(np.arange(3), nfp)
-            f_cell = np.repeat(pc, 3)
-            fo = np.argsort(f_node, kind='stable')
-            n2f = f_ref[fo]
-            n2f_ptr = np.zeros(nn + 1, dtype=np.int64)
-            np.add.at(n2f_ptr, f_node + 1, 1)
-            n2f_ptr = np.cumsum(n2f_ptr)
-            # index of the (node, parent cell) pair in n2e
-            pair_key = pn * ne + (n2e >> 3)                                      # sorted by node
-            n2f_pair = np.searchsorted(pair_key, f_node[fo] * ne + f_cell[fo])
-        else:
-            pc = np.zeros(0, np.int64); pf_loc = np.zeros((0, 3), np.int64)
-            pf_geo = np.zeros((0, 3)); n2f = np.zeros(0, np.int64)
-            n2f_ptr = np.zeros(nn + 1, np.int64); n2f_pair = np.zeros(0, np.int64)
-        # Dirichlet nodes: closure of the fixed edges
-        fixed = np.zeros(nn, dtype=np.uint8)
-        if fixed_edges is not None and len(fixed_edges):
-            fe = np.sort(np.asarray(fixed_edges, dtype=np.int64).reshape(-1, 2), axis=1)
-            ekey = edges[:, 0] * self.nv + edges[:, 1]
-            idx = np.searchsorted(ekey, fe[:, 0] * self.nv + fe[:, 1])
-            fixed[vid[fe.ravel()]] = 1
-            fixed[enode[idx]] = 1
-        self.fixed_nodes = np.nonzero(fixed)[0]
-        self.brptr, self.bcol = brptr, bcol
-        # thread -> node map: vertex nodes, then mid-edge nodes (each class in node order)
-        node_order = np.concatenate([np.sort(vid), np.sort(enode)])
-        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
-        keep = [np.ascontiguousarray(c6), i32(cells6), i32(brptr), i32(bcol), i32(n2e_ptr),
-                i32(n2e), np.ascontiguousarray(slots.astype(np.uint32)), i32(n2f_ptr), i32(n2f),
-                i32(n2f_pair), i32(pc), i32(pf_loc), np.ascontiguousarray(pf_geo),
-                np.ascontiguousarray(fixed), i32(node_order)]
+        self.fixed_nodes = T['fixed_nodes']
+        self.brptr, self.bcol = T['brptr'], T['bcol']
+        keep = T['keep']
         handle = C.c_void_p()
         with torch.cuda.device(self.device):
             stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)

@@ -35,6 +35,8 @@ FORM_SPECS = {
         ('state/v1', _CG1V, 0.0), ('prop/rho', _DG0, 0.0), ('prop/emod', _DG0, 0.0),
         ('prop/nu', _CONST_S, 0.45), ('prop/rayleigh_m', _CONST_S, 1.0),
         ('prop/rayleigh_k', _CONST_S, 1.0)],
+    # form.py:1037-1062: contributes 0 * (x . w) dx; its coefficient moves the mesh (set_prop)
+    'ShapeForm': [('prop/umesh', _CG1V, 0.0)],
     'IsotropicMembraneForm': [
         ('state/u1', _CG1V, 0.0), ('prop/emod_membrane', _DG0, 0.0),
         ('prop/nu_membrane', _DG0, 0.45), ('prop/th_membrane', _DG0, 0.0)],
@@ -106,6 +108,17 @@ class KelvinVoigt(PredefinedSolidResidual):
 
     FORM_NAMES = ['InertialForm', 'KelvinVoigtForm', 'IsotropicElasticForm',
                   'SurfacePressureForm', 'ManualSurfaceContactTractionForm']
+    TERMS = {'membrane': False}
+
+
+class KelvinVoigtWShape(PredefinedSolidResidual):
+    """``KelvinVoigt`` with a shape parameter (``solid.py:192-215``): ``ShapeForm`` adds nothing to
+    the residual; its coefficient ``umesh`` (a nodal displacement of the reference mesh, last in
+    the property vector) is applied to the mesh coordinates by ``FenicsModel.set_prop``
+    (``models/transient.py:347-360``)."""
+
+    FORM_NAMES = ['InertialForm', 'IsotropicElasticForm', 'KelvinVoigtForm',
+                  'SurfacePressureForm', 'ManualSurfaceContactTractionForm', 'ShapeForm']
     TERMS = {'membrane': False}
 
 
