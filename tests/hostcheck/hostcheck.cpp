@@ -257,9 +257,7 @@ extern "C" int hostcheck_p2_assemble(
         }
       }
       if (A.jac)
-        for (int tid = 0; tid < block; ++tid) {
-          const int lane0 = tid & ~31;  // rows of a warp are written by that warp, lane by lane
-          (void)lane0;
+        for (int tid = 0; tid < block; ++tid) {  // a warp copies its 32 rows one after another
           const double* rs = s_rows + (size_t)tid * stride;
           double* out = J + (size_t)4 * b0[tid];
           for (int j = 0; j < 4 * deg[tid]; ++j) out[j] = rs[j];
