@@ -253,6 +253,12 @@ __global__ void __launch_bounds__(64) p2_assemble_kernel(vf_p2 P, P2Args A, int 
   }
 }
 
+// Pre-pass of version 2 (optional, VF_P2_PACK=1): packed nodal (u1, v_nmk, a_nmk).
+__global__ void p2_pack_state_kernel(P2Args A, int nn, double* __restrict__ uva) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n < nn) p2_pack_state(A, newmark_coef(A.dt), n, uva);
+}
+
 // Second version of the kernel above; same node-owner scheme, same summation order per entry
 // (so the two agree to the last bits), three changes for the memory system:
 //   * the private row is kept in the layout of the CSR array ([row 0: deg x (c0, c1)][row 1: ...])
@@ -264,11 +270,6 @@ __global__ void __launch_bounds__(64) p2_assemble_kernel(vf_p2 P, P2Args A, int 
 //     the class of the launch (CLS 0: vertex nodes, 1: mid-edge nodes) fixes the count and only
 //     those terms are summed, in the same (k, l) order;
 //   * nodal pairs (x, y) are fetched by 16-byte loads.
-__global__ void p2_pack_state_kernel(P2Args A, int nn, double* __restrict__ uva) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n < nn) p2_pack_state(A, newmark_coef(A.dt), n, uva);
-}
-
 template <int CLS>
 __global__ void __launch_bounds__(64) p2_assemble_warp_kernel(vf_p2 P, P2Args A, int first,
                                                               int count, int max_deg) {
