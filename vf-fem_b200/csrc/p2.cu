@@ -259,7 +259,7 @@ __global__ void p2_pack_state_kernel(P2Args A, int nn, double* __restrict__ uva)
   if (n < nn) p2_pack_state(A, newmark_coef(A.dt), n, uva);
 }
 
-// Second version of the kernel above; same node-owner scheme, same summation order per entry
+// Second version of p2_assemble_kernel: same node-owner scheme, same summation order per entry
 // (so the two agree to the last bits), three changes for the memory system:
 //   * the private row is kept in the layout of the CSR array ([row 0: deg x (c0, c1)][row 1: ...])
 //     at an ODD stride in doubles (rows of the 32 lanes start on different banks), and a warp
