@@ -336,3 +336,22 @@ def test_shape_change_drops_the_shared_fsi_engine():
     prop['umesh'][:] = 2e-3
     with pytest.raises(NotImplementedError):
         model.set_prop(prop)
+
+
+def test_large_blockvector_assignment_is_chunked_and_exact():
+    """Assignments of >= 2 M elements go through the threaded, chunked copy (blockvec._parallel_copy):
+    same values, for one or several blocks, odd sizes and a 2-D block."""
+    rng = np.random.default_rng(3)
+    a = bv.BlockVector([rng.random(1500001), rng.random(7), rng.random((300000, 2))],
+                       labels=[('x', 'y', 'z')])
+    b = a.copy()
+    for v in b.vecs:
+        v[...] = -1.0
+    b[:] = a
+    assert all(np.array_equal(x, y) for x, y in zip(a.vecs, b.vecs))
+    c = bv.BlockVector([rng.random(2200003)], labels=[('x',)])
+    d = c.copy(); d['x'][:] = 0.0
+    d[:] = c
+    assert np.array_equal(c['x'], d['x'])
+    pool, workers = bv._copy_pool()
+    assert 2 <= workers <= 8

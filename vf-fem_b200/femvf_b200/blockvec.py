@@ -20,11 +20,40 @@ _POOL = None
 
 
 def _copy_pool():
+    """(pool, workers): threads for large host-to-host copies.  One process per GPU shares the
+    host's cores with its sibling ranks (torchrun sets LOCAL_WORLD_SIZE), so the pool is sized
+    to this rank's share, between 2 and 8 threads."""
     global _POOL
     if _POOL is None:
+        import os
         from concurrent.futures import ThreadPoolExecutor
-        _POOL = ThreadPoolExecutor(max_workers=4)
+        try:
+            ranks = max(int(os.environ.get('LOCAL_WORLD_SIZE', '1')), 1)
+        except ValueError:
+            ranks = 1
+        workers = min(max((os.cpu_count() or 2) // ranks, 2), 8)
+        _POOL = (ThreadPoolExecutor(max_workers=workers), workers)
     return _POOL
+
+
+def _parallel_copy(pairs):
+    """Copy every (target, value) pair; large 1-D blocks are split into cache-line aligned chunks
+    so that all threads of the pool move data (numpy releases the GIL inside the copy; a single
+    thread does ~10 GB/s, far below what the page-locked upload that follows can take)."""
+    pool, workers = _copy_pool()
+    total = sum(t.size for t, _ in pairs)
+    jobs = []
+    for t, v in pairs:
+        v = np.reshape(v, t.shape)
+        # about two chunks per thread over all blocks, shared out by size
+        per_block = int(round(2.0 * workers * t.size / max(total, 1)))
+        if per_block > 1 and t.ndim == 1 and t.size >= (1 << 18):
+            bounds = (np.linspace(0, t.size, per_block + 1).astype(np.int64) // 8) * 8
+            bounds[-1] = t.size
+            jobs += [(t[a:b], v[a:b]) for a, b in zip(bounds[:-1], bounds[1:]) if b > a]
+        else:
+            jobs.append((t, v))
+    list(pool.map(lambda tv: np.copyto(tv[0], tv[1]), jobs))
 
 
 def _as_block(x):
@@ -133,11 +162,8 @@ class BlockVector:
                 if len(value) != len(target):
                     raise ValueError("block count mismatch in assignment")
                 pairs = list(zip(target.vecs, value.vecs))
-                if len(pairs) > 1 and sum(t.size for t, _ in pairs) >= _PARALLEL_COPY_MIN:
-                    # large blocks: numpy releases the GIL inside the copy, so the blocks
-                    # move concurrently (a single thread does ~10 GB/s)
-                    list(_copy_pool().map(lambda tv: np.copyto(tv[0], np.reshape(tv[1], tv[0].shape)),
-                                          pairs))
+                if sum(t.size for t, _ in pairs) >= _PARALLEL_COPY_MIN:
+                    _parallel_copy(pairs)
                 else:
                     for t, v in pairs:
                         t[...] = np.reshape(v, t.shape)
