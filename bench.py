@@ -11,13 +11,19 @@ Contract (one JSON line on stdout, rank 0):
 Workload (config.workload): BASELINE.json configs[2] -- residual + Jacobian assembly
 microbenchmark on the M5_CB outline red-refined 7x (4.0e6 P1 triangles, 4.0e6 DOF,
 5.6e7 non-zeros).  The reference's elements are P1 only; the P2 variant named
-in BASELINE.json has no reference behaviour and is the next row to add.  One step = one
-assembly of F_u and J_uu (Dirichlet rows applied) from state/properties resident in HBM.
+in BASELINE.json has no reference behaviour: it is measured as written (1.0 M P2 triangles) in
+the `p2` object of the same line.  One step = one assembly of F_u and J_uu (Dirichlet rows
+applied) from state/properties resident in HBM.
 
 Also measured in the same run and attached to the line: the SpMV kernel's roofline
 (`spmv`), the single-simulation forward step rate on config 1 (`forward`), the 1024-member
 ensemble of config 4 through the device-resident time loop and through the host-buffer C ABI
-(`ensemble`), and the CPU oracle timed on a bounded sample (`cpu_baseline`).
+(`ensemble`, strong-scaled over the ranks), forward.integrate on a refined mesh through the
+whole-GPU Newton (`forward_refined`), the P2 triangle assembly (`p2`, both kernel versions in
+`ms_per_step_by_kernel`), the mesh-partitioned tetrahedral assembly + GMRES of config 5 on the
+same ranks (`partition`, both node kernels in `assembly_ms_per_step_by_kernel`, and at N > 1
+the check that the N-rank iterate equals the single-rank one), and the CPU oracle timed on a
+bounded sample on all host cores (`cpu_baseline`).
 """
 
 import argparse
