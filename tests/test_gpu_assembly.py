@@ -275,3 +275,32 @@ def test_state0_and_control_sensitivities(torch_cuda, mesh_name, variant):
     got = B @ dp
     assert np.max(np.abs(got[free] - fd[free])) <= 1e-9 * np.max(np.abs(fd))
     assert B.shape == (N, prob.nn)
+
+
+@pytest.mark.xfail(strict=False, reason="first GPU run pending: written after the GPU budget of "
+                   "round 2 was spent.  The host logic (mesh moved, tables rebuilt, engine "
+                   "dropped) is covered on the CPU in tests/test_host_logic.py; the kernels are "
+                   "the ones of the tests above")
+def test_shape_parameter_moves_the_device_mesh(torch_cuda):
+    """KelvinVoigtWShape: 'umesh' displaces the mesh (reference models/transient.py:347-360); the
+    device assembles on the moved mesh: residual and Jacobian against the oracle built on the
+    displaced coordinates, before and after the move, and after moving back."""
+    from femvf_b200.models import transient
+    from femvf_b200.residuals import solid as slr
+    model = transient.FenicsModel(slr.KelvinVoigtWShape(*mesh_tuples()['m5']()))
+    ref = model.residual.mesh().coordinates().copy()
+    _assemble_and_compare(model, np.random.default_rng(21))
+    engine0 = model.engine
+    rng = np.random.default_rng(22)
+    prop = model.prop.copy()
+    du = 2e-3 * rng.standard_normal(ref.shape)
+    prop['umesh'][:] = du.ravel()
+    model.set_prop(prop)
+    assert np.array_equal(model.residual.mesh().coordinates(), ref + du)
+    _assemble_and_compare(model, np.random.default_rng(23))
+    assert model.engine is not engine0
+    prop = model.prop.copy()
+    prop['umesh'][:] = 0.0
+    model.set_prop(prop)
+    assert np.array_equal(model.residual.mesh().coordinates(), ref)
+    _assemble_and_compare(model, np.random.default_rng(24))

@@ -256,3 +256,55 @@ def test_p2_second_kernel_arithmetic_on_cpu(lib, mesh_name, interleave, flags):
         assert np.max(np.abs(F - F_ref_n)) <= 1e-12 * np.max(np.abs(F_ref_n))
     else:
         assert np.all(np.isnan(F))
+
+
+def test_shape_parameter_tables_on_cpu(lib):
+    """KelvinVoigtWShape after ``set_prop`` with a non-zero 'umesh': the rebuilt device tables
+    (``FenicsModel.assembly_tables``) run through the kernels' element code give the oracle's
+    residual and Jacobian on the displaced mesh (the CPU half of
+    tests/test_gpu_assembly.py::test_shape_parameter_moves_the_device_mesh)."""
+    from femvf_b200.models import transient
+    model = transient.FenicsModel(slr.KelvinVoigtWShape(*mesh_tuples()['m5']()))
+    mesh = model.residual.mesh()
+    ref = mesh.coordinates().copy()
+    rng = np.random.default_rng(5)
+    prop_bv = model.prop.copy()
+    du = 2e-3 * rng.standard_normal(ref.shape)
+    prop_bv['umesh'][:] = du.ravel()
+    model.set_prop(prop_bv)
+    T = model.assembly_tables
+    assert np.array_equal(T['xyz'], (ref + du).T)
+    prob = oracle_problem(model.residual)
+    assert np.array_equal(prob.coords, ref + du)
+    N, ne, nn = prob.N, prob.ne, prob.nn
+    prop = random_solid_prop(prob, rng, membrane=True)
+    so = om.SolidOracle(prob, contact=False, membrane=False)
+    u1, u0, v0, a0 = random_state(N, rng)
+    p1 = rng.uniform(0, 8e3, nn)
+    dt = 1e-4
+    Jo = so.jac(u1, dt, prop, p1)
+    Fo = so.res(u1, (u0, v0, a0), dt, prop, p1)
+    scal = np.zeros(10)
+    scal[0], scal[1], scal[2] = 0.45, prop['ycontact'], prop['kcontact']
+    scal[3:5] = prop['ncontact']
+    J = np.zeros(len(T['colidx']))
+    F = np.zeros(N)
+    rc = lib.hostcheck_assemble(
+        2, nn, ne, T['nfp'], P(T['xyz']), P(T['cells']), P(T['brptr']), P(T['bcol']),
+        P(T['n2e_ptr']), P(T['n2e']), P(T['n2f_ptr']), P(T['n2f']), P(T['pf_cell']),
+        P(T['pf_opp']), P(T['bc']), P(prop['rho']), P(prop['eta']), P(prop['emod']), P(scal),
+        P(prop['emod_membrane']), P(prop['nu_membrane']), P(prop['th_membrane']),
+        0, 0, 0, P(u1), P(u0), P(v0), P(a0), P(p1), ctypes.c_double(dt), P(J), P(F))
+    assert rc == 0
+    assert rel_row_err(J, Jo) <= 1e-12
+    assert np.max(np.abs(F - Fo)) <= 1e-12 * np.max(np.abs(Fo))
+    # moving back restores the reference mesh and its tables
+    model.set_prop(_with(model.prop, 'umesh', 0.0))
+    assert np.array_equal(mesh.coordinates(), ref)
+    assert np.array_equal(model.assembly_tables['xyz'], ref.T)
+
+
+def _with(prop, key, value):
+    out = prop.copy()
+    out[key][:] = value
+    return out
