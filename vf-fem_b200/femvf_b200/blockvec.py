@@ -24,16 +24,18 @@ def _copy_pool():
     host's cores with its sibling ranks (torchrun sets LOCAL_WORLD_SIZE), so the pool is sized
     to this rank's share, between 2 and 8 threads."""
     global _POOL
+    import os
+    if _POOL is not None and _POOL[2] != os.getpid():
+        _POOL = None   # forked child: the parent's worker threads do not exist here
     if _POOL is None:
-        import os
         from concurrent.futures import ThreadPoolExecutor
         try:
             ranks = max(int(os.environ.get('LOCAL_WORLD_SIZE', '1')), 1)
         except ValueError:
             ranks = 1
         workers = min(max((os.cpu_count() or 2) // ranks, 2), 8)
-        _POOL = (ThreadPoolExecutor(max_workers=workers), workers)
-    return _POOL
+        _POOL = (ThreadPoolExecutor(max_workers=workers), workers, os.getpid())
+    return _POOL[:2]
 
 
 def _parallel_copy(pairs):
